@@ -1,0 +1,150 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the LIVE reference (build container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference
+
+The reference is imported read-only from /root/reference (it cannot travel to the GPU
+box); its outputs are committed as small fixtures so the oracle restatement
+(oracle/qd_oracle.py) and the CUDA path can be checked anywhere.  Nothing in tests/,
+smoke() or bench.py reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+import qd_cases  # noqa: E402
+from quantum_distortion.dsp import pipeline as ref_pipeline  # noqa: E402
+from quantum_distortion.dsp import quantizer as ref_q  # noqa: E402
+from quantum_distortion.dsp import spectral_fx as ref_fx  # noqa: E402
+from quantum_distortion.dsp import stft_utils as ref_stft  # noqa: E402
+from quantum_distortion.dsp.crossover import design_linkwitz_riley_sos, linkwitz_riley_split  # noqa: E402
+from quantum_distortion.dsp.distortion import apply_distortion  # noqa: E402
+from quantum_distortion.dsp.limiter import peak_limiter  # noqa: E402
+from quantum_distortion.dsp.saturation import saturate_lowband  # noqa: E402
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def gen_pipeline():
+    out = {}
+    for name, (kind, seed, n, sr, n_fft, rng_seed, kw) in qd_cases.CASES.items():
+        x = qd_cases.make_signal(kind, seed, n, sr)
+        ref_pipeline.N_FFT_DEFAULT = n_fft
+        if rng_seed is not None:
+            np.random.seed(rng_seed)
+        y, taps = quiet(ref_pipeline.process_audio, x, sr, quantize_mode="spectral_bins", **kw)
+        ref_pipeline.N_FFT_DEFAULT = 2048
+        out[f"{name}/x"] = x
+        out[f"{name}/y"] = y
+        out[f"{name}/pre_quant"] = taps["pre_quant"].astype(np.float32)
+        out[f"{name}/post_dist"] = taps["post_dist"].astype(np.float32)
+        print(f"pipeline {name}: n={n} peak={np.max(np.abs(y)):.4f}")
+    np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **out)
+
+
+def gen_tables():
+    out = {}
+    for sr, n_fft, key, scale in [(48000, 2048, "D", "minor"), (44100, 2048, "D", "minor"),
+                                  (48000, 2048, "F", "minor"), (48000, 512, "D", "minor"),
+                                  (48000, 1024, "Bb", "dorian"), (48000, 4096, "C", "major"),
+                                  (48000, 8192, "D", "minor"), (48000, 2048, "A", "pentatonic"),
+                                  (96000, 2048, "G#", "harmonic_minor"), (48000, 2048, "Eb", "mixolydian")]:
+        freqs = np.fft.rfftfreq(n_fft, d=1.0 / sr)
+        tag = f"{sr}_{n_fft}_{key}_{scale}"
+        out[f"tb/{tag}"] = ref_q.build_target_bins_for_freqs(freqs, key, scale).astype(np.int64)
+        out[f"mask/{tag}"] = ref_pipeline._build_quantize_band_mask(freqs, 110.0, 5000.0)
+    freqs = np.fft.rfftfreq(2048, d=1.0 / 48000)
+    out["mask/wide"] = ref_pipeline._build_quantize_band_mask(freqs, 0.0, 0.0)
+    for f0 in (55.0, 110.0, 441.3):
+        out[f"htb/{f0}"] = ref_q.build_harmonic_target_bins(freqs, f0).astype(np.int64)
+    # reference KAT (tests/test_quantizer.py:10-23)
+    out["tb/kat4"] = ref_q.build_target_bins_for_freqs(np.array([0.0, 430.0, 440.0, 450.0]), "A", "minor")
+    np.savez_compressed(os.path.join(HERE, "tables.npz"), **out)
+    print("tables:", len(out))
+
+
+def gen_stages():
+    out = {}
+    rng = np.random.default_rng(7)
+    sr, n_fft = 48000, 2048
+    freqs = np.fft.rfftfreq(n_fft, d=1.0 / sr)
+    tb = ref_q.build_target_bins_for_freqs(freqs, "D", "minor")
+    mask = ref_pipeline._build_quantize_band_mask(freqs, 110.0, 5000.0)
+    # --- quantize_spectrum on random frames (incl. a silent frame and exact zeros)
+    mags = np.abs(rng.standard_normal((6, 1025))) * np.exp(-np.arange(1025) / 200.0)[None, :]
+    mags[3] = 0.0
+    mags[4, ::3] = 0.0
+    phases = rng.uniform(-np.pi, np.pi, size=(6, 1025))
+    out["q/mags"], out["q/phases"] = mags, phases
+    for tag, (snap, smear, smooth, m) in {"default": (1.0, 0.1, True, mask), "growl": (0.9, 0.3, True, mask),
+                                          "nosmooth": (0.75, 0.4, False, mask), "nomask": (1.0, 0.1, True, None),
+                                          "smear0": (1.0, 0.0, True, mask), "smear1": (0.5, 1.0, True, mask)}.items():
+        nm, nph = [], []
+        for t in range(mags.shape[0]):
+            a, b = ref_q.quantize_spectrum(mags[t], phases[t], freqs, "D", "minor", snap, smear, smooth,
+                                           target_bins=tb, active_mask=m)
+            nm.append(a)
+            nph.append(b)
+        out[f"q/{tag}/mags"], out[f"q/{tag}/phases"] = np.array(nm), np.array(nph)
+    # --- STFT / iSTFT
+    x = qd_cases.make_signal("bass", 40, 9000, sr)
+    for nf in (512, 2048):
+        S, fr = ref_stft.stft_mono(x, sr, n_fft=nf)
+        out[f"stft/{nf}/S"] = S
+        out[f"stft/{nf}/y"] = ref_stft.istft_mono(S, sr, n_fft=nf, length=len(x))
+    out["stft/x"] = x
+    # --- spectral FX per frame with seeded global RNG
+    fm = np.abs(rng.standard_normal(1025)) * np.exp(-np.arange(1025) / 150.0)
+    fp = rng.uniform(-np.pi, np.pi, size=1025)
+    out["fx/mag"], out["fx/phase"] = fm, fp
+    for tag, (mode, s) in {"bitcrush05": ("bitcrush", 0.5), "bitcrush03": ("bitcrush", 0.3),
+                           "bitcrush08": ("bitcrush", 0.8), "disp06": ("phase_dispersal", 0.6),
+                           "disp03": ("phase_dispersal", 0.3), "scr055": ("bin_scramble", 0.55),
+                           "scr03": ("bin_scramble", 0.3), "scr09": ("bin_scramble", 0.9)}.items():
+        np.random.seed(99)
+        cfg = ref_pipeline._SpectralFXConfig(mode, s, {})
+        frames_m, frames_p = [], []
+        for _ in range(3):  # three consecutive frames consume the RNG in order
+            a, b = ref_pipeline.apply_spectral_fx(fm.copy(), fp.copy(), cfg)
+            frames_m.append(np.array(a))
+            frames_p.append(np.array(b))
+        out[f"fx/{tag}/mag"], out[f"fx/{tag}/phase"] = np.array(frames_m), np.array(frames_p)
+    a, b = ref_fx.bitcrush(fm, fp, method="uniform", step=0.07, threshold=0.01)
+    out["fx/uniform/mag"] = a
+    # --- time-domain stages
+    xl = qd_cases.make_signal("loud", 41, 6000, sr)
+    out["td/x"] = xl
+    out["td/wavefold"] = apply_distortion(xl, "wavefold", fold_amount=5.0, bias=0.1)
+    out["td/tube"] = apply_distortion(xl, "tube", drive=4.0, warmth=0.7)
+    for srr in (48000, 44100):
+        y, g = peak_limiter(xl, srr, ceiling_db=-1.0, lookahead_ms=5.0, release_ms=30.0)
+        out[f"td/lim/{srr}/y"], out[f"td/lim/{srr}/g"] = y, g
+    lo, hi = linkwitz_riley_split(xl, sr, 300.0)
+    out["td/xo/low"], out["td/xo/high"] = lo, hi
+    sl, sh = design_linkwitz_riley_sos(sr, 300.0)
+    out["td/xo/sos_low"], out["td/xo/sos_high"] = sl, sh
+    out["td/sat"] = saturate_lowband(lo, drive=2.5)
+    np.savez_compressed(os.path.join(HERE, "stages.npz"), **out)
+    print("stages:", len(out))
+
+
+if __name__ == "__main__":
+    gen_tables()
+    gen_stages()
+    gen_pipeline()
+    for f in ("tables.npz", "stages.npz", "pipeline.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
