@@ -1,0 +1,178 @@
+// qd_host_tables.hpp -- host-side (plain C++) builders for the device tables of qd_spec.cuh.
+// Pure arithmetic in double, rounded once to float; no CUDA dependency (also used by the
+// g++ emulation tests).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/qd_b200.h"
+
+namespace qd_host {
+
+struct F2 { float x, y; };
+
+struct AffEntryH {  // must match qd::AffEntry
+    int16_t slot[5];
+    int16_t pad;
+    float coef[5];
+};
+static_assert(sizeof(AffEntryH) == 32, "AffEntry layout");
+
+struct FftRadices { int r1, r2, r3; };
+inline bool fft_radices(int nc, FftRadices *o) {
+    switch (nc) {
+        case 256:  *o = {8, 8, 4};   return true;
+        case 512:  *o = {8, 8, 8};   return true;
+        case 1024: *o = {32, 32, 1}; return true;
+        case 2048: *o = {16, 16, 8}; return true;
+        case 4096: *o = {16, 16, 16}; return true;
+    }
+    return false;
+}
+
+struct SpecTables {
+    int nc = 0, hop = 0;
+    std::vector<F2> wtab, tw1, tw2, wsplit;
+    std::vector<float> invw;  // [16][hop]
+};
+
+// periodic Hann, hop = n_fft/4 (dsp/stft_utils.py:51-56, 137-141)
+inline double hann_periodic(int n, int n_fft) { return 0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)n_fft); }
+
+inline bool build_spec_tables(int n_fft, SpecTables *t) {
+    const int nc = n_fft / 2;
+    FftRadices r;
+    if (!fft_radices(nc, &r)) return false;
+    t->nc = nc;
+    t->hop = n_fft / 4;
+    t->wtab.resize(nc);
+    for (int n = 0; n < nc; ++n)
+        t->wtab[n] = F2{(float)hann_periodic(2 * n, n_fft), (float)hann_periodic(2 * n + 1, n_fft)};
+    // access-ordered twiddles: entry [(i*R + k)*32 + lane] = exp(-2 pi i j k / M),
+    // butterfly u = lane + 32 i of a pass with sub-size M, radix R, stride S = M/R, j = u % S
+    auto fill = [&](std::vector<F2> &tw, int M, int R) {
+        const int S = M / R, nb = nc / R / 32;
+        tw.assign((size_t)nb * R * 32, F2{1.0f, 0.0f});
+        for (int i = 0; i < nb; ++i)
+            for (int k = 0; k < R; ++k)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int j = (lane + 32 * i) % S;
+                    const double ang = -2.0 * M_PI * (double)(((long long)j * k) % M) / (double)M;
+                    tw[((size_t)i * R + k) * 32 + lane] = F2{(float)std::cos(ang), (float)std::sin(ang)};
+                }
+    };
+    fill(t->tw1, nc, r.r1);
+    if (r.r3 > 1) fill(t->tw2, nc / r.r1, r.r2);
+    else t->tw2.assign(1, F2{1.0f, 0.0f});
+    t->wsplit.resize(nc / 2 + 1);
+    for (int k = 0; k <= nc / 2; ++k) {
+        const double ang = -2.0 * M_PI * (double)k / (double)n_fft;
+        t->wsplit[k] = F2{(float)std::cos(ang), (float)std::sin(ang)};
+    }
+    // 1 / max(sum of w^2 over the frames covering a hop-block, 1e-10)  (dsp/stft_utils.py:174-186, 214)
+    // frames are added in ascending t = descending slice index.
+    const int hop = t->hop;
+    t->invw.assign((size_t)16 * hop, 0.0f);
+    for (int a = 0; a < 4; ++a)
+        for (int b = a; b < 4; ++b)
+            for (int c = 0; c < hop; ++c) {
+                double s = 0.0;
+                for (int sl = b; sl >= a; --sl) {
+                    const double w = hann_periodic(sl * hop + c, n_fft);
+                    s += w * w;
+                }
+                t->invw[(size_t)(a * 4 + b) * hop + c] = (float)(1.0 / std::max(s, 1e-10));
+            }
+    return true;
+}
+
+struct QuantTablesH {
+    int n_bins = 0, n_slots = 0, n_aff = 0, rows = 0;
+    std::vector<uint16_t> slot_begin, src_bin, row_aff_base;
+    std::vector<int32_t> slot_bin;
+    std::vector<uint32_t> row_active, row_aff;
+    std::vector<AffEntryH> aff;
+    float keep_active = 1.0f;
+};
+
+// Gather form of dsp/quantizer.py:424-515 derived from the reference's own integer tables.
+inline bool build_quant_tables(const qd_tables &in, QuantTablesH *q, std::string *err) {
+    const int n = in.n_bins;
+    if (n < 3 || n > 8193 || !in.target_bins || !in.active_mask) { if (err) *err = "bad quantizer tables"; return false; }
+    const int radius = in.smear_radius;
+    if (radius < 0 || radius > 2) { if (err) *err = "smear_radius must be 0..2"; return false; }
+    if (radius > 0 && !in.smear_w) { if (err) *err = "smear_w missing"; return false; }
+    q->n_bins = n;
+    q->rows = (n + 31) / 32;
+    // sources: active bins with an in-range target (dsp/quantizer.py:426-431); E > 0 is a per-frame test
+    std::vector<std::vector<uint16_t>> by_target(n);
+    q->row_active.assign(q->rows, 0u);
+    for (int i = 0; i < n; ++i) {
+        const int t = in.target_bins[i];
+        if (in.active_mask[i] && t >= 0 && t < n) {
+            by_target[t].push_back((uint16_t)i);
+            q->row_active[i >> 5] |= 1u << (i & 31);
+        }
+    }
+    std::vector<int> slot_of(n, -1);
+    q->slot_begin.clear(); q->src_bin.clear(); q->slot_bin.clear();
+    for (int t = 0; t < n; ++t)
+        if (!by_target[t].empty()) {
+            slot_of[t] = (int)q->slot_bin.size();
+            q->slot_bin.push_back(t);
+            q->slot_begin.push_back((uint16_t)q->src_bin.size());
+            for (uint16_t s : by_target[t]) q->src_bin.push_back(s);
+        }
+    q->slot_begin.push_back((uint16_t)q->src_bin.size());
+    q->n_slots = (int)q->slot_bin.size();
+    if (q->src_bin.empty()) q->src_bin.push_back(0);
+    const double snap = in.snap, smear = in.smear;
+    const bool do_smear = smear > 0.0 && radius > 0;  // dsp/quantizer.py:458
+    q->keep_active = (float)(1.0 - snap);
+    q->row_aff.assign(q->rows, 0u);
+    q->row_aff_base.assign(q->rows, 0);
+    q->aff.clear();
+    for (int d = 0; d < n; ++d) {
+        AffEntryH e;
+        bool any = false;
+        for (int k = 0; k < 5; ++k) { e.slot[k] = (int16_t)q->n_slots; e.coef[k] = 0.0f; }
+        e.pad = 0;
+        for (int k = 0; k < 5; ++k) {
+            const int t = d + (k - 2);
+            if (t < 0 || t >= n || slot_of[t] < 0) continue;
+            double c = 0.0;
+            if (k == 2) c += snap * (1.0 - smear);  // base energy lands on the target itself (:437, :446)
+            const int o = d - t;                      // offset of d inside the target's smear window
+            if (do_smear && o >= -radius && o <= radius) {
+                // local kernel re-normalised over the part of [t-r, t+r] inside [0, n)  (:311-330)
+                const int a = std::max(0, t - radius), b = std::min(n, t + radius + 1);
+                const int k0 = std::max(0, radius - t);
+                double ksum = 0.0;
+                for (int qq = k0; qq < k0 + (b - a); ++qq) ksum += in.smear_w[qq];
+                if (ksum > 0.0) c += snap * smear * (in.smear_w[o + radius] / ksum);
+            }
+            if (c != 0.0) {
+                e.slot[k] = (int16_t)slot_of[t];
+                e.coef[k] = (float)c;
+                any = true;
+            }
+        }
+        if (any) {
+            q->row_aff[d >> 5] |= 1u << (d & 31);
+            q->aff.push_back(e);
+        }
+    }
+    q->n_aff = (int)q->aff.size();
+    int run = 0;
+    for (int r = 0; r < q->rows; ++r) {
+        q->row_aff_base[r] = (uint16_t)run;
+        run += __builtin_popcount(q->row_aff[r]);
+    }
+    if (q->aff.empty()) q->aff.push_back(AffEntryH{});
+    return true;
+}
+
+}  // namespace qd_host

@@ -1,0 +1,130 @@
+"""CPU: single-step the CUDA kernel SOURCE through tests/emu/cuda_emu.h (g++ -DQD_EMU) and compare
+with the oracle.  This checks index math / table layout / branch shapes of
+quantumdistortion_b200/csrc/qd_spec.cuh in the GPU-less container; it is not the product path
+(the shipped library is the nvcc build of the same source) and proves nothing about speed."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import qd_oracle as orc
+from quantumdistortion_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+CSRC = os.path.join(os.path.dirname(HERE), "quantumdistortion_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu_spec():
+    exe = os.path.join(tempfile.gettempdir(), "qd_emu_spec")
+    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_spec.cpp", "cuda_emu.h")]
+    srcs += [os.path.join(CSRC, f) for f in ("qd_spec.cuh", "qd_common.cuh", "qd_host_tables.hpp")]
+    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-DQD_EMU", "-I", EMU_DIR, "-o", exe,
+                               os.path.join(EMU_DIR, "emu_spec.cpp"), "-lpthread"])
+    return exe
+
+
+def run_emu(exe, x, sr, n_fft, nw, tile_blocks, quant, smoothing, snap, smear, epilogue=0, fold=1.0,
+            bias=0.0, tg=1.0, tn=1.0, key="D", scale="minor", lo=110.0, hi=5000.0):
+    freqs = np.fft.rfftfreq(n_fft, d=1.0 / sr)
+    tb = orc.target_bins_for_freqs(freqs, key, scale).astype(np.int32)
+    mask = orc.quantize_band_mask(freqs, lo, hi).astype(np.uint8)
+    with tempfile.TemporaryDirectory() as d:
+        p = lambda n: os.path.join(d, n)
+        x.astype(np.float32).tofile(p("x"))
+        tb.tofile(p("tb"))
+        mask.tofile(p("mask"))
+        subprocess.check_call([exe, str(n_fft), str(nw), str(len(x)), str(tile_blocks), str(int(quant)),
+                               str(int(smoothing)), repr(float(snap)), repr(float(smear)), str(epilogue),
+                               repr(float(fold)), repr(float(bias)), repr(float(tg)), repr(float(tn)),
+                               p("x"), p("tb"), p("mask"), p("y"), p("tap")], stdout=subprocess.DEVNULL)
+        return np.fromfile(p("y"), dtype=np.float32), np.fromfile(p("tap"), dtype=np.float32)
+
+
+def oracle_pass(x, sr, n_fft, quant, smoothing, snap, smear, key="D", scale="minor", lo=110.0, hi=5000.0):
+    S, freqs = orc.stft(x, sr, n_fft)
+    if quant:
+        S = orc.spectral_quantize_stft(S, freqs, key, scale, snap, smear, smoothing,
+                                       quantize_min_hz=lo, quantize_max_hz=hi)
+    return orc.istft(S, sr, n_fft, length=len(x))
+
+
+@pytest.mark.parametrize("n_fft,nw,n,tile", [(2048, 4, 6000, 64), (2048, 8, 5003, 5), (512, 4, 1500, 7),
+                                             (1024, 4, 2100, 64), (4096, 4, 9000, 3), (8192, 4, 17000, 64),
+                                             (2048, 4, 700, 64)])
+def test_emu_passthrough(emu_spec, n_fft, nw, n, tile):
+    x = synth.bass_clip(3, n)
+    y, tap = run_emu(emu_spec, x, 48000, n_fft, nw, tile, False, False, 1.0, 0.1)
+    ref = oracle_pass(x, 48000, n_fft, False, False, 1.0, 0.1)
+    assert np.max(np.abs(y - ref)) < 2e-6
+    assert np.array_equal(y, tap)
+    assert orc.null_test_db(y, x) < -110.0
+
+
+@pytest.mark.parametrize("n_fft,nw,n,tile,snap,smear,smooth", [
+    (2048, 4, 6000, 64, 1.0, 0.1, True), (2048, 8, 5003, 4, 0.9, 0.3, True), (2048, 4, 4000, 64, 0.75, 0.0, False),
+    (512, 4, 1500, 64, 1.0, 0.1, True), (1024, 4, 2100, 6, 1.0, 0.1, True), (4096, 4, 9000, 64, 1.0, 0.1, True)])
+def test_emu_quantized_pass(emu_spec, n_fft, nw, n, tile, snap, smear, smooth):
+    x = synth.noise_clip(5, n)
+    y, _ = run_emu(emu_spec, x, 48000, n_fft, nw, tile, True, smooth, snap, smear)
+    ref = oracle_pass(x, 48000, n_fft, True, smooth, snap, smear)
+    err = float(np.max(np.abs(y - ref)))
+    assert err < 1e-5, err
+
+
+def test_emu_wide_mask_and_epilogue(emu_spec):
+    x = synth.loud_clip(6, 5000)
+    y, tap = run_emu(emu_spec, x, 48000, 2048, 4, 64, True, True, 0.9, 0.3, epilogue=1, fold=5.0, bias=0.1,
+                     key="A", scale="pentatonic", lo=0.0, hi=0.0)
+    ref_tap = oracle_pass(x, 48000, 2048, True, True, 0.9, 0.3, key="A", scale="pentatonic", lo=0.0, hi=0.0)
+    assert np.max(np.abs(tap - ref_tap)) < 1e-5
+    ref = orc.apply_distortion(tap, "wavefold", fold_amount=5.0, bias=0.1)
+    assert np.max(np.abs(y - ref)) < 1e-5
+
+
+@pytest.fixture(scope="module")
+def emu_time():
+    exe = os.path.join(tempfile.gettempdir(), "qd_emu_time")
+    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_time.cpp", "cuda_emu.h")]
+    srcs += [os.path.join(CSRC, f) for f in ("qd_time.cuh", "qd_common.cuh", "qd_host_time.hpp")]
+    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-DQD_EMU", "-I", EMU_DIR, "-o", exe,
+                               os.path.join(EMU_DIR, "emu_time.cpp"), "-lpthread"])
+    return exe
+
+
+@pytest.mark.parametrize("n,sr,kind", [(6000, 48000, "loud"), (2048, 44100, "noise"), (5000, 48000, "noise"),
+                                       (300, 48000, "noise"), (4097, 1000, "noise")])
+def test_emu_limiter(emu_time, n, sr, kind):
+    x = (synth.loud_clip(1, n) if kind == "loud" else 2.0 * synth.noise_clip(2, n)).astype(np.float32)
+    ceiling, L, c = orc.limiter_constants(sr, -1.0, 5.0, 30.0)
+    with tempfile.TemporaryDirectory() as d:
+        x.tofile(os.path.join(d, "x"))
+        subprocess.check_call([emu_time, "limiter", str(n), str(L), repr(ceiling), repr(c),
+                               os.path.join(d, "x"), os.path.join(d, "y")])
+        y = np.fromfile(os.path.join(d, "y"), dtype=np.float32)
+    ref, _ = orc.peak_limiter(x, sr, -1.0, 5.0, 30.0)
+    assert np.max(np.abs(ref)) > 0 and np.max(np.abs(ref - x)) > 1e-3, "limiter must engage in this test"
+    assert np.max(np.abs(y.astype(np.float64) - ref)) <= 6e-8, float(np.max(np.abs(y - ref)))
+
+
+@pytest.mark.parametrize("n,delay", [(6000, 0), (5003, 1024), (100, 0), (2048, 300)])
+def test_emu_crossover(emu_time, n, delay):
+    x = synth.loud_clip(3, n)
+    sl, sh = orc.linkwitz_riley_sos(48000, 300.0)
+    with tempfile.TemporaryDirectory() as d:
+        p = lambda f: os.path.join(d, f)
+        x.tofile(p("x"))
+        sl.astype(np.float64).tofile(p("lp"))
+        sh.astype(np.float64).tofile(p("hp"))
+        subprocess.check_call([emu_time, "crossover", str(n), str(delay), p("lp"), p("hp"), p("x"), p("lo"), p("hi")])
+        lo = np.fromfile(p("lo"), dtype=np.float32)
+        hi = np.fromfile(p("hi"), dtype=np.float32)
+    rlo, rhi = orc.linkwitz_riley_split(x, 48000, 300.0)
+    rlo = np.concatenate([np.zeros(delay, dtype=np.float32), rlo])[:n]
+    assert np.max(np.abs(hi - rhi)) <= 1.2e-7
+    assert np.max(np.abs(lo - rlo)) <= 1.2e-7
