@@ -144,6 +144,20 @@ size_t qd_plan_workspace_bytes(const qd_plan *plan, int64_t batch);
 int    qd_plan_launches_per_render(const qd_plan *plan);
 
 /*
+ * Optional device-side timing: when enabled, qd_render_device brackets the launches of each
+ * kernel class with CUDA events on the launch stream.  qd_plan_read_timing waits for the
+ * recorded events, returns the accumulated milliseconds and launch counts per class since
+ * the last read, and resets them.
+ */
+#define QD_KERNEL_SPECTRAL  0   /* STFT -> FX -> quantizer -> iSTFT -> OLA (-> distortion) */
+#define QD_KERNEL_LIMITER   1   /* lookahead limiter + dry/wet + trim + recombine + delta */
+#define QD_KERNEL_CROSSOVER 2   /* LR4 split + low-band delay/saturation */
+#define QD_KERNEL_OTHER     3
+#define QD_KERNEL_CLASSES   4
+int qd_plan_enable_timing(qd_plan *plan, int on);
+int qd_plan_read_timing(qd_plan *plan, double ms[QD_KERNEL_CLASSES], int64_t launches[QD_KERNEL_CLASSES]);
+
+/*
  * FX random tables replayed from np.random on the host:
  *   SCRAMBLE_PICK: int16 source index per bin   [tables][2 passes][frames][n_bins]
  *   SCRAMBLE_SWAP: int16 source index per bin   (same shape; the swap permutation)

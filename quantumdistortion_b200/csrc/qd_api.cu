@@ -1,0 +1,560 @@
+// qd_api.cu -- C ABI of libqd_b200.so (see include/qd_b200.h).  sm_100a only; no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qd_b200.h"
+#include "qd_host_tables.hpp"
+#include "qd_host_time.hpp"
+#include "qd_spec.cuh"
+#include "qd_time.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define QD_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(QD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+template <class T>
+cudaError_t upload(const std::vector<T> &h, T **d) {
+    *d = nullptr;
+    const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)d, bytes);
+    if (e != cudaSuccess) return e;
+    if (!h.empty()) e = cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+struct HostPipe {   // resources of qd_render_host
+    int64_t chunk = 0;
+    float *dx[2] = {nullptr, nullptr};
+    float *dy[2] = {nullptr, nullptr};
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+};
+
+}  // namespace
+
+struct qd_plan {
+    qd_params p;
+    int nc = 0, hop = 0, n_frames = 0, nw = 0;
+    bool has_quant = false;
+    std::vector<void *> owned;  // device allocations
+    qd::SpecArgs spec{};        // table pointers filled once
+    size_t spec_smem = 0;
+    const void *fx_table = nullptr;
+    int64_t fx_tables = 0;
+    HostPipe pipe;
+    int sm_count = 148;
+    // optional per-kernel device timing (qd_plan_enable_timing)
+    bool timing = false;
+    struct Stamp { cudaEvent_t a, b; int cls; };
+    std::vector<Stamp> stamps;
+    std::vector<cudaEvent_t> free_events;
+    double t_ms[QD_KERNEL_CLASSES] = {0, 0, 0, 0};
+    int64_t t_launches[QD_KERNEL_CLASSES] = {0, 0, 0, 0};
+};
+
+namespace {
+struct TimeScope {  // brackets the launches of one kernel class with events on the launch stream
+    qd_plan *pl; cudaStream_t st; int cls; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(qd_plan *p) {
+        cudaEvent_t e = nullptr;
+        if (!p->free_events.empty()) { e = p->free_events.back(); p->free_events.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    TimeScope(qd_plan *p, cudaStream_t s, int c) : pl(p), st(s), cls(c) {
+        if (pl->timing) { a = get(pl); b = get(pl); cudaEventRecord(a, st); }
+    }
+    ~TimeScope() {
+        if (pl->timing) { cudaEventRecord(b, st); pl->stamps.push_back({a, b, cls}); }
+    }
+};
+}  // namespace
+
+namespace {
+
+template <int NC, int NW>
+int launch_spec_t(qd_plan *pl, const qd::SpecArgs &a, int tiles, int64_t batch, cudaStream_t st) {
+    static bool attr_set = false;  // per instantiation; plans are single-threaded per the ABI contract
+    auto kern = qd::spec_pass_kernel<NC, NW>;
+    if (!attr_set) {
+        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {  // gridDim.y limit
+        const int64_t nb = std::min<int64_t>(65535, batch - b0);
+        qd::SpecArgs c = a;
+        c.x = a.x + (size_t)b0 * a.n;
+        c.y = a.y + (size_t)b0 * a.n;
+        if (a.tap) c.tap = a.tap + (size_t)b0 * a.n;
+        kern<<<dim3((unsigned)tiles, (unsigned)nb, 1), 32 * NW, pl->spec_smem, st>>>(c);
+    }
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+int spec_nw(int nc) { return nc <= 1024 ? 8 : 4; }
+
+size_t spec_smem_bytes(int nc, int nw, int n_slots) {
+    switch (nc) {
+        case 256:  return nw == 8 ? qd::SpecSmem<256, 8>::bytes(n_slots) : 0;
+        case 512:  return nw == 8 ? qd::SpecSmem<512, 8>::bytes(n_slots) : 0;
+        case 1024: return nw == 8 ? qd::SpecSmem<1024, 8>::bytes(n_slots) : 0;
+        case 2048: return nw == 4 ? qd::SpecSmem<2048, 4>::bytes(n_slots) : 0;
+        case 4096: return nw == 4 ? qd::SpecSmem<4096, 4>::bytes(n_slots) : 0;
+    }
+    return 0;
+}
+
+// One spectral pass over [batch, n]: src -> dst (+ optional tap of the pre-epilogue signal).
+int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant, int epilogue,
+                int64_t batch, cudaStream_t st) {
+    TimeScope ts(pl, st, QD_KERNEL_SPECTRAL);
+    qd::SpecArgs a = pl->spec;
+    a.x = src;
+    a.y = dst;
+    a.tap = tap;
+    a.quant = quant;
+    a.epilogue = epilogue;
+    // tiling: whole clips when the batch alone fills the GPU, else cut clips along time
+    const int total_blocks = (a.n + pl->hop - 1) / pl->hop;
+    const int ctas_per_sm = std::max<int>(1, (int)((227 * 1024) / (pl->spec_smem + 1024)));
+    const int64_t want = (int64_t)pl->sm_count * ctas_per_sm * 2;
+    int tile = total_blocks;
+    if (batch < want) {
+        const int64_t per_clip = (want + batch - 1) / batch;
+        tile = (int)((total_blocks + per_clip - 1) / per_clip);
+        const int min_tile = 4 * pl->nw - 3;  // keeps the 3-frame halo recompute below 10 %
+        if (tile < min_tile) tile = min_tile;
+        tile = ((tile + 3 + pl->nw - 1) / pl->nw) * pl->nw - 3;  // whole batches of NW frames
+        if (tile > total_blocks) tile = total_blocks;
+    }
+    if (tile < 1) tile = 1;
+    a.tile_blocks = tile;
+    const int tiles = (total_blocks + tile - 1) / tile;
+    switch (pl->nc) {
+        case 256:  return launch_spec_t<256, 8>(pl, a, tiles, batch, st);
+        case 512:  return launch_spec_t<512, 8>(pl, a, tiles, batch, st);
+        case 1024: return launch_spec_t<1024, 8>(pl, a, tiles, batch, st);
+        case 2048: return launch_spec_t<2048, 4>(pl, a, tiles, batch, st);
+        case 4096: return launch_spec_t<4096, 4>(pl, a, tiles, batch, st);
+    }
+    return fail(QD_ERR_UNSUPPORTED, "n_fft not supported");
+}
+
+int launch_limiter(const qd::LimiterArgs &a, int64_t batch, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = qd_host::limiter_smem_bytes(a.lookahead);
+    if (smem > 200 * 1024) return fail(QD_ERR_UNSUPPORTED, "limiter lookahead too long");
+    if (!attr_set) {
+        QD_CUDA(cudaFuncSetAttribute(qd::limiter_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    for (int64_t b0 = 0; b0 < batch; b0 += (1 << 30)) {
+        const int64_t nb = std::min<int64_t>(1 << 30, batch - b0);
+        qd::LimiterArgs c = a;
+        const size_t off = (size_t)b0 * (size_t)a.n;
+        c.x = a.x + off; c.y = a.y + off;
+        if (a.dry) c.dry = a.dry + off;
+        if (a.low) c.low = a.low + off;
+        if (a.orig) c.orig = a.orig + off;
+        qd::limiter_mix_kernel<<<(unsigned)nb, qd::QD_TT, smem, st>>>(c);
+    }
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+int ew_grid(int64_t count, int sm_count) {
+    const int64_t blocks = (count + 255) / 256;
+    return (int)std::min<int64_t>(blocks, (int64_t)sm_count * 16);
+}
+
+}  // namespace
+
+extern "C" {
+
+int qd_abi_version(void) { return QD_ABI_VERSION; }
+
+const char *qd_last_error(void) { return g_err.c_str(); }
+
+int qd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp pr;
+        if (cudaGetDeviceProperties(&pr, i) == cudaSuccess && pr.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **out) {
+    if (!params || !out) return fail(QD_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (params->struct_size != sizeof(qd_params)) return fail(QD_ERR_INVALID_ARG, "qd_params size mismatch (ABI)");
+    const qd_params &p = *params;
+    if (p.n_samples < 0 || p.sample_rate <= 0) return fail(QD_ERR_INVALID_ARG, "bad n_samples / sample_rate");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(QD_ERR_NO_DEVICE, "no CUDA device: libqd_b200 has no CPU path"); }
+    cudaDeviceProp pr;
+    QD_CUDA(cudaGetDeviceProperties(&pr, dev));
+    if (pr.major != 10) return fail(QD_ERR_NO_DEVICE, "device is not sm_100 (B200)");
+    qd_host::SpecTables st;
+    if (!qd_host::build_spec_tables(p.n_fft, &st)) return fail(QD_ERR_UNSUPPORTED, "n_fft must be one of 512, 1024, 2048, 4096, 8192");
+    const bool need_quant = !p.passthrough && (p.pre_quant || p.post_quant);
+    if (need_quant && !tables) return fail(QD_ERR_INVALID_ARG, "quantizer tables required");
+    if (p.fx_mode != QD_FX_NONE) return fail(QD_ERR_UNSUPPORTED, "spectral FX are not built into this round's kernels yet");
+
+    qd_plan *pl = new qd_plan();
+    pl->p = p;
+    pl->nc = st.nc;
+    pl->hop = st.hop;
+    pl->n_frames = 1 + p.n_samples / st.hop;
+    pl->nw = spec_nw(st.nc);
+    pl->sm_count = pr.multiProcessorCount;
+    pl->has_quant = need_quant;
+    auto keep = [&](void *d) { pl->owned.push_back(d); };
+    auto bail = [&](int code, const std::string &m) { qd_plan_destroy(pl); return fail(code, m); };
+#define QD_UP(vec, ptr)                                                                   \
+    do {                                                                                  \
+        cudaError_t e_ = upload(vec, &ptr);                                               \
+        if (ptr) keep(ptr);                                                               \
+        if (e_ != cudaSuccess) return bail(QD_ERR_CUDA, cudaGetErrorString(e_));          \
+    } while (0)
+    qd_host::F2 *d_wtab, *d_tw1, *d_tw2, *d_wsplit;
+    float *d_invw;
+    QD_UP(st.wtab, d_wtab);
+    QD_UP(st.tw1, d_tw1);
+    QD_UP(st.tw2, d_tw2);
+    QD_UP(st.wsplit, d_wsplit);
+    QD_UP(st.invw, d_invw);
+    qd::SpecArgs &a = pl->spec;
+    a.n = p.n_samples;
+    a.n_frames = pl->n_frames;
+    a.fold = p.fold_amount; a.bias = p.bias; a.tube_gain = p.tube_gain; a.tube_norm = p.tube_norm;
+    a.wtab = reinterpret_cast<const float2 *>(d_wtab);
+    a.tw1 = reinterpret_cast<const float2 *>(d_tw1);
+    a.tw2 = reinterpret_cast<const float2 *>(d_tw2);
+    a.wsplit = reinterpret_cast<const float2 *>(d_wsplit);
+    a.invw = d_invw;
+    int n_slots = 0;
+    if (need_quant) {
+        if (tables->n_bins != st.nc + 1) return bail(QD_ERR_INVALID_ARG, "tables->n_bins != n_fft/2+1");
+        qd_host::QuantTablesH qt;
+        std::string err;
+        if (!qd_host::build_quant_tables(*tables, &qt, &err)) return bail(QD_ERR_INVALID_ARG, err);
+        uint16_t *d_sb, *d_src, *d_rab;
+        uint32_t *d_ra, *d_rf;
+        qd_host::AffEntryH *d_aff;
+        QD_UP(qt.slot_begin, d_sb);
+        QD_UP(qt.src_bin, d_src);
+        QD_UP(qt.row_active, d_ra);
+        QD_UP(qt.row_aff, d_rf);
+        QD_UP(qt.row_aff_base, d_rab);
+        QD_UP(qt.aff, d_aff);
+        a.q.n_slots = qt.n_slots;
+        a.q.n_aff = qt.n_aff;
+        a.q.slot_begin = d_sb;
+        a.q.src_bin = d_src;
+        a.q.row_active = d_ra;
+        a.q.row_aff = d_rf;
+        a.q.row_aff_base = d_rab;
+        a.q.aff = reinterpret_cast<const qd::AffEntry *>(d_aff);
+        a.q.keep_active = qt.keep_active;
+        a.q.smoothing = p.bin_smoothing ? 1 : 0;
+        n_slots = qt.n_slots;
+    }
+#undef QD_UP
+    pl->spec_smem = spec_smem_bytes(pl->nc, pl->nw, n_slots);
+    if (pl->spec_smem == 0 || pl->spec_smem > 227 * 1024)
+        return bail(QD_ERR_UNSUPPORTED, "shared memory need of this (n_fft, target table) exceeds 227 KB");
+    *out = pl;
+    return QD_OK;
+}
+
+void qd_plan_destroy(qd_plan *pl) {
+    if (!pl) return;
+    for (void *d : pl->owned) cudaFree(d);
+    for (auto &sp : pl->stamps) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : pl->free_events) cudaEventDestroy(e);
+    HostPipe &hp = pl->pipe;
+    for (int i = 0; i < 2; ++i) {
+        if (hp.dx[i]) cudaFree(hp.dx[i]);
+        if (hp.dy[i]) cudaFree(hp.dy[i]);
+        if (hp.ev_in[i]) cudaEventDestroy(hp.ev_in[i]);
+        if (hp.ev_run[i]) cudaEventDestroy(hp.ev_run[i]);
+        if (hp.ev_out[i]) cudaEventDestroy(hp.ev_out[i]);
+    }
+    if (hp.ws) cudaFree(hp.ws);
+    if (hp.s_in) cudaStreamDestroy(hp.s_in);
+    if (hp.s_run) cudaStreamDestroy(hp.s_run);
+    if (hp.s_out) cudaStreamDestroy(hp.s_out);
+    delete pl;
+}
+
+size_t qd_plan_workspace_bytes(const qd_plan *pl, int64_t batch) {
+    if (!pl || batch <= 0) return 0;
+    const size_t clip = (size_t)pl->p.n_samples * sizeof(float);
+    const size_t bufs = pl->p.multiband ? 3 : 1;  // [x_dist] (+ [low][high])
+    return bufs * clip * (size_t)batch + 256;
+}
+
+int qd_plan_launches_per_render(const qd_plan *pl) {
+    if (!pl) return 0;
+    const qd_params &p = pl->p;
+    int n = 0;
+    if (p.multiband) n += 1;                        // crossover
+    if (p.passthrough) return n + 1 + (p.multiband ? 1 : 0);
+    if (p.pre_quant) n += 1;                        // pass A
+    if (p.post_quant || !p.pre_quant) n += 1;       // pass B (or the bare STFT->iSTFT)
+    n += 1;                                         // limiter + mix
+    return n;
+}
+
+int qd_plan_enable_timing(qd_plan *pl, int on) {
+    if (!pl) return fail(QD_ERR_INVALID_ARG, "null plan");
+    pl->timing = on != 0;
+    return QD_OK;
+}
+
+int qd_plan_read_timing(qd_plan *pl, double *ms, int64_t *launches) {
+    if (!pl || !ms || !launches) return fail(QD_ERR_INVALID_ARG, "null argument");
+    for (auto &sp : pl->stamps) {
+        QD_CUDA(cudaEventSynchronize(sp.b));
+        float t = 0.0f;
+        QD_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
+        pl->t_ms[sp.cls] += (double)t;
+        pl->t_launches[sp.cls] += 1;
+        pl->free_events.push_back(sp.a);
+        pl->free_events.push_back(sp.b);
+    }
+    pl->stamps.clear();
+    for (int i = 0; i < QD_KERNEL_CLASSES; ++i) {
+        ms[i] = pl->t_ms[i];
+        launches[i] = pl->t_launches[i];
+        pl->t_ms[i] = 0.0;
+        pl->t_launches[i] = 0;
+    }
+    return QD_OK;
+}
+
+int qd_plan_set_fx_table(qd_plan *pl, const void *device_table, int64_t n_tables) {
+    if (!pl) return fail(QD_ERR_INVALID_ARG, "null plan");
+    pl->fx_table = device_table;
+    pl->fx_tables = n_tables;
+    return QD_OK;
+}
+
+int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const qd_taps *taps,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+    if (!pl || !x || !y || batch < 0) return fail(QD_ERR_INVALID_ARG, "null argument");
+    if (batch == 0 || pl->p.n_samples == 0) return QD_OK;
+    if (workspace_bytes < qd_plan_workspace_bytes(pl, batch) || !workspace)
+        return fail(QD_ERR_WORKSPACE, "workspace too small (see qd_plan_workspace_bytes)");
+    const qd_params &p = pl->p;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)p.n_samples;
+    const size_t count = n * (size_t)batch;
+    float *tap_pre = taps ? taps->pre_quant : nullptr;
+    float *tap_dist = taps ? taps->post_dist : nullptr;
+    float *w_a = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    float *w_low = w_a + count;
+    float *w_high = w_low + count;
+    int rc;
+
+    const float *src = x;   // what the single-band chain sees (dsp/pipeline.py:1076: the high band)
+    const float *low = nullptr;
+    if (p.multiband) {
+        qd::CrossoverArgs c{};
+        c.x = x; c.low = w_low; c.high = w_high; c.n = (long long)n;
+        qd_host::fill_crossover(c, &p.sos_low[0][0], &p.sos_high[0][0]);
+        c.low_delay = p.low_delay;
+        c.process_low = 1;
+        c.low_gain = p.low_gain; c.low_norm = p.low_norm;
+        c.mono_a = p.mono_a; c.mono_b = p.mono_b; c.apply_mono = p.apply_mono_blend;
+        c.low_trim = p.low_trim_gain; c.apply_low_trim = p.apply_low_trim;
+        {
+            TimeScope ts(pl, st, QD_KERNEL_CROSSOVER);
+            qd::crossover_kernel<<<(unsigned)batch, qd::QD_TT, 0, st>>>(c);
+        }
+        QD_CUDA(cudaGetLastError());
+        src = w_high;
+        low = w_low;
+    }
+
+    if (p.passthrough) {  // dsp/pipeline.py:477-535: no distortion, limiter or mix
+        float *dst = p.multiband ? w_a : y;
+        if ((rc = launch_spec(pl, src, dst, nullptr, 0, 0, batch, st)) != QD_OK) return rc;
+        if (tap_pre) QD_CUDA(cudaMemcpyAsync(tap_pre, src, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (p.multiband) {
+            qd::add_kernel<<<ew_grid((int64_t)count, pl->sm_count), 256, 0, st>>>(low, w_a, y, (long long)count);
+            QD_CUDA(cudaGetLastError());
+            if (tap_dist) QD_CUDA(cudaMemcpyAsync(tap_dist, y, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        } else if (tap_dist) {
+            QD_CUDA(cudaMemcpyAsync(tap_dist, y, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        if (p.delta_listen) {
+            // output = input - processed (dsp/pipeline.py:1371-1375)
+            qd::LimiterArgs d{};
+            d.x = y; d.y = y; d.dry = y; d.orig = x; d.n = (long long)n; d.limiter_on = 0; d.lookahead = 1;
+            d.wet = 1.0f; d.dry_gain = 0.0f; d.apply_mix = 1;
+            if ((rc = launch_limiter(d, batch, st)) != QD_OK) return rc;
+        }
+        return QD_OK;
+    }
+
+    const int epi = p.distortion_mode == QD_DIST_TUBE ? 2 : 1;
+    const float *x_pq = nullptr;  // limiter input
+    if (p.pre_quant) {
+        // pass A: STFT -> quantize -> iSTFT (= pre_quant tap) -> distortion        (:635-721)
+        if ((rc = launch_spec(pl, src, w_a, tap_pre, 1, epi, batch, st)) != QD_OK) return rc;
+        if (p.post_quant) {  // pass B on the distorted signal                         (:729-801)
+            if ((rc = launch_spec(pl, w_a, y, nullptr, 1, 0, batch, st)) != QD_OK) return rc;
+            x_pq = y;
+        } else {
+            x_pq = w_a;       // :851-853
+        }
+    } else {
+        // distortion only reaches the tap
+        if (tap_pre) QD_CUDA(cudaMemcpyAsync(tap_pre, src, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (tap_dist) {
+            qd::distort_kernel<<<ew_grid((int64_t)count, pl->sm_count), 256, 0, st>>>(
+                src, w_a, (long long)count, p.distortion_mode, p.fold_amount, p.bias, p.tube_gain, p.tube_norm);
+            QD_CUDA(cudaGetLastError());
+        }
+        if ((rc = launch_spec(pl, src, y, nullptr, p.post_quant ? 1 : 0, 0, batch, st)) != QD_OK) return rc;
+        x_pq = y;
+    }
+    if (tap_dist) {  // dsp/pipeline.py:916 / :1107 (low band added in multiband mode)
+        if (low) {
+            qd::add_kernel<<<ew_grid((int64_t)count, pl->sm_count), 256, 0, st>>>(low, w_a, tap_dist, (long long)count);
+            QD_CUDA(cudaGetLastError());
+        } else {
+            QD_CUDA(cudaMemcpyAsync(tap_dist, w_a, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    qd::LimiterArgs l{};
+    l.x = x_pq; l.dry = src; l.low = low; l.orig = p.delta_listen ? x : nullptr; l.y = y; l.n = (long long)n;
+    l.limiter_on = p.limiter_on; l.lookahead = p.lookahead > 0 ? p.lookahead : 1;
+    l.ceiling = p.ceiling_lin; l.c = p.release_coeff;
+    l.wet = p.wet; l.dry_gain = p.dry; l.trim = p.trim_gain; l.apply_trim = p.apply_trim; l.apply_mix = 1;
+    TimeScope ts(pl, st, QD_KERNEL_LIMITER);
+    return launch_limiter(l, batch, st);
+}
+
+int qd_render_host(qd_plan *pl, const float *x_host, float *y_host, int64_t batch, int64_t chunk_clips) {
+    if (!pl || !x_host || !y_host || batch < 0) return fail(QD_ERR_INVALID_ARG, "null argument");
+    if (batch == 0 || pl->p.n_samples == 0) return QD_OK;
+    if (chunk_clips <= 0) chunk_clips = 128;
+    if (chunk_clips > batch) chunk_clips = batch;
+    HostPipe &hp = pl->pipe;
+    const size_t clip = (size_t)pl->p.n_samples * sizeof(float);
+    if (hp.chunk < chunk_clips) {  // (re)allocate the double buffers once per plan / chunk size
+        for (int i = 0; i < 2; ++i) {
+            if (hp.dx[i]) cudaFree(hp.dx[i]);
+            if (hp.dy[i]) cudaFree(hp.dy[i]);
+            hp.dx[i] = hp.dy[i] = nullptr;
+        }
+        if (hp.ws) cudaFree(hp.ws);
+        hp.ws = nullptr;
+        for (int i = 0; i < 2; ++i) {
+            QD_CUDA(cudaMalloc((void **)&hp.dx[i], clip * chunk_clips));
+            QD_CUDA(cudaMalloc((void **)&hp.dy[i], clip * chunk_clips));
+        }
+        hp.ws_bytes = qd_plan_workspace_bytes(pl, chunk_clips);
+        QD_CUDA(cudaMalloc(&hp.ws, hp.ws_bytes));
+        hp.chunk = chunk_clips;
+    }
+    if (!hp.s_in) {
+        QD_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+        QD_CUDA(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
+        QD_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            QD_CUDA(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
+            QD_CUDA(cudaEventCreateWithFlags(&hp.ev_run[i], cudaEventDisableTiming));
+            QD_CUDA(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    int64_t idx = 0;
+    for (int64_t b0 = 0; b0 < batch; b0 += chunk_clips, ++idx) {
+        const int buf = (int)(idx & 1);
+        const int64_t nb = std::min<int64_t>(chunk_clips, batch - b0);
+        if (idx >= 2) QD_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_run[buf], 0));   // dx[buf] consumed
+        QD_CUDA(cudaMemcpyAsync(hp.dx[buf], x_host + (size_t)b0 * pl->p.n_samples, clip * nb, cudaMemcpyHostToDevice, hp.s_in));
+        QD_CUDA(cudaEventRecord(hp.ev_in[buf], hp.s_in));
+        QD_CUDA(cudaStreamWaitEvent(hp.s_run, hp.ev_in[buf], 0));
+        if (idx >= 2) QD_CUDA(cudaStreamWaitEvent(hp.s_run, hp.ev_out[buf], 0));  // dy[buf] drained
+        int rc = qd_render_device(pl, hp.dx[buf], hp.dy[buf], nb, nullptr, hp.ws, hp.ws_bytes, hp.s_run);
+        if (rc != QD_OK) return rc;
+        QD_CUDA(cudaEventRecord(hp.ev_run[buf], hp.s_run));
+        QD_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_run[buf], 0));
+        QD_CUDA(cudaMemcpyAsync(y_host + (size_t)b0 * pl->p.n_samples, hp.dy[buf], clip * nb, cudaMemcpyDeviceToHost, hp.s_out));
+        QD_CUDA(cudaEventRecord(hp.ev_out[buf], hp.s_out));
+    }
+    QD_CUDA(cudaStreamSynchronize(hp.s_out));
+    QD_CUDA(cudaStreamSynchronize(hp.s_run));
+    return QD_OK;
+}
+
+int qd_limiter_device(const float *x, float *y, int64_t batch, int64_t n, int32_t lookahead, double ceiling_lin,
+                      double release_coeff, void *stream) {
+    if (!x || !y || batch < 0 || n < 0 || lookahead < 1) return fail(QD_ERR_INVALID_ARG, "bad limiter argument");
+    if (batch == 0 || n == 0) return QD_OK;
+    qd::LimiterArgs a{};
+    a.x = x; a.y = y; a.n = (long long)n; a.limiter_on = 1; a.lookahead = lookahead;
+    a.ceiling = ceiling_lin; a.c = release_coeff; a.apply_mix = 0;
+    return launch_limiter(a, batch, (cudaStream_t)stream);
+}
+
+int qd_crossover_device(const float *x, float *low, float *high, int64_t batch, int64_t n,
+                        const double sos_low[2][6], const double sos_high[2][6], void *stream) {
+    if (!x || !low || !high || !sos_low || !sos_high || batch < 0 || n < 0) return fail(QD_ERR_INVALID_ARG, "bad crossover argument");
+    if (batch == 0 || n == 0) return QD_OK;
+    qd::CrossoverArgs c{};
+    c.x = x; c.low = low; c.high = high; c.n = (long long)n;
+    qd_host::fill_crossover(c, &sos_low[0][0], &sos_high[0][0]);
+    qd::crossover_kernel<<<(unsigned)batch, qd::QD_TT, 0, (cudaStream_t)stream>>>(c);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+int qd_distort_device(const float *x, float *y, int64_t count, int32_t mode, float fold_amount, float bias,
+                      float tube_gain, float tube_norm, void *stream) {
+    if (!x || !y || count < 0) return fail(QD_ERR_INVALID_ARG, "bad distortion argument");
+    if (mode != QD_DIST_WAVEFOLD && mode != QD_DIST_TUBE) return fail(QD_ERR_INVALID_ARG, "unsupported distortion mode");
+    if (count == 0) return QD_OK;
+    int sm = 148;
+    qd::distort_kernel<<<ew_grid(count, sm), 256, 0, (cudaStream_t)stream>>>(x, y, (long long)count, mode, fold_amount,
+                                                                               bias, tube_gain, tube_norm);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+void *qd_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void qd_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

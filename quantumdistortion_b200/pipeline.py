@@ -1,0 +1,288 @@
+"""Batched STFT-path renderer behind the reference's ``process_audio`` parameter API.
+
+``process_audio(audio, sr, **kwargs)`` keeps the reference's signature and return value
+(quantum_distortion/dsp/pipeline.py:1113-1155: ``(float32[n], taps)``) for one clip;
+``process_batch`` renders ``[B, n]`` clips in one go, which is what the hardware wants.
+The arithmetic runs in the hand-written sm_100a kernels of ``csrc/`` through the C ABI of
+``include/qd_b200.h``; PyTorch only provides device memory and streams.  There is no CPU
+fallback: without a B200 and the built library every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Tuple, Union
+
+import numpy as np
+
+from . import _lib, tables
+from .config import (DEFAULT_AIR_CUT_HZ, DEFAULT_BIN_SMOOTHING, DEFAULT_DISTORTION_MODE, DEFAULT_DRY_WET,
+                     DEFAULT_KEY, DEFAULT_LIMITER_CEILING_DB, DEFAULT_LIMITER_ON, DEFAULT_QUANTIZE_MODE,
+                     DEFAULT_SAMPLE_RATE, DEFAULT_SCALE, DEFAULT_SMEAR, DEFAULT_SNAP_STRENGTH, DEFAULT_SUB_CUT_HZ,
+                     N_FFT_DEFAULT, PREVIEW_ENABLED_DEFAULT, PREVIEW_MAX_SECONDS, PipelineConfig,
+                     ensure_mono_float32)
+
+_PC_FIELDS = ("key", "scale", "quantize_mode", "snap_strength", "smear", "bin_smoothing", "pre_quant", "post_quant",
+              "sub_cut_hz", "air_cut_hz", "distortion_mode", "distortion_params", "limiter_on",
+              "limiter_ceiling_db", "dry_wet", "preview_enabled", "use_multiband", "crossover_hz", "lowband_drive",
+              "passthrough_test", "spectral_fx_mode", "spectral_fx_strength", "spectral_fx_params",
+              "spectral_freeze", "formant_shift", "harmonic_lock_hz", "delta_listen", "mono_strength",
+              "output_trim_db")
+
+
+@dataclass
+class RenderTiming:
+    """Device-side timing of the last render (cf. RenderTiming, dsp/pipeline.py:153-161)."""
+    total_ms: float = 0.0
+    launches: int = 0
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.QdError("no CUDA device visible: quantumdistortion_b200 renders only on a B200 "
+                           "(there is no CPU fallback; the CPU oracle lives in oracle/ for tests)")
+    return torch
+
+
+class Renderer:
+    """One resolved parameter set bound to a CUDA plan on the current device."""
+
+    def __init__(self, resolved: tables.Resolved):
+        self._lib = _lib.load()
+        self.resolved = resolved
+        self.n = int(resolved.params.n_samples)
+        handle = C.c_void_p()
+        _lib.check(self._lib.qd_plan_create(C.byref(resolved.params),
+                                            C.byref(resolved.tables) if resolved.tables is not None else None,
+                                            C.byref(handle)))
+        self._plan = handle
+        self._ws = None
+        self.launches_per_render = int(self._lib.qd_plan_launches_per_render(self._plan))
+
+    def close(self) -> None:
+        if getattr(self, "_plan", None):
+            self._lib.qd_plan_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def enable_timing(self, on: bool = True) -> None:
+        """Bracket every kernel class with CUDA events on the launch stream (qd_plan_enable_timing)."""
+        _lib.check(self._lib.qd_plan_enable_timing(self._plan, int(on)))
+
+    def read_timing(self) -> Dict[str, Dict[str, float]]:
+        """Milliseconds and launch counts per kernel class since the last read (waits for the events)."""
+        ms, cnt = (C.c_double * 4)(), (C.c_int64 * 4)()
+        _lib.check(self._lib.qd_plan_read_timing(self._plan, C.byref(ms), C.byref(cnt)))
+        names = ("spectral", "limiter", "crossover", "other")
+        return {n: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, n in enumerate(names)}
+
+    def _workspace(self, batch: int):
+        torch = _torch()
+        need = int(self._lib.qd_plan_workspace_bytes(self._plan, batch))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+        return self._ws, need
+
+    def render_device(self, x, want_taps: bool = False):
+        """x: CUDA float32 tensor [B, n] -> (y [B, n], taps or None).  Asynchronous on the current stream."""
+        torch = _torch()
+        if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.n or not x.is_cuda:
+            raise ValueError(f"expected a CUDA float32 tensor of shape [B, {self.n}]")
+        x = x.contiguous()
+        batch = int(x.shape[0])
+        y = torch.empty_like(x)
+        taps = None
+        ctaps = None
+        if want_taps:
+            taps = {"pre_quant": torch.empty_like(x), "post_dist": torch.empty_like(x)}
+            ctaps = _lib.QdTaps(taps["pre_quant"].data_ptr(), taps["post_dist"].data_ptr())
+        if batch and self.n:
+            ws, need = self._workspace(batch)
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(self._lib.qd_render_device(self._plan, x.data_ptr(), y.data_ptr(), batch,
+                                                  C.byref(ctaps) if ctaps is not None else None,
+                                                  ws.data_ptr(), need, stream))
+        return y, taps
+
+    def render_host(self, x_host, y_host, chunk_clips: int = 128) -> None:
+        """x_host / y_host: CPU float32 [B, n] (pinned for full speed).  Synchronous; H2D, kernels and
+        D2H of consecutive chunks overlap inside the library."""
+        batch = int(x_host.shape[0])
+        _lib.check(self._lib.qd_render_host(self._plan, x_host.data_ptr(), y_host.data_ptr(), batch, int(chunk_clips)))
+
+
+_RENDERERS: Dict[Any, Renderer] = {}
+
+
+def _renderer_for(resolved: tables.Resolved) -> Renderer:
+    torch = _torch()
+    key = (torch.cuda.current_device(), bytes(resolved.params),
+           None if resolved.tables is None else (resolved.target_bins.tobytes(), resolved.active_mask.tobytes(),
+                                                 resolved.tables.snap, resolved.tables.smear))
+    r = _RENDERERS.get(key)
+    if r is None:
+        if len(_RENDERERS) > 32:
+            _RENDERERS.pop(next(iter(_RENDERERS))).close()
+        r = _RENDERERS[key] = Renderer(resolved)
+    return r
+
+
+def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> Tuple[tables.Resolved, Dict[str, Any]]:
+    """Apply the reference's argument rules (dsp/pipeline.py:1201-1327) and build the C structs."""
+    pc = kw.pop("pipeline_config", None)
+    if pc is not None:  # overrides every individual keyword (:1201-1238)
+        for f in _PC_FIELDS:
+            kw[f] = getattr(pc, f)
+    if kw.pop("config", None) is not None:
+        raise NotImplementedError("the Streamlit UI dict (config=) is outside the STFT hot path (SURVEY.md 8(f) rank 2)")
+    g = lambda k, d: kw.pop(k, d)  # noqa: E731
+    key, scale = g("key", DEFAULT_KEY), g("scale", DEFAULT_SCALE)
+    quantize_mode = g("quantize_mode", DEFAULT_QUANTIZE_MODE)
+    snap, smear = g("snap_strength", DEFAULT_SNAP_STRENGTH), g("smear", DEFAULT_SMEAR)
+    bin_smoothing = g("bin_smoothing", DEFAULT_BIN_SMOOTHING)
+    pre_quant, post_quant = g("pre_quant", True), g("post_quant", True)
+    distortion_mode = g("distortion_mode", DEFAULT_DISTORTION_MODE)
+    distortion_params = g("distortion_params", None) or {}
+    limiter_on, ceiling_db = g("limiter_on", DEFAULT_LIMITER_ON), g("limiter_ceiling_db", DEFAULT_LIMITER_CEILING_DB)
+    dry_wet = g("dry_wet", DEFAULT_DRY_WET)
+    use_multiband, crossover_hz = g("use_multiband", False), g("crossover_hz", 300.0)
+    lowband_drive = g("lowband_drive", 1.0)
+    passthrough = g("passthrough_test", False)
+    fx_mode, fx_strength = g("spectral_fx_mode", None), g("spectral_fx_strength", 0.0)
+    fx_params = g("spectral_fx_params", None) or {}
+    freeze, formant, lock_hz = g("spectral_freeze", False), g("formant_shift", 0.0), g("harmonic_lock_hz", 0.0)
+    delta_listen, mono_strength = g("delta_listen", False), g("mono_strength", 1.0)
+    trim_db = g("output_trim_db", 0.0)
+    sub_cut, air_cut = g("sub_cut_hz", DEFAULT_SUB_CUT_HZ), g("air_cut_hz", DEFAULT_AIR_CUT_HZ)
+    low_trim_db = g("low_trim_db", 0.0)
+    g("preview_enabled", None)
+    for ignored in ("sub_enabled", "sub_source", "sub_note", "sub_scale_degree", "sub_octave", "sub_level", "air_mix"):
+        kw.pop(ignored, None)  # autotune-only fields (config.py:80-89)
+    if kw:
+        raise TypeError(f"process_audio() got unexpected keyword arguments: {sorted(kw)}")
+    if quantize_mode == "autotune_v1" and (fx_mode is not None or freeze or formant != 0.0 or lock_hz > 0.0):
+        quantize_mode = "spectral_bins"  # :1315-1324
+    if quantize_mode != "spectral_bins":
+        raise NotImplementedError("only quantize_mode='spectral_bins' (the STFT path) is implemented; "
+                                  "autotune_v1 is a different algorithm (SURVEY.md 8(f) rank 3)")
+    if freeze or formant != 0.0:
+        raise NotImplementedError("spectral_freeze / formant_shift are not built yet (SURVEY.md 8(f) rank 1)")
+    fx_active = bool(use_multiband and fx_mode and float(fx_strength) > 0.0 and not passthrough
+                     and fx_mode in ("bitcrush", "phase_dispersal", "bin_scramble"))
+    if fx_active:
+        raise NotImplementedError("spectral FX kernels are not built yet (SURVEY.md 8(a) a8-a11)")
+    res = tables.resolve(sr=sr, n_samples=n_samples, n_fft=n_fft, key=key, scale=scale, snap_strength=snap,
+                         smear=smear, bin_smoothing=bin_smoothing, pre_quant=pre_quant, post_quant=post_quant,
+                         distortion_mode=distortion_mode, distortion_params=distortion_params,
+                         limiter_on=limiter_on, limiter_ceiling_db=ceiling_db, dry_wet=dry_wet,
+                         use_multiband=use_multiband, crossover_hz=crossover_hz, lowband_drive=lowband_drive,
+                         passthrough_test=passthrough, harmonic_lock_hz=lock_hz, delta_listen=delta_listen,
+                         mono_strength=mono_strength, output_trim_db=trim_db, low_trim_db=low_trim_db,
+                         sub_cut_hz=sub_cut, air_cut_hz=air_cut)
+    return res, {"fx_params": fx_params}
+
+
+def make_renderer(n_samples: int, sr: int = DEFAULT_SAMPLE_RATE, n_fft: int = N_FFT_DEFAULT, **kwargs) -> Renderer:
+    """Resolve the reference keyword arguments once and return the cached CUDA renderer."""
+    res, _ = _resolve_kwargs(int(n_samples), int(sr), int(n_fft), dict(kwargs))
+    return _renderer_for(res)
+
+
+def process_batch(x, sr: int = DEFAULT_SAMPLE_RATE, *, n_fft: int = N_FFT_DEFAULT, return_taps: bool = False,
+                  chunk_clips: int = 128, out=None, **kwargs):
+    """Render a batch of mono clips ``x[B, n]`` with one parameter set.
+
+    ``x`` may be a CUDA tensor (returns CUDA tensors, asynchronous), a CPU tensor or a NumPy array
+    (returns the same kind; the copy/compute pipeline of ``qd_render_host`` is used when no taps are
+    requested).  ``out`` (CPU tensor, ideally pinned like ``x``) receives the result of the host path
+    without a fresh allocation.  Keyword arguments are the reference's ``process_audio`` arguments.
+    """
+    torch = _torch()
+    is_np = isinstance(x, np.ndarray)
+    xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) if is_np else x
+    if xt.dim() != 2:
+        raise ValueError("process_batch expects [batch, samples]")
+    r = make_renderer(xt.shape[1], sr, n_fft, **kwargs)
+    if xt.is_cuda:
+        return r.render_device(xt.float(), want_taps=return_taps)
+    if return_taps:
+        y, taps = r.render_device(xt.float().cuda(), want_taps=True)
+        y, taps = y.cpu(), {k: v.cpu() for k, v in taps.items()}
+    else:
+        xin = xt.float().contiguous()
+        if out is not None:
+            if out.shape != xin.shape or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+                raise ValueError("out must be a contiguous CPU float32 tensor shaped like x")
+            y = out
+        else:
+            y = torch.empty_like(xin, pin_memory=xin.is_pinned())
+        r.render_host(xin, y, chunk_clips=chunk_clips)
+        taps = None
+    if is_np:
+        return y.numpy(), (None if taps is None else {k: v.numpy() for k, v in taps.items()})
+    return y, taps
+
+
+def process_audio(audio: np.ndarray, sr: int = DEFAULT_SAMPLE_RATE, key: str = DEFAULT_KEY, scale: str = DEFAULT_SCALE,
+                  quantize_mode: str = DEFAULT_QUANTIZE_MODE, snap_strength: float = DEFAULT_SNAP_STRENGTH,
+                  smear: float = DEFAULT_SMEAR, bin_smoothing: bool = DEFAULT_BIN_SMOOTHING, pre_quant: bool = True,
+                  post_quant: bool = True, distortion_mode: str = DEFAULT_DISTORTION_MODE,
+                  distortion_params: Optional[Dict[str, Any]] = None, limiter_on: bool = DEFAULT_LIMITER_ON,
+                  limiter_ceiling_db: float = DEFAULT_LIMITER_CEILING_DB, dry_wet: float = DEFAULT_DRY_WET,
+                  preview_enabled: Optional[bool] = None, use_multiband: bool = False, crossover_hz: float = 300.0,
+                  lowband_drive: float = 1.0, passthrough_test: bool = False,
+                  spectral_fx_mode: Optional[str] = None, spectral_fx_strength: float = 0.0,
+                  spectral_fx_params: Optional[Dict[str, Any]] = None, config: Optional[Dict[str, Any]] = None,
+                  spectral_freeze: bool = False, formant_shift: float = 0.0, harmonic_lock_hz: float = 0.0,
+                  delta_listen: bool = False, mono_strength: float = 1.0, output_trim_db: float = 0.0,
+                  sub_enabled: bool = True, sub_source: str = "root", sub_note: str = "C",
+                  sub_scale_degree: int = 0, sub_octave: int = 2, sub_level: float = 0.35,
+                  sub_cut_hz: float = DEFAULT_SUB_CUT_HZ, air_cut_hz: float = DEFAULT_AIR_CUT_HZ,
+                  air_mix: float = 1.0, *, pipeline_config: Optional[PipelineConfig] = None,
+                  n_fft: int = N_FFT_DEFAULT) -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
+    """Drop-in for the reference's ``process_audio`` on the STFT path (one clip).
+
+    Same positional/keyword arguments and defaults as dsp/pipeline.py:1113-1155, except that
+    ``quantize_mode`` defaults to "spectral_bins" (see config.py) and ``n_fft`` exposes the
+    reference's module global N_FFT_DEFAULT (:149).  Returns ``(float32[n], taps)`` with taps
+    ``input / pre_quant / post_dist / output`` (:1368, :1104-1109).
+    """
+    if preview_enabled is None and pipeline_config is not None:
+        preview_enabled = pipeline_config.preview_enabled
+    if preview_enabled is None:  # :1241-1249
+        env = os.getenv("DSP_PREVIEW_MODE", "").strip().lower()
+        preview_enabled = True if env in ("1", "true", "yes", "on") else PREVIEW_ENABLED_DEFAULT
+    audio = np.asarray(audio)
+    if preview_enabled:  # :1303-1310
+        max_samples = int(sr * PREVIEW_MAX_SECONDS)
+        if audio.shape[0] > max_samples:
+            audio = audio[:max_samples]
+    x = ensure_mono_float32(audio)  # :1312
+    if x.ndim != 1:
+        raise ValueError("stft_mono expects mono (1D) audio")  # dsp/stft_utils.py:47
+    kw = dict(key=key, scale=scale, quantize_mode=quantize_mode, snap_strength=snap_strength, smear=smear,
+              bin_smoothing=bin_smoothing, pre_quant=pre_quant, post_quant=post_quant,
+              distortion_mode=distortion_mode, distortion_params=distortion_params, limiter_on=limiter_on,
+              limiter_ceiling_db=limiter_ceiling_db, dry_wet=dry_wet, use_multiband=use_multiband,
+              crossover_hz=crossover_hz, lowband_drive=lowband_drive, passthrough_test=passthrough_test,
+              spectral_fx_mode=spectral_fx_mode, spectral_fx_strength=spectral_fx_strength,
+              spectral_fx_params=spectral_fx_params, config=config, spectral_freeze=spectral_freeze,
+              formant_shift=formant_shift, harmonic_lock_hz=harmonic_lock_hz, delta_listen=delta_listen,
+              mono_strength=mono_strength, output_trim_db=output_trim_db, sub_cut_hz=sub_cut_hz,
+              air_cut_hz=air_cut_hz, pipeline_config=pipeline_config)
+    tap_input = x.copy()
+    if x.shape[0] == 0:
+        _resolve_kwargs(0, int(sr), int(n_fft), dict(kw))  # argument validation only
+        e = np.zeros(0, dtype=np.float32)
+        return e, {"input": tap_input, "pre_quant": e.copy(), "post_dist": e.copy(), "output": e.copy()}
+    y, taps = process_batch(x[None, :], sr, n_fft=n_fft, return_taps=True, **kw)
+    out = y[0]
+    return out, {"input": tap_input, "pre_quant": taps["pre_quant"][0], "post_dist": taps["post_dist"][0],
+                 "output": out.copy()}

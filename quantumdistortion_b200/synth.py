@@ -38,3 +38,34 @@ def noise_clip(seed: int, n: int) -> np.ndarray:
 def loud_clip(seed: int, n: int, sr: int = 48000) -> np.ndarray:
     """Bass clip scaled to exceed the limiter ceiling often."""
     return np.clip(1.6 * bass_clip(seed, n, sr), -1.5, 1.5).astype(np.float32)
+
+
+def bass_batch_torch(batch: int, n: int, sr: int, device, seed: int = 0, rows_per_step: int = 64):
+    """Device-side version of ``bass_clip`` for large benchmark batches (same recipe, torch RNG):
+    returns float32 ``[batch, n]`` on ``device``.  Built ``rows_per_step`` clips at a time."""
+    import math
+
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1000 + seed)
+    out = torch.empty(batch, n, dtype=torch.float32, device=device)
+    t = torch.arange(n, dtype=torch.float32, device=device) / float(sr)
+    nf = min(int(0.05 * sr), n // 2)
+    ramp = torch.linspace(0.0, 1.0, nf, device=device) if nf > 0 else None
+    for b0 in range(0, batch, rows_per_step):
+        rows = min(rows_per_step, batch - b0)
+        f0 = 40.0 + 70.0 * torch.rand(rows, 1, generator=gen, device=device)
+        fl = 1.0 + 4.0 * torch.rand(rows, 1, generator=gen, device=device)
+        ph = 2.0 * math.pi * torch.rand(rows, 40, generator=gen, device=device)
+        x = torch.zeros(rows, n, dtype=torch.float32, device=device)
+        base = 2.0 * math.pi * f0 * t[None, :]
+        for h in range(1, 41):
+            x += torch.sin(base * h + ph[:, h - 1:h]) / h
+        x *= 0.6 + 0.4 * (1.0 + torch.sin(2.0 * math.pi * fl * t[None, :])) / 2.0
+        x += 0.01 * torch.randn(rows, n, generator=gen, device=device)
+        x *= 0.6 / x.abs().amax(dim=1, keepdim=True).clamp_min(1e-12)
+        if nf > 0:
+            x[:, :nf] *= ramp[None, :]
+            x[:, n - nf:] *= ramp.flip(0)[None, :]
+        out[b0:b0 + rows] = x
+    return out

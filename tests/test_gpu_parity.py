@@ -1,0 +1,160 @@
+"""GPU (B200): the CUDA path through the C ABI vs the oracle and the live-reference fixtures.
+
+Tolerances are the north-star's: float32 audio max-abs error <= 1e-4 and null-test residual
+<= -80 dBFS (reference tests/utils/audio_test_utils.py definition); integer tables are checked
+bit-exact on the CPU in test_host_logic.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import qd_cases
+from oracle import qd_oracle as orc
+from quantumdistortion_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MAX_ABS = 1e-4
+NULL_DB = -80.0
+FX_NOT_BUILT = {k for k, v in qd_cases.CASES.items() if v[6].get("spectral_fx_mode")}
+
+
+@pytest.fixture(scope="module")
+def qd():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import quantumdistortion_b200 as q
+    from quantumdistortion_b200 import _lib
+    lib = _lib.load()
+    assert lib.qd_device_count() >= 1, "libqd_b200.so sees no sm_100 device"
+    return q
+
+
+@pytest.fixture(scope="module")
+def pipe():
+    return np.load(os.path.join(G, "pipeline.npz"))
+
+
+def _check(got, ref, what, max_abs=MAX_ABS):
+    got = np.asarray(got)
+    assert got.dtype == np.float32 and got.shape == ref.shape, what
+    err = float(np.max(np.abs(got.astype(np.float64) - ref))) if ref.size else 0.0
+    null = orc.null_test_db(got, ref) if ref.size else -200.0
+    assert err <= max_abs, f"{what}: max abs err {err:.3e}"
+    assert null <= NULL_DB, f"{what}: null {null:.1f} dB"
+    return err
+
+
+@pytest.mark.parametrize("name", [k for k in qd_cases.CASES if k not in FX_NOT_BUILT])
+def test_pipeline_vs_reference_fixtures(qd, pipe, name):
+    kind, seed, n, sr, n_fft, rng_seed, kw = qd_cases.CASES[name]
+    x = pipe[f"{name}/x"]
+    y, taps = qd.process_audio(x, sr, n_fft=n_fft, **kw)
+    tol = MAX_ABS if n_fft <= 4096 else 3e-4  # fp32 FFT at n_fft 8192: SURVEY.md 7.4 item 2
+    _check(y, pipe[f"{name}/y"], f"{name}/y", tol)
+    _check(taps["pre_quant"], pipe[f"{name}/pre_quant"], f"{name}/pre_quant", tol)
+    _check(taps["post_dist"], pipe[f"{name}/post_dist"], f"{name}/post_dist", tol)
+    assert np.array_equal(taps["input"], x) and np.array_equal(taps["output"], y)
+
+
+def test_batch_vs_oracle_default_config(qd):
+    """Config #2 shape (single-band defaults) on a small seeded batch, every clip against the oracle."""
+    n, sr, b = 48000, 48000, 6
+    x = np.stack([synth.bass_clip(i, n, sr) if i % 2 == 0 else synth.noise_clip(i, n) for i in range(b)])
+    y, taps = qd.process_batch(x, sr, return_taps=True)
+    worst = 0.0
+    for i in range(b):
+        ref, rt = orc.process_audio(x[i], sr)
+        worst = max(worst, _check(y[i], ref, f"clip {i}"))
+        _check(taps["pre_quant"][i], rt["pre_quant"], f"clip {i} pre_quant")
+        _check(taps["post_dist"][i], rt["post_dist"], f"clip {i} post_dist")
+    print(f"worst max-abs error vs oracle: {worst:.3e}")
+    y2, _ = qd.process_batch(x, sr)  # host pipeline path (qd_render_host) must agree bit for bit
+    assert np.array_equal(y, y2)
+
+
+def test_multiband_batch_vs_oracle(qd):
+    n, sr = 30000, 48000
+    x = np.stack([synth.loud_clip(40 + i, n, sr) for i in range(3)])
+    kw = dict(use_multiband=True, crossover_hz=300.0, lowband_drive=1.5, dry_wet=0.9)
+    y, taps = qd.process_batch(x, sr, return_taps=True, **kw)
+    for i in range(3):
+        ref, rt = orc.process_audio(x[i], sr, **kw)
+        _check(y[i], ref, f"mb clip {i}")
+        _check(taps["post_dist"][i], rt["post_dist"], f"mb clip {i} post_dist")
+
+
+def test_tiling_and_batch_size_do_not_change_bits(qd):
+    """A clip rendered alone (time-tiled over many CTAs) equals the same clip inside a large batch
+    (whole-clip CTAs): overlap-add always sums frames in ascending order."""
+    import torch
+    n, sr = 100000, 48000
+    clip = synth.bass_clip(77, n, sr)
+    y1, _ = qd.process_batch(torch.from_numpy(clip[None, :]).cuda(), sr)
+    big = torch.from_numpy(np.repeat(clip[None, :], 700, axis=0)).cuda()
+    y700, _ = qd.process_batch(big, sr)
+    assert torch.equal(y700[0], y1[0]) and torch.equal(y700[699], y1[0]) and torch.equal(y700[350], y1[0])
+
+
+def test_full_size_properties(qd):
+    """BASELINE config #2 clip length (480 000 samples): passthrough null, limiter ceiling, determinism."""
+    import torch
+    n, sr, b = 480000, 48000, 24
+    x = synth.bass_batch_torch(b, n, sr, "cuda", seed=5)
+    y, _ = qd.process_batch(x, sr, passthrough_test=True)
+    d = (y - x).double()
+    null = 20.0 * torch.log10(torch.sqrt((d * d).mean()).clamp_min(1e-10)).item()
+    assert null < -110.0, null  # reference test bar is -80 dB (tests/test_passthrough_null.py:56-148)
+    loud = (x * 3.0).clamp(-1.5, 1.5)
+    kw = dict(distortion_params={"fold_amount": 3.0})
+    y, _ = qd.process_batch(loud, sr, **kw)
+    ceiling = 10.0 ** (-1.0 / 20.0)
+    assert float(y.abs().max()) <= ceiling * 1.01  # reference tests/test_limiter.py:7-58 bound
+    assert torch.isfinite(y).all()
+    y_again, _ = qd.process_batch(loud, sr, **kw)
+    assert torch.equal(y, y_again)
+    # one clip of the batch against the oracle at full length
+    ref, _ = orc.process_audio(loud[3].cpu().numpy(), sr, **kw)
+    _check(y[3].cpu().numpy(), ref, "full-size clip")
+
+
+def test_stage_limiter_and_crossover_and_distortion(qd):
+    st = np.load(os.path.join(G, "stages.npz"))
+    x = st["td/x"]
+    for sr in (48000, 44100):
+        y = qd.peak_limiter(x, sr, ceiling_db=-1.0, lookahead_ms=5.0, release_ms=30.0)
+        assert np.max(np.abs(y.astype(np.float64) - st[f"td/lim/{sr}/y"])) <= 6e-8
+    lo, hi = qd.linkwitz_riley_split(x, 48000, 300.0)
+    assert np.max(np.abs(lo - st["td/xo/low"])) <= 1.2e-7 and np.max(np.abs(hi - st["td/xo/high"])) <= 1.2e-7
+    wf = qd.apply_distortion(x, "wavefold", fold_amount=5.0, bias=0.1)
+    assert np.max(np.abs(wf - st["td/wavefold"])) <= 2e-6
+    tb = qd.apply_distortion(x, "tube", drive=4.0, warmth=0.7)
+    assert np.max(np.abs(tb - st["td/tube"])) <= 1e-6
+    with pytest.raises(ValueError):
+        qd.apply_distortion(x, "fuzz")
+    # long clip: chunk carries of both scans
+    xl = np.clip(2.0 * synth.noise_clip(9, 200001), -2, 2).astype(np.float32)
+    ref, _ = orc.peak_limiter(xl, 48000, -1.0, 5.0, 30.0)
+    assert np.max(np.abs(qd.peak_limiter(xl, 48000, -1.0, 5.0, 30.0).astype(np.float64) - ref)) <= 6e-8
+    rlo, rhi = orc.linkwitz_riley_split(xl, 48000, 300.0)
+    lo, hi = qd.linkwitz_riley_split(xl, 48000, 300.0)
+    assert np.max(np.abs(lo - rlo)) <= 2.4e-7 and np.max(np.abs(hi - rhi)) <= 2.4e-7
+
+
+def test_edge_cases(qd):
+    y, taps = qd.process_audio(np.zeros(0, dtype=np.float32), 48000)
+    assert y.shape == (0,) and set(taps) == {"input", "pre_quant", "post_dist", "output"}
+    for n in (1, 5, 511, 512, 513, 2047):
+        x = synth.noise_clip(n, n)
+        y, _ = qd.process_audio(x, 48000)
+        ref, _ = orc.process_audio(x, 48000)
+        _check(y, ref, f"n={n}")
+    silent = np.zeros(4096, dtype=np.float32)
+    y, _ = qd.process_audio(silent, 48000)
+    assert np.array_equal(y, silent)
+    stereo = np.stack([synth.bass_clip(1, 3000), synth.noise_clip(2, 3000)], axis=1)
+    y, _ = qd.process_audio(stereo, 48000)
+    ref, _ = orc.process_audio(stereo, 48000)
+    _check(y, ref, "stereo->mono")

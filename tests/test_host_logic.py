@@ -1,0 +1,133 @@
+"""CPU: host-side logic of the product (tables, parameter resolution, error behaviour, C ABI surface)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from quantumdistortion_b200 import PipelineConfig, get_preset, list_presets, tables
+from quantumdistortion_b200 import _lib as qlib
+from quantumdistortion_b200 import build as qbuild
+from quantumdistortion_b200.pipeline import _resolve_kwargs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_integer_tables_bit_exact_vs_reference_fixtures():
+    t = np.load(os.path.join(G, "tables.npz"))
+    n = 0
+    for k in t.files:
+        if k.startswith("tb/") and k != "tb/kat4":
+            sr, n_fft, key, scale = k[3:].split("_", 3)
+            freqs = np.fft.rfftfreq(int(n_fft), d=1.0 / int(sr))
+            assert np.array_equal(tables.build_target_bins_for_freqs(freqs, key, scale), t[k]), k
+            assert np.array_equal(tables.build_quantize_band_mask(freqs, 110.0, 5000.0), t["mask/" + k[3:]]), k
+            n += 1
+    assert n == 10
+    freqs = np.fft.rfftfreq(2048, d=1.0 / 48000)
+    assert np.array_equal(tables.build_quantize_band_mask(freqs, 0.0, 0.0), t["mask/wide"])
+    for f0 in (55.0, 110.0, 441.3):
+        assert np.array_equal(tables.build_harmonic_target_bins(freqs, f0), t[f"htb/{f0}"])
+    assert list(tables.build_target_bins_for_freqs(np.array([0.0, 430.0, 440.0, 450.0]), "A", "minor")) == [0, 2, 2, 2]
+
+
+def test_default_table_structure_matches_survey():
+    freqs = np.fft.rfftfreq(2048, d=1.0 / 48000)
+    tb = tables.build_target_bins_for_freqs(freqs, "D", "minor")
+    mask = tables.build_quantize_band_mask(freqs, 110.0, 5000.0)
+    assert mask.sum() == 209 and mask[5] and mask[213] and not mask[4] and not mask[214]
+    assert len(np.unique(tb[mask])) == 36 and np.max(np.abs(tb[mask] - np.nonzero(mask)[0])) == 13
+    assert np.max(np.bincount(tb[mask])) == 27
+
+
+def test_constants_half_even_rounding_and_sos():
+    assert tables.limiter_constants(44100, -1.0)[1] == 220       # round(220.5) -> 220
+    assert tables.limiter_constants(48000, -1.0)[1] == 240
+    c = tables.limiter_constants(44100, -1.0)[2]
+    assert c == float(np.exp(-1.0 / 1323))
+    lo, hi = tables.design_linkwitz_riley_sos(48000, 300.0)
+    assert lo.shape == (2, 6) and hi.shape == (2, 6)
+    assert abs(lo[0, 4] + 1.9444776577670935) < 1e-15 and abs(hi[0, 0] - 0.9726138984998438) < 1e-15
+    st = np.load(os.path.join(G, "stages.npz"))
+    assert np.array_equal(lo, st["td/xo/sos_low"]) and np.array_equal(hi, st["td/xo/sos_high"])
+
+
+def test_reference_error_behaviour_before_launch():
+    base = dict(sr=48000, n_samples=1000, key="D", scale="minor", snap_strength=1.0, smear=0.1, bin_smoothing=True,
+                pre_quant=True, post_quant=True, distortion_mode="wavefold", distortion_params={}, limiter_on=True,
+                limiter_ceiling_db=-1.0, dry_wet=1.0, use_multiband=False, crossover_hz=300.0, lowband_drive=1.0,
+                passthrough_test=False, harmonic_lock_hz=0.0, delta_listen=False, mono_strength=1.0,
+                output_trim_db=0.0, low_trim_db=0.0, sub_cut_hz=110.0, air_cut_hz=5000.0)
+    tables.resolve(**base)
+    with pytest.raises(ValueError, match="Unsupported key name"):
+        tables.resolve(**dict(base, key="H"))
+    with pytest.raises(KeyError):
+        tables.resolve(**dict(base, scale="lydian"))
+    with pytest.raises(ValueError, match="Unsupported distortion mode"):
+        tables.resolve(**dict(base, distortion_mode="fuzz"))
+    with pytest.raises(ValueError, match="Crossover frequency"):
+        tables.resolve(**dict(base, use_multiband=True, crossover_hz=24000.0))
+    with pytest.raises(ValueError):
+        tables.resolve(**dict(base, n_fft=3000))
+
+
+def test_resolved_flags_follow_reference_gates():
+    r, _ = _resolve_kwargs(1000, 48000, 2048, {"snap_strength": 0.0})
+    assert r.params.pre_quant == 0 and r.params.post_quant == 0 and r.tables is None
+    r, _ = _resolve_kwargs(1000, 48000, 2048, {"dry_wet": 1.7, "output_trim_db": -6.0, "snap_strength": 2.0})
+    assert r.params.wet == 1.0 and r.params.dry == 0.0 and r.params.apply_trim == 1
+    assert r.tables.snap == 1.0 and r.params.pre_quant == 1
+    assert abs(r.params.trim_gain - np.float32(10 ** (-6 / 20))) == 0.0
+    r, _ = _resolve_kwargs(1000, 44100, 2048, {"pipeline_config": PipelineConfig.from_preset("Subtle Tube Glue")})
+    assert r.params.post_quant == 0 and r.params.distortion_mode == 1 and abs(r.params.wet - np.float32(0.7)) == 0
+    assert r.params.lookahead == 220
+    with pytest.raises(NotImplementedError):
+        _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1"})
+    r, _ = _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1", "harmonic_lock_hz": 55.0})
+    assert r.params.pre_quant == 1
+    with pytest.raises(TypeError):
+        _resolve_kwargs(1000, 48000, 2048, {"bogus": 1})
+
+
+def test_presets_mirror_reference():
+    assert list_presets() == ["Chordal Noise Wash", "Controlled Dubstep Growl", "Perc To Tonal Clang",
+                              "Subtle Tube Glue"]
+    g = get_preset("Controlled Dubstep Growl")
+    assert g["key"] == "F" and g["snap_strength"] == 0.9 and g["distortion_params"]["fold_amount"] == 5.0
+    with pytest.raises(KeyError):
+        get_preset("nope")
+    pc = PipelineConfig()
+    assert pc.key == "D" and pc.sub_cut_hz == 110.0 and pc.air_cut_hz == 5000.0 and pc.crossover_hz == 300.0
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    """No compute call here: only dlopen + symbol lookup (no GPU needed)."""
+    lib_path = qbuild.build()
+    lib = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, "include", "qd_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(qd_[a-z0-9_]+)\s*\(", header))
+    assert {"qd_plan_create", "qd_render_device", "qd_render_host", "qd_limiter_device", "qd_crossover_device",
+            "qd_distort_device", "qd_plan_read_timing"} <= names
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/qd_b200.h but not exported"
+    lib.qd_abi_version.restype = ctypes.c_int
+    assert lib.qd_abi_version() == qlib.QD_ABI_VERSION
+    assert ctypes.sizeof(qlib.QdParams) % 8 == 0
+
+
+def test_params_struct_layout_matches_header():
+    """ctypes mirror vs the C compiler's view of qd_params (offsets of a few late fields)."""
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "qd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(qd_params), offsetof(qd_params, ceiling_lin), offsetof(qd_params, sos_low), offsetof(qd_params, low_norm), offsetof(qd_params, fx_a));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
+        got = [int(v) for v in subprocess.check_output([exe]).split()]
+    P = qlib.QdParams
+    assert got == [ctypes.sizeof(P), P.ceiling_lin.offset, P.sos_low.offset, P.low_norm.offset, P.fx_a.offset]
