@@ -383,17 +383,20 @@ struct SpecSmem {
     static constexpr size_t off_tail = off_stage + (size_t)STAGE * sizeof(float);
     static constexpr size_t off_flags = off_tail + (size_t)TAIL * sizeof(float);
     static constexpr size_t off_slot = off_flags + 64 * sizeof(int);
+    // per-warp gather scratch: G[cap] floats then P[cap] float2, cap even so P stays 8-byte aligned
+    static int slot_cap(int n_slots) { return (n_slots + 2) & ~1; }
     static size_t bytes(int n_slots) {
-        return off_slot + (size_t)NW * (size_t)(n_slots + 1) * 3 * sizeof(float) + 16;
+        return off_slot + (size_t)NW * (size_t)slot_cap(n_slots) * 3 * sizeof(float) + 16;
     }
 };
 
 // wavefold / tube on the float32 iSTFT sample (dsp/distortion.py:18-90)
 QD_DEV float epilogue_apply(float v, int mode, float fold, float bias, float tg, float tn) {
     if (mode == 1) {
+        // dsp/distortion.py:44-56: the negative fold is tested on the already folded value
         float y = (v + bias) * fold;
         if (y > 1.0f) y = 2.0f - y;
-        else if (y < -1.0f) y = -2.0f - y;
+        if (y < -1.0f) y = -2.0f - y;
         return fminf(fmaxf(y, -1.0f), 1.0f);
     }
     if (mode == 2) return tanhf(tg * v) * tn;
@@ -414,8 +417,9 @@ spec_pass_kernel(const SpecArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = 32 * NW;
     float2 *buf = bufs + (size_t)warp * L::BUF;
-    float *slotG = reinterpret_cast<float *>(smem + L::off_slot) + (size_t)warp * (a.q.n_slots + 1) * 3;
-    float2 *slotP = reinterpret_cast<float2 *>(slotG + (a.q.n_slots + 1));
+    const int slot_cap = (a.q.n_slots + 2) & ~1;
+    float *slotG = reinterpret_cast<float *>(smem + L::off_slot) + (size_t)warp * slot_cap * 3;
+    float2 *slotP = reinterpret_cast<float2 *>(slotG + slot_cap);
 
     const int clip = blockIdx.y;
     const float *x = a.x + (size_t)clip * a.n;

@@ -328,7 +328,7 @@ __global__ void distort_kernel(const float *__restrict__ x, float *__restrict__ 
         if (mode == 0) {
             float t = (v + bias) * fold;
             if (t > 1.0f) t = 2.0f - t;
-            else if (t < -1.0f) t = -2.0f - t;
+            if (t < -1.0f) t = -2.0f - t;  // sequential masks, dsp/distortion.py:44-53
             r = fminf(fmaxf(t, -1.0f), 1.0f);
         } else {
             r = tanhf(tg * v) * tn;
