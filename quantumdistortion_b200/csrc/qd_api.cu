@@ -260,19 +260,19 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         qd_host::QuantTablesH qt;
         std::string err;
         if (!qd_host::build_quant_tables(*tables, &qt, &err)) return bail(QD_ERR_INVALID_ARG, err);
-        uint16_t *d_sb, *d_src, *d_rab;
-        uint32_t *d_ra, *d_rf;
+        uint16_t *d_rab;
+        uint32_t *d_ra, *d_rf, *d_st;
         qd_host::AffEntryH *d_aff;
-        QD_UP(qt.slot_begin, d_sb);
-        QD_UP(qt.src_bin, d_src);
+        QD_UP(qt.src_tab, d_st);
         QD_UP(qt.row_active, d_ra);
         QD_UP(qt.row_aff, d_rf);
         QD_UP(qt.row_aff_base, d_rab);
         QD_UP(qt.aff, d_aff);
         a.q.n_slots = qt.n_slots;
         a.q.n_aff = qt.n_aff;
-        a.q.slot_begin = d_sb;
-        a.q.src_bin = d_src;
+        a.q.n_src = (int)qt.src_tab.size();
+    a.q.row_limit = qt.row_limit;
+        a.q.src_tab = d_st;
         a.q.row_active = d_ra;
         a.q.row_aff = d_rf;
         a.q.row_aff_base = d_rab;

@@ -89,8 +89,19 @@ inline bool build_spec_tables(int n_fft, SpecTables *t) {
     return true;
 }
 
+// host mirror of qd::spos<NC>: position of spectrum bin k inside a warp buffer
+inline int host_spos(int nc, int k) {
+    FftRadices r;
+    if (!fft_radices(nc, &r)) return -1;
+    if (k >= nc) return 32;  // QD_NYQ_SLOT
+    const int k1 = k % r.r1, k2 = (k / r.r1) % r.r2, k3 = k / (r.r1 * r.r2);
+    const int a = k1 * (nc / r.r1) + k2 * (nc / (r.r1 * r.r2)) + k3;
+    return a + (a >> 5);
+}
+
 struct QuantTablesH {
-    int n_bins = 0, n_slots = 0, n_aff = 0, rows = 0;
+    int n_bins = 0, n_slots = 0, n_aff = 0, rows = 0, row_limit = 0;
+    std::vector<uint32_t> src_tab;  // tail<<31 | off<<26 | slot<<13 | buffer position, grouped by slot
     std::vector<uint16_t> slot_begin, src_bin, row_aff_base;
     std::vector<int32_t> slot_bin;
     std::vector<uint32_t> row_active, row_aff;
@@ -128,6 +139,22 @@ inline bool build_quant_tables(const qd_tables &in, QuantTablesH *q, std::string
         }
     q->slot_begin.push_back((uint16_t)q->src_bin.size());
     q->n_slots = (int)q->slot_bin.size();
+    // entry i of the gather table; `off` = same-slot sources before it inside its group of 32,
+    // `tail` = last source of its slot inside the group (see quantize_frame Q1)
+    q->src_tab.clear();
+    {
+        std::vector<int> slot_of_src;
+        for (int s = 0; s < q->n_slots; ++s)
+            for (int i = q->slot_begin[s]; i < q->slot_begin[s + 1]; ++i) slot_of_src.push_back(s);
+        const int ns = (int)slot_of_src.size();
+        for (int i = 0; i < ns; ++i) {
+            int off = 0;
+            for (int j = i - 1; j >= (i / 32) * 32 && slot_of_src[j] == slot_of_src[i]; --j) ++off;
+            const bool tail = (i % 32 == 31) || (i == ns - 1) || (slot_of_src[i + 1] != slot_of_src[i]);
+            const uint32_t pos = (uint32_t)host_spos(n - 1, q->src_bin[i]);
+            q->src_tab.push_back(((uint32_t)tail << 31) | ((uint32_t)off << 26) | ((uint32_t)slot_of_src[i] << 13) | pos);
+        }
+    }
     if (q->src_bin.empty()) q->src_bin.push_back(0);
     const double snap = in.snap, smear = in.smear;
     const bool do_smear = smear > 0.0 && radius > 0;  // dsp/quantizer.py:458
@@ -166,6 +193,9 @@ inline bool build_quant_tables(const qd_tables &in, QuantTablesH *q, std::string
         }
     }
     q->n_aff = (int)q->aff.size();
+    q->row_limit = 0;
+    for (int r = 0; r < q->rows; ++r)
+        if (q->row_active[r] | q->row_aff[r]) q->row_limit = r + 1;
     int run = 0;
     for (int r = 0; r < q->rows; ++r) {
         q->row_aff_base[r] = (uint16_t)run;

@@ -49,6 +49,20 @@ QD_DEV int spos(int k) {
     return pidx(k1 * (NC / C::R1) + k2 * (NC / (C::R1 * C::R2)) + k3);
 }
 
+// position of bin 32*row + lane.  For the 32x32 plan this is 33*lane + row for every bin including the
+// Nyquist bin (row 32, lane 0 -> slot 32), so row loops advance by one slot per row.
+template <int NC>
+QD_DEV int rpos(int lane, int row) {
+    if constexpr (NC == 1024) return 33 * lane + row;
+    else return spos<NC>(32 * row + lane);
+}
+// position of the mirror bin NC - (32*row + lane), row < NC/64
+template <int NC>
+QD_DEV int mpos(int lane, int row) {
+    if constexpr (NC == 1024) return lane == 0 ? 32 - row : 33 * (32 - lane) + 31 - row;
+    else return spos<NC>(NC - (32 * row + lane));
+}
+
 // ---------------------------------------------------------------- device-side tables
 struct AffEntry {          // one destination bin that can receive moved energy
     int16_t slot[5];       // slot of the target at bin d-2..d+2 (n_slots = "none", reads 0)
@@ -59,8 +73,9 @@ struct AffEntry {          // one destination bin that can receive moved energy
 struct QuantDev {
     int n_slots;                    // distinct target bins
     int n_aff;
-    const uint16_t *slot_begin;     // [n_slots+1] CSR offsets into src_bin
-    const uint16_t *src_bin;        // source bins, grouped by target, ascending
+    int n_src;
+    int row_limit;                  // rows >= row_limit hold no source and no affected bin
+    const uint32_t *src_tab;        // [n_src] tail<<31 | off<<26 | slot<<13 | buffer position, grouped by slot
     const uint32_t *row_active;     // [rows] bit l: bin 32*row+l gives its energy away
     const uint32_t *row_aff;        // [rows] bit l: bin 32*row+l is in the affected list
     const uint16_t *row_aff_base;   // [rows] affected bins before this row
@@ -223,16 +238,17 @@ QD_DEV void fft_inverse(float2 *buf, const float2 *wtab, const float2 *tw1, cons
 //   X[k] = E + T,  X[NC-k] = conj(E - T)
 template <int NC>
 QD_DEV void real_split(float2 *buf, const float2 *wsplit, int lane) {
-#pragma unroll 2
-    for (int k = lane; k < NC / 2; k += 32) {
+#pragma unroll 4
+    for (int row = 0; row < NC / 64; ++row) {
+        const int k = lane + 32 * row;
         if (k == 0) {
-            const float2 z0 = buf[spos<NC>(0)];
-            buf[spos<NC>(0)] = make_float2(z0.x + z0.y, 0.0f);
+            const float2 z0 = buf[0];
+            buf[0] = make_float2(z0.x + z0.y, 0.0f);
             buf[QD_NYQ_SLOT] = make_float2(z0.x - z0.y, 0.0f);
             const int pm = spos<NC>(NC / 2);
             buf[pm] = cconj(buf[pm]);
         } else {
-            const int pa = spos<NC>(k), pb = spos<NC>(NC - k);
+            const int pa = rpos<NC>(lane, row), pb = mpos<NC>(lane, row);
             const float2 za = buf[pa], zb = buf[pb];
             const float2 e = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
             const float2 o = make_float2(0.5f * (za.y + zb.y), -0.5f * (za.x - zb.x));  // (za - conj zb)/(2i)
@@ -249,16 +265,17 @@ QD_DEV void real_split(float2 *buf, const float2 *wsplit, int lane) {
 //   Z'[k] = E2 + i O2,  Z'[NC-k] = conj(E2 - i O2)
 template <int NC>
 QD_DEV void real_merge(float2 *buf, const float2 *wsplit, int lane) {
-#pragma unroll 2
-    for (int k = lane; k < NC / 2; k += 32) {
+#pragma unroll 4
+    for (int row = 0; row < NC / 64; ++row) {
+        const int k = lane + 32 * row;
         if (k == 0) {
-            const float a = buf[spos<NC>(0)].x, b = buf[QD_NYQ_SLOT].x;
-            buf[spos<NC>(0)] = make_float2(a + b, a - b);
+            const float a = buf[0].x, b = buf[QD_NYQ_SLOT].x;
+            buf[0] = make_float2(a + b, a - b);
             const int pm = spos<NC>(NC / 2);
             const float2 xm = buf[pm];
             buf[pm] = make_float2(2.0f * xm.x, -2.0f * xm.y);
         } else {
-            const int pa = spos<NC>(k), pb = spos<NC>(NC - k);
+            const int pa = rpos<NC>(lane, row), pb = mpos<NC>(lane, row);
             const float2 xa = buf[pa], xb = buf[pb];
             const float2 e = make_float2(xa.x + xb.x, xa.y - xb.y);
             const float2 t = make_float2(xa.x - xb.x, xa.y + xb.y);
@@ -276,97 +293,153 @@ QD_DEV void real_merge(float2 *buf, const float2 *wsplit, int lane) {
 //   tE_d = sum_e coef[d][e] G_{t(d,e)},  PS_d = sum_e coef[d][e] P_{t(d,e)}
 //   new_d = |X_d| keep_d + tE_d ;  phasor_d = PS_d/|PS_d| if tE_d > 0 else X_d/|X_d|
 //   out_d = smooth(new)_d * phasor_d      with [1/4,1/2,1/4], edges replicated
+// 1/sqrt(x) as a single MUFU.RSQ (2 ulp); callers guard x against zero / denormals
+QD_DEV float rsqrt_fast(float x) {
+#ifdef QD_EMU
+    return 1.0f / std::sqrt(x);
+#else
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+constexpr float QD_TINY2 = 1e-30f;  // |X|^2 below this is treated as an exact zero (|X| < 1e-15)
+
+// magnitude and unit phasor of one bin (np.angle(0) = 0 -> phasor 1)
+QD_DEV void mag_phasor(float2 xv, float &m, float2 &u) {
+    const float m2 = xv.x * xv.x + xv.y * xv.y;
+    const bool ok = m2 > QD_TINY2;
+    const float r = rsqrt_fast(m2);
+    m = ok ? m2 * r : 0.0f;
+    u.x = ok ? xv.x * r : 1.0f;
+    u.y = ok ? xv.y * r : 0.0f;
+}
+
+// [1/4,1/2,1/4] smoothing of row `cur` with two shuffles: lane 31 lends its previous-row value to lane 0,
+// lane 0 lends its next-row value to lane 31 (nobody else needs those two lanes' own m_cur as a neighbour
+// on that side).
+QD_DEV float smooth_row(float m_prev, float m_cur, float m_next, int lane, bool first_bin, bool last_bin) {
+    float left = __shfl_sync(QD_FULL, lane == 31 ? m_prev : m_cur, (lane + 31) & 31);
+    float right = __shfl_sync(QD_FULL, lane == 0 ? m_next : m_cur, (lane + 1) & 31);
+    if (first_bin) left = m_cur;   // scipy convolve1d mode="nearest"
+    if (last_bin) right = m_cur;
+    return 0.5f * m_cur + 0.25f * (left + right);
+}
+
+// one bin of a row that may give energy away (active) or receive it (affected): new magnitude and phasor
+template <int NC>
+QD_DEV void quant_bin(const float2 *buf, const float *slotG, const float2 *slotP, const QuantDev &q, int lane,
+                      int row, uint32_t bit, float &nm, float2 &u) {
+    float m;
+    mag_phasor(buf[rpos<NC>(lane, row)], m, u);
+    nm = (__ldg(q.row_active + row) & bit) ? m * q.keep_active : m;
+    const uint32_t am = __ldg(q.row_aff + row);
+    if (am & bit) {
+        const AffEntry &ae = q.aff[__ldg(q.row_aff_base + row) + __popc(am & (bit - 1u))];
+        float te = 0.0f;
+        float2 ps = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+            const int s = ae.slot[e];
+            const float c = ae.coef[e];
+            te += c * slotG[s];
+            const float2 pv = slotP[s];
+            ps.x += c * pv.x;
+            ps.y += c * pv.y;
+        }
+        nm += te;
+        if (te > 0.0f) {
+            const float p2 = ps.x * ps.x + ps.y * ps.y;
+            const bool ok = p2 > QD_TINY2;
+            const float r = rsqrt_fast(p2);
+            u = make_float2(ok ? ps.x * r : 1.0f, ok ? ps.y * r : 0.0f);
+        }
+    }
+}
+
 template <int NC>
 QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const QuantDev &q, int lane) {
-    // Q1: per-target gathers
-    for (int s = lane; s < q.n_slots; s += 32) {
-        const int b = q.slot_begin[s], e = q.slot_begin[s + 1];
-        float g = 0.0f;
-        float2 p = make_float2(0.0f, 0.0f);
-        for (int i = b; i < e; ++i) {
-            const float2 xv = buf[spos<NC>(q.src_bin[i])];
-            g += sqrtf(xv.x * xv.x + xv.y * xv.y);
-            p = cadd(p, xv);
-        }
-        slotG[s] = g;
-        slotP[s] = p;
-    }
-    if (lane == 0) {
-        slotG[q.n_slots] = 0.0f;
-        slotP[q.n_slots] = make_float2(0.0f, 0.0f);
+    // Q1: per-target gathers.  Sources are grouped by target slot; 32 of them are loaded per step and
+    // summed with a segmented warp scan.  The segment structure is static, so the host stores, per
+    // source, how many sources of the same slot precede it inside its step (`off`) and whether it is the
+    // last one of its slot in the step (`tail`): no slot ids have to be shuffled.
+    for (int s = lane; s <= q.n_slots; s += 32) {
+        slotG[s] = 0.0f;
+        slotP[s] = make_float2(0.0f, 0.0f);
     }
     __syncwarp();
+#pragma unroll 1
+    for (int i0 = 0; i0 < q.n_src; i0 += 32) {
+        const int i = i0 + lane;
+        uint32_t e = 0u;  // pos 0, slot 0, off 0, tail 0: a lane past the end adds nothing
+        float g = 0.0f;
+        float2 p = make_float2(0.0f, 0.0f);
+        if (i < q.n_src) {
+            e = __ldg(q.src_tab + i);
+            p = buf[e & 0x1fffu];
+            const float m2 = p.x * p.x + p.y * p.y;
+            g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
+        }
+        const int off = (int)((e >> 26) & 31u);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float go = __shfl_up_sync(QD_FULL, g, d);
+            const float pxo = __shfl_up_sync(QD_FULL, p.x, d);
+            const float pyo = __shfl_up_sync(QD_FULL, p.y, d);
+            if (off >= d) { g += go; p.x += pxo; p.y += pyo; }
+        }
+        if (e >> 31) {
+            const int sid = (int)((e >> 13) & 0x1fffu);
+            slotG[sid] += g;
+            const float2 t = slotP[sid];
+            slotP[sid] = make_float2(t.x + p.x, t.y + p.y);
+        }
+        __syncwarp();
+    }
 
-    // Q3: rows of 32 bins, rolling window of three rows for the smoothing
+    // Q3: rows of 32 bins with a rolling window of three rows for the smoothing.  Rows below
+    // q.row_limit may give energy away or receive it; the rows above only need |X|, the phasor and the
+    // smoothing, and run in a tight loop.
     constexpr int NBINS = NC + 1;
-    constexpr int ROWS = (NBINS + 31) / 32;
+    constexpr int ROWS = (NBINS + 31) / 32;   // the last row holds only the Nyquist bin (lane 0)
     float m_prev = 0.0f, m_cur = 0.0f, m_next = 0.0f;
     float2 u_cur = make_float2(1.0f, 0.0f), u_next = make_float2(1.0f, 0.0f);
+    const uint32_t bit = 1u << lane;
+    const bool smooth = q.smoothing != 0;
+    const int row_limit = q.row_limit < ROWS - 1 ? q.row_limit : ROWS - 1;
+    // ---- rows [0, row_limit): full logic
 #pragma unroll 1
-    for (int row = 0; row <= ROWS; ++row) {
-        // ---- compute row `row` into (m_next, u_next)
+    for (int row = 0; row < row_limit; ++row) {
+        quant_bin<NC>(buf, slotG, slotP, q, lane, row, bit, m_next, u_next);
+        if (row > 0) {
+            const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
+            buf[rpos<NC>(lane, row - 1)] = make_float2(out * u_cur.x, out * u_cur.y);
+        }
+        m_prev = m_cur; m_cur = m_next; u_cur = u_next;
+    }
+    // ---- rows [row_limit, ROWS-1): nothing moves, only the smoothing couples neighbours
+#pragma unroll 4
+    for (int row = row_limit; row < ROWS - 1; ++row) {
+        mag_phasor(buf[rpos<NC>(lane, row)], m_next, u_next);
+        if (row > 0) {
+            const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
+            buf[rpos<NC>(lane, row - 1)] = make_float2(out * u_cur.x, out * u_cur.y);
+        }
+        m_prev = m_cur; m_cur = m_next; u_cur = u_next;
+    }
+    // ---- Nyquist row (lane 0 only), then flush the last two rows
+    {
         m_next = 0.0f;
         u_next = make_float2(1.0f, 0.0f);
-        const int d = 32 * row + lane;
-        if (row < ROWS && d < NBINS) {
-            const float2 xv = buf[spos<NC>(d)];
-            const float m2 = xv.x * xv.x + xv.y * xv.y;
-            const float m = sqrtf(m2);
-            float2 u = make_float2(1.0f, 0.0f);  // np.angle(0) = 0
-            if (m > 0.0f) {
-                const float r = 1.0f / m;
-                u = make_float2(xv.x * r, xv.y * r);
-            }
-            const uint32_t bit = 1u << lane;
-            float nm = (q.row_active[row] & bit) ? m * q.keep_active : m;
-            const uint32_t am = q.row_aff[row];
-            if (am & bit) {
-                const AffEntry &ae = q.aff[q.row_aff_base[row] + __popc(am & (bit - 1u))];
-                float te = 0.0f;
-                float2 ps = make_float2(0.0f, 0.0f);
-#pragma unroll
-                for (int e = 0; e < 5; ++e) {
-                    const int s = ae.slot[e];
-                    const float c = ae.coef[e];
-                    te += c * slotG[s];
-                    const float2 pv = slotP[s];
-                    ps.x += c * pv.x;
-                    ps.y += c * pv.y;
-                }
-                nm += te;
-                if (te > 0.0f) {
-                    const float p2 = ps.x * ps.x + ps.y * ps.y;
-                    if (p2 > 0.0f) {
-                        const float r = rsqrtf(p2);
-                        u = make_float2(ps.x * r, ps.y * r);
-                    } else {
-                        u = make_float2(1.0f, 0.0f);
-                    }
-                }
-            }
-            m_next = nm;
-            u_next = u;
+        if (lane == 0) {
+            if (q.row_limit >= ROWS) quant_bin<NC>(buf, slotG, slotP, q, 0, ROWS - 1, 1u, m_next, u_next);
+            else mag_phasor(buf[rpos<NC>(0, ROWS - 1)], m_next, u_next);
         }
-        // ---- finish row-1 (needs its neighbours: lane-1/lane+1, across rows at the ends)
-        if (row > 0) {
-            const int dc = 32 * (row - 1) + lane;
-            float out = m_cur;
-            if (q.smoothing) {
-                float left = __shfl_up_sync(QD_FULL, m_cur, 1);
-                const float left_wrap = __shfl_sync(QD_FULL, m_prev, 31);
-                float right = __shfl_down_sync(QD_FULL, m_cur, 1);
-                const float right_wrap = __shfl_sync(QD_FULL, m_next, 0);
-                if (lane == 0) left = left_wrap;
-                if (lane == 31) right = right_wrap;
-                if (dc == 0) left = m_cur;              // mode="nearest"
-                if (dc == NBINS - 1) right = m_cur;
-                out = 0.5f * m_cur + 0.25f * (left + right);
-            }
-            if (dc < NBINS) buf[spos<NC>(dc)] = make_float2(out * u_cur.x, out * u_cur.y);
-        }
-        m_prev = m_cur;
-        m_cur = m_next;
-        u_cur = u_next;
+        const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, ROWS == 2 && lane == 0, false) : m_cur;
+        buf[rpos<NC>(lane, ROWS - 2)] = make_float2(out * u_cur.x, out * u_cur.y);
+        m_prev = m_cur; m_cur = m_next; u_cur = u_next;
+        const float outn = smooth ? smooth_row(m_prev, m_cur, 0.0f, lane, false, lane == 0) : m_cur;
+        if (lane == 0) buf[rpos<NC>(0, ROWS - 1)] = make_float2(outn * u_cur.x, outn * u_cur.y);
     }
     __syncwarp();
 }
@@ -408,14 +481,14 @@ __global__ void __launch_bounds__(32 * NW)
 spec_pass_kernel(const SpecArgs a) {
     using L = SpecSmem<NC, NW>;
     constexpr int HOP = L::HOP;
-    constexpr int NFFT = 2 * NC;
+    constexpr int HP = HOP / 2;              // float2 pairs per hop
+    constexpr int HPP = HP + HP / 32;        // the same span inside a padded warp buffer
     QD_DYN_SMEM(smem);
     float2 *bufs = reinterpret_cast<float2 *>(smem + L::off_buf);
     float *stage = reinterpret_cast<float *>(smem + L::off_stage);
-    float *tail = reinterpret_cast<float *>(smem + L::off_tail);
-    int *flags = reinterpret_cast<int *>(smem + L::off_flags);
+    float2 *tail = reinterpret_cast<float2 *>(smem + L::off_tail);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nthreads = 32 * NW;
+    constexpr int nthreads = 32 * NW;
     float2 *buf = bufs + (size_t)warp * L::BUF;
     const int slot_cap = (a.q.n_slots + 2) & ~1;
     float *slotG = reinterpret_cast<float *>(smem + L::off_slot) + (size_t)warp * slot_cap * 3;
@@ -425,6 +498,10 @@ spec_pass_kernel(const SpecArgs a) {
     const float *x = a.x + (size_t)clip * a.n;
     float *y = a.y + (size_t)clip * a.n;
     float *tap = a.tap ? a.tap + (size_t)clip * a.n : nullptr;
+    // 8-byte vector stores need an even clip length (every row then starts 8-byte aligned)
+    const bool vec2 = ((a.n & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 7) == 0) &&
+                      (!a.tap || (reinterpret_cast<uintptr_t>(a.tap) & 7) == 0);
+    const bool vec4 = ((a.n & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
 
     // output hop-blocks (of the zero-padded timeline) this CTA owns: [j0, j1); block 2 <-> sample 0
     const int j_end = 2 + (a.n + HOP - 1) / HOP;
@@ -433,68 +510,85 @@ spec_pass_kernel(const SpecArgs a) {
     if (j0 >= j1) return;
     const int t_first = j0 - 3;  // first frame that touches block j0 (may be < 0: skipped)
 
-    for (int i = tid; i < L::TAIL; i += nthreads) tail[i] = 0.0f;
+    for (int i = tid; i < 3 * HP; i += nthreads) tail[i] = make_float2(0.0f, 0.0f);
 
     for (int tb = t_first; tb < j1; tb += NW) {
         // ---- stage the samples of frames tb .. tb+NW-1 (zero outside the clip)
         {
             const long long s0 = (long long)tb * HOP - NC;  // clip index of staging[0]
-            for (int i = tid; i < L::STAGE; i += nthreads) {
-                const long long s = s0 + i;
-                stage[i] = (s >= 0 && s < a.n) ? x[s] : 0.0f;
+            if (vec4 && s0 >= 0 && s0 + L::STAGE <= a.n) {
+                const float4 *src = reinterpret_cast<const float4 *>(x + s0);
+                float4 *dst = reinterpret_cast<float4 *>(stage);
+#pragma unroll 4
+                for (int i = tid; i < L::STAGE / 4; i += nthreads) dst[i] = src[i];
+            } else {
+                for (int i = tid; i < L::STAGE; i += nthreads) {
+                    const long long s = s0 + i;
+                    stage[i] = (s >= 0 && s < a.n) ? x[s] : 0.0f;
+                }
             }
         }
         __syncthreads();
-        // ---- one frame per warp
+        // ---- one frame per warp (a frame outside the clip contributes zeros)
         const int t = tb + warp;
-        const bool live = (t >= 0 && t < a.n_frames);
-        if (lane == 0) flags[warp] = live ? 1 : 0;
-        if (live) {
+        if (t >= 0 && t < a.n_frames) {
             const float2 *frame = reinterpret_cast<const float2 *>(stage + warp * HOP);
             fft_forward<NC>(buf, frame, a, a.wtab, a.tw1, a.tw2, lane);
             real_split<NC>(buf, a.wsplit, lane);
             if (a.quant) quantize_frame<NC>(buf, slotG, slotP, a.q, lane);
             real_merge<NC>(buf, a.wsplit, lane);
             fft_inverse<NC>(buf, a.wtab, a.tw1, a.tw2, lane);
+        } else {
+            for (int i = lane; i < L::BUF; i += 32) buf[i] = make_float2(0.0f, 0.0f);
         }
         __syncthreads();
-        // ---- overlap-add in frame order; blocks tb .. tb+NW-1 are now complete
-        for (int c = tid; c < HOP; c += nthreads) {
-            float carry[3];
+        // ---- overlap-add in frame order; blocks tb .. tb+NW-1 are now complete.  A thread owns one
+        //      column of sample pairs: slice sl of warp w's frame sits at bufs[w][sl*HPP + pidx(c)].
+        for (int c = tid; c < HP; c += nthreads) {
+            const int pc = pidx(c);
+            float2 carry[3];
 #pragma unroll
-            for (int g = 0; g < 3; ++g) carry[g] = tail[g * HOP + c];
-            // sample c of hop-slice `sl` of warp w's frame
-            auto fr = [&](int w, int sl) -> float {
-                const int s = sl * HOP + c;
-                return reinterpret_cast<const float *>(bufs + (size_t)w * L::BUF)[2 * pidx(s >> 1) + (s & 1)];
-            };
-#pragma unroll 1
+            for (int g = 0; g < 3; ++g) carry[g] = tail[g * HP + c];
+#pragma unroll
             for (int h = 0; h < NW + 3; ++h) {
-                float v = (h < 3) ? carry[h] : 0.0f;
-                const int w_lo = h - 3 > 0 ? h - 3 : 0;
-                const int w_hi = h < NW - 1 ? h : NW - 1;
-                for (int w = w_lo; w <= w_hi; ++w)
-                    if (flags[w]) v += fr(w, h - w);
+                float2 v = (h < 3) ? carry[h] : make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int w = (h - 3 > 0 ? h - 3 : 0); w <= (h < NW - 1 ? h : NW - 1); ++w) {
+                    const float2 f = bufs[(size_t)w * L::BUF + (h - w) * HPP + pc];
+                    v.x += f.x;
+                    v.y += f.y;
+                }
                 if (h >= NW) {
-                    tail[(h - NW) * HOP + c] = v;  // partial sums of the next three blocks
+                    tail[(h - NW) * HP + c] = v;  // partial sums of the next three blocks
                     continue;
                 }
                 const int j = tb + h;
                 if (j < j0 || j >= j1) continue;
-                const long long nidx = (long long)(j - 2) * HOP + c;
+                const long long nidx = (long long)(j - 2) * HOP + 2 * c;
                 if (nidx >= a.n) continue;
                 // frames covering block j: slices sl = j - t with t in [max(0,j-3), min(j,T-1)]
                 const int sl_a = j - a.n_frames + 1 > 0 ? j - a.n_frames + 1 : 0;
                 const int sl_b = j < 3 ? j : 3;
-                const float inv = sl_a <= sl_b ? a.invw[(sl_a * 4 + sl_b) * HOP + c] : 0.0f;
-                const float o = v * inv;
-                if (tap) tap[nidx] = o;
-                y[nidx] = epilogue_apply(o, a.epilogue, a.fold, a.bias, a.tube_gain, a.tube_norm);
+                float2 inv = make_float2(0.0f, 0.0f);
+                if (sl_a <= sl_b) inv = __ldg(reinterpret_cast<const float2 *>(a.invw + (sl_a * 4 + sl_b) * HOP) + c);
+                const float2 o = make_float2(v.x * inv.x, v.y * inv.y);
+                const float2 r = make_float2(epilogue_apply(o.x, a.epilogue, a.fold, a.bias, a.tube_gain, a.tube_norm),
+                                             epilogue_apply(o.y, a.epilogue, a.fold, a.bias, a.tube_gain, a.tube_norm));
+                if (vec2) {  // nidx is even and n is even, so nidx + 1 < n
+                    if (tap) *reinterpret_cast<float2 *>(tap + nidx) = o;
+                    *reinterpret_cast<float2 *>(y + nidx) = r;
+                } else {
+                    if (tap) tap[nidx] = o.x;
+                    y[nidx] = r.x;
+                    if (nidx + 1 < a.n) {
+                        if (tap) tap[nidx + 1] = o.y;
+                        y[nidx + 1] = r.y;
+                    }
+                }
             }
         }
         __syncthreads();
     }
-    (void)NFFT;
 }
 
 }  // namespace qd

@@ -92,8 +92,9 @@ int main(int argc, char **argv) {
     a.invw = st.invw.data();
     a.q.n_slots = qt.n_slots;
     a.q.n_aff = qt.n_aff;
-    a.q.slot_begin = qt.slot_begin.data();
-    a.q.src_bin = qt.src_bin.data();
+    a.q.n_src = (int)qt.src_tab.size();
+    a.q.row_limit = qt.row_limit;
+    a.q.src_tab = qt.src_tab.data();
     a.q.row_active = qt.row_active.data();
     a.q.row_aff = qt.row_aff.data();
     a.q.row_aff_base = qt.row_aff_base.data();
