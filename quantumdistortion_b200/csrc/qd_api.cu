@@ -12,6 +12,10 @@
 #include "qd_spec.cuh"
 #include "qd_time.cuh"
 
+#ifndef QD_NW_1024
+#define QD_NW_1024 16
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -90,10 +94,10 @@ struct TimeScope {  // brackets the launches of one kernel class with events on 
 
 namespace {
 
-template <int NC, int NW>
+template <int NC, int NW, bool TS = false>
 int launch_spec_t(qd_plan *pl, const qd::SpecArgs &a, int tiles, int64_t batch, cudaStream_t st) {
     static bool attr_set = false;  // per instantiation; plans are single-threaded per the ABI contract
-    auto kern = qd::spec_pass_kernel<NC, NW>;
+    auto kern = qd::spec_pass_kernel<NC, NW, TS>;
     if (!attr_set) {
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
@@ -110,13 +114,20 @@ int launch_spec_t(qd_plan *pl, const qd::SpecArgs &a, int tiles, int64_t batch, 
     return QD_OK;
 }
 
-int spec_nw(int nc) { return nc <= 1024 ? 8 : 4; }
+// n_fft 2048 (the headline size) runs 16 warps per CTA, one CTA per SM, with its tables in shared memory
+int spec_nw(int nc) { return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4; }
 
-size_t spec_smem_bytes(int nc, int nw, int n_slots) {
+size_t spec_smem_bytes(int nc, int nw, int n_slots, int n_src, int n_aff) {
     switch (nc) {
         case 256:  return nw == 8 ? qd::SpecSmem<256, 8>::bytes(n_slots) : 0;
         case 512:  return nw == 8 ? qd::SpecSmem<512, 8>::bytes(n_slots) : 0;
-        case 1024: return nw == 8 ? qd::SpecSmem<1024, 8>::bytes(n_slots) : 0;
+        case 1024: {
+            if (nw == 16) {
+                const size_t b = qd::SpecSmem<1024, 16>::bytes(n_slots, true, n_src, n_aff);
+                if (b <= 227 * 1024) return b;
+            }
+            return qd::SpecSmem<1024, 8>::bytes(n_slots);
+        }
         case 2048: return nw == 4 ? qd::SpecSmem<2048, 4>::bytes(n_slots) : 0;
         case 4096: return nw == 4 ? qd::SpecSmem<4096, 4>::bytes(n_slots) : 0;
     }
@@ -152,7 +163,9 @@ int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant
     switch (pl->nc) {
         case 256:  return launch_spec_t<256, 8>(pl, a, tiles, batch, st);
         case 512:  return launch_spec_t<512, 8>(pl, a, tiles, batch, st);
-        case 1024: return launch_spec_t<1024, 8>(pl, a, tiles, batch, st);
+        case 1024:
+            if (pl->nw == 16) return launch_spec_t<1024, 16, true>(pl, a, tiles, batch, st);
+            return launch_spec_t<1024, 8>(pl, a, tiles, batch, st);
         case 2048: return launch_spec_t<2048, 4>(pl, a, tiles, batch, st);
         case 4096: return launch_spec_t<4096, 4>(pl, a, tiles, batch, st);
     }
@@ -282,7 +295,9 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         n_slots = qt.n_slots;
     }
 #undef QD_UP
-    pl->spec_smem = spec_smem_bytes(pl->nc, pl->nw, n_slots);
+    pl->spec_smem = spec_smem_bytes(pl->nc, pl->nw, n_slots, a.q.n_src, a.q.n_aff);
+    if (pl->nc == 1024 && pl->nw == 16 && pl->spec_smem == qd::SpecSmem<1024, 8>::bytes(n_slots))
+        pl->nw = 8;  // tables too large for the shared-memory variant: fall back to 8 warps, tables through L1
     if (pl->spec_smem == 0 || pl->spec_smem > 227 * 1024)
         return bail(QD_ERR_UNSUPPORTED, "shared memory need of this (n_fft, target table) exceeds 227 KB");
     *out = pl;

@@ -327,15 +327,22 @@ QD_DEV float smooth_row(float m_prev, float m_cur, float m_next, int lane, bool 
 }
 
 // one bin of a row that may give energy away (active) or receive it (affected): new magnitude and phasor
-template <int NC>
+// table read: read-only global path, or a plain load when the table was copied into shared memory
+template <bool TS, class T>
+QD_DEV T tld(const T *p) {
+    if constexpr (TS) return *p;
+    else return __ldg(p);
+}
+
+template <int NC, bool TS>
 QD_DEV void quant_bin(const float2 *buf, const float *slotG, const float2 *slotP, const QuantDev &q, int lane,
                       int row, uint32_t bit, float &nm, float2 &u) {
     float m;
     mag_phasor(buf[rpos<NC>(lane, row)], m, u);
-    nm = (__ldg(q.row_active + row) & bit) ? m * q.keep_active : m;
-    const uint32_t am = __ldg(q.row_aff + row);
+    nm = (tld<TS>(q.row_active + row) & bit) ? m * q.keep_active : m;
+    const uint32_t am = tld<TS>(q.row_aff + row);
     if (am & bit) {
-        const AffEntry &ae = q.aff[__ldg(q.row_aff_base + row) + __popc(am & (bit - 1u))];
+        const AffEntry &ae = q.aff[tld<TS>(q.row_aff_base + row) + __popc(am & (bit - 1u))];
         float te = 0.0f;
         float2 ps = make_float2(0.0f, 0.0f);
 #pragma unroll
@@ -357,7 +364,7 @@ QD_DEV void quant_bin(const float2 *buf, const float *slotG, const float2 *slotP
     }
 }
 
-template <int NC>
+template <int NC, bool TS>
 QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const QuantDev &q, int lane) {
     // Q1: per-target gathers.  Sources are grouped by target slot; 32 of them are loaded per step and
     // summed with a segmented warp scan.  The segment structure is static, so the host stores, per
@@ -375,7 +382,7 @@ QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const Quant
         float g = 0.0f;
         float2 p = make_float2(0.0f, 0.0f);
         if (i < q.n_src) {
-            e = __ldg(q.src_tab + i);
+            e = tld<TS>(q.src_tab + i);
             p = buf[e & 0x1fffu];
             const float m2 = p.x * p.x + p.y * p.y;
             g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
@@ -410,7 +417,7 @@ QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const Quant
     // ---- rows [0, row_limit): full logic
 #pragma unroll 1
     for (int row = 0; row < row_limit; ++row) {
-        quant_bin<NC>(buf, slotG, slotP, q, lane, row, bit, m_next, u_next);
+        quant_bin<NC, TS>(buf, slotG, slotP, q, lane, row, bit, m_next, u_next);
         if (row > 0) {
             const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
             buf[rpos<NC>(lane, row - 1)] = make_float2(out * u_cur.x, out * u_cur.y);
@@ -432,7 +439,7 @@ QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const Quant
         m_next = 0.0f;
         u_next = make_float2(1.0f, 0.0f);
         if (lane == 0) {
-            if (q.row_limit >= ROWS) quant_bin<NC>(buf, slotG, slotP, q, 0, ROWS - 1, 1u, m_next, u_next);
+            if (q.row_limit >= ROWS) quant_bin<NC, TS>(buf, slotG, slotP, q, 0, ROWS - 1, 1u, m_next, u_next);
             else mag_phasor(buf[rpos<NC>(0, ROWS - 1)], m_next, u_next);
         }
         const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, ROWS == 2 && lane == 0, false) : m_cur;
@@ -457,9 +464,22 @@ struct SpecSmem {
     static constexpr size_t off_flags = off_tail + (size_t)TAIL * sizeof(float);
     static constexpr size_t off_slot = off_flags + 64 * sizeof(int);
     // per-warp gather scratch: G[cap] floats then P[cap] float2, cap even so P stays 8-byte aligned
-    static int slot_cap(int n_slots) { return (n_slots + 2) & ~1; }
-    static size_t bytes(int n_slots) {
-        return off_slot + (size_t)NW * (size_t)slot_cap(n_slots) * 3 * sizeof(float) + 16;
+    __host__ __device__ static int slot_cap(int n_slots) { return (n_slots + 2) & ~1; }
+    __host__ __device__ static size_t off_tables(int n_slots) {
+        return (off_slot + (size_t)NW * (size_t)slot_cap(n_slots) * 3 * sizeof(float) + 15) & ~(size_t)15;
+    }
+    // shared-memory copies of the hot tables (TS kernels): window, pass-1 twiddles, split twiddles,
+    // then the quantizer tables (gather list, row masks, affected-bin entries)
+    static size_t table_bytes(int n_src, int n_aff) {
+        const int rows = (NC + 1 + 31) / 32;
+        size_t b = (size_t)(NC + NC + NC / 2 + 2) * sizeof(float2);
+        b += ((size_t)n_src * 4 + 15) & ~(size_t)15;
+        b += ((size_t)rows * (4 + 4 + 2) + 15 + 16) & ~(size_t)15;
+        b += (size_t)(n_aff > 0 ? n_aff : 1) * 32;
+        return b + 64;
+    }
+    static size_t bytes(int n_slots, bool tables_in_smem = false, int n_src = 0, int n_aff = 0) {
+        return off_tables(n_slots) + (tables_in_smem ? table_bytes(n_src, n_aff) : 16);
     }
 };
 
@@ -476,7 +496,7 @@ QD_DEV float epilogue_apply(float v, int mode, float fold, float bias, float tg,
     return v;
 }
 
-template <int NC, int NW>
+template <int NC, int NW, bool TS = false>
 __global__ void __launch_bounds__(32 * NW)
 spec_pass_kernel(const SpecArgs a) {
     using L = SpecSmem<NC, NW>;
@@ -512,6 +532,38 @@ spec_pass_kernel(const SpecArgs a) {
 
     for (int i = tid; i < 3 * HP; i += nthreads) tail[i] = make_float2(0.0f, 0.0f);
 
+    // hot tables: read through L1/L2, or (TS) copied once per CTA into shared memory
+    const float2 *wtab = a.wtab, *tw1 = a.tw1, *wsplit = a.wsplit;
+    QuantDev qq = a.q;
+    if constexpr (TS) {
+        float2 *t_w = reinterpret_cast<float2 *>(smem + L::off_tables(a.q.n_slots));
+        float2 *t_tw = t_w + NC;
+        float2 *t_ws = t_tw + NC;
+        for (int i = tid; i < NC; i += nthreads) { t_w[i] = a.wtab[i]; t_tw[i] = a.tw1[i]; }
+        for (int i = tid; i <= NC / 2; i += nthreads) t_ws[i] = a.wsplit[i];
+        wtab = t_w; tw1 = t_tw; wsplit = t_ws;
+        if (a.quant) {
+            constexpr int ROWS = (NC + 1 + 31) / 32;
+            unsigned char *qb = reinterpret_cast<unsigned char *>(t_ws + NC / 2 + 2);
+            uint32_t *s_src = reinterpret_cast<uint32_t *>(qb);
+            qb += ((size_t)a.q.n_src * 4 + 15) & ~(size_t)15;
+            uint32_t *s_ra = reinterpret_cast<uint32_t *>(qb);
+            uint32_t *s_rf = s_ra + ROWS;
+            uint16_t *s_rb = reinterpret_cast<uint16_t *>(s_rf + ROWS);
+            qb += ((size_t)ROWS * 10 + 15 + 16) & ~(size_t)15;
+            uint4 *s_aff = reinterpret_cast<uint4 *>(qb);
+            for (int i = tid; i < a.q.n_src; i += nthreads) s_src[i] = a.q.src_tab[i];
+            for (int i = tid; i < ROWS; i += nthreads) {
+                s_ra[i] = a.q.row_active[i]; s_rf[i] = a.q.row_aff[i]; s_rb[i] = a.q.row_aff_base[i];
+            }
+            const uint4 *g_aff = reinterpret_cast<const uint4 *>(a.q.aff);
+            for (int i = tid; i < 2 * a.q.n_aff; i += nthreads) s_aff[i] = g_aff[i];
+            qq.src_tab = s_src; qq.row_active = s_ra; qq.row_aff = s_rf; qq.row_aff_base = s_rb;
+            qq.aff = reinterpret_cast<const AffEntry *>(s_aff);
+        }
+        __syncthreads();
+    }
+
     for (int tb = t_first; tb < j1; tb += NW) {
         // ---- stage the samples of frames tb .. tb+NW-1 (zero outside the clip)
         {
@@ -533,11 +585,11 @@ spec_pass_kernel(const SpecArgs a) {
         const int t = tb + warp;
         if (t >= 0 && t < a.n_frames) {
             const float2 *frame = reinterpret_cast<const float2 *>(stage + warp * HOP);
-            fft_forward<NC>(buf, frame, a, a.wtab, a.tw1, a.tw2, lane);
-            real_split<NC>(buf, a.wsplit, lane);
-            if (a.quant) quantize_frame<NC>(buf, slotG, slotP, a.q, lane);
-            real_merge<NC>(buf, a.wsplit, lane);
-            fft_inverse<NC>(buf, a.wtab, a.tw1, a.tw2, lane);
+            fft_forward<NC>(buf, frame, a, wtab, tw1, a.tw2, lane);
+            real_split<NC>(buf, wsplit, lane);
+            if (a.quant) quantize_frame<NC, TS>(buf, slotG, slotP, qq, lane);
+            real_merge<NC>(buf, wsplit, lane);
+            fft_inverse<NC>(buf, wtab, tw1, a.tw2, lane);
         } else {
             for (int i = lane; i < L::BUF; i += 32) buf[i] = make_float2(0.0f, 0.0f);
         }

@@ -28,9 +28,9 @@ static std::vector<T> read_all(const char *path) {
     return v;
 }
 
-template <int NC, int NW>
+template <int NC, int NW, bool TS = false>
 static void run(qd::SpecArgs a, int n_tiles, size_t smem) {
-    qd_emu::launch(dim3(n_tiles, 1, 1), dim3(32 * NW, 1, 1), smem, [&] { qd::spec_pass_kernel<NC, NW>(a); });
+    qd_emu::launch(dim3(n_tiles, 1, 1), dim3(32 * NW, 1, 1), smem, [&] { qd::spec_pass_kernel<NC, NW, TS>(a); });
 }
 
 int main(int argc, char **argv) {
@@ -111,6 +111,10 @@ int main(int argc, char **argv) {
         goto done;                                                               \
     }
     QD_CASE(256, 4) QD_CASE(512, 4) QD_CASE(1024, 4) QD_CASE(1024, 8) QD_CASE(2048, 4) QD_CASE(4096, 4)
+    if (nc == 1024 && nw == 16) {  // the shared-memory-table variant used for n_fft 2048 on the GPU
+        run<1024, 16, true>(a, n_tiles, qd::SpecSmem<1024, 16>::bytes(qt.n_slots, true, a.q.n_src, a.q.n_aff));
+        goto done;
+    }
     std::cerr << "no instantiation for nc=" << nc << " nw=" << nw << "\n";
     return 2;
 done:
