@@ -60,11 +60,12 @@ struct qd_plan {
     bool has_quant = false;
     std::vector<void *> owned;  // device allocations
     qd::SpecArgs spec{};        // table pointers filled once
-    size_t spec_smem = 0;
+    size_t spec_smem = 0;      // dynamic shared memory of the pass kernel in use
     const void *fx_table = nullptr;
     int64_t fx_tables = 0;
     HostPipe pipe;
     int sm_count = 148;
+    int clip_offset = 0;       // first clip of the current render inside a per-clip FX table
     // optional per-kernel device timing (qd_plan_enable_timing)
     bool timing = false;
     struct Stamp { cudaEvent_t a, b; int cls; };
@@ -94,10 +95,10 @@ struct TimeScope {  // brackets the launches of one kernel class with events on 
 
 namespace {
 
-template <int NC, int NW, bool TS = false>
+template <int NC, int NW, bool TS = false, bool FX = false>
 int launch_spec_t(qd_plan *pl, const qd::SpecArgs &a, int tiles, int64_t batch, cudaStream_t st) {
     static bool attr_set = false;  // per instantiation; plans are single-threaded per the ABI contract
-    auto kern = qd::spec_pass_kernel<NC, NW, TS>;
+    auto kern = qd::spec_pass_kernel<NC, NW, TS, FX>;
     if (!attr_set) {
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
@@ -108,7 +109,10 @@ int launch_spec_t(qd_plan *pl, const qd::SpecArgs &a, int tiles, int64_t batch, 
         c.x = a.x + (size_t)b0 * a.n;
         c.y = a.y + (size_t)b0 * a.n;
         if (a.tap) c.tap = a.tap + (size_t)b0 * a.n;
-        kern<<<dim3((unsigned)tiles, (unsigned)nb, 1), 32 * NW, pl->spec_smem, st>>>(c);
+        c.fx.clip_offset = a.fx.clip_offset + (int)b0;
+        const size_t smem = FX ? pl->spec_smem
+                               : qd::SpecSmem<NC, NW>::bytes(a.q.n_slots, TS, a.q.n_src, a.q.n_aff, false);
+        kern<<<dim3((unsigned)tiles, (unsigned)nb, 1), 32 * NW, smem, st>>>(c);
     }
     QD_CUDA(cudaGetLastError());
     return QD_OK;
@@ -117,7 +121,17 @@ int launch_spec_t(qd_plan *pl, const qd::SpecArgs &a, int tiles, int64_t batch, 
 // n_fft 2048 (the headline size) runs 16 warps per CTA, one CTA per SM, with its tables in shared memory
 int spec_nw(int nc) { return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4; }
 
-size_t spec_smem_bytes(int nc, int nw, int n_slots, int n_src, int n_aff) {
+size_t spec_smem_bytes(int nc, int nw, int n_slots, int n_src, int n_aff, bool fx) {
+    if (fx) {  // FX kernels: tables through L1, one extra magnitude plane per warp
+        switch (nc) {
+            case 256:  return qd::SpecSmem<256, 8>::bytes(n_slots, false, 0, 0, true);
+            case 512:  return qd::SpecSmem<512, 8>::bytes(n_slots, false, 0, 0, true);
+            case 1024: return qd::SpecSmem<1024, 8>::bytes(n_slots, false, 0, 0, true);
+            case 2048: return qd::SpecSmem<2048, 4>::bytes(n_slots, false, 0, 0, true);
+            case 4096: return qd::SpecSmem<4096, 4>::bytes(n_slots, false, 0, 0, true);
+        }
+        return 0;
+    }
     switch (nc) {
         case 256:  return nw == 8 ? qd::SpecSmem<256, 8>::bytes(n_slots) : 0;
         case 512:  return nw == 8 ? qd::SpecSmem<512, 8>::bytes(n_slots) : 0;
@@ -136,7 +150,7 @@ size_t spec_smem_bytes(int nc, int nw, int n_slots, int n_src, int n_aff) {
 
 // One spectral pass over [batch, n]: src -> dst (+ optional tap of the pre-epilogue signal).
 int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant, int epilogue,
-                int64_t batch, cudaStream_t st) {
+                int64_t batch, cudaStream_t st, int fx_pass = 0, int clip_offset = 0) {
     TimeScope ts(pl, st, QD_KERNEL_SPECTRAL);
     qd::SpecArgs a = pl->spec;
     a.x = src;
@@ -144,6 +158,10 @@ int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant
     a.tap = tap;
     a.quant = quant;
     a.epilogue = epilogue;
+    const bool fx = quant && pl->p.fx_mode != QD_FX_NONE;
+    a.fx.pass = fx_pass;
+    a.fx.clip_offset = clip_offset;
+    a.fx.table = pl->fx_table;
     // tiling: whole clips when the batch alone fills the GPU, else cut clips along time
     const int total_blocks = (a.n + pl->hop - 1) / pl->hop;
     const int ctas_per_sm = std::max<int>(1, (int)((227 * 1024) / (pl->spec_smem + 1024)));
@@ -160,6 +178,16 @@ int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant
     if (tile < 1) tile = 1;
     a.tile_blocks = tile;
     const int tiles = (total_blocks + tile - 1) / tile;
+    if (fx) {
+        switch (pl->nc) {
+            case 256:  return launch_spec_t<256, 8, false, true>(pl, a, tiles, batch, st);
+            case 512:  return launch_spec_t<512, 8, false, true>(pl, a, tiles, batch, st);
+            case 1024: return launch_spec_t<1024, 8, false, true>(pl, a, tiles, batch, st);
+            case 2048: return launch_spec_t<2048, 4, false, true>(pl, a, tiles, batch, st);
+            case 4096: return launch_spec_t<4096, 4, false, true>(pl, a, tiles, batch, st);
+        }
+        return fail(QD_ERR_UNSUPPORTED, "n_fft not supported");
+    }
     switch (pl->nc) {
         case 256:  return launch_spec_t<256, 8>(pl, a, tiles, batch, st);
         case 512:  return launch_spec_t<512, 8>(pl, a, tiles, batch, st);
@@ -233,7 +261,10 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
     if (!qd_host::build_spec_tables(p.n_fft, &st)) return fail(QD_ERR_UNSUPPORTED, "n_fft must be one of 512, 1024, 2048, 4096, 8192");
     const bool need_quant = !p.passthrough && (p.pre_quant || p.post_quant);
     if (need_quant && !tables) return fail(QD_ERR_INVALID_ARG, "quantizer tables required");
-    if (p.fx_mode != QD_FX_NONE) return fail(QD_ERR_UNSUPPORTED, "spectral FX are not built into this round's kernels yet");
+    if (p.fx_mode < QD_FX_NONE || p.fx_mode > QD_FX_SCRAMBLE_SWAP) return fail(QD_ERR_INVALID_ARG, "bad fx_mode");
+    if (p.fx_mode != QD_FX_NONE && !p.multiband) return fail(QD_ERR_INVALID_ARG, "spectral FX act on the high band of a multiband render only");
+    if ((p.fx_mode == QD_FX_SCRAMBLE_PICK || p.fx_mode == QD_FX_SCRAMBLE_SWAP) && p.n_fft > 4096)
+        return fail(QD_ERR_UNSUPPORTED, "bin scramble is built for n_fft <= 4096");
 
     qd_plan *pl = new qd_plan();
     pl->p = p;
@@ -295,9 +326,16 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         n_slots = qt.n_slots;
     }
 #undef QD_UP
-    pl->spec_smem = spec_smem_bytes(pl->nc, pl->nw, n_slots, a.q.n_src, a.q.n_aff);
-    if (pl->nc == 1024 && pl->nw == 16 && pl->spec_smem == qd::SpecSmem<1024, 8>::bytes(n_slots))
+    const bool fx = need_quant && p.fx_mode != QD_FX_NONE;
+    if (fx) pl->nw = pl->nc <= 1024 ? 8 : 4;
+    pl->spec_smem = spec_smem_bytes(pl->nc, pl->nw, n_slots, a.q.n_src, a.q.n_aff, fx);
+    if (!fx && pl->nc == 1024 && pl->nw == 16 && pl->spec_smem == qd::SpecSmem<1024, 8>::bytes(n_slots))
         pl->nw = 8;  // tables too large for the shared-memory variant: fall back to 8 warps, tables through L1
+    a.fx.mode = fx ? p.fx_mode : 0;
+    a.fx.a = (float)p.fx_a; a.fx.b = (float)p.fx_b; a.fx.c = (float)p.fx_c;
+    a.fx.step = p.fx_a;
+    a.fx.table_frames = p.fx_table_frames > 0 ? p.fx_table_frames : 1;
+    a.fx.table_per_clip = p.fx_table_per_clip;
     if (pl->spec_smem == 0 || pl->spec_smem > 227 * 1024)
         return bail(QD_ERR_UNSUPPORTED, "shared memory need of this (n_fft, target table) exceeds 227 KB");
     *out = pl;
@@ -384,6 +422,13 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
     if (workspace_bytes < qd_plan_workspace_bytes(pl, batch) || !workspace)
         return fail(QD_ERR_WORKSPACE, "workspace too small (see qd_plan_workspace_bytes)");
     const qd_params &p = pl->p;
+    if (p.fx_mode != QD_FX_NONE && (p.pre_quant || p.post_quant) && !p.passthrough) {
+        const bool needs_table = p.fx_mode == QD_FX_SCRAMBLE_PICK || p.fx_mode == QD_FX_SCRAMBLE_SWAP ||
+                                 (p.fx_mode == QD_FX_PHASE_DISPERSAL && p.fx_b != 0.0);
+        if (needs_table && !pl->fx_table) return fail(QD_ERR_INVALID_ARG, "FX table missing (qd_plan_set_fx_table)");
+        if (needs_table && p.fx_table_per_clip && pl->clip_offset + batch > pl->fx_tables)
+            return fail(QD_ERR_INVALID_ARG, "per-clip FX table shorter than the batch");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)p.n_samples;
     const size_t count = n * (size_t)batch;
@@ -439,9 +484,9 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
     const float *x_pq = nullptr;  // limiter input
     if (p.pre_quant) {
         // pass A: STFT -> quantize -> iSTFT (= pre_quant tap) -> distortion        (:635-721)
-        if ((rc = launch_spec(pl, src, w_a, tap_pre, 1, epi, batch, st)) != QD_OK) return rc;
+        if ((rc = launch_spec(pl, src, w_a, tap_pre, 1, epi, batch, st, 0, pl->clip_offset)) != QD_OK) return rc;
         if (p.post_quant) {  // pass B on the distorted signal                         (:729-801)
-            if ((rc = launch_spec(pl, w_a, y, nullptr, 1, 0, batch, st)) != QD_OK) return rc;
+            if ((rc = launch_spec(pl, w_a, y, nullptr, 1, 0, batch, st, 1, pl->clip_offset)) != QD_OK) return rc;
             x_pq = y;
         } else {
             x_pq = w_a;       // :851-853
@@ -454,7 +499,7 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
                 src, w_a, (long long)count, p.distortion_mode, p.fold_amount, p.bias, p.tube_gain, p.tube_norm);
             QD_CUDA(cudaGetLastError());
         }
-        if ((rc = launch_spec(pl, src, y, nullptr, p.post_quant ? 1 : 0, 0, batch, st)) != QD_OK) return rc;
+        if ((rc = launch_spec(pl, src, y, nullptr, p.post_quant ? 1 : 0, 0, batch, st, 0, pl->clip_offset)) != QD_OK) return rc;
         x_pq = y;
     }
     if (tap_dist) {  // dsp/pipeline.py:916 / :1107 (low band added in multiband mode)
@@ -516,7 +561,9 @@ int qd_render_host(qd_plan *pl, const float *x_host, float *y_host, int64_t batc
         QD_CUDA(cudaEventRecord(hp.ev_in[buf], hp.s_in));
         QD_CUDA(cudaStreamWaitEvent(hp.s_run, hp.ev_in[buf], 0));
         if (idx >= 2) QD_CUDA(cudaStreamWaitEvent(hp.s_run, hp.ev_out[buf], 0));  // dy[buf] drained
+        pl->clip_offset = (int)b0;
         int rc = qd_render_device(pl, hp.dx[buf], hp.dy[buf], nb, nullptr, hp.ws, hp.ws_bytes, hp.s_run);
+        pl->clip_offset = 0;
         if (rc != QD_OK) return rc;
         QD_CUDA(cudaEventRecord(hp.ev_run[buf], hp.s_run));
         QD_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_run[buf], 0));

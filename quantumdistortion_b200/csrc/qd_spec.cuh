@@ -84,6 +84,18 @@ struct QuantDev {
     int smoothing;                  // dsp/quantizer.py:523
 };
 
+// spectral FX of the high band (dsp/pipeline.py:64-141, dsp/spectral_fx.py:198-390); host-resolved numbers
+struct FxDev {
+    int mode;               // qd_fx_mode (0 = none)
+    float a, b, c;          // see qd_params.fx_a / fx_b / fx_c
+    double step;            // bitcrush step (dB or linear) in double for the rounding decision
+    const void *table;      // int16 source bins (scramble) or float32 jitter in [-1,1) (dispersal), or null
+    int table_frames;       // frames per pass in the table
+    int table_per_clip;     // 0: shared by all clips
+    int pass;               // 0 / 1: which quantised pass of the render this launch is
+    int clip_offset;        // index of the launch's first clip inside the per-clip table
+};
+
 struct SpecArgs {
     const float *x;        // [batch, n] input clips
     float *y;              // [batch, n] output (after the epilogue)
@@ -100,6 +112,7 @@ struct SpecArgs {
     const float2 *wsplit;  // [NC/2+1] exp(-2 pi i k / n_fft)
     const float *invw;     // [16][hop]: 1/max(sum_{sl=a..b} w^2[sl*hop+c], 1e-10) at [(a*4+b)*hop + c]
     QuantDev q;
+    FxDev fx;
 };
 
 // ---------------------------------------------------------------- FFT passes (warp level)
@@ -327,6 +340,110 @@ QD_DEV float smooth_row(float m_prev, float m_cur, float m_next, int lane, bool 
 }
 
 // one bin of a row that may give energy away (active) or receive it (affected): new magnitude and phasor
+QD_DEV float warp_max(float v) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v = fmaxf(v, __shfl_xor_sync(QD_FULL, v, d));
+    return v;
+}
+QD_DEV float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(QD_FULL, v, d);
+    return v;
+}
+
+// Spectral FX on one frame (high band only).  On entry buf holds X; on exit buf holds the unit phasors and
+// mags[pos] the (processed) magnitudes, both indexed by buffer position, so that a bin whose magnitude
+// becomes 0 keeps its phase for the smoothing that follows.
+template <int NC>
+QD_DEV void fx_frame(float2 *buf, float *mags, const FxDev &fx, int lane, long long tab_base) {
+    constexpr int NBINS = NC + 1;
+    constexpr int ROWS = (NBINS + 31) / 32;
+    float mx = 0.0f, sm = 0.0f;
+#pragma unroll 4
+    for (int row = 0; row < ROWS; ++row) {
+        if (row < ROWS - 1 || lane == 0) {
+            const int p = rpos<NC>(lane, row);
+            float m;
+            float2 u;
+            mag_phasor(buf[p], m, u);
+            buf[p] = u;
+            mags[p] = m;
+            mx = fmaxf(mx, m);
+            sm += m;
+        }
+    }
+    mx = warp_max(mx);  // max / sum of the magnitudes BEFORE the effect (dsp/pipeline.py:90,105; spectral_fx.py:387)
+    __syncwarp();
+    if (fx.mode == 1 || fx.mode == 2) {
+        // bitcrush (dsp/spectral_fx.py:198-260); np.round is half-to-even = rint
+        const float thr = fx.c > 0.0f ? fx.c : fx.b * mx;
+        for (int row = 0; row < ROWS; ++row) {
+            if (row < ROWS - 1 || lane == 0) {
+                const int p = rpos<NC>(lane, row);
+                float m = mags[p];
+                if (fx.step > 0.0) {
+                    if (fx.mode == 1) {
+                        const float mm = fmaxf(m, 1e-12f);
+                        const float q = 20.0f * log10f(mm) / (float)fx.step;
+                        float rq = rintf(q);
+                        if (fabsf(fabsf(q - rq) - 0.5f) < 0.02f)  // close to a rounding boundary: decide in double
+                            rq = (float)rint(20.0 * log10((double)mm) / fx.step);
+                        m = QD_EXP10F((float)((double)rq * fx.step / 20.0));
+                    } else {
+                        m = fmaxf((float)(rint((double)m / fx.step) * fx.step), 0.0f);
+                    }
+                }
+                if (thr > 0.0f && m < thr) m = 0.0f;
+                mags[p] = m;
+            }
+        }
+    } else if (fx.mode == 3) {
+        // phase dispersal (dsp/spectral_fx.py:263-323)
+        const float thresh = fx.c >= 0.0f ? fx.c : 0.01f * mx;
+        const float inv_mx = 1.0f / (mx + 1e-12f);
+        const float *jit = reinterpret_cast<const float *>(fx.table);
+        for (int row = 0; row < ROWS; ++row) {
+            if (row < ROWS - 1 || lane == 0) {
+                const int p = rpos<NC>(lane, row);
+                const float m = mags[p];
+                if (!(thresh > 0.0f) || m > thresh) {
+                    float rot = fx.a * (m * inv_mx);
+                    if (jit) rot += __ldg(jit + tab_base + 32 * row + lane) * fx.b;
+                    float sn, cs;
+                    QD_SINCOSF(rot, &sn, &cs);
+                    const float2 u = buf[p];
+                    buf[p] = make_float2(u.x * cs - u.y * sn, u.x * sn + u.y * cs);
+                }
+            }
+        }
+    } else if (fx.mode == 4 || fx.mode == 5) {
+        // bin scramble (dsp/spectral_fx.py:326-390): gather through the host-replayed index table
+        static_assert(ROWS <= 72 || NC > 2048, "row registers");
+        if constexpr (NC <= 2048) {
+            sm = warp_sum(sm);
+            const int16_t *idx = reinterpret_cast<const int16_t *>(fx.table);
+            float val[ROWS];
+            float s2 = 0.0f;
+#pragma unroll
+            for (int row = 0; row < ROWS; ++row) {
+                val[row] = 0.0f;
+                if (row < ROWS - 1 || lane == 0) {
+                    const int src = idx ? (int)__ldg(idx + tab_base + 32 * row + lane) : 32 * row + lane;
+                    val[row] = mags[spos<NC>(src)];
+                    s2 += val[row];
+                }
+            }
+            s2 = warp_sum(s2);
+            const float scale = sm / (s2 + 1e-12f);
+            __syncwarp();
+#pragma unroll
+            for (int row = 0; row < ROWS; ++row)
+                if (row < ROWS - 1 || lane == 0) mags[rpos<NC>(lane, row)] = val[row] * scale;
+        }
+    }
+    __syncwarp();
+}
+
 // table read: read-only global path, or a plain load when the table was copied into shared memory
 template <bool TS, class T>
 QD_DEV T tld(const T *p) {
@@ -334,11 +451,18 @@ QD_DEV T tld(const T *p) {
     else return __ldg(p);
 }
 
-template <int NC, bool TS>
-QD_DEV void quant_bin(const float2 *buf, const float *slotG, const float2 *slotP, const QuantDev &q, int lane,
-                      int row, uint32_t bit, float &nm, float2 &u) {
+// magnitude / phasor of a bin: from X, or (FX) from the separate magnitude plane
+template <bool FX>
+QD_DEV void load_bin(const float2 *buf, const float *mags, int p, float &m, float2 &u) {
+    if constexpr (FX) { m = mags[p]; u = buf[p]; }
+    else mag_phasor(buf[p], m, u);
+}
+
+template <int NC, bool TS, bool FX>
+QD_DEV void quant_bin(const float2 *buf, const float *mags, const float *slotG, const float2 *slotP,
+                      const QuantDev &q, int lane, int row, uint32_t bit, float &nm, float2 &u) {
     float m;
-    mag_phasor(buf[rpos<NC>(lane, row)], m, u);
+    load_bin<FX>(buf, mags, rpos<NC>(lane, row), m, u);
     nm = (tld<TS>(q.row_active + row) & bit) ? m * q.keep_active : m;
     const uint32_t am = tld<TS>(q.row_aff + row);
     if (am & bit) {
@@ -364,8 +488,8 @@ QD_DEV void quant_bin(const float2 *buf, const float *slotG, const float2 *slotP
     }
 }
 
-template <int NC, bool TS>
-QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const QuantDev &q, int lane) {
+template <int NC, bool TS, bool FX>
+QD_DEV void quantize_frame(float2 *buf, const float *mags, float *slotG, float2 *slotP, const QuantDev &q, int lane) {
     // Q1: per-target gathers.  Sources are grouped by target slot; 32 of them are loaded per step and
     // summed with a segmented warp scan.  The segment structure is static, so the host stores, per
     // source, how many sources of the same slot precede it inside its step (`off`) and whether it is the
@@ -384,8 +508,13 @@ QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const Quant
         if (i < q.n_src) {
             e = tld<TS>(q.src_tab + i);
             p = buf[e & 0x1fffu];
-            const float m2 = p.x * p.x + p.y * p.y;
-            g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
+            if constexpr (FX) {
+                g = mags[e & 0x1fffu];
+                p = make_float2(g * p.x, g * p.y);
+            } else {
+                const float m2 = p.x * p.x + p.y * p.y;
+                g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
+            }
         }
         const int off = (int)((e >> 26) & 31u);
 #pragma unroll
@@ -417,7 +546,7 @@ QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const Quant
     // ---- rows [0, row_limit): full logic
 #pragma unroll 1
     for (int row = 0; row < row_limit; ++row) {
-        quant_bin<NC, TS>(buf, slotG, slotP, q, lane, row, bit, m_next, u_next);
+        quant_bin<NC, TS, FX>(buf, mags, slotG, slotP, q, lane, row, bit, m_next, u_next);
         if (row > 0) {
             const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
             buf[rpos<NC>(lane, row - 1)] = make_float2(out * u_cur.x, out * u_cur.y);
@@ -427,7 +556,7 @@ QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const Quant
     // ---- rows [row_limit, ROWS-1): nothing moves, only the smoothing couples neighbours
 #pragma unroll 4
     for (int row = row_limit; row < ROWS - 1; ++row) {
-        mag_phasor(buf[rpos<NC>(lane, row)], m_next, u_next);
+        load_bin<FX>(buf, mags, rpos<NC>(lane, row), m_next, u_next);
         if (row > 0) {
             const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
             buf[rpos<NC>(lane, row - 1)] = make_float2(out * u_cur.x, out * u_cur.y);
@@ -439,8 +568,8 @@ QD_DEV void quantize_frame(float2 *buf, float *slotG, float2 *slotP, const Quant
         m_next = 0.0f;
         u_next = make_float2(1.0f, 0.0f);
         if (lane == 0) {
-            if (q.row_limit >= ROWS) quant_bin<NC, TS>(buf, slotG, slotP, q, 0, ROWS - 1, 1u, m_next, u_next);
-            else mag_phasor(buf[rpos<NC>(0, ROWS - 1)], m_next, u_next);
+            if (q.row_limit >= ROWS) quant_bin<NC, TS, FX>(buf, mags, slotG, slotP, q, 0, ROWS - 1, 1u, m_next, u_next);
+            else load_bin<FX>(buf, mags, rpos<NC>(0, ROWS - 1), m_next, u_next);
         }
         const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, ROWS == 2 && lane == 0, false) : m_cur;
         buf[rpos<NC>(lane, ROWS - 2)] = make_float2(out * u_cur.x, out * u_cur.y);
@@ -478,8 +607,10 @@ struct SpecSmem {
         b += (size_t)(n_aff > 0 ? n_aff : 1) * 32;
         return b + 64;
     }
-    static size_t bytes(int n_slots, bool tables_in_smem = false, int n_src = 0, int n_aff = 0) {
-        return off_tables(n_slots) + (tables_in_smem ? table_bytes(n_src, n_aff) : 16);
+    static size_t bytes(int n_slots, bool tables_in_smem = false, int n_src = 0, int n_aff = 0, bool fx = false) {
+        // FX kernels append one magnitude plane (BUF floats) per warp
+        return off_tables(n_slots) + (tables_in_smem ? table_bytes(n_src, n_aff) : 16) +
+               (fx ? (size_t)NW * BUF * sizeof(float) : 0);
     }
 };
 
@@ -496,7 +627,7 @@ QD_DEV float epilogue_apply(float v, int mode, float fold, float bias, float tg,
     return v;
 }
 
-template <int NC, int NW, bool TS = false>
+template <int NC, int NW, bool TS = false, bool FX = false>
 __global__ void __launch_bounds__(32 * NW)
 spec_pass_kernel(const SpecArgs a) {
     using L = SpecSmem<NC, NW>;
@@ -587,7 +718,19 @@ spec_pass_kernel(const SpecArgs a) {
             const float2 *frame = reinterpret_cast<const float2 *>(stage + warp * HOP);
             fft_forward<NC>(buf, frame, a, wtab, tw1, a.tw2, lane);
             real_split<NC>(buf, wsplit, lane);
-            if (a.quant) quantize_frame<NC, TS>(buf, slotG, slotP, qq, lane);
+            if (a.quant) {
+                if constexpr (FX) {
+                    static_assert(!TS, "FX kernels read their tables through L1");
+                    float *mags = reinterpret_cast<float *>(smem + L::off_tables(a.q.n_slots) + 16) + (size_t)warp * L::BUF;
+                    const int tf = t < a.fx.table_frames ? t : a.fx.table_frames - 1;
+                    const long long tab_base =
+                        (((long long)(a.fx.table_per_clip ? a.fx.clip_offset + clip : 0) * 2 + a.fx.pass) * a.fx.table_frames + tf) * (NC + 1);
+                    fx_frame<NC>(buf, mags, a.fx, lane, tab_base);
+                    quantize_frame<NC, TS, true>(buf, mags, slotG, slotP, qq, lane);
+                } else {
+                    quantize_frame<NC, TS, false>(buf, nullptr, slotG, slotP, qq, lane);
+                }
+            }
             real_merge<NC>(buf, wsplit, lane);
             fft_inverse<NC>(buf, wtab, tw1, a.tw2, lane);
         } else {

@@ -90,6 +90,36 @@ class Renderer:
             self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
         return self._ws, need
 
+    def set_fx_seeds(self, batch: int, seeds=None) -> None:
+        """Replay the reference's np.random draws for the spectral FX (tables.replay_fx_table) and upload them.
+
+        seeds=None : draw from the current global np.random state, clip after clip -- what a loop of reference
+                     ``process_audio`` calls would consume;
+        seeds=int  : ``np.random.seed(s)`` before EVERY clip -> one table shared by the whole batch;
+        seeds=[..] : one seed per clip."""
+        r = self.resolved
+        if not r.fx_rng:
+            return
+        torch = _torch()
+        if seeds is None:
+            tabs = [tables.replay_fx_table(r.fx_rng, r.fx_passes, r.n_frames, r.n_bins) for _ in range(batch)]
+        elif isinstance(seeds, (int, np.integer)):
+            np.random.seed(int(seeds))
+            tabs = [tables.replay_fx_table(r.fx_rng, r.fx_passes, r.n_frames, r.n_bins)]
+        else:
+            if len(seeds) != batch:
+                raise ValueError("need one seed per clip")
+            tabs = []
+            for sd in seeds:
+                np.random.seed(int(sd))
+                tabs.append(tables.replay_fx_table(r.fx_rng, r.fx_passes, r.n_frames, r.n_bins))
+        shared = isinstance(seeds, (int, np.integer))
+        if bool(r.params.fx_table_per_clip) == shared:
+            raise ValueError("renderer built for %s FX tables; use make_renderer(..., seeds=...) with the same kind of seeds"
+                             % ("per-clip" if r.params.fx_table_per_clip else "shared"))
+        self._fx_table = torch.from_numpy(np.ascontiguousarray(np.stack(tabs))).cuda()
+        _lib.check(self._lib.qd_plan_set_fx_table(self._plan, self._fx_table.data_ptr(), len(tabs)))
+
     def render_device(self, x, want_taps: bool = False):
         """x: CUDA float32 tensor [B, n] -> (y [B, n], taps or None).  Asynchronous on the current stream."""
         torch = _torch()
@@ -174,10 +204,6 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
                                   "autotune_v1 is a different algorithm (SURVEY.md 8(f) rank 3)")
     if freeze or formant != 0.0:
         raise NotImplementedError("spectral_freeze / formant_shift are not built yet (SURVEY.md 8(f) rank 1)")
-    fx_active = bool(use_multiband and fx_mode and float(fx_strength) > 0.0 and not passthrough
-                     and fx_mode in ("bitcrush", "phase_dispersal", "bin_scramble"))
-    if fx_active:
-        raise NotImplementedError("spectral FX kernels are not built yet (SURVEY.md 8(a) a8-a11)")
     res = tables.resolve(sr=sr, n_samples=n_samples, n_fft=n_fft, key=key, scale=scale, snap_strength=snap,
                          smear=smear, bin_smoothing=bin_smoothing, pre_quant=pre_quant, post_quant=post_quant,
                          distortion_mode=distortion_mode, distortion_params=distortion_params,
@@ -185,20 +211,27 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
                          use_multiband=use_multiband, crossover_hz=crossover_hz, lowband_drive=lowband_drive,
                          passthrough_test=passthrough, harmonic_lock_hz=lock_hz, delta_listen=delta_listen,
                          mono_strength=mono_strength, output_trim_db=trim_db, low_trim_db=low_trim_db,
-                         sub_cut_hz=sub_cut, air_cut_hz=air_cut)
+                         sub_cut_hz=sub_cut, air_cut_hz=air_cut, spectral_fx_mode=fx_mode,
+                         spectral_fx_strength=fx_strength, spectral_fx_params=fx_params)
     return res, {"fx_params": fx_params}
 
 
-def make_renderer(n_samples: int, sr: int = DEFAULT_SAMPLE_RATE, n_fft: int = N_FFT_DEFAULT, **kwargs) -> Renderer:
-    """Resolve the reference keyword arguments once and return the cached CUDA renderer."""
+def make_renderer(n_samples: int, sr: int = DEFAULT_SAMPLE_RATE, n_fft: int = N_FFT_DEFAULT, seeds=None,
+                  **kwargs) -> Renderer:
+    """Resolve the reference keyword arguments once and return the cached CUDA renderer.  ``seeds`` only
+    matters for the random spectral FX (see Renderer.set_fx_seeds): an int selects one shared table."""
     res, _ = _resolve_kwargs(int(n_samples), int(sr), int(n_fft), dict(kwargs))
+    if res.fx_rng:
+        res.params.fx_table_per_clip = 0 if isinstance(seeds, (int, np.integer)) else 1
     return _renderer_for(res)
 
 
 def process_batch(x, sr: int = DEFAULT_SAMPLE_RATE, *, n_fft: int = N_FFT_DEFAULT, return_taps: bool = False,
-                  chunk_clips: int = 128, out=None, **kwargs):
+                  chunk_clips: int = 128, out=None, seeds=None, **kwargs):
     """Render a batch of mono clips ``x[B, n]`` with one parameter set.
 
+    ``seeds`` controls the np.random replay of the random spectral FX (None: consume the global state clip by
+    clip like a loop of reference calls; int: reseed before every clip; list: one seed per clip).
     ``x`` may be a CUDA tensor (returns CUDA tensors, asynchronous), a CPU tensor or a NumPy array
     (returns the same kind; the copy/compute pipeline of ``qd_render_host`` is used when no taps are
     requested).  ``out`` (CPU tensor, ideally pinned like ``x``) receives the result of the host path
@@ -209,7 +242,8 @@ def process_batch(x, sr: int = DEFAULT_SAMPLE_RATE, *, n_fft: int = N_FFT_DEFAUL
     xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) if is_np else x
     if xt.dim() != 2:
         raise ValueError("process_batch expects [batch, samples]")
-    r = make_renderer(xt.shape[1], sr, n_fft, **kwargs)
+    r = make_renderer(xt.shape[1], sr, n_fft, seeds=seeds, **kwargs)
+    r.set_fx_seeds(int(xt.shape[0]), seeds)  # no-op unless a random spectral FX is active
     if xt.is_cuda:
         return r.render_device(xt.float(), want_taps=return_taps)
     if return_taps:

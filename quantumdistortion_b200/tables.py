@@ -158,6 +158,88 @@ def design_linkwitz_riley_sos(sr: int, crossover_hz: float, order_per_side: int 
     return np.concatenate([lp, lp], axis=0), np.concatenate([hp, hp], axis=0)
 
 
+# ----------------------------------------------------------------------------- spectral FX (high band)
+def resolve_spectral_fx(mode: Optional[str], strength: float, params: Optional[Dict[str, Any]]) -> Dict[str, Any]:
+    """dsp/pipeline.py:64-141: strength -> concrete FX parameters.  Returns the qd_params fx_* values plus
+    ``rng``: None, ("jitter",), ("pick", half) or ("swap",) -- the np.random draws one frame consumes."""
+    s = float(strength)
+    params = params or {}
+    none = {"fx_mode": 0, "a": 0.0, "b": 0.0, "c": 0.0, "rng": None}
+    if not mode or s <= 0.0:
+        return none
+    if mode == "bitcrush":
+        method = params.get("method", "log")
+        step_db = params.get("step_db", 0.5 + 7.5 * (s ** 1.3))
+        step = params.get("step", 0.01 + 0.09 * (s ** 1.2))
+        threshold = params.get("threshold", None)
+        rel = 0.0
+        absolute = 0.0
+        if threshold is None and s >= 0.4:
+            rel = 0.02 * (s ** 1.5)            # x frame max (:90)
+        elif threshold is not None and threshold > 0.0:
+            absolute = float(threshold)
+        if method == "log":
+            return {"fx_mode": _lib.QD_FX["bitcrush_log"], "a": float(step_db), "b": rel, "c": absolute, "rng": None}
+        if method == "uniform":
+            return {"fx_mode": _lib.QD_FX["bitcrush_uniform"], "a": float(step), "b": rel, "c": absolute, "rng": None}
+        # unknown method: magnitudes unchanged, threshold still applies (dsp/spectral_fx.py:252-258)
+        return {"fx_mode": _lib.QD_FX["bitcrush_uniform"], "a": 0.0, "b": rel, "c": absolute, "rng": None}
+    if mode == "phase_dispersal":
+        amount = params.get("amount", (s ** 1.7) * np.pi)
+        thresh = params.get("thresh", None)      # default 0.01 * frame max (:105)
+        randomized = bool(params.get("randomized", s > 0.35))
+        rand_amt = params.get("rand_amt", 0.0 if not randomized else 0.2 * (s ** 1.3) * np.pi)
+        if amount <= 0 and not randomized:       # dsp/spectral_fx.py:297-298
+            return none
+        c = -1.0 if thresh is None else max(float(thresh), 0.0)
+        return {"fx_mode": _lib.QD_FX["phase_dispersal"], "a": float(amount), "b": float(rand_amt) if randomized else 0.0,
+                "c": c, "rng": ("jitter",) if randomized else None}
+    if mode == "bin_scramble":
+        window = params.get("window", None)
+        if window is None:
+            window = int(3 + (12 * (s ** 1.2)))
+        if window < 3:
+            window = 3
+        if window % 2 == 0:
+            window += 1
+        mode_name = params.get("mode", "swap" if s < 0.4 else "random_pick")
+        if mode_name == "random_pick":
+            return {"fx_mode": _lib.QD_FX["scramble_pick"], "a": 0.0, "b": 0.0, "c": 0.0, "rng": ("pick", window // 2)}
+        if mode_name == "swap":
+            return {"fx_mode": _lib.QD_FX["scramble_swap"], "a": 0.0, "b": 0.0, "c": 0.0, "rng": ("swap",)}
+        # unknown scramble mode: copy + energy rescale = identity (dsp/spectral_fx.py:382-388)
+        return none
+    return none  # unknown FX mode is a silent no-op (:140-141)
+
+
+def replay_fx_table(rng_kind, n_passes: int, n_frames: int, n_bins: int) -> np.ndarray:
+    """Replay, from the GLOBAL np.random state, the draws one reference ``process_audio`` call makes:
+    pass 1 frames 0..T-1 then pass 2, one call per frame.  Returns
+    ``[2, n_frames, n_bins]`` (int16 source bins, or float32 jitter in [-1, 1)); unused passes stay identity/zero."""
+    kind = rng_kind[0]
+    if kind == "jitter":
+        out = np.zeros((2, n_frames, n_bins), dtype=np.float32)
+    else:
+        out = np.empty((2, n_frames, n_bins), dtype=np.int16)
+        out[:] = np.arange(n_bins, dtype=np.int16)[None, None, :]
+    base = np.arange(n_bins)
+    for p in range(n_passes):
+        for t in range(n_frames):
+            if kind == "jitter":      # dsp/spectral_fx.py:314
+                out[p, t] = (np.random.rand(n_bins) * 2.0 - 1.0).astype(np.float32)
+            elif kind == "pick":      # :360-367
+                half = rng_kind[1]
+                out[p, t] = np.clip(base + np.random.randint(-half, half + 1, size=n_bins), 0, n_bins - 1)
+            else:                     # swap, :368-381
+                sw = np.where(np.random.rand(n_bins - 1) < 0.25)[0]
+                if len(sw) > 1:
+                    sw = sw[np.concatenate([[True], np.diff(sw) > 1])]
+                idx = base.copy()
+                idx[sw], idx[sw + 1] = sw + 1, sw
+                out[p, t] = idx
+    return out
+
+
 # ----------------------------------------------------------------------------- resolved render
 @dataclass
 class Resolved:
@@ -167,6 +249,10 @@ class Resolved:
     keepalive: tuple
     target_bins: Optional[np.ndarray]
     active_mask: Optional[np.ndarray]
+    fx_rng: Optional[tuple] = None       # np.random draws per frame (see replay_fx_table)
+    fx_passes: int = 0                   # quantised passes that consume them
+    n_frames: int = 0
+    n_bins: int = 0
 
 
 def _sos_fill(dst, sos: np.ndarray) -> None:
@@ -182,7 +268,9 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
             distortion_params: Optional[Dict[str, Any]], limiter_on: bool, limiter_ceiling_db: float,
             dry_wet: float, use_multiband: bool, crossover_hz: float, lowband_drive: float,
             passthrough_test: bool, harmonic_lock_hz: float, delta_listen: bool, mono_strength: float,
-            output_trim_db: float, low_trim_db: float, sub_cut_hz: float, air_cut_hz: float) -> Resolved:
+            output_trim_db: float, low_trim_db: float, sub_cut_hz: float, air_cut_hz: float,
+            spectral_fx_mode: Optional[str] = None, spectral_fx_strength: float = 0.0,
+            spectral_fx_params: Optional[Dict[str, Any]] = None) -> Resolved:
     """Turn the reference's keyword arguments into qd_params / qd_tables.  Raises the reference's
     exceptions (SURVEY.md section 8(b) "Errors") before anything is launched."""
     if n_fft not in SUPPORTED_N_FFT:
@@ -235,6 +323,17 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
         p.mono_a = float(np.float32(mono_strength))
         p.mono_b = float(np.float32(1.0 - mono_strength))
     p.fx_mode = 0
+    n_frames = 1 + int(n_samples) // (n_fft // 4)
+    fx_rng = None
+    fx_passes = 0
+    quant_on = (not passthrough_test) and (p.pre_quant or p.post_quant)
+    if use_multiband and quant_on:   # FX runs inside the quantiser call of the HIGH band only (:291, :313-314)
+        fx = resolve_spectral_fx(spectral_fx_mode, spectral_fx_strength, spectral_fx_params)
+        p.fx_mode, p.fx_a, p.fx_b, p.fx_c = fx["fx_mode"], fx["a"], fx["b"], fx["c"]
+        if p.fx_mode:
+            fx_rng = fx["rng"]
+            fx_passes = int(p.pre_quant) + int(p.post_quant)
+            p.fx_table_frames = n_frames if fx_rng else 0
     tables = None
     tb = mask = None
     if not passthrough_test and (p.pre_quant or p.post_quant):
@@ -259,4 +358,5 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
     else:
         # still validate key / scale like the reference would on its first quantizer call
         pass
-    return Resolved(params=p, tables=tables, keepalive=tuple(keep), target_bins=tb, active_mask=mask)
+    return Resolved(params=p, tables=tables, keepalive=tuple(keep), target_bins=tb, active_mask=mask,
+                    fx_rng=fx_rng, fx_passes=fx_passes, n_frames=n_frames, n_bins=n_fft // 2 + 1)

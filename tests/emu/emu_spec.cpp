@@ -4,6 +4,7 @@
 //
 //   emu_spec <n_fft> <nw> <n> <tile_blocks> <quant> <smoothing> <snap> <smear> <epilogue> <fold> <bias>
 //            <tube_gain> <tube_norm> <x.f32> <target_bins.i32> <mask.u8> <y_out.f32> <tap_out.f32>
+//            [<fx_mode> <fx_a> <fx_b> <fx_c> <fx_table file or -> <fx_pass>]
 #include "cuda_emu.h"
 
 namespace qd_emu {
@@ -16,6 +17,7 @@ thread_local dim3 g_tid, g_bid;
 
 #include <fstream>
 #include <iostream>
+#include <string>
 
 template <class T>
 static std::vector<T> read_all(const char *path) {
@@ -28,13 +30,13 @@ static std::vector<T> read_all(const char *path) {
     return v;
 }
 
-template <int NC, int NW, bool TS = false>
+template <int NC, int NW, bool TS = false, bool FX = false>
 static void run(qd::SpecArgs a, int n_tiles, size_t smem) {
-    qd_emu::launch(dim3(n_tiles, 1, 1), dim3(32 * NW, 1, 1), smem, [&] { qd::spec_pass_kernel<NC, NW, TS>(a); });
+    qd_emu::launch(dim3(n_tiles, 1, 1), dim3(32 * NW, 1, 1), smem, [&] { qd::spec_pass_kernel<NC, NW, TS, FX>(a); });
 }
 
 int main(int argc, char **argv) {
-    if (argc != 19) { std::cerr << "usage: see source\n"; return 2; }
+    if (argc != 19 && argc != 25) { std::cerr << "usage: see source\n"; return 2; }
     int ai = 1;
     const int n_fft = std::atoi(argv[ai++]);
     const int nw = std::atoi(argv[ai++]);
@@ -55,6 +57,16 @@ int main(int argc, char **argv) {
     const char *y_path = argv[ai++];
     const char *tap_path = argv[ai++];
     if ((int)x.size() != n) { std::cerr << "x size\n"; return 2; }
+    int fx_mode = 0, fx_pass = 0;
+    double fx_a = 0, fx_b = 0, fx_c = 0;
+    std::vector<unsigned char> fx_table;
+    if (argc == 25) {
+        fx_mode = std::atoi(argv[ai++]);
+        fx_a = std::atof(argv[ai++]); fx_b = std::atof(argv[ai++]); fx_c = std::atof(argv[ai++]);
+        const char *tp = argv[ai++];
+        if (std::string(tp) != "-") fx_table = read_all<unsigned char>(tp);
+        fx_pass = std::atoi(argv[ai++]);
+    }
 
     qd_host::SpecTables st;
     if (!qd_host::build_spec_tables(n_fft, &st)) { std::cerr << "unsupported n_fft\n"; return 2; }
@@ -102,9 +114,19 @@ int main(int argc, char **argv) {
     a.q.keep_active = qt.keep_active;
     a.q.smoothing = smoothing;
 
+    a.fx.mode = fx_mode;
+    a.fx.a = (float)fx_a; a.fx.b = (float)fx_b; a.fx.c = (float)fx_c; a.fx.step = fx_a;
+    a.fx.table = fx_table.empty() ? nullptr : fx_table.data();
+    a.fx.table_frames = a.n_frames; a.fx.table_per_clip = 0; a.fx.pass = fx_pass; a.fx.clip_offset = 0;
     const int blocks_total = (n + st.hop - 1) / st.hop;
     const int n_tiles = (blocks_total + tile_blocks - 1) / tile_blocks;
     const int nc = n_fft / 2;
+#define QD_FXCASE(NC_, NW_)                                                                          \
+    if (fx_mode && nc == NC_ && nw == NW_) {                                                         \
+        run<NC_, NW_, false, true>(a, n_tiles, qd::SpecSmem<NC_, NW_>::bytes(qt.n_slots, false, 0, 0, true)); \
+        goto done;                                                                                   \
+    }
+    QD_FXCASE(1024, 8) QD_FXCASE(256, 4) QD_FXCASE(2048, 4)
 #define QD_CASE(NC_, NW_)                                                        \
     if (nc == NC_ && nw == NW_) {                                                \
         run<NC_, NW_>(a, n_tiles, qd::SpecSmem<NC_, NW_>::bytes(qt.n_slots));    \

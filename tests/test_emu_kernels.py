@@ -29,7 +29,7 @@ def emu_spec():
 
 
 def run_emu(exe, x, sr, n_fft, nw, tile_blocks, quant, smoothing, snap, smear, epilogue=0, fold=1.0,
-            bias=0.0, tg=1.0, tn=1.0, key="D", scale="minor", lo=110.0, hi=5000.0):
+            bias=0.0, tg=1.0, tn=1.0, key="D", scale="minor", lo=110.0, hi=5000.0, fx=None):
     freqs = np.fft.rfftfreq(n_fft, d=1.0 / sr)
     tb = orc.target_bins_for_freqs(freqs, key, scale).astype(np.int32)
     mask = orc.quantize_band_mask(freqs, lo, hi).astype(np.uint8)
@@ -38,10 +38,17 @@ def run_emu(exe, x, sr, n_fft, nw, tile_blocks, quant, smoothing, snap, smear, e
         x.astype(np.float32).tofile(p("x"))
         tb.tofile(p("tb"))
         mask.tofile(p("mask"))
-        subprocess.check_call([exe, str(n_fft), str(nw), str(len(x)), str(tile_blocks), str(int(quant)),
-                               str(int(smoothing)), repr(float(snap)), repr(float(smear)), str(epilogue),
-                               repr(float(fold)), repr(float(bias)), repr(float(tg)), repr(float(tn)),
-                               p("x"), p("tb"), p("mask"), p("y"), p("tap")], stdout=subprocess.DEVNULL)
+        cmd = [exe, str(n_fft), str(nw), str(len(x)), str(tile_blocks), str(int(quant)),
+               str(int(smoothing)), repr(float(snap)), repr(float(smear)), str(epilogue),
+               repr(float(fold)), repr(float(bias)), repr(float(tg)), repr(float(tn)),
+               p("x"), p("tb"), p("mask"), p("y"), p("tap")]
+        if fx is not None:  # (fx_mode, a, b, c, table ndarray or None, pass index)
+            tab = "-"
+            if fx[4] is not None:
+                fx[4].tofile(p("fxt"))
+                tab = p("fxt")
+            cmd += [str(fx[0]), repr(float(fx[1])), repr(float(fx[2])), repr(float(fx[3])), tab, str(fx[5])]
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
         return np.fromfile(p("y"), dtype=np.float32), np.fromfile(p("tap"), dtype=np.float32)
 
 
@@ -128,3 +135,28 @@ def test_emu_crossover(emu_time, n, delay):
     rlo = np.concatenate([np.zeros(delay, dtype=np.float32), rlo])[:n]
     assert np.max(np.abs(hi - rhi)) <= 1.2e-7
     assert np.max(np.abs(lo - rlo)) <= 1.2e-7
+
+
+@pytest.mark.parametrize("mode,strength,seed", [("bitcrush", 0.5, None), ("bitcrush", 0.3, None),
+                                                ("phase_dispersal", 0.6, 7), ("phase_dispersal", 0.3, None),
+                                                ("bin_scramble", 0.55, 11), ("bin_scramble", 0.3, 12)])
+def test_emu_spectral_fx_pass(emu_spec, mode, strength, seed):
+    """One high-band pass with a spectral FX: kernel source (emulated) vs the oracle with the same np.random seed."""
+    from quantumdistortion_b200 import tables
+    n, sr, n_fft = 5000, 48000, 2048
+    x = synth.loud_clip(8, n)
+    fxr = tables.resolve_spectral_fx(mode, strength, {})
+    tab = None
+    if fxr["rng"]:
+        np.random.seed(seed)
+        tab = tables.replay_fx_table(fxr["rng"], 1, 1 + n // (n_fft // 4), n_fft // 2 + 1)
+    y, _ = run_emu(emu_spec, x, sr, n_fft, 8, 64, True, True, 0.9, 0.3, key="F",
+                   fx=(fxr["fx_mode"], fxr["a"], fxr["b"], fxr["c"], tab, 0))
+    S, freqs = orc.stft(x, sr, n_fft)
+    if seed is not None:
+        np.random.seed(seed)
+    Sq = orc.spectral_quantize_stft(S, freqs, "F", "minor", 0.9, 0.3, True, is_high_band=True,
+                                    spectral_fx_mode=mode, spectral_fx_strength=strength, spectral_fx_params={})
+    ref = orc.istft(Sq, sr, n_fft, length=n)
+    err = float(np.max(np.abs(y - ref)))
+    assert err < 2e-5, err

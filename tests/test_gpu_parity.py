@@ -18,7 +18,6 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MAX_ABS = 1e-4
 NULL_DB = -80.0
-FX_NOT_BUILT = {k for k, v in qd_cases.CASES.items() if v[6].get("spectral_fx_mode")}
 # Ill-conditioned in float32: with the band mask wide open (sub_cut_hz = air_cut_hz = 0) a target near 21 kHz gathers
 # ~60 source bins whose phasors cancel to ~1e-5 of their sum, so the phase of the sum needs a float64 FFT.
 NEEDS_F64 = {"sb_wide_mask"}
@@ -50,12 +49,14 @@ def _check(got, ref, what, max_abs=MAX_ABS):
     return err
 
 
-@pytest.mark.parametrize("name", [k for k in qd_cases.CASES if k not in FX_NOT_BUILT])
+@pytest.mark.parametrize("name", list(qd_cases.CASES))
 def test_pipeline_vs_reference_fixtures(qd, pipe, name):
     kind, seed, n, sr, n_fft, rng_seed, kw = qd_cases.CASES[name]
     if name in NEEDS_F64:
         pytest.xfail("needs the float64 spectral pass (DESIGN.md section 7)")
     x = pipe[f"{name}/x"]
+    if rng_seed is not None:
+        np.random.seed(rng_seed)  # the random spectral FX replay the global np.random state like the reference
     y, taps = qd.process_audio(x, sr, n_fft=n_fft, **kw)
     tol = MAX_ABS if n_fft <= 4096 else 3e-4  # fp32 FFT at n_fft 8192: SURVEY.md 7.4 item 2
     _check(y, pipe[f"{name}/y"], f"{name}/y", tol)
@@ -167,3 +168,21 @@ def test_edge_cases(qd):
     y, _ = qd.process_audio(stereo, 48000)
     ref, _ = orc.process_audio(stereo, 48000)
     _check(y, ref, "stereo->mono")
+
+
+def test_spectral_fx_batch_shared_and_per_clip_seeds(qd):
+    """BASELINE config #4 shape: Growl preset + multiband + each FX; shared-seed batch and per-clip seeds."""
+    n, sr = 20000, 48000
+    x = np.stack([synth.loud_clip(60 + i, n, sr) for i in range(3)])
+    base = dict(qd_cases.GROWL, use_multiband=True)
+    for mode, s in (("bitcrush", 0.5), ("phase_dispersal", 0.6), ("bin_scramble", 0.55), ("bin_scramble", 0.3)):
+        kw = dict(base, spectral_fx_mode=mode, spectral_fx_strength=s)
+        y, _ = qd.process_batch(x, sr, seeds=1234, **kw)            # np.random.seed(1234) before every clip
+        ys, _ = qd.process_batch(x, sr, seeds=[5, 6, 7], **kw)      # one seed per clip
+        for i in range(3):
+            np.random.seed(1234)
+            ref, _ = orc.process_audio(x[i], sr, **kw)
+            _check(y[i], ref, f"{mode} {s} shared clip {i}")
+            np.random.seed(5 + i)
+            ref, _ = orc.process_audio(x[i], sr, **kw)
+            _check(ys[i], ref, f"{mode} {s} per-clip clip {i}")
