@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 1
+#define QD_ABI_VERSION 2
 
 typedef enum qd_status {
     QD_OK = 0,
@@ -104,7 +104,15 @@ typedef struct qd_params {
     double   fx_c;               /* bitcrush: absolute threshold; dispersal: absolute thresh (<0: 0.01*max) */
     int32_t  fx_table_frames;    /* frames per pass in the FX random table (0 = no table) */
     int32_t  fx_table_per_clip;  /* 0: one table shared by every clip; 1: [batch] tables */
+
+    int32_t  precision;          /* QD_PRECISION_F32: float32 FFT/quantizer (fast path);
+                                    QD_PRECISION_F64: the same kernels instantiated in float64 -- the parity path
+                                    for ill-conditioned configurations (band mask wide open, n_fft 8192) */
+    int32_t  reserved0;
 } qd_params;
+
+#define QD_PRECISION_F32 0
+#define QD_PRECISION_F64 1
 
 /*
  * Integer/float tables built on the host in float64 (bit-exact with the reference):

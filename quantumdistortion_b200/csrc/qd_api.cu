@@ -59,7 +59,10 @@ struct qd_plan {
     int nc = 0, hop = 0, n_frames = 0, nw = 0;
     bool has_quant = false;
     std::vector<void *> owned;  // device allocations
-    qd::SpecArgs spec{};        // table pointers filled once
+    qd::SpecArgsT<float> spec{};     // table pointers filled once (float32 FFT)
+    qd::SpecArgsT<double> spec64{};  // the same for the float64 parity path
+    bool f64 = false;
+    bool ts = false;           // float32 n_fft 2048: tables fit the shared-memory kernel variant
     size_t spec_smem = 0;      // dynamic shared memory of the pass kernel in use
     const void *fx_table = nullptr;
     int64_t fx_tables = 0;
@@ -95,64 +98,78 @@ struct TimeScope {  // brackets the launches of one kernel class with events on 
 
 namespace {
 
-template <int NC, int NW, bool TS = false, bool FX = false>
-int launch_spec_t(qd_plan *pl, const qd::SpecArgs &a, int tiles, int64_t batch, cudaStream_t st) {
+// ---- kernel selection.  float32: n_fft 2048 (the headline size) runs 16 warps per CTA with its tables in
+//      shared memory (falls back to 8 warps + L1 tables when they do not fit); float64 (parity path) and the
+//      FX variants read tables through L1.  Must stay in sync with the switch in dispatch_spec().
+template <class T> int pick_nw(int nc, bool fx) {
+    if (sizeof(T) == 8) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 2;
+    if (fx) return nc <= 1024 ? 8 : 4;
+    return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4;
+}
+
+template <class T, int NC, int NW>
+size_t smem_of(int n_slots, bool ts, int n_src, int n_aff, bool fx) {
+    return qd::SpecSmem<T, NC, NW>::bytes(n_slots, ts, n_src, n_aff, fx);
+}
+
+template <class T>
+size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int n_aff, bool fx) {
+    switch (nc) {
+        case 256:  return nw == 8 ? smem_of<T, 256, 8>(n_slots, false, 0, 0, fx) : 0;
+        case 512:  return nw == 8 ? smem_of<T, 512, 8>(n_slots, false, 0, 0, fx) : 0;
+        case 1024:
+            if (nw == 16) return smem_of<T, 1024, 16>(n_slots, ts, n_src, n_aff, fx);
+            return nw == 8 ? smem_of<T, 1024, 8>(n_slots, false, 0, 0, fx) : 0;
+        case 2048: return nw == 4 ? smem_of<T, 2048, 4>(n_slots, false, 0, 0, fx) : 0;
+        case 4096: return nw == 4 ? smem_of<T, 4096, 4>(n_slots, false, 0, 0, fx)
+                        : nw == 2 ? smem_of<T, 4096, 2>(n_slots, false, 0, 0, fx) : 0;
+    }
+    return 0;
+}
+
+template <class T, int NC, int NW, bool TS, bool FX>
+int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st) {
     static bool attr_set = false;  // per instantiation; plans are single-threaded per the ABI contract
-    auto kern = qd::spec_pass_kernel<NC, NW, TS, FX>;
+    auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX>;
     if (!attr_set) {
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
+    const size_t smem = qd::SpecSmem<T, NC, NW>::bytes(a.q.n_slots, TS, a.q.n_src, a.q.n_aff, FX);
     for (int64_t b0 = 0; b0 < batch; b0 += 65535) {  // gridDim.y limit
         const int64_t nb = std::min<int64_t>(65535, batch - b0);
-        qd::SpecArgs c = a;
+        qd::SpecArgsT<T> c = a;
         c.x = a.x + (size_t)b0 * a.n;
         c.y = a.y + (size_t)b0 * a.n;
         if (a.tap) c.tap = a.tap + (size_t)b0 * a.n;
         c.fx.clip_offset = a.fx.clip_offset + (int)b0;
-        const size_t smem = FX ? pl->spec_smem
-                               : qd::SpecSmem<NC, NW>::bytes(a.q.n_slots, TS, a.q.n_src, a.q.n_aff, false);
         kern<<<dim3((unsigned)tiles, (unsigned)nb, 1), 32 * NW, smem, st>>>(c);
     }
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }
 
-// n_fft 2048 (the headline size) runs 16 warps per CTA, one CTA per SM, with its tables in shared memory
-int spec_nw(int nc) { return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4; }
-
-size_t spec_smem_bytes(int nc, int nw, int n_slots, int n_src, int n_aff, bool fx) {
-    if (fx) {  // FX kernels: tables through L1, one extra magnitude plane per warp
-        switch (nc) {
-            case 256:  return qd::SpecSmem<256, 8>::bytes(n_slots, false, 0, 0, true);
-            case 512:  return qd::SpecSmem<512, 8>::bytes(n_slots, false, 0, 0, true);
-            case 1024: return qd::SpecSmem<1024, 8>::bytes(n_slots, false, 0, 0, true);
-            case 2048: return qd::SpecSmem<2048, 4>::bytes(n_slots, false, 0, 0, true);
-            case 4096: return qd::SpecSmem<4096, 4>::bytes(n_slots, false, 0, 0, true);
-        }
-        return 0;
-    }
+template <class T, bool FX>
+int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st) {
     switch (nc) {
-        case 256:  return nw == 8 ? qd::SpecSmem<256, 8>::bytes(n_slots) : 0;
-        case 512:  return nw == 8 ? qd::SpecSmem<512, 8>::bytes(n_slots) : 0;
-        case 1024: {
-            if (nw == 16) {
-                const size_t b = qd::SpecSmem<1024, 16>::bytes(n_slots, true, n_src, n_aff);
-                if (b <= 227 * 1024) return b;
+        case 256:  return launch_spec_t<T, 256, 8, false, FX>(a, tiles, batch, st);
+        case 512:  return launch_spec_t<T, 512, 8, false, FX>(a, tiles, batch, st);
+        case 1024:
+            if constexpr (sizeof(T) == 4 && !FX) {
+                if (nw == 16 && ts) return launch_spec_t<T, 1024, 16, true, false>(a, tiles, batch, st);
             }
-            return qd::SpecSmem<1024, 8>::bytes(n_slots);
-        }
-        case 2048: return nw == 4 ? qd::SpecSmem<2048, 4>::bytes(n_slots) : 0;
-        case 4096: return nw == 4 ? qd::SpecSmem<4096, 4>::bytes(n_slots) : 0;
+            return launch_spec_t<T, 1024, 8, false, FX>(a, tiles, batch, st);
+        case 2048: return launch_spec_t<T, 2048, 4, false, FX>(a, tiles, batch, st);
+        case 4096:
+            if constexpr (sizeof(T) == 8) return launch_spec_t<T, 4096, 2, false, FX>(a, tiles, batch, st);
+            else return launch_spec_t<T, 4096, 4, false, FX>(a, tiles, batch, st);
     }
-    return 0;
+    return fail(QD_ERR_UNSUPPORTED, "n_fft not supported");
 }
 
-// One spectral pass over [batch, n]: src -> dst (+ optional tap of the pre-epilogue signal).
-int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant, int epilogue,
-                int64_t batch, cudaStream_t st, int fx_pass = 0, int clip_offset = 0) {
-    TimeScope ts(pl, st, QD_KERNEL_SPECTRAL);
-    qd::SpecArgs a = pl->spec;
+template <class T>
+int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *dst, float *tap, int quant,
+                     int epilogue, int64_t batch, cudaStream_t st, int fx_pass, int clip_offset) {
     a.x = src;
     a.y = dst;
     a.tap = tap;
@@ -162,6 +179,9 @@ int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant
     a.fx.pass = fx_pass;
     a.fx.clip_offset = clip_offset;
     a.fx.table = pl->fx_table;
+    // a pass that does not run the FX uses the plain kernel of the same warp count
+    const int nw = pl->nw;
+    const bool ts = pl->ts && !fx;
     // tiling: whole clips when the batch alone fills the GPU, else cut clips along time
     const int total_blocks = (a.n + pl->hop - 1) / pl->hop;
     const int ctas_per_sm = std::max<int>(1, (int)((227 * 1024) / (pl->spec_smem + 1024)));
@@ -170,34 +190,24 @@ int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant
     if (batch < want) {
         const int64_t per_clip = (want + batch - 1) / batch;
         tile = (int)((total_blocks + per_clip - 1) / per_clip);
-        const int min_tile = 4 * pl->nw - 3;  // keeps the 3-frame halo recompute below 10 %
+        const int min_tile = 4 * nw - 3;  // keeps the 3-frame halo recompute below 10 %
         if (tile < min_tile) tile = min_tile;
-        tile = ((tile + 3 + pl->nw - 1) / pl->nw) * pl->nw - 3;  // whole batches of NW frames
+        tile = ((tile + 3 + nw - 1) / nw) * nw - 3;  // whole batches of NW frames
         if (tile > total_blocks) tile = total_blocks;
     }
     if (tile < 1) tile = 1;
     a.tile_blocks = tile;
     const int tiles = (total_blocks + tile - 1) / tile;
-    if (fx) {
-        switch (pl->nc) {
-            case 256:  return launch_spec_t<256, 8, false, true>(pl, a, tiles, batch, st);
-            case 512:  return launch_spec_t<512, 8, false, true>(pl, a, tiles, batch, st);
-            case 1024: return launch_spec_t<1024, 8, false, true>(pl, a, tiles, batch, st);
-            case 2048: return launch_spec_t<2048, 4, false, true>(pl, a, tiles, batch, st);
-            case 4096: return launch_spec_t<4096, 4, false, true>(pl, a, tiles, batch, st);
-        }
-        return fail(QD_ERR_UNSUPPORTED, "n_fft not supported");
-    }
-    switch (pl->nc) {
-        case 256:  return launch_spec_t<256, 8>(pl, a, tiles, batch, st);
-        case 512:  return launch_spec_t<512, 8>(pl, a, tiles, batch, st);
-        case 1024:
-            if (pl->nw == 16) return launch_spec_t<1024, 16, true>(pl, a, tiles, batch, st);
-            return launch_spec_t<1024, 8>(pl, a, tiles, batch, st);
-        case 2048: return launch_spec_t<2048, 4>(pl, a, tiles, batch, st);
-        case 4096: return launch_spec_t<4096, 4>(pl, a, tiles, batch, st);
-    }
-    return fail(QD_ERR_UNSUPPORTED, "n_fft not supported");
+    if (fx) return dispatch_spec<T, true>(pl->nc, nw, false, a, tiles, batch, st);
+    return dispatch_spec<T, false>(pl->nc, nw, ts, a, tiles, batch, st);
+}
+
+// One spectral pass over [batch, n]: src -> dst (+ optional tap of the pre-epilogue signal).
+int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant, int epilogue,
+                int64_t batch, cudaStream_t st, int fx_pass = 0, int clip_offset = 0) {
+    TimeScope ts(pl, st, QD_KERNEL_SPECTRAL);
+    if (pl->f64) return launch_spec_prec<double>(pl, pl->spec64, src, dst, tap, quant, epilogue, batch, st, fx_pass, clip_offset);
+    return launch_spec_prec<float>(pl, pl->spec, src, dst, tap, quant, epilogue, batch, st, fx_pass, clip_offset);
 }
 
 int launch_limiter(const qd::LimiterArgs &a, int64_t batch, cudaStream_t st) {
@@ -258,20 +268,21 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
     QD_CUDA(cudaGetDeviceProperties(&pr, dev));
     if (pr.major != 10) return fail(QD_ERR_NO_DEVICE, "device is not sm_100 (B200)");
     qd_host::SpecTables st;
-    if (!qd_host::build_spec_tables(p.n_fft, &st)) return fail(QD_ERR_UNSUPPORTED, "n_fft must be one of 512, 1024, 2048, 4096, 8192");
+    if (!qd_host::build_spec_tables<float>(p.n_fft, &st)) return fail(QD_ERR_UNSUPPORTED, "n_fft must be one of 512, 1024, 2048, 4096, 8192");
     const bool need_quant = !p.passthrough && (p.pre_quant || p.post_quant);
     if (need_quant && !tables) return fail(QD_ERR_INVALID_ARG, "quantizer tables required");
     if (p.fx_mode < QD_FX_NONE || p.fx_mode > QD_FX_SCRAMBLE_SWAP) return fail(QD_ERR_INVALID_ARG, "bad fx_mode");
     if (p.fx_mode != QD_FX_NONE && !p.multiband) return fail(QD_ERR_INVALID_ARG, "spectral FX act on the high band of a multiband render only");
     if ((p.fx_mode == QD_FX_SCRAMBLE_PICK || p.fx_mode == QD_FX_SCRAMBLE_SWAP) && p.n_fft > 4096)
         return fail(QD_ERR_UNSUPPORTED, "bin scramble is built for n_fft <= 4096");
+    if (p.precision != QD_PRECISION_F32 && p.precision != QD_PRECISION_F64) return fail(QD_ERR_INVALID_ARG, "bad precision");
 
     qd_plan *pl = new qd_plan();
     pl->p = p;
     pl->nc = st.nc;
     pl->hop = st.hop;
     pl->n_frames = 1 + p.n_samples / st.hop;
-    pl->nw = spec_nw(st.nc);
+    pl->f64 = p.precision == QD_PRECISION_F64;
     pl->sm_count = pr.multiProcessorCount;
     pl->has_quant = need_quant;
     auto keep = [&](void *d) { pl->owned.push_back(d); };
@@ -282,28 +293,13 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         if (ptr) keep(ptr);                                                               \
         if (e_ != cudaSuccess) return bail(QD_ERR_CUDA, cudaGetErrorString(e_));          \
     } while (0)
-    qd_host::F2 *d_wtab, *d_tw1, *d_tw2, *d_wsplit;
-    float *d_invw;
-    QD_UP(st.wtab, d_wtab);
-    QD_UP(st.tw1, d_tw1);
-    QD_UP(st.tw2, d_tw2);
-    QD_UP(st.wsplit, d_wsplit);
-    QD_UP(st.invw, d_invw);
-    qd::SpecArgs &a = pl->spec;
-    a.n = p.n_samples;
-    a.n_frames = pl->n_frames;
-    a.fold = p.fold_amount; a.bias = p.bias; a.tube_gain = p.tube_gain; a.tube_norm = p.tube_norm;
-    a.wtab = reinterpret_cast<const float2 *>(d_wtab);
-    a.tw1 = reinterpret_cast<const float2 *>(d_tw1);
-    a.tw2 = reinterpret_cast<const float2 *>(d_tw2);
-    a.wsplit = reinterpret_cast<const float2 *>(d_wsplit);
-    a.invw = d_invw;
+    qd::QuantDev qdev{};
     int n_slots = 0;
     if (need_quant) {
         if (tables->n_bins != st.nc + 1) return bail(QD_ERR_INVALID_ARG, "tables->n_bins != n_fft/2+1");
         qd_host::QuantTablesH qt;
         std::string err;
-        if (!qd_host::build_quant_tables(*tables, &qt, &err)) return bail(QD_ERR_INVALID_ARG, err);
+        if (!qd_host::build_quant_tables(*tables, &qt, &err, pl->f64)) return bail(QD_ERR_INVALID_ARG, err);
         uint16_t *d_rab;
         uint32_t *d_ra, *d_rf, *d_st;
         qd_host::AffEntryH *d_aff;
@@ -312,32 +308,81 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         QD_UP(qt.row_aff, d_rf);
         QD_UP(qt.row_aff_base, d_rab);
         QD_UP(qt.aff, d_aff);
-        a.q.n_slots = qt.n_slots;
-        a.q.n_aff = qt.n_aff;
-        a.q.n_src = (int)qt.src_tab.size();
-    a.q.row_limit = qt.row_limit;
-        a.q.src_tab = d_st;
-        a.q.row_active = d_ra;
-        a.q.row_aff = d_rf;
-        a.q.row_aff_base = d_rab;
-        a.q.aff = reinterpret_cast<const qd::AffEntry *>(d_aff);
-        a.q.keep_active = qt.keep_active;
-        a.q.smoothing = p.bin_smoothing ? 1 : 0;
+        qdev.n_slots = qt.n_slots;
+        qdev.n_aff = qt.n_aff;
+        qdev.n_src = (int)qt.src_tab.size();
+        qdev.row_limit = qt.row_limit;
+        qdev.src_tab = d_st;
+        qdev.row_active = d_ra;
+        qdev.row_aff = d_rf;
+        qdev.row_aff_base = d_rab;
+        qdev.aff = reinterpret_cast<const qd::AffEntry *>(d_aff);
+        qdev.keep_active = qt.keep_active;
+        qdev.smoothing = p.bin_smoothing ? 1 : 0;
         n_slots = qt.n_slots;
     }
-#undef QD_UP
     const bool fx = need_quant && p.fx_mode != QD_FX_NONE;
-    if (fx) pl->nw = pl->nc <= 1024 ? 8 : 4;
-    pl->spec_smem = spec_smem_bytes(pl->nc, pl->nw, n_slots, a.q.n_src, a.q.n_aff, fx);
-    if (!fx && pl->nc == 1024 && pl->nw == 16 && pl->spec_smem == qd::SpecSmem<1024, 8>::bytes(n_slots))
-        pl->nw = 8;  // tables too large for the shared-memory variant: fall back to 8 warps, tables through L1
-    a.fx.mode = fx ? p.fx_mode : 0;
-    a.fx.a = (float)p.fx_a; a.fx.b = (float)p.fx_b; a.fx.c = (float)p.fx_c;
-    a.fx.step = p.fx_a;
-    a.fx.table_frames = p.fx_table_frames > 0 ? p.fx_table_frames : 1;
-    a.fx.table_per_clip = p.fx_table_per_clip;
+    qd::FxDev fxd{};
+    fxd.mode = fx ? p.fx_mode : 0;
+    fxd.a = (float)p.fx_a; fxd.b = (float)p.fx_b; fxd.c = (float)p.fx_c;
+    fxd.step = p.fx_a;
+    fxd.table_frames = p.fx_table_frames > 0 ? p.fx_table_frames : 1;
+    fxd.table_per_clip = p.fx_table_per_clip;
+    if (pl->f64) {
+        qd_host::SpecTablesT<double> sd;
+        qd_host::build_spec_tables<double>(p.n_fft, &sd);
+        qd_host::D2 *d_wtab, *d_tw1, *d_tw2, *d_wsplit;
+        double *d_invw;
+        QD_UP(sd.wtab, d_wtab);
+        QD_UP(sd.tw1, d_tw1);
+        QD_UP(sd.tw2, d_tw2);
+        QD_UP(sd.wsplit, d_wsplit);
+        QD_UP(sd.invw, d_invw);
+        qd::SpecArgsT<double> &a = pl->spec64;
+        a.n = p.n_samples;
+        a.n_frames = pl->n_frames;
+        a.fold = p.fold_amount; a.bias = p.bias; a.tube_gain = p.tube_gain; a.tube_norm = p.tube_norm;
+        a.wtab = reinterpret_cast<const double2 *>(d_wtab);
+        a.tw1 = reinterpret_cast<const double2 *>(d_tw1);
+        a.tw2 = reinterpret_cast<const double2 *>(d_tw2);
+        a.wsplit = reinterpret_cast<const double2 *>(d_wsplit);
+        a.invw = d_invw;
+        a.q = qdev;
+        a.fx = fxd;
+        pl->nw = pick_nw<double>(pl->nc, fx);
+        pl->ts = false;
+        pl->spec_smem = spec_smem_bytes<double>(pl->nc, pl->nw, false, n_slots, qdev.n_src, qdev.n_aff, fx);
+    } else {
+        qd_host::F2 *d_wtab, *d_tw1, *d_tw2, *d_wsplit;
+        float *d_invw;
+        QD_UP(st.wtab, d_wtab);
+        QD_UP(st.tw1, d_tw1);
+        QD_UP(st.tw2, d_tw2);
+        QD_UP(st.wsplit, d_wsplit);
+        QD_UP(st.invw, d_invw);
+        qd::SpecArgsT<float> &a = pl->spec;
+        a.n = p.n_samples;
+        a.n_frames = pl->n_frames;
+        a.fold = p.fold_amount; a.bias = p.bias; a.tube_gain = p.tube_gain; a.tube_norm = p.tube_norm;
+        a.wtab = reinterpret_cast<const float2 *>(d_wtab);
+        a.tw1 = reinterpret_cast<const float2 *>(d_tw1);
+        a.tw2 = reinterpret_cast<const float2 *>(d_tw2);
+        a.wsplit = reinterpret_cast<const float2 *>(d_wsplit);
+        a.invw = d_invw;
+        a.q = qdev;
+        a.fx = fxd;
+        pl->nw = pick_nw<float>(pl->nc, fx);
+        pl->ts = (pl->nc == 1024 && pl->nw == 16);
+        pl->spec_smem = spec_smem_bytes<float>(pl->nc, pl->nw, pl->ts, n_slots, qdev.n_src, qdev.n_aff, fx);
+        if (pl->ts && pl->spec_smem > 227 * 1024) {  // tables too large for shared memory: 8 warps, tables through L1
+            pl->nw = 8;
+            pl->ts = false;
+            pl->spec_smem = spec_smem_bytes<float>(pl->nc, 8, false, n_slots, qdev.n_src, qdev.n_aff, fx);
+        }
+    }
+#undef QD_UP
     if (pl->spec_smem == 0 || pl->spec_smem > 227 * 1024)
-        return bail(QD_ERR_UNSUPPORTED, "shared memory need of this (n_fft, target table) exceeds 227 KB");
+        return bail(QD_ERR_UNSUPPORTED, "shared memory need of this (n_fft, target table, precision) exceeds 227 KB");
     *out = pl;
     return QD_OK;
 }

@@ -23,47 +23,68 @@
 
 namespace qd {
 
-// ---------------------------------------------------------------- complex helpers
-QD_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-QD_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-QD_DEV float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-// a * conj(b)
-QD_DEV float2 cmulc(float2 a, float2 b) {
-    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-}
-QD_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-QD_DEV float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+// ---------------------------------------------------------------- precision-generic complex helpers
+// The spectral pass is written once for T = float (the fast path) and T = double (the parity path for
+// ill-conditioned configurations: wide-open band mask, n_fft >= 4096).
+template <class T> struct Vec2;
+template <> struct Vec2<float>  { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+template <class T> using V2 = typename Vec2<T>::type;
+template <class T> QD_DEV V2<T> mk2(T a, T b);
+template <> QD_DEV float2  mk2<float>(float a, float b)    { return make_float2(a, b); }
+template <> QD_DEV double2 mk2<double>(double a, double b) { return make_double2(a, b); }
+
+#define QD_COMPLEX_OPS(T2, MK)                                                                         \
+    QD_DEV T2 cadd(T2 a, T2 b) { return MK(a.x + b.x, a.y + b.y); }                                    \
+    QD_DEV T2 csub(T2 a, T2 b) { return MK(a.x - b.x, a.y - b.y); }                                    \
+    QD_DEV T2 cmul(T2 a, T2 b) { return MK(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }            \
+    /* a * conj(b) */                                                                                  \
+    QD_DEV T2 cmulc(T2 a, T2 b) { return MK(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }           \
+    QD_DEV T2 cconj(T2 a) { return MK(a.x, -a.y); }
+QD_COMPLEX_OPS(float2, make_float2)
+QD_COMPLEX_OPS(double2, make_double2)
+
+QD_DEV float  qd_max(float a, float b)   { return fmaxf(a, b); }
+QD_DEV double qd_max(double a, double b) { return fmax(a, b); }
+QD_DEV float  qd_abs(float a)  { return fabsf(a); }
+QD_DEV double qd_abs(double a) { return fabs(a); }
+QD_DEV float  qd_rint(float a)  { return rintf(a); }
+QD_DEV double qd_rint(double a) { return rint(a); }
+QD_DEV float  qd_log10(float a)  { return log10f(a); }
+QD_DEV double qd_log10(double a) { return log10(a); }
+QD_DEV float  qd_exp10(float a)  { return QD_EXP10F(a); }
+QD_DEV double qd_exp10(double a) { return pow(10.0, a); }
+QD_DEV void qd_sincos(float a, float *s, float *c)    { QD_SINCOSF(a, s, c); }
+QD_DEV void qd_sincos(double a, double *s, double *c) { *s = sin(a); *c = cos(a); }
 
 // cos(2*pi*k/32), k = 0..8 (quarter wave); everything else by symmetry
-__host__ __device__ constexpr float qd_cos32_q(int k) {
-    return k == 0 ? 1.0f
-         : k == 1 ? 0.98078528040323043f
-         : k == 2 ? 0.92387953251128674f
-         : k == 3 ? 0.83146961230254524f
-         : k == 4 ? 0.70710678118654752f
-         : k == 5 ? 0.55557023301960218f
-         : k == 6 ? 0.38268343236508978f
-         : k == 7 ? 0.19509032201612825f
-                  : 0.0f;
+__host__ __device__ constexpr double qd_cos32_q(int k) {
+    return k == 0 ? 1.0
+         : k == 1 ? 0.98078528040323044913
+         : k == 2 ? 0.92387953251128675613
+         : k == 3 ? 0.83146961230254523708
+         : k == 4 ? 0.70710678118654752440
+         : k == 5 ? 0.55557023301960222474
+         : k == 6 ? 0.38268343236508977173
+         : k == 7 ? 0.19509032201612826785
+                  : 0.0;
 }
-__host__ __device__ constexpr float qd_cos32(int k) {  // k in [0,32)
+__host__ __device__ constexpr double qd_cos32(int k) {  // k in [0,32)
     return k <= 8 ? qd_cos32_q(k) : k <= 16 ? -qd_cos32_q(16 - k) : k <= 24 ? -qd_cos32_q(k - 16) : qd_cos32_q(32 - k);
 }
-__host__ __device__ constexpr float qd_sin32(int k) { return qd_cos32((k + 24) & 31); }  // sin(a) = cos(a - pi/2)
+__host__ __device__ constexpr double qd_sin32(int k) { return qd_cos32((k + 24) & 31); }  // sin(a) = cos(a - pi/2)
 
 // d * exp(DIR * 2*pi*i * k/32);  k is a compile-time constant after unrolling.
-template <int DIR>
-QD_DEV float2 mul_w32(float2 d, int k) {
+template <int DIR, class T>
+QD_DEV V2<T> mul_w32(V2<T> d, int k) {
     k &= 31;
     if (k == 0) return d;
-    if (k == 16) return make_float2(-d.x, -d.y);
-    if (k == 8) return DIR > 0 ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
-    if (k == 24) return DIR > 0 ? make_float2(d.y, -d.x) : make_float2(-d.y, d.x);
-    const float c = qd_cos32(k);
-    const float s = DIR > 0 ? qd_sin32(k) : -qd_sin32(k);
-    return make_float2(d.x * c - d.y * s, d.x * s + d.y * c);
+    if (k == 16) return mk2<T>(-d.x, -d.y);
+    if (k == 8) return DIR > 0 ? mk2<T>(-d.y, d.x) : mk2<T>(d.y, -d.x);
+    if (k == 24) return DIR > 0 ? mk2<T>(d.y, -d.x) : mk2<T>(-d.y, d.x);
+    const T c = (T)qd_cos32(k);
+    const T s = (T)(DIR > 0 ? qd_sin32(k) : -qd_sin32(k));
+    return mk2<T>(d.x * c - d.y * s, d.x * s + d.y * c);
 }
 
 __host__ __device__ constexpr int qd_log2(int r) { return r <= 1 ? 0 : 1 + qd_log2(r >> 1); }
@@ -76,18 +97,18 @@ __host__ __device__ constexpr int qd_bitrev(int v, int bits) {
 // In-register radix-2 decimation-in-frequency DFT of R points (R = 2..32), fully unrolled.
 // Input natural order; on return v[r] holds output index qd_bitrev(r, log2 R).
 // DIR = -1: forward (exp(-2 pi i nk/R)); DIR = +1: inverse, unnormalised.
-template <int R, int DIR>
-QD_DEV void dft_reg(float2 (&v)[R]) {
+template <int R, int DIR, class T>
+QD_DEV void dft_reg(V2<T> (&v)[R]) {
 #pragma unroll
     for (int half = R / 2; half >= 1; half >>= 1) {
 #pragma unroll
         for (int base = 0; base < R; base += 2 * half) {
 #pragma unroll
             for (int i = 0; i < half; ++i) {
-                const float2 a = v[base + i];
-                const float2 b = v[base + i + half];
+                const V2<T> a = v[base + i];
+                const V2<T> b = v[base + i + half];
                 v[base + i] = cadd(a, b);
-                v[base + i + half] = mul_w32<DIR>(csub(a, b), i * (16 / half));
+                v[base + i + half] = mul_w32<DIR, T>(csub(a, b), i * (16 / half));
             }
         }
     }

@@ -13,6 +13,10 @@
 namespace qd_host {
 
 struct F2 { float x, y; };
+struct D2 { double x, y; };
+template <class T> struct Pair;
+template <> struct Pair<float>  { using type = F2; };
+template <> struct Pair<double> { using type = D2; };
 
 struct AffEntryH {  // must match qd::AffEntry
     int16_t slot[5];
@@ -22,60 +26,67 @@ struct AffEntryH {  // must match qd::AffEntry
 static_assert(sizeof(AffEntryH) == 32, "AffEntry layout");
 
 struct FftRadices { int r1, r2, r3; };
-inline bool fft_radices(int nc, FftRadices *o) {
+// must mirror qd::FftCfg<T, NC>
+inline bool fft_radices(int nc, FftRadices *o, bool is_double = false) {
     switch (nc) {
         case 256:  *o = {8, 8, 4};   return true;
         case 512:  *o = {8, 8, 8};   return true;
-        case 1024: *o = {32, 32, 1}; return true;
+        case 1024: if (is_double) *o = {16, 8, 8}; else *o = {32, 32, 1}; return true;
         case 2048: *o = {16, 16, 8}; return true;
         case 4096: *o = {16, 16, 16}; return true;
     }
     return false;
 }
 
-struct SpecTables {
+template <class T>
+struct SpecTablesT {
+    using P = typename Pair<T>::type;
     int nc = 0, hop = 0;
-    std::vector<F2> wtab, tw1, tw2, wsplit;
-    std::vector<float> invw;  // [16][hop]
+    std::vector<P> wtab, tw1, tw2, wsplit;
+    std::vector<T> invw;  // [16][hop]
 };
+using SpecTables = SpecTablesT<float>;
 
 // periodic Hann, hop = n_fft/4 (dsp/stft_utils.py:51-56, 137-141)
 inline double hann_periodic(int n, int n_fft) { return 0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)n_fft); }
 
-inline bool build_spec_tables(int n_fft, SpecTables *t) {
+template <class T>
+inline bool build_spec_tables(int n_fft, SpecTablesT<T> *t) {
+    using F2 = typename Pair<T>::type;
+    constexpr bool is_double = sizeof(T) == 8;
     const int nc = n_fft / 2;
     FftRadices r;
-    if (!fft_radices(nc, &r)) return false;
+    if (!fft_radices(nc, &r, is_double)) return false;
     t->nc = nc;
     t->hop = n_fft / 4;
     t->wtab.resize(nc);
     for (int n = 0; n < nc; ++n)
-        t->wtab[n] = F2{(float)hann_periodic(2 * n, n_fft), (float)hann_periodic(2 * n + 1, n_fft)};
+        t->wtab[n] = F2{(T)hann_periodic(2 * n, n_fft), (T)hann_periodic(2 * n + 1, n_fft)};
     // access-ordered twiddles: entry [(i*R + k)*32 + lane] = exp(-2 pi i j k / M),
     // butterfly u = lane + 32 i of a pass with sub-size M, radix R, stride S = M/R, j = u % S
     auto fill = [&](std::vector<F2> &tw, int M, int R) {
         const int S = M / R, nb = nc / R / 32;
-        tw.assign((size_t)nb * R * 32, F2{1.0f, 0.0f});
+        tw.assign((size_t)nb * R * 32, F2{(T)1, (T)0});
         for (int i = 0; i < nb; ++i)
             for (int k = 0; k < R; ++k)
                 for (int lane = 0; lane < 32; ++lane) {
                     const int j = (lane + 32 * i) % S;
                     const double ang = -2.0 * M_PI * (double)(((long long)j * k) % M) / (double)M;
-                    tw[((size_t)i * R + k) * 32 + lane] = F2{(float)std::cos(ang), (float)std::sin(ang)};
+                    tw[((size_t)i * R + k) * 32 + lane] = F2{(T)std::cos(ang), (T)std::sin(ang)};
                 }
     };
     fill(t->tw1, nc, r.r1);
     if (r.r3 > 1) fill(t->tw2, nc / r.r1, r.r2);
-    else t->tw2.assign(1, F2{1.0f, 0.0f});
+    else t->tw2.assign(1, F2{(T)1, (T)0});
     t->wsplit.resize(nc / 2 + 1);
     for (int k = 0; k <= nc / 2; ++k) {
         const double ang = -2.0 * M_PI * (double)k / (double)n_fft;
-        t->wsplit[k] = F2{(float)std::cos(ang), (float)std::sin(ang)};
+        t->wsplit[k] = F2{(T)std::cos(ang), (T)std::sin(ang)};
     }
     // 1 / max(sum of w^2 over the frames covering a hop-block, 1e-10)  (dsp/stft_utils.py:174-186, 214)
     // frames are added in ascending t = descending slice index.
     const int hop = t->hop;
-    t->invw.assign((size_t)16 * hop, 0.0f);
+    t->invw.assign((size_t)16 * hop, (T)0);
     for (int a = 0; a < 4; ++a)
         for (int b = a; b < 4; ++b)
             for (int c = 0; c < hop; ++c) {
@@ -84,15 +95,15 @@ inline bool build_spec_tables(int n_fft, SpecTables *t) {
                     const double w = hann_periodic(sl * hop + c, n_fft);
                     s += w * w;
                 }
-                t->invw[(size_t)(a * 4 + b) * hop + c] = (float)(1.0 / std::max(s, 1e-10));
+                t->invw[(size_t)(a * 4 + b) * hop + c] = (T)(1.0 / std::max(s, 1e-10));
             }
     return true;
 }
 
 // host mirror of qd::spos<NC>: position of spectrum bin k inside a warp buffer
-inline int host_spos(int nc, int k) {
+inline int host_spos(int nc, int k, bool is_double = false) {
     FftRadices r;
-    if (!fft_radices(nc, &r)) return -1;
+    if (!fft_radices(nc, &r, is_double)) return -1;
     if (k >= nc) return 32;  // QD_NYQ_SLOT
     const int k1 = k % r.r1, k2 = (k / r.r1) % r.r2, k3 = k / (r.r1 * r.r2);
     const int a = k1 * (nc / r.r1) + k2 * (nc / (r.r1 * r.r2)) + k3;
@@ -110,7 +121,7 @@ struct QuantTablesH {
 };
 
 // Gather form of dsp/quantizer.py:424-515 derived from the reference's own integer tables.
-inline bool build_quant_tables(const qd_tables &in, QuantTablesH *q, std::string *err) {
+inline bool build_quant_tables(const qd_tables &in, QuantTablesH *q, std::string *err, bool is_double = false) {
     const int n = in.n_bins;
     if (n < 3 || n > 8193 || !in.target_bins || !in.active_mask) { if (err) *err = "bad quantizer tables"; return false; }
     const int radius = in.smear_radius;
@@ -151,7 +162,7 @@ inline bool build_quant_tables(const qd_tables &in, QuantTablesH *q, std::string
             int off = 0;
             for (int j = i - 1; j >= (i / 32) * 32 && slot_of_src[j] == slot_of_src[i]; --j) ++off;
             const bool tail = (i % 32 == 31) || (i == ns - 1) || (slot_of_src[i + 1] != slot_of_src[i]);
-            const uint32_t pos = (uint32_t)host_spos(n - 1, q->src_bin[i]);
+            const uint32_t pos = (uint32_t)host_spos(n - 1, q->src_bin[i], is_double);
             q->src_tab.push_back(((uint32_t)tail << 31) | ((uint32_t)off << 26) | ((uint32_t)slot_of_src[i] << 13) | pos);
         }
     }

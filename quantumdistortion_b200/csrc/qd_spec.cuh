@@ -25,12 +25,13 @@
 namespace qd {
 
 // ---------------------------------------------------------------- FFT configuration
-template <int NC> struct FftCfg;
-template <> struct FftCfg<256>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 4;  };
-template <> struct FftCfg<512>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 8;  };
-template <> struct FftCfg<1024> { static constexpr int R1 = 32, R2 = 32, R3 = 1;  };
-template <> struct FftCfg<2048> { static constexpr int R1 = 16, R2 = 16, R3 = 8;  };
-template <> struct FftCfg<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16; };
+template <class T, int NC> struct FftCfg;
+template <class T> struct FftCfg<T, 256>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 4;  };
+template <class T> struct FftCfg<T, 512>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 8;  };
+template <> struct FftCfg<float, 1024>    { static constexpr int R1 = 32, R2 = 32, R3 = 1;  };
+template <> struct FftCfg<double, 1024>   { static constexpr int R1 = 16, R2 = 8,  R3 = 8;  };  // 32 double2 would spill
+template <class T> struct FftCfg<T, 2048> { static constexpr int R1 = 16, R2 = 16, R3 = 8;  };
+template <class T> struct FftCfg<T, 4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16; };
 
 // one pad slot per 32 complex values keeps the stride-32 accesses of the 32x32 plan
 // conflict-free (stride 33); slot 32 is never produced by pidx() and holds the Nyquist bin.
@@ -39,9 +40,9 @@ constexpr int QD_NYQ_SLOT = 32;
 template <int NC> constexpr int buf_slots() { return NC + NC / 32; }
 
 // position of spectrum bin k (0..NC) inside the warp buffer after the in-place DIF passes
-template <int NC>
+template <class T, int NC>
 QD_DEV int spos(int k) {
-    using C = FftCfg<NC>;
+    using C = FftCfg<T, NC>;
     if (k >= NC) return QD_NYQ_SLOT;
     const int k1 = k & (C::R1 - 1);
     const int k2 = (k / C::R1) & (C::R2 - 1);
@@ -51,16 +52,16 @@ QD_DEV int spos(int k) {
 
 // position of bin 32*row + lane.  For the 32x32 plan this is 33*lane + row for every bin including the
 // Nyquist bin (row 32, lane 0 -> slot 32), so row loops advance by one slot per row.
-template <int NC>
+template <class T, int NC>
 QD_DEV int rpos(int lane, int row) {
-    if constexpr (NC == 1024) return 33 * lane + row;
-    else return spos<NC>(32 * row + lane);
+    if constexpr (FftCfg<T, NC>::R1 == 32 && NC == 1024) return 33 * lane + row;
+    else return spos<T, NC>(32 * row + lane);
 }
 // position of the mirror bin NC - (32*row + lane), row < NC/64
-template <int NC>
+template <class T, int NC>
 QD_DEV int mpos(int lane, int row) {
-    if constexpr (NC == 1024) return lane == 0 ? 32 - row : 33 * (32 - lane) + 31 - row;
-    else return spos<NC>(NC - (32 * row + lane));
+    if constexpr (FftCfg<T, NC>::R1 == 32 && NC == 1024) return lane == 0 ? 32 - row : 33 * (32 - lane) + 31 - row;
+    else return spos<T, NC>(NC - (32 * row + lane));
 }
 
 // ---------------------------------------------------------------- device-side tables
@@ -96,7 +97,8 @@ struct FxDev {
     int clip_offset;        // index of the launch's first clip inside the per-clip table
 };
 
-struct SpecArgs {
+template <class T>
+struct SpecArgsT {
     const float *x;        // [batch, n] input clips
     float *y;              // [batch, n] output (after the epilogue)
     float *tap;            // optional [batch, n]: iSTFT output before the epilogue
@@ -106,18 +108,19 @@ struct SpecArgs {
     int quant;             // run the quantizer (else pure STFT -> iSTFT)
     int epilogue;          // 0 none, 1 wavefold, 2 tube
     float fold, bias, tube_gain, tube_norm;
-    const float2 *wtab;    // [NC] Hann window as pairs (w[2n], w[2n+1])
-    const float2 *tw1;     // access-ordered twiddles of pass 1 / pass 2 (see host builder)
-    const float2 *tw2;
-    const float2 *wsplit;  // [NC/2+1] exp(-2 pi i k / n_fft)
-    const float *invw;     // [16][hop]: 1/max(sum_{sl=a..b} w^2[sl*hop+c], 1e-10) at [(a*4+b)*hop + c]
+    const V2<T> *wtab;     // [NC] Hann window as pairs (w[2n], w[2n+1])
+    const V2<T> *tw1;      // access-ordered twiddles of pass 1 / pass 2 (see host builder)
+    const V2<T> *tw2;
+    const V2<T> *wsplit;   // [NC/2+1] exp(-2 pi i k / n_fft)
+    const T *invw;         // [16][hop]: 1/max(sum_{sl=a..b} w^2[sl*hop+c], 1e-10) at [(a*4+b)*hop + c]
     QuantDev q;
     FxDev fx;
 };
+using SpecArgs = SpecArgsT<float>;
 
 // ---------------------------------------------------------------- FFT passes (warp level)
-template <int NC, int M, int R, bool TW>
-QD_DEV void fwd_pass(float2 *buf, const float2 *tw, int lane) {
+template <class T, int NC, int M, int R, bool TW>
+QD_DEV void fwd_pass(V2<T> *buf, const V2<T> *tw, int lane) {
     constexpr int S = M / R;
     constexpr int NB = NC / R / 32;
     constexpr int LG = qd_log2(R);
@@ -125,14 +128,14 @@ QD_DEV void fwd_pass(float2 *buf, const float2 *tw, int lane) {
     for (int i = 0; i < NB; ++i) {
         const int u = lane + 32 * i;
         const int a0 = (u / S) * M + (u % S);
-        float2 v[R];
+        V2<T> v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = buf[pidx(a0 + q * S)];
-        dft_reg<R, -1>(v);
+        dft_reg<R, -1, T>(v);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int k = qd_bitrev(r, LG);
-            float2 t = v[r];
+            V2<T> t = v[r];
             if (TW && k > 0) t = cmul(t, tw[(i * R + k) * 32 + lane]);
             buf[pidx(a0 + k * S)] = t;
         }
@@ -140,8 +143,8 @@ QD_DEV void fwd_pass(float2 *buf, const float2 *tw, int lane) {
     __syncwarp();
 }
 
-template <int NC, int M, int R, bool TW>
-QD_DEV void inv_pass(float2 *buf, const float2 *tw, int lane) {
+template <class T, int NC, int M, int R, bool TW>
+QD_DEV void inv_pass(V2<T> *buf, const V2<T> *tw, int lane) {
     constexpr int S = M / R;
     constexpr int NB = NC / R / 32;
     constexpr int LG = qd_log2(R);
@@ -149,14 +152,14 @@ QD_DEV void inv_pass(float2 *buf, const float2 *tw, int lane) {
     for (int i = 0; i < NB; ++i) {
         const int u = lane + 32 * i;
         const int a0 = (u / S) * M + (u % S);
-        float2 v[R];
+        V2<T> v[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            float2 t = buf[pidx(a0 + k * S)];
+            V2<T> t = buf[pidx(a0 + k * S)];
             if (TW && k > 0) t = cmulc(t, tw[(i * R + k) * 32 + lane]);
             v[k] = t;
         }
-        dft_reg<R, +1>(v);
+        dft_reg<R, +1, T>(v);
 #pragma unroll
         for (int r = 0; r < R; ++r) buf[pidx(a0 + qd_bitrev(r, LG) * S)] = v[r];
     }
@@ -164,26 +167,26 @@ QD_DEV void inv_pass(float2 *buf, const float2 *tw, int lane) {
 }
 
 // first forward pass: reads the frame from the staging buffer, applies the analysis window
-template <int NC, int R>
-QD_DEV void fwd_first(float2 *buf, const float2 *frame, const float2 *wtab, const float2 *tw, int lane) {
+template <class T, int NC, int R>
+QD_DEV void fwd_first(V2<T> *buf, const float2 *frame, const V2<T> *wtab, const V2<T> *tw, int lane) {
     constexpr int S = NC / R;
     constexpr int NB = NC / R / 32;
     constexpr int LG = qd_log2(R);
 #pragma unroll 1
     for (int i = 0; i < NB; ++i) {
         const int a0 = lane + 32 * i;
-        float2 v[R];
+        V2<T> v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const float2 s = frame[a0 + q * S];
-            const float2 w = wtab[a0 + q * S];
-            v[q] = make_float2(s.x * w.x, s.y * w.y);
+            const V2<T> w = wtab[a0 + q * S];
+            v[q] = mk2<T>((T)s.x * w.x, (T)s.y * w.y);
         }
-        dft_reg<R, -1>(v);
+        dft_reg<R, -1, T>(v);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int k = qd_bitrev(r, LG);
-            float2 t = v[r];
+            V2<T> t = v[r];
             if (k > 0) t = cmul(t, tw[(i * R + k) * 32 + lane]);
             buf[pidx(a0 + k * S)] = t;
         }
@@ -192,80 +195,80 @@ QD_DEV void fwd_first(float2 *buf, const float2 *frame, const float2 *wtab, cons
 }
 
 // last inverse pass: synthesis window and 1/n_fft, leaves the time-domain frame in buf
-template <int NC, int R>
-QD_DEV void inv_last(float2 *buf, const float2 *wtab, const float2 *tw, int lane) {
+template <class T, int NC, int R>
+QD_DEV void inv_last(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw, int lane) {
     constexpr int S = NC / R;
     constexpr int NB = NC / R / 32;
     constexpr int LG = qd_log2(R);
-    const float scale = 1.0f / (float)(2 * NC);
+    const T scale = (T)1 / (T)(2 * NC);
 #pragma unroll 1
     for (int i = 0; i < NB; ++i) {
         const int a0 = lane + 32 * i;
-        float2 v[R];
+        V2<T> v[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            float2 t = buf[pidx(a0 + k * S)];
+            V2<T> t = buf[pidx(a0 + k * S)];
             if (k > 0) t = cmulc(t, tw[(i * R + k) * 32 + lane]);
             v[k] = t;
         }
-        dft_reg<R, +1>(v);
+        dft_reg<R, +1, T>(v);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int n = a0 + qd_bitrev(r, LG) * S;
-            const float2 w = wtab[n];
-            buf[pidx(n)] = make_float2(v[r].x * (w.x * scale), v[r].y * (w.y * scale));
+            const V2<T> w = wtab[n];
+            buf[pidx(n)] = mk2<T>(v[r].x * (w.x * scale), v[r].y * (w.y * scale));
         }
     }
     __syncwarp();
 }
 
-template <int NC>
-QD_DEV void fft_forward(float2 *buf, const float2 *frame, const SpecArgs &a, const float2 *wtab,
-                        const float2 *tw1, const float2 *tw2, int lane) {
-    using C = FftCfg<NC>;
-    fwd_first<NC, C::R1>(buf, frame, wtab, tw1, lane);
+template <class T, int NC>
+QD_DEV void fft_forward(V2<T> *buf, const float2 *frame, const SpecArgsT<T> &a, const V2<T> *wtab,
+                        const V2<T> *tw1, const V2<T> *tw2, int lane) {
+    using C = FftCfg<T, NC>;
+    fwd_first<T, NC, C::R1>(buf, frame, wtab, tw1, lane);
     if constexpr (C::R3 > 1) {
-        fwd_pass<NC, NC / C::R1, C::R2, true>(buf, tw2, lane);
-        fwd_pass<NC, C::R3, C::R3, false>(buf, nullptr, lane);
+        fwd_pass<T, NC, NC / C::R1, C::R2, true>(buf, tw2, lane);
+        fwd_pass<T, NC, C::R3, C::R3, false>(buf, nullptr, lane);
     } else {
-        fwd_pass<NC, NC / C::R1, C::R2, false>(buf, nullptr, lane);
+        fwd_pass<T, NC, NC / C::R1, C::R2, false>(buf, nullptr, lane);
     }
     (void)a;
 }
 
-template <int NC>
-QD_DEV void fft_inverse(float2 *buf, const float2 *wtab, const float2 *tw1, const float2 *tw2, int lane) {
-    using C = FftCfg<NC>;
+template <class T, int NC>
+QD_DEV void fft_inverse(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw1, const V2<T> *tw2, int lane) {
+    using C = FftCfg<T, NC>;
     if constexpr (C::R3 > 1) {
-        inv_pass<NC, C::R3, C::R3, false>(buf, nullptr, lane);
-        inv_pass<NC, NC / C::R1, C::R2, true>(buf, tw2, lane);
+        inv_pass<T, NC, C::R3, C::R3, false>(buf, nullptr, lane);
+        inv_pass<T, NC, NC / C::R1, C::R2, true>(buf, tw2, lane);
     } else {
-        inv_pass<NC, NC / C::R1, C::R2, false>(buf, nullptr, lane);
+        inv_pass<T, NC, NC / C::R1, C::R2, false>(buf, nullptr, lane);
     }
-    inv_last<NC, C::R1>(buf, wtab, tw1, lane);
+    inv_last<T, NC, C::R1>(buf, wtab, tw1, lane);
 }
 
 // ---------------------------------------------------------------- real <-> complex packing
 // Z = FFT_NC(x[2n] + i x[2n+1])  ->  X[k], k = 0..NC   (in place, Nyquist in the pad slot)
 //   E = (Z[k] + conj Z[NC-k]) / 2,  T = W_N^k (Z[k] - conj Z[NC-k]) / (2i)
 //   X[k] = E + T,  X[NC-k] = conj(E - T)
-template <int NC>
-QD_DEV void real_split(float2 *buf, const float2 *wsplit, int lane) {
+template <class T, int NC>
+QD_DEV void real_split(V2<T> *buf, const V2<T> *wsplit, int lane) {
 #pragma unroll 4
     for (int row = 0; row < NC / 64; ++row) {
         const int k = lane + 32 * row;
         if (k == 0) {
-            const float2 z0 = buf[0];
-            buf[0] = make_float2(z0.x + z0.y, 0.0f);
-            buf[QD_NYQ_SLOT] = make_float2(z0.x - z0.y, 0.0f);
-            const int pm = spos<NC>(NC / 2);
+            const V2<T> z0 = buf[0];
+            buf[0] = mk2<T>(z0.x + z0.y, 0.0f);
+            buf[QD_NYQ_SLOT] = mk2<T>(z0.x - z0.y, 0.0f);
+            const int pm = spos<T, NC>(NC / 2);
             buf[pm] = cconj(buf[pm]);
         } else {
-            const int pa = rpos<NC>(lane, row), pb = mpos<NC>(lane, row);
-            const float2 za = buf[pa], zb = buf[pb];
-            const float2 e = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
-            const float2 o = make_float2(0.5f * (za.y + zb.y), -0.5f * (za.x - zb.x));  // (za - conj zb)/(2i)
-            const float2 t = cmul(o, wsplit[k]);
+            const int pa = rpos<T, NC>(lane, row), pb = mpos<T, NC>(lane, row);
+            const V2<T> za = buf[pa], zb = buf[pb];
+            const V2<T> e = mk2<T>(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
+            const V2<T> o = mk2<T>(0.5f * (za.y + zb.y), -0.5f * (za.x - zb.x));  // (za - conj zb)/(2i)
+            const V2<T> t = cmul(o, wsplit[k]);
             buf[pa] = cadd(e, t);
             buf[pb] = cconj(csub(e, t));
         }
@@ -276,25 +279,25 @@ QD_DEV void real_split(float2 *buf, const float2 *wsplit, int lane) {
 // X'[k] (only Re of DC / Nyquist used, like pocketfft c2r) -> Z' with z = IFFT_NC(Z') * 1/(2 NC)
 //   E2 = X'[k] + conj X'[NC-k],  T2 = X'[k] - conj X'[NC-k],  O2 = conj(W_N^k) T2
 //   Z'[k] = E2 + i O2,  Z'[NC-k] = conj(E2 - i O2)
-template <int NC>
-QD_DEV void real_merge(float2 *buf, const float2 *wsplit, int lane) {
+template <class T, int NC>
+QD_DEV void real_merge(V2<T> *buf, const V2<T> *wsplit, int lane) {
 #pragma unroll 4
     for (int row = 0; row < NC / 64; ++row) {
         const int k = lane + 32 * row;
         if (k == 0) {
-            const float a = buf[0].x, b = buf[QD_NYQ_SLOT].x;
-            buf[0] = make_float2(a + b, a - b);
-            const int pm = spos<NC>(NC / 2);
-            const float2 xm = buf[pm];
-            buf[pm] = make_float2(2.0f * xm.x, -2.0f * xm.y);
+            const T a = buf[0].x, b = buf[QD_NYQ_SLOT].x;
+            buf[0] = mk2<T>(a + b, a - b);
+            const int pm = spos<T, NC>(NC / 2);
+            const V2<T> xm = buf[pm];
+            buf[pm] = mk2<T>(2.0f * xm.x, -2.0f * xm.y);
         } else {
-            const int pa = rpos<NC>(lane, row), pb = mpos<NC>(lane, row);
-            const float2 xa = buf[pa], xb = buf[pb];
-            const float2 e = make_float2(xa.x + xb.x, xa.y - xb.y);
-            const float2 t = make_float2(xa.x - xb.x, xa.y + xb.y);
-            const float2 o = cmulc(t, wsplit[k]);
-            buf[pa] = make_float2(e.x - o.y, e.y + o.x);   // E2 + i O2
-            buf[pb] = make_float2(e.x + o.y, o.x - e.y);   // conj(E2 - i O2)
+            const int pa = rpos<T, NC>(lane, row), pb = mpos<T, NC>(lane, row);
+            const V2<T> xa = buf[pa], xb = buf[pb];
+            const V2<T> e = mk2<T>(xa.x + xb.x, xa.y - xb.y);
+            const V2<T> t = mk2<T>(xa.x - xb.x, xa.y + xb.y);
+            const V2<T> o = cmulc(t, wsplit[k]);
+            buf[pa] = mk2<T>(e.x - o.y, e.y + o.x);   // E2 + i O2
+            buf[pb] = mk2<T>(e.x + o.y, o.x - e.y);   // conj(E2 - i O2)
         }
     }
     __syncwarp();
@@ -316,13 +319,15 @@ QD_DEV float rsqrt_fast(float x) {
     return r;
 #endif
 }
+QD_DEV double rsqrt_fast(double x) { return 1.0 / sqrt(x); }
 constexpr float QD_TINY2 = 1e-30f;  // |X|^2 below this is treated as an exact zero (|X| < 1e-15)
 
 // magnitude and unit phasor of one bin (np.angle(0) = 0 -> phasor 1)
-QD_DEV void mag_phasor(float2 xv, float &m, float2 &u) {
-    const float m2 = xv.x * xv.x + xv.y * xv.y;
+template <class T>
+QD_DEV void mag_phasor(V2<T> xv, T &m, V2<T> &u) {
+    const T m2 = xv.x * xv.x + xv.y * xv.y;
     const bool ok = m2 > QD_TINY2;
-    const float r = rsqrt_fast(m2);
+    const T r = rsqrt_fast(m2);
     m = ok ? m2 * r : 0.0f;
     u.x = ok ? xv.x * r : 1.0f;
     u.y = ok ? xv.y * r : 0.0f;
@@ -331,21 +336,24 @@ QD_DEV void mag_phasor(float2 xv, float &m, float2 &u) {
 // [1/4,1/2,1/4] smoothing of row `cur` with two shuffles: lane 31 lends its previous-row value to lane 0,
 // lane 0 lends its next-row value to lane 31 (nobody else needs those two lanes' own m_cur as a neighbour
 // on that side).
-QD_DEV float smooth_row(float m_prev, float m_cur, float m_next, int lane, bool first_bin, bool last_bin) {
-    float left = __shfl_sync(QD_FULL, lane == 31 ? m_prev : m_cur, (lane + 31) & 31);
-    float right = __shfl_sync(QD_FULL, lane == 0 ? m_next : m_cur, (lane + 1) & 31);
+template <class T>
+QD_DEV T smooth_row(T m_prev, T m_cur, T m_next, int lane, bool first_bin, bool last_bin) {
+    T left = __shfl_sync(QD_FULL, lane == 31 ? m_prev : m_cur, (lane + 31) & 31);
+    T right = __shfl_sync(QD_FULL, lane == 0 ? m_next : m_cur, (lane + 1) & 31);
     if (first_bin) left = m_cur;   // scipy convolve1d mode="nearest"
     if (last_bin) right = m_cur;
     return 0.5f * m_cur + 0.25f * (left + right);
 }
 
 // one bin of a row that may give energy away (active) or receive it (affected): new magnitude and phasor
-QD_DEV float warp_max(float v) {
+template <class T>
+QD_DEV T warp_max(T v) {
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v = fmaxf(v, __shfl_xor_sync(QD_FULL, v, d));
+    for (int d = 16; d >= 1; d >>= 1) v = qd_max(v, __shfl_xor_sync(QD_FULL, v, d));
     return v;
 }
-QD_DEV float warp_sum(float v) {
+template <class T>
+QD_DEV T warp_sum(T v) {
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(QD_FULL, v, d);
     return v;
@@ -354,21 +362,21 @@ QD_DEV float warp_sum(float v) {
 // Spectral FX on one frame (high band only).  On entry buf holds X; on exit buf holds the unit phasors and
 // mags[pos] the (processed) magnitudes, both indexed by buffer position, so that a bin whose magnitude
 // becomes 0 keeps its phase for the smoothing that follows.
-template <int NC>
-QD_DEV void fx_frame(float2 *buf, float *mags, const FxDev &fx, int lane, long long tab_base) {
+template <class T, int NC>
+QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long tab_base) {
     constexpr int NBINS = NC + 1;
     constexpr int ROWS = (NBINS + 31) / 32;
-    float mx = 0.0f, sm = 0.0f;
+    T mx = 0.0f, sm = 0.0f;
 #pragma unroll 4
     for (int row = 0; row < ROWS; ++row) {
         if (row < ROWS - 1 || lane == 0) {
-            const int p = rpos<NC>(lane, row);
-            float m;
-            float2 u;
-            mag_phasor(buf[p], m, u);
+            const int p = rpos<T, NC>(lane, row);
+            T m;
+            V2<T> u;
+            mag_phasor<T>(buf[p], m, u);
             buf[p] = u;
             mags[p] = m;
-            mx = fmaxf(mx, m);
+            mx = qd_max(mx, m);
             sm += m;
         }
     }
@@ -376,21 +384,21 @@ QD_DEV void fx_frame(float2 *buf, float *mags, const FxDev &fx, int lane, long l
     __syncwarp();
     if (fx.mode == 1 || fx.mode == 2) {
         // bitcrush (dsp/spectral_fx.py:198-260); np.round is half-to-even = rint
-        const float thr = fx.c > 0.0f ? fx.c : fx.b * mx;
+        const T thr = fx.c > 0.0f ? fx.c : fx.b * mx;
         for (int row = 0; row < ROWS; ++row) {
             if (row < ROWS - 1 || lane == 0) {
-                const int p = rpos<NC>(lane, row);
-                float m = mags[p];
+                const int p = rpos<T, NC>(lane, row);
+                T m = mags[p];
                 if (fx.step > 0.0) {
                     if (fx.mode == 1) {
-                        const float mm = fmaxf(m, 1e-12f);
-                        const float q = 20.0f * log10f(mm) / (float)fx.step;
-                        float rq = rintf(q);
-                        if (fabsf(fabsf(q - rq) - 0.5f) < 0.02f)  // close to a rounding boundary: decide in double
-                            rq = (float)rint(20.0 * log10((double)mm) / fx.step);
-                        m = QD_EXP10F((float)((double)rq * fx.step / 20.0));
+                        const T mm = qd_max(m, 1e-12f);
+                        const T q = 20.0f * qd_log10(mm) / (T)fx.step;
+                        T rq = qd_rint(q);
+                        if (qd_abs(qd_abs(q - rq) - 0.5f) < 0.02f)  // close to a rounding boundary: decide in double
+                            rq = (T)rint(20.0 * log10((double)mm) / fx.step);
+                        m = qd_exp10((T)((double)rq * fx.step / 20.0));
                     } else {
-                        m = fmaxf((float)(rint((double)m / fx.step) * fx.step), 0.0f);
+                        m = qd_max((T)(rint((double)m / fx.step) * fx.step), 0.0f);
                     }
                 }
                 if (thr > 0.0f && m < thr) m = 0.0f;
@@ -399,20 +407,20 @@ QD_DEV void fx_frame(float2 *buf, float *mags, const FxDev &fx, int lane, long l
         }
     } else if (fx.mode == 3) {
         // phase dispersal (dsp/spectral_fx.py:263-323)
-        const float thresh = fx.c >= 0.0f ? fx.c : 0.01f * mx;
-        const float inv_mx = 1.0f / (mx + 1e-12f);
+        const T thresh = fx.c >= 0.0f ? fx.c : 0.01f * mx;
+        const T inv_mx = 1.0f / (mx + 1e-12f);
         const float *jit = reinterpret_cast<const float *>(fx.table);
         for (int row = 0; row < ROWS; ++row) {
             if (row < ROWS - 1 || lane == 0) {
-                const int p = rpos<NC>(lane, row);
-                const float m = mags[p];
+                const int p = rpos<T, NC>(lane, row);
+                const T m = mags[p];
                 if (!(thresh > 0.0f) || m > thresh) {
-                    float rot = fx.a * (m * inv_mx);
-                    if (jit) rot += __ldg(jit + tab_base + 32 * row + lane) * fx.b;
-                    float sn, cs;
-                    QD_SINCOSF(rot, &sn, &cs);
-                    const float2 u = buf[p];
-                    buf[p] = make_float2(u.x * cs - u.y * sn, u.x * sn + u.y * cs);
+                    T rot = fx.a * (m * inv_mx);
+                    if (jit) rot += (T)__ldg(jit + tab_base + 32 * row + lane) * (T)fx.b;
+                    T sn, cs;
+                    qd_sincos(rot, &sn, &cs);
+                    const V2<T> u = buf[p];
+                    buf[p] = mk2<T>(u.x * cs - u.y * sn, u.x * sn + u.y * cs);
                 }
             }
         }
@@ -422,23 +430,23 @@ QD_DEV void fx_frame(float2 *buf, float *mags, const FxDev &fx, int lane, long l
         if constexpr (NC <= 2048) {
             sm = warp_sum(sm);
             const int16_t *idx = reinterpret_cast<const int16_t *>(fx.table);
-            float val[ROWS];
-            float s2 = 0.0f;
+            T val[ROWS];
+            T s2 = 0.0f;
 #pragma unroll
             for (int row = 0; row < ROWS; ++row) {
                 val[row] = 0.0f;
                 if (row < ROWS - 1 || lane == 0) {
                     const int src = idx ? (int)__ldg(idx + tab_base + 32 * row + lane) : 32 * row + lane;
-                    val[row] = mags[spos<NC>(src)];
+                    val[row] = mags[spos<T, NC>(src)];
                     s2 += val[row];
                 }
             }
             s2 = warp_sum(s2);
-            const float scale = sm / (s2 + 1e-12f);
+            const T scale = sm / (s2 + 1e-12f);
             __syncwarp();
 #pragma unroll
             for (int row = 0; row < ROWS; ++row)
-                if (row < ROWS - 1 || lane == 0) mags[rpos<NC>(lane, row)] = val[row] * scale;
+                if (row < ROWS - 1 || lane == 0) mags[rpos<T, NC>(lane, row)] = val[row] * scale;
         }
     }
     __syncwarp();
@@ -452,83 +460,83 @@ QD_DEV T tld(const T *p) {
 }
 
 // magnitude / phasor of a bin: from X, or (FX) from the separate magnitude plane
-template <bool FX>
-QD_DEV void load_bin(const float2 *buf, const float *mags, int p, float &m, float2 &u) {
+template <class T, bool FX>
+QD_DEV void load_bin(const V2<T> *buf, const T *mags, int p, T &m, V2<T> &u) {
     if constexpr (FX) { m = mags[p]; u = buf[p]; }
-    else mag_phasor(buf[p], m, u);
+    else mag_phasor<T>(buf[p], m, u);
 }
 
-template <int NC, bool TS, bool FX>
-QD_DEV void quant_bin(const float2 *buf, const float *mags, const float *slotG, const float2 *slotP,
-                      const QuantDev &q, int lane, int row, uint32_t bit, float &nm, float2 &u) {
-    float m;
-    load_bin<FX>(buf, mags, rpos<NC>(lane, row), m, u);
+template <class T, int NC, bool TS, bool FX>
+QD_DEV void quant_bin(const V2<T> *buf, const T *mags, const T *slotG, const V2<T> *slotP,
+                      const QuantDev &q, int lane, int row, uint32_t bit, T &nm, V2<T> &u) {
+    T m;
+    load_bin<T, FX>(buf, mags, rpos<T, NC>(lane, row), m, u);
     nm = (tld<TS>(q.row_active + row) & bit) ? m * q.keep_active : m;
     const uint32_t am = tld<TS>(q.row_aff + row);
     if (am & bit) {
         const AffEntry &ae = q.aff[tld<TS>(q.row_aff_base + row) + __popc(am & (bit - 1u))];
-        float te = 0.0f;
-        float2 ps = make_float2(0.0f, 0.0f);
+        T te = 0.0f;
+        V2<T> ps = mk2<T>(0.0f, 0.0f);
 #pragma unroll
         for (int e = 0; e < 5; ++e) {
             const int s = ae.slot[e];
-            const float c = ae.coef[e];
+            const T c = ae.coef[e];
             te += c * slotG[s];
-            const float2 pv = slotP[s];
+            const V2<T> pv = slotP[s];
             ps.x += c * pv.x;
             ps.y += c * pv.y;
         }
         nm += te;
         if (te > 0.0f) {
-            const float p2 = ps.x * ps.x + ps.y * ps.y;
+            const T p2 = ps.x * ps.x + ps.y * ps.y;
             const bool ok = p2 > QD_TINY2;
-            const float r = rsqrt_fast(p2);
-            u = make_float2(ok ? ps.x * r : 1.0f, ok ? ps.y * r : 0.0f);
+            const T r = rsqrt_fast(p2);
+            u = mk2<T>(ok ? ps.x * r : 1.0f, ok ? ps.y * r : 0.0f);
         }
     }
 }
 
-template <int NC, bool TS, bool FX>
-QD_DEV void quantize_frame(float2 *buf, const float *mags, float *slotG, float2 *slotP, const QuantDev &q, int lane) {
+template <class T, int NC, bool TS, bool FX>
+QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, const QuantDev &q, int lane) {
     // Q1: per-target gathers.  Sources are grouped by target slot; 32 of them are loaded per step and
     // summed with a segmented warp scan.  The segment structure is static, so the host stores, per
     // source, how many sources of the same slot precede it inside its step (`off`) and whether it is the
     // last one of its slot in the step (`tail`): no slot ids have to be shuffled.
     for (int s = lane; s <= q.n_slots; s += 32) {
         slotG[s] = 0.0f;
-        slotP[s] = make_float2(0.0f, 0.0f);
+        slotP[s] = mk2<T>(0.0f, 0.0f);
     }
     __syncwarp();
 #pragma unroll 1
     for (int i0 = 0; i0 < q.n_src; i0 += 32) {
         const int i = i0 + lane;
         uint32_t e = 0u;  // pos 0, slot 0, off 0, tail 0: a lane past the end adds nothing
-        float g = 0.0f;
-        float2 p = make_float2(0.0f, 0.0f);
+        T g = 0.0f;
+        V2<T> p = mk2<T>(0.0f, 0.0f);
         if (i < q.n_src) {
             e = tld<TS>(q.src_tab + i);
             p = buf[e & 0x1fffu];
             if constexpr (FX) {
                 g = mags[e & 0x1fffu];
-                p = make_float2(g * p.x, g * p.y);
+                p = mk2<T>(g * p.x, g * p.y);
             } else {
-                const float m2 = p.x * p.x + p.y * p.y;
+                const T m2 = p.x * p.x + p.y * p.y;
                 g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
             }
         }
         const int off = (int)((e >> 26) & 31u);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const float go = __shfl_up_sync(QD_FULL, g, d);
-            const float pxo = __shfl_up_sync(QD_FULL, p.x, d);
-            const float pyo = __shfl_up_sync(QD_FULL, p.y, d);
+            const T go = __shfl_up_sync(QD_FULL, g, d);
+            const T pxo = __shfl_up_sync(QD_FULL, p.x, d);
+            const T pyo = __shfl_up_sync(QD_FULL, p.y, d);
             if (off >= d) { g += go; p.x += pxo; p.y += pyo; }
         }
         if (e >> 31) {
             const int sid = (int)((e >> 13) & 0x1fffu);
             slotG[sid] += g;
-            const float2 t = slotP[sid];
-            slotP[sid] = make_float2(t.x + p.x, t.y + p.y);
+            const V2<T> t = slotP[sid];
+            slotP[sid] = mk2<T>(t.x + p.x, t.y + p.y);
         }
         __syncwarp();
     }
@@ -538,70 +546,70 @@ QD_DEV void quantize_frame(float2 *buf, const float *mags, float *slotG, float2 
     // smoothing, and run in a tight loop.
     constexpr int NBINS = NC + 1;
     constexpr int ROWS = (NBINS + 31) / 32;   // the last row holds only the Nyquist bin (lane 0)
-    float m_prev = 0.0f, m_cur = 0.0f, m_next = 0.0f;
-    float2 u_cur = make_float2(1.0f, 0.0f), u_next = make_float2(1.0f, 0.0f);
+    T m_prev = 0.0f, m_cur = 0.0f, m_next = 0.0f;
+    V2<T> u_cur = mk2<T>(1.0f, 0.0f), u_next = mk2<T>(1.0f, 0.0f);
     const uint32_t bit = 1u << lane;
     const bool smooth = q.smoothing != 0;
     const int row_limit = q.row_limit < ROWS - 1 ? q.row_limit : ROWS - 1;
     // ---- rows [0, row_limit): full logic
 #pragma unroll 1
     for (int row = 0; row < row_limit; ++row) {
-        quant_bin<NC, TS, FX>(buf, mags, slotG, slotP, q, lane, row, bit, m_next, u_next);
+        quant_bin<T, NC, TS, FX>(buf, mags, slotG, slotP, q, lane, row, bit, m_next, u_next);
         if (row > 0) {
-            const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
-            buf[rpos<NC>(lane, row - 1)] = make_float2(out * u_cur.x, out * u_cur.y);
+            const T out = smooth ? smooth_row<T>(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
+            buf[rpos<T, NC>(lane, row - 1)] = mk2<T>(out * u_cur.x, out * u_cur.y);
         }
         m_prev = m_cur; m_cur = m_next; u_cur = u_next;
     }
     // ---- rows [row_limit, ROWS-1): nothing moves, only the smoothing couples neighbours
 #pragma unroll 4
     for (int row = row_limit; row < ROWS - 1; ++row) {
-        load_bin<FX>(buf, mags, rpos<NC>(lane, row), m_next, u_next);
+        load_bin<T, FX>(buf, mags, rpos<T, NC>(lane, row), m_next, u_next);
         if (row > 0) {
-            const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
-            buf[rpos<NC>(lane, row - 1)] = make_float2(out * u_cur.x, out * u_cur.y);
+            const T out = smooth ? smooth_row<T>(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
+            buf[rpos<T, NC>(lane, row - 1)] = mk2<T>(out * u_cur.x, out * u_cur.y);
         }
         m_prev = m_cur; m_cur = m_next; u_cur = u_next;
     }
     // ---- Nyquist row (lane 0 only), then flush the last two rows
     {
         m_next = 0.0f;
-        u_next = make_float2(1.0f, 0.0f);
+        u_next = mk2<T>(1.0f, 0.0f);
         if (lane == 0) {
-            if (q.row_limit >= ROWS) quant_bin<NC, TS, FX>(buf, mags, slotG, slotP, q, 0, ROWS - 1, 1u, m_next, u_next);
-            else load_bin<FX>(buf, mags, rpos<NC>(0, ROWS - 1), m_next, u_next);
+            if (q.row_limit >= ROWS) quant_bin<T, NC, TS, FX>(buf, mags, slotG, slotP, q, 0, ROWS - 1, 1u, m_next, u_next);
+            else load_bin<T, FX>(buf, mags, rpos<T, NC>(0, ROWS - 1), m_next, u_next);
         }
-        const float out = smooth ? smooth_row(m_prev, m_cur, m_next, lane, ROWS == 2 && lane == 0, false) : m_cur;
-        buf[rpos<NC>(lane, ROWS - 2)] = make_float2(out * u_cur.x, out * u_cur.y);
+        const T out = smooth ? smooth_row<T>(m_prev, m_cur, m_next, lane, ROWS == 2 && lane == 0, false) : m_cur;
+        buf[rpos<T, NC>(lane, ROWS - 2)] = mk2<T>(out * u_cur.x, out * u_cur.y);
         m_prev = m_cur; m_cur = m_next; u_cur = u_next;
-        const float outn = smooth ? smooth_row(m_prev, m_cur, 0.0f, lane, false, lane == 0) : m_cur;
-        if (lane == 0) buf[rpos<NC>(0, ROWS - 1)] = make_float2(outn * u_cur.x, outn * u_cur.y);
+        const T outn = smooth ? smooth_row<T>(m_prev, m_cur, 0.0f, lane, false, lane == 0) : m_cur;
+        if (lane == 0) buf[rpos<T, NC>(0, ROWS - 1)] = mk2<T>(outn * u_cur.x, outn * u_cur.y);
     }
     __syncwarp();
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int NC, int NW>
+template <class T, int NC, int NW>
 struct SpecSmem {
     static constexpr int HOP = NC / 2;                       // n_fft / 4 samples
-    static constexpr int BUF = buf_slots<NC>();               // float2 per warp buffer
+    static constexpr int BUF = buf_slots<NC>();               // V2<T> per warp buffer
     static constexpr int STAGE = (NW + 3) * HOP;              // floats
     static constexpr int TAIL = 3 * HOP;                      // floats
     static constexpr size_t off_buf = 0;
-    static constexpr size_t off_stage = off_buf + (size_t)NW * BUF * sizeof(float2);
+    static constexpr size_t off_stage = off_buf + (size_t)NW * BUF * sizeof(V2<T>);
     static constexpr size_t off_tail = off_stage + (size_t)STAGE * sizeof(float);
-    static constexpr size_t off_flags = off_tail + (size_t)TAIL * sizeof(float);
+    static constexpr size_t off_flags = off_tail + (size_t)TAIL * sizeof(T);
     static constexpr size_t off_slot = off_flags + 64 * sizeof(int);
-    // per-warp gather scratch: G[cap] floats then P[cap] float2, cap even so P stays 8-byte aligned
+    // per-warp gather scratch: G[cap] floats then P[cap] V2<T>, cap even so P stays 8-byte aligned
     __host__ __device__ static int slot_cap(int n_slots) { return (n_slots + 2) & ~1; }
     __host__ __device__ static size_t off_tables(int n_slots) {
-        return (off_slot + (size_t)NW * (size_t)slot_cap(n_slots) * 3 * sizeof(float) + 15) & ~(size_t)15;
+        return (off_slot + (size_t)NW * (size_t)slot_cap(n_slots) * 3 * sizeof(T) + 15) & ~(size_t)15;
     }
     // shared-memory copies of the hot tables (TS kernels): window, pass-1 twiddles, split twiddles,
     // then the quantizer tables (gather list, row masks, affected-bin entries)
     static size_t table_bytes(int n_src, int n_aff) {
         const int rows = (NC + 1 + 31) / 32;
-        size_t b = (size_t)(NC + NC + NC / 2 + 2) * sizeof(float2);
+        size_t b = (size_t)(NC + NC + NC / 2 + 2) * sizeof(V2<T>);
         b += ((size_t)n_src * 4 + 15) & ~(size_t)15;
         b += ((size_t)rows * (4 + 4 + 2) + 15 + 16) & ~(size_t)15;
         b += (size_t)(n_aff > 0 ? n_aff : 1) * 32;
@@ -610,7 +618,7 @@ struct SpecSmem {
     static size_t bytes(int n_slots, bool tables_in_smem = false, int n_src = 0, int n_aff = 0, bool fx = false) {
         // FX kernels append one magnitude plane (BUF floats) per warp
         return off_tables(n_slots) + (tables_in_smem ? table_bytes(n_src, n_aff) : 16) +
-               (fx ? (size_t)NW * BUF * sizeof(float) : 0);
+               (fx ? (size_t)NW * BUF * sizeof(T) : 0);
     }
 };
 
@@ -627,23 +635,23 @@ QD_DEV float epilogue_apply(float v, int mode, float fold, float bias, float tg,
     return v;
 }
 
-template <int NC, int NW, bool TS = false, bool FX = false>
+template <class T, int NC, int NW, bool TS = false, bool FX = false>
 __global__ void __launch_bounds__(32 * NW)
-spec_pass_kernel(const SpecArgs a) {
-    using L = SpecSmem<NC, NW>;
+spec_pass_kernel(const SpecArgsT<T> a) {
+    using L = SpecSmem<T, NC, NW>;
     constexpr int HOP = L::HOP;
-    constexpr int HP = HOP / 2;              // float2 pairs per hop
+    constexpr int HP = HOP / 2;              // V2<T> pairs per hop
     constexpr int HPP = HP + HP / 32;        // the same span inside a padded warp buffer
     QD_DYN_SMEM(smem);
-    float2 *bufs = reinterpret_cast<float2 *>(smem + L::off_buf);
+    V2<T> *bufs = reinterpret_cast<V2<T> *>(smem + L::off_buf);
     float *stage = reinterpret_cast<float *>(smem + L::off_stage);
-    float2 *tail = reinterpret_cast<float2 *>(smem + L::off_tail);
+    V2<T> *tail = reinterpret_cast<V2<T> *>(smem + L::off_tail);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nthreads = 32 * NW;
-    float2 *buf = bufs + (size_t)warp * L::BUF;
+    V2<T> *buf = bufs + (size_t)warp * L::BUF;
     const int slot_cap = (a.q.n_slots + 2) & ~1;
-    float *slotG = reinterpret_cast<float *>(smem + L::off_slot) + (size_t)warp * slot_cap * 3;
-    float2 *slotP = reinterpret_cast<float2 *>(slotG + slot_cap);
+    T *slotG = reinterpret_cast<T *>(smem + L::off_slot) + (size_t)warp * slot_cap * 3;
+    V2<T> *slotP = reinterpret_cast<V2<T> *>(slotG + slot_cap);
 
     const int clip = blockIdx.y;
     const float *x = a.x + (size_t)clip * a.n;
@@ -661,15 +669,15 @@ spec_pass_kernel(const SpecArgs a) {
     if (j0 >= j1) return;
     const int t_first = j0 - 3;  // first frame that touches block j0 (may be < 0: skipped)
 
-    for (int i = tid; i < 3 * HP; i += nthreads) tail[i] = make_float2(0.0f, 0.0f);
+    for (int i = tid; i < 3 * HP; i += nthreads) tail[i] = mk2<T>(0.0f, 0.0f);
 
     // hot tables: read through L1/L2, or (TS) copied once per CTA into shared memory
-    const float2 *wtab = a.wtab, *tw1 = a.tw1, *wsplit = a.wsplit;
+    const V2<T> *wtab = a.wtab, *tw1 = a.tw1, *wsplit = a.wsplit;
     QuantDev qq = a.q;
     if constexpr (TS) {
-        float2 *t_w = reinterpret_cast<float2 *>(smem + L::off_tables(a.q.n_slots));
-        float2 *t_tw = t_w + NC;
-        float2 *t_ws = t_tw + NC;
+        V2<T> *t_w = reinterpret_cast<V2<T> *>(smem + L::off_tables(a.q.n_slots));
+        V2<T> *t_tw = t_w + NC;
+        V2<T> *t_ws = t_tw + NC;
         for (int i = tid; i < NC; i += nthreads) { t_w[i] = a.wtab[i]; t_tw[i] = a.tw1[i]; }
         for (int i = tid; i <= NC / 2; i += nthreads) t_ws[i] = a.wsplit[i];
         wtab = t_w; tw1 = t_tw; wsplit = t_ws;
@@ -716,40 +724,40 @@ spec_pass_kernel(const SpecArgs a) {
         const int t = tb + warp;
         if (t >= 0 && t < a.n_frames) {
             const float2 *frame = reinterpret_cast<const float2 *>(stage + warp * HOP);
-            fft_forward<NC>(buf, frame, a, wtab, tw1, a.tw2, lane);
-            real_split<NC>(buf, wsplit, lane);
+            fft_forward<T, NC>(buf, frame, a, wtab, tw1, a.tw2, lane);
+            real_split<T, NC>(buf, wsplit, lane);
             if (a.quant) {
                 if constexpr (FX) {
                     static_assert(!TS, "FX kernels read their tables through L1");
-                    float *mags = reinterpret_cast<float *>(smem + L::off_tables(a.q.n_slots) + 16) + (size_t)warp * L::BUF;
+                    T *mags = reinterpret_cast<T *>(smem + L::off_tables(a.q.n_slots) + 16) + (size_t)warp * L::BUF;
                     const int tf = t < a.fx.table_frames ? t : a.fx.table_frames - 1;
                     const long long tab_base =
                         (((long long)(a.fx.table_per_clip ? a.fx.clip_offset + clip : 0) * 2 + a.fx.pass) * a.fx.table_frames + tf) * (NC + 1);
-                    fx_frame<NC>(buf, mags, a.fx, lane, tab_base);
-                    quantize_frame<NC, TS, true>(buf, mags, slotG, slotP, qq, lane);
+                    fx_frame<T, NC>(buf, mags, a.fx, lane, tab_base);
+                    quantize_frame<T, NC, TS, true>(buf, mags, slotG, slotP, qq, lane);
                 } else {
-                    quantize_frame<NC, TS, false>(buf, nullptr, slotG, slotP, qq, lane);
+                    quantize_frame<T, NC, TS, false>(buf, nullptr, slotG, slotP, qq, lane);
                 }
             }
-            real_merge<NC>(buf, wsplit, lane);
-            fft_inverse<NC>(buf, wtab, tw1, a.tw2, lane);
+            real_merge<T, NC>(buf, wsplit, lane);
+            fft_inverse<T, NC>(buf, wtab, tw1, a.tw2, lane);
         } else {
-            for (int i = lane; i < L::BUF; i += 32) buf[i] = make_float2(0.0f, 0.0f);
+            for (int i = lane; i < L::BUF; i += 32) buf[i] = mk2<T>(0.0f, 0.0f);
         }
         __syncthreads();
         // ---- overlap-add in frame order; blocks tb .. tb+NW-1 are now complete.  A thread owns one
         //      column of sample pairs: slice sl of warp w's frame sits at bufs[w][sl*HPP + pidx(c)].
         for (int c = tid; c < HP; c += nthreads) {
             const int pc = pidx(c);
-            float2 carry[3];
+            V2<T> carry[3];
 #pragma unroll
             for (int g = 0; g < 3; ++g) carry[g] = tail[g * HP + c];
 #pragma unroll
             for (int h = 0; h < NW + 3; ++h) {
-                float2 v = (h < 3) ? carry[h] : make_float2(0.0f, 0.0f);
+                V2<T> v = (h < 3) ? carry[h] : mk2<T>(0.0f, 0.0f);
 #pragma unroll
                 for (int w = (h - 3 > 0 ? h - 3 : 0); w <= (h < NW - 1 ? h : NW - 1); ++w) {
-                    const float2 f = bufs[(size_t)w * L::BUF + (h - w) * HPP + pc];
+                    const V2<T> f = bufs[(size_t)w * L::BUF + (h - w) * HPP + pc];
                     v.x += f.x;
                     v.y += f.y;
                 }
@@ -764,9 +772,9 @@ spec_pass_kernel(const SpecArgs a) {
                 // frames covering block j: slices sl = j - t with t in [max(0,j-3), min(j,T-1)]
                 const int sl_a = j - a.n_frames + 1 > 0 ? j - a.n_frames + 1 : 0;
                 const int sl_b = j < 3 ? j : 3;
-                float2 inv = make_float2(0.0f, 0.0f);
-                if (sl_a <= sl_b) inv = __ldg(reinterpret_cast<const float2 *>(a.invw + (sl_a * 4 + sl_b) * HOP) + c);
-                const float2 o = make_float2(v.x * inv.x, v.y * inv.y);
+                V2<T> inv = mk2<T>(0.0f, 0.0f);
+                if (sl_a <= sl_b) inv = __ldg(reinterpret_cast<const V2<T> *>(a.invw + (sl_a * 4 + sl_b) * HOP) + c);
+                const float2 o = make_float2((float)(v.x * inv.x), (float)(v.y * inv.y));  // float32 like istft_mono
                 const float2 r = make_float2(epilogue_apply(o.x, a.epilogue, a.fold, a.bias, a.tube_gain, a.tube_norm),
                                              epilogue_apply(o.y, a.epilogue, a.fold, a.bias, a.tube_gain, a.tube_norm));
                 if (vec2) {  // nidx is even and n is even, so nidx + 1 < n

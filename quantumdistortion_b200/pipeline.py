@@ -192,6 +192,7 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
     trim_db = g("output_trim_db", 0.0)
     sub_cut, air_cut = g("sub_cut_hz", DEFAULT_SUB_CUT_HZ), g("air_cut_hz", DEFAULT_AIR_CUT_HZ)
     low_trim_db = g("low_trim_db", 0.0)
+    precision = g("precision", "auto")
     g("preview_enabled", None)
     for ignored in ("sub_enabled", "sub_source", "sub_note", "sub_scale_degree", "sub_octave", "sub_level", "air_mix"):
         kw.pop(ignored, None)  # autotune-only fields (config.py:80-89)
@@ -212,7 +213,7 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
                          passthrough_test=passthrough, harmonic_lock_hz=lock_hz, delta_listen=delta_listen,
                          mono_strength=mono_strength, output_trim_db=trim_db, low_trim_db=low_trim_db,
                          sub_cut_hz=sub_cut, air_cut_hz=air_cut, spectral_fx_mode=fx_mode,
-                         spectral_fx_strength=fx_strength, spectral_fx_params=fx_params)
+                         spectral_fx_strength=fx_strength, spectral_fx_params=fx_params, precision=precision)
     return res, {"fx_params": fx_params}
 
 
@@ -280,12 +281,13 @@ def process_audio(audio: np.ndarray, sr: int = DEFAULT_SAMPLE_RATE, key: str = D
                   sub_scale_degree: int = 0, sub_octave: int = 2, sub_level: float = 0.35,
                   sub_cut_hz: float = DEFAULT_SUB_CUT_HZ, air_cut_hz: float = DEFAULT_AIR_CUT_HZ,
                   air_mix: float = 1.0, *, pipeline_config: Optional[PipelineConfig] = None,
-                  n_fft: int = N_FFT_DEFAULT) -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
+                  n_fft: int = N_FFT_DEFAULT, precision: str = "auto") -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
     """Drop-in for the reference's ``process_audio`` on the STFT path (one clip).
 
     Same positional/keyword arguments and defaults as dsp/pipeline.py:1113-1155, except that
     ``quantize_mode`` defaults to "spectral_bins" (see config.py) and ``n_fft`` exposes the
-    reference's module global N_FFT_DEFAULT (:149).  Returns ``(float32[n], taps)`` with taps
+    reference's module global N_FFT_DEFAULT (:149); ``precision`` ("auto" | "float32" | "float64") selects the
+    arithmetic of the spectral pass (tables.choose_precision).  Returns ``(float32[n], taps)`` with taps
     ``input / pre_quant / post_dist / output`` (:1368, :1104-1109).
     """
     if preview_enabled is None and pipeline_config is not None:
@@ -310,7 +312,7 @@ def process_audio(audio: np.ndarray, sr: int = DEFAULT_SAMPLE_RATE, key: str = D
               spectral_fx_params=spectral_fx_params, config=config, spectral_freeze=spectral_freeze,
               formant_shift=formant_shift, harmonic_lock_hz=harmonic_lock_hz, delta_listen=delta_listen,
               mono_strength=mono_strength, output_trim_db=output_trim_db, sub_cut_hz=sub_cut_hz,
-              air_cut_hz=air_cut_hz, pipeline_config=pipeline_config)
+              air_cut_hz=air_cut_hz, pipeline_config=pipeline_config, precision=precision)
     tap_input = x.copy()
     if x.shape[0] == 0:
         _resolve_kwargs(0, int(sr), int(n_fft), dict(kw))  # argument validation only

@@ -240,6 +240,33 @@ def replay_fx_table(rng_kind, n_passes: int, n_frames: int, n_bins: int) -> np.n
     return out
 
 
+# ----------------------------------------------------------------------------- precision of the spectral pass
+F64_FAN_IN = 64   # more sources than this per target: their phasor sum can cancel below float32 resolution
+
+
+def max_fan_in(target_bins: Optional[np.ndarray], active_mask: Optional[np.ndarray]) -> int:
+    if target_bins is None or active_mask is None or not np.any(active_mask):
+        return 0
+    return int(np.max(np.bincount(np.asarray(target_bins)[np.asarray(active_mask, dtype=bool)])))
+
+
+def choose_precision(precision: str, n_fft: int, target_bins, active_mask) -> int:
+    """0 = float32 kernels, 1 = float64 kernels.  "auto" keeps the fast float32 path for the reference's
+    defaults and switches to float64 where float32 cannot hold the 1e-4 parity bound: n_fft 8192
+     and quantiser tables whose targets gather more than F64_FAN_IN source bins
+    (e.g. sub_cut_hz = air_cut_hz = 0), where the phase of a near-cancelling phasor sum is decided below
+    float32 resolution."""
+    if precision in ("float32", "f32", "fp32"):
+        return 0
+    if precision in ("float64", "f64", "fp64"):
+        return 1
+    if precision != "auto":
+        raise ValueError("precision must be 'auto', 'float32' or 'float64'")
+    if n_fft >= 8192:
+        return 1
+    return 1 if max_fan_in(target_bins, active_mask) > F64_FAN_IN else 0
+
+
 # ----------------------------------------------------------------------------- resolved render
 @dataclass
 class Resolved:
@@ -270,7 +297,7 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
             passthrough_test: bool, harmonic_lock_hz: float, delta_listen: bool, mono_strength: float,
             output_trim_db: float, low_trim_db: float, sub_cut_hz: float, air_cut_hz: float,
             spectral_fx_mode: Optional[str] = None, spectral_fx_strength: float = 0.0,
-            spectral_fx_params: Optional[Dict[str, Any]] = None) -> Resolved:
+            spectral_fx_params: Optional[Dict[str, Any]] = None, precision: str = "auto") -> Resolved:
     """Turn the reference's keyword arguments into qd_params / qd_tables.  Raises the reference's
     exceptions (SURVEY.md section 8(b) "Errors") before anything is launched."""
     if n_fft not in SUPPORTED_N_FFT:
@@ -358,5 +385,6 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
     else:
         # still validate key / scale like the reference would on its first quantizer call
         pass
+    p.precision = choose_precision(precision, n_fft, tb, mask)
     return Resolved(params=p, tables=tables, keepalive=tuple(keep), target_bins=tb, active_mask=mask,
                     fx_rng=fx_rng, fx_passes=fx_passes, n_frames=n_frames, n_bins=n_fft // 2 + 1)

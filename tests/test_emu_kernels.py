@@ -29,7 +29,7 @@ def emu_spec():
 
 
 def run_emu(exe, x, sr, n_fft, nw, tile_blocks, quant, smoothing, snap, smear, epilogue=0, fold=1.0,
-            bias=0.0, tg=1.0, tn=1.0, key="D", scale="minor", lo=110.0, hi=5000.0, fx=None):
+            bias=0.0, tg=1.0, tn=1.0, key="D", scale="minor", lo=110.0, hi=5000.0, fx=None, prec="f32"):
     freqs = np.fft.rfftfreq(n_fft, d=1.0 / sr)
     tb = orc.target_bins_for_freqs(freqs, key, scale).astype(np.int32)
     mask = orc.quantize_band_mask(freqs, lo, hi).astype(np.uint8)
@@ -38,7 +38,7 @@ def run_emu(exe, x, sr, n_fft, nw, tile_blocks, quant, smoothing, snap, smear, e
         x.astype(np.float32).tofile(p("x"))
         tb.tofile(p("tb"))
         mask.tofile(p("mask"))
-        cmd = [exe, str(n_fft), str(nw), str(len(x)), str(tile_blocks), str(int(quant)),
+        cmd = [exe, prec, str(n_fft), str(nw), str(len(x)), str(tile_blocks), str(int(quant)),
                str(int(smoothing)), repr(float(snap)), repr(float(smear)), str(epilogue),
                repr(float(fold)), repr(float(bias)), repr(float(tg)), repr(float(tn)),
                p("x"), p("tb"), p("mask"), p("y"), p("tap")]
@@ -160,3 +160,23 @@ def test_emu_spectral_fx_pass(emu_spec, mode, strength, seed):
     ref = orc.istft(Sq, sr, n_fft, length=n)
     err = float(np.max(np.abs(y - ref)))
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("n_fft,nw,n", [(2048, 4, 6000), (512, 4, 1500), (8192, 2, 17000)])
+def test_emu_float64_pass(emu_spec, n_fft, nw, n):
+    """The float64 instantiation of the same kernel source (parity path for ill-conditioned configurations)."""
+    x = synth.noise_clip(5, n)
+    y, _ = run_emu(emu_spec, x, 48000, n_fft, nw, 64, True, True, 1.0, 0.1, prec="f64")
+    ref = oracle_pass(x, 48000, n_fft, True, True, 1.0, 0.1)
+    assert float(np.max(np.abs(y - ref))) <= 6e-8
+
+
+def test_emu_float64_wide_mask_second_pass(emu_spec):
+    """The case float32 cannot do: wide-open band mask, pass 2 on the distorted pass-1 signal (near-cancelling
+    phasor sums with ~60 sources).  float64 reproduces the reference to float32 rounding."""
+    g = np.load(os.path.join(HERE, "golden", "pipeline.npz"))
+    xd = g["sb_wide_mask/post_dist"]
+    kw = dict(key="A", scale="pentatonic", lo=0.0, hi=0.0)
+    y64, _ = run_emu(emu_spec, xd, 48000, 2048, 4, 64, True, True, 1.0, 0.1, prec="f64", **kw)
+    ref = oracle_pass(xd, 48000, 2048, True, True, 1.0, 0.1, **kw)
+    assert float(np.max(np.abs(y64 - ref))) <= 2e-7

@@ -13,14 +13,10 @@ import qd_cases
 from oracle import qd_oracle as orc
 from quantumdistortion_b200 import synth
 
-pytestmark = pytest.mark.gpu
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MAX_ABS = 1e-4
 NULL_DB = -80.0
-# Ill-conditioned in float32: with the band mask wide open (sub_cut_hz = air_cut_hz = 0) a target near 21 kHz gathers
-# ~60 source bins whose phasors cancel to ~1e-5 of their sum, so the phase of the sum needs a float64 FFT.
-NEEDS_F64 = {"sb_wide_mask"}
 
 
 @pytest.fixture(scope="module")
@@ -49,22 +45,22 @@ def _check(got, ref, what, max_abs=MAX_ABS):
     return err
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", list(qd_cases.CASES))
 def test_pipeline_vs_reference_fixtures(qd, pipe, name):
     kind, seed, n, sr, n_fft, rng_seed, kw = qd_cases.CASES[name]
-    if name in NEEDS_F64:
-        pytest.xfail("needs the float64 spectral pass (DESIGN.md section 7)")
     x = pipe[f"{name}/x"]
     if rng_seed is not None:
         np.random.seed(rng_seed)  # the random spectral FX replay the global np.random state like the reference
     y, taps = qd.process_audio(x, sr, n_fft=n_fft, **kw)
-    tol = MAX_ABS if n_fft <= 4096 else 3e-4  # fp32 FFT at n_fft 8192: SURVEY.md 7.4 item 2
-    _check(y, pipe[f"{name}/y"], f"{name}/y", tol)
-    _check(taps["pre_quant"], pipe[f"{name}/pre_quant"], f"{name}/pre_quant", tol)
-    _check(taps["post_dist"], pipe[f"{name}/post_dist"], f"{name}/post_dist", tol)
+    # precision="auto": float32 kernels, except sb_wide_mask (fan-in > 64) and nfft8192, which run in float64
+    _check(y, pipe[f"{name}/y"], f"{name}/y")
+    _check(taps["pre_quant"], pipe[f"{name}/pre_quant"], f"{name}/pre_quant")
+    _check(taps["post_dist"], pipe[f"{name}/post_dist"], f"{name}/post_dist")
     assert np.array_equal(taps["input"], x) and np.array_equal(taps["output"], y)
 
 
+@pytest.mark.gpu
 def test_batch_vs_oracle_default_config(qd):
     """Config #2 shape (single-band defaults) on a small seeded batch, every clip against the oracle."""
     n, sr, b = 48000, 48000, 6
@@ -81,6 +77,7 @@ def test_batch_vs_oracle_default_config(qd):
     assert np.array_equal(y, y2)
 
 
+@pytest.mark.gpu
 def test_multiband_batch_vs_oracle(qd):
     n, sr = 30000, 48000
     x = np.stack([synth.loud_clip(40 + i, n, sr) for i in range(3)])
@@ -92,6 +89,7 @@ def test_multiband_batch_vs_oracle(qd):
         _check(taps["post_dist"][i], rt["post_dist"], f"mb clip {i} post_dist")
 
 
+@pytest.mark.gpu
 def test_tiling_and_batch_size_do_not_change_bits(qd):
     """A clip rendered alone (time-tiled over many CTAs) equals the same clip inside a large batch
     (whole-clip CTAs): overlap-add always sums frames in ascending order."""
@@ -104,6 +102,7 @@ def test_tiling_and_batch_size_do_not_change_bits(qd):
     assert torch.equal(y700[0], y1[0]) and torch.equal(y700[699], y1[0]) and torch.equal(y700[350], y1[0])
 
 
+@pytest.mark.gpu
 def test_full_size_properties(qd):
     """BASELINE config #2 clip length (480 000 samples): passthrough null, limiter ceiling, determinism."""
     import torch
@@ -126,6 +125,7 @@ def test_full_size_properties(qd):
     _check(y[3].cpu().numpy(), ref, "full-size clip")
 
 
+@pytest.mark.gpu
 def test_stage_limiter_and_crossover_and_distortion(qd):
     st = np.load(os.path.join(G, "stages.npz"))
     x = st["td/x"]
@@ -149,6 +149,7 @@ def test_stage_limiter_and_crossover_and_distortion(qd):
     assert np.max(np.abs(lo - rlo)) <= 2.4e-7 and np.max(np.abs(hi - rhi)) <= 2.4e-7
 
 
+@pytest.mark.gpu
 def test_edge_cases(qd):
     y, taps = qd.process_audio(np.zeros(0, dtype=np.float32), 48000)
     assert y.shape == (0,) and set(taps) == {"input", "pre_quant", "post_dist", "output"}
@@ -170,6 +171,7 @@ def test_edge_cases(qd):
     _check(y, ref, "stereo->mono")
 
 
+@pytest.mark.gpu
 def test_spectral_fx_batch_shared_and_per_clip_seeds(qd):
     """BASELINE config #4 shape: Growl preset + multiband + each FX; shared-seed batch and per-clip seeds."""
     n, sr = 20000, 48000
@@ -186,3 +188,24 @@ def test_spectral_fx_batch_shared_and_per_clip_seeds(qd):
             np.random.seed(5 + i)
             ref, _ = orc.process_audio(x[i], sr, **kw)
             _check(ys[i], ref, f"{mode} {s} per-clip clip {i}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sb_default_noise", "sb_growl", "mb_growl_bitcrush", "mb_growl_scramble_pick",
+                                  "nfft512", "nfft4096", "sb_ragged_len"])
+def test_float64_kernels_vs_reference_fixtures(qd, pipe, name):
+    """The float64 instantiation of the spectral pass: reference parity to float32 rounding of the output."""
+    kind, seed, n, sr, n_fft, rng_seed, kw = qd_cases.CASES[name]
+    if rng_seed is not None:
+        np.random.seed(rng_seed)
+    y, taps = qd.process_audio(pipe[f"{name}/x"], sr, n_fft=n_fft, precision="float64", **kw)
+    _check(y, pipe[f"{name}/y"], f"{name}/y f64", 2e-6)
+    _check(taps["pre_quant"], pipe[f"{name}/pre_quant"], f"{name}/pre_quant f64", 2e-6)
+
+
+def test_auto_precision_rule():
+    from quantumdistortion_b200.pipeline import _resolve_kwargs
+    assert _resolve_kwargs(1000, 48000, 2048, {})[0].params.precision == 0
+    assert _resolve_kwargs(1000, 48000, 8192, {})[0].params.precision == 1
+    assert _resolve_kwargs(1000, 48000, 2048, {"sub_cut_hz": 0.0, "air_cut_hz": 0.0})[0].params.precision == 1
+    assert _resolve_kwargs(1000, 48000, 2048, {"precision": "float64"})[0].params.precision == 1
