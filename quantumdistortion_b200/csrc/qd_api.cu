@@ -102,6 +102,7 @@ namespace {
 //      shared memory (falls back to 8 warps + L1 tables when they do not fit); float64 (parity path) and the
 //      FX variants read tables through L1.  Must stay in sync with the switch in dispatch_spec().
 template <class T> int pick_nw(int nc, bool fx) {
+    if (sizeof(T) == 8 && fx) return nc <= 512 ? 8 : nc == 1024 ? 4 : nc == 2048 ? 2 : 0;  // n_fft 8192: not built
     if (sizeof(T) == 8) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 2;
     if (fx) return nc <= 1024 ? 8 : 4;
     return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4;
@@ -119,8 +120,10 @@ size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int n_af
         case 512:  return nw == 8 ? smem_of<T, 512, 8>(n_slots, false, 0, 0, fx) : 0;
         case 1024:
             if (nw == 16) return smem_of<T, 1024, 16>(n_slots, ts, n_src, n_aff, fx);
-            return nw == 8 ? smem_of<T, 1024, 8>(n_slots, false, 0, 0, fx) : 0;
-        case 2048: return nw == 4 ? smem_of<T, 2048, 4>(n_slots, false, 0, 0, fx) : 0;
+            return nw == 8 ? smem_of<T, 1024, 8>(n_slots, false, 0, 0, fx)
+                 : nw == 4 ? smem_of<T, 1024, 4>(n_slots, false, 0, 0, fx) : 0;
+        case 2048: return nw == 4 ? smem_of<T, 2048, 4>(n_slots, false, 0, 0, fx)
+                        : nw == 2 ? smem_of<T, 2048, 2>(n_slots, false, 0, 0, fx) : 0;
         case 4096: return nw == 4 ? smem_of<T, 4096, 4>(n_slots, false, 0, 0, fx)
                         : nw == 2 ? smem_of<T, 4096, 2>(n_slots, false, 0, 0, fx) : 0;
     }
@@ -158,10 +161,14 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
             if constexpr (sizeof(T) == 4 && !FX) {
                 if (nw == 16 && ts) return launch_spec_t<T, 1024, 16, true, false>(a, tiles, batch, st);
             }
-            return launch_spec_t<T, 1024, 8, false, FX>(a, tiles, batch, st);
-        case 2048: return launch_spec_t<T, 2048, 4, false, FX>(a, tiles, batch, st);
+            if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 1024, 4, false, true>(a, tiles, batch, st);
+            else return launch_spec_t<T, 1024, 8, false, FX>(a, tiles, batch, st);
+        case 2048:
+            if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 2048, 2, false, true>(a, tiles, batch, st);
+            else return launch_spec_t<T, 2048, 4, false, FX>(a, tiles, batch, st);
         case 4096:
-            if constexpr (sizeof(T) == 8) return launch_spec_t<T, 4096, 2, false, FX>(a, tiles, batch, st);
+            if constexpr (sizeof(T) == 8 && FX) return fail(QD_ERR_UNSUPPORTED, "float64 spectral FX are not built for n_fft 8192");
+            else if constexpr (sizeof(T) == 8) return launch_spec_t<T, 4096, 2, false, false>(a, tiles, batch, st);
             else return launch_spec_t<T, 4096, 4, false, FX>(a, tiles, batch, st);
     }
     return fail(QD_ERR_UNSUPPORTED, "n_fft not supported");
@@ -180,7 +187,7 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
     a.fx.clip_offset = clip_offset;
     a.fx.table = pl->fx_table;
     // a pass that does not run the FX uses the plain kernel of the same warp count
-    const int nw = pl->nw;
+    const int nw = fx ? pl->nw : pick_nw<T>(pl->nc, false) == 16 && !pl->ts ? 8 : pick_nw<T>(pl->nc, false);
     const bool ts = pl->ts && !fx;
     // tiling: whole clips when the batch alone fills the GPU, else cut clips along time
     const int total_blocks = (a.n + pl->hop - 1) / pl->hop;

@@ -1,0 +1,60 @@
+"""Multi-GPU sharding of a batch of clips: one process per GPU, clips are independent units.
+
+There is NO collective on the data path: every rank renders its own contiguous
+slice of the batch with the same parameters; the only communication is the optional final gather of the
+finished clips to one rank (``torch.distributed.gather``: NCCL for CUDA tensors, gloo for CPU tensors).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of ``n_items`` over ``world`` ranks; the first ``n_items % world`` ranks get one extra."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank / world size")
+    base, rem = divmod(int(n_items), world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def render_sharded(x, render: Callable, *, gather_to: Optional[int] = 0, group=None):
+    """Render ``x[lo:hi]`` of the (replicated) batch ``x[B, n]`` on this rank with ``render(shard) -> shard_out``
+    and gather the results in rank order on ``gather_to`` (None: no gather, every rank keeps its shard).
+
+    Returns ``(out, (lo, hi))``: ``out`` is the full ``[B, n]`` result on rank ``gather_to``, the local shard's
+    result elsewhere (or everywhere when ``gather_to`` is None)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return render(x), (0, int(x.shape[0]))
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_bounds(int(x.shape[0]), rank, world)
+    y_local = render(x[lo:hi])
+    if gather_to is None:
+        return y_local, (lo, hi)
+    # ranks may hold one clip more or less: pad to the largest shard for the fixed-size gather
+    most = shard_bounds(int(x.shape[0]), 0, world)
+    most = most[1] - most[0]
+    padded = y_local
+    if hi - lo < most:
+        pad = torch.zeros((most - (hi - lo),) + tuple(y_local.shape[1:]), dtype=y_local.dtype, device=y_local.device)
+        padded = torch.cat([y_local, pad], dim=0)
+    padded = padded.contiguous()
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == gather_to else None
+    dist.gather(padded, bufs, dst=gather_to, group=group)
+    if rank != gather_to:
+        return y_local, (lo, hi)
+    parts = []
+    for r in range(world):
+        a, b = shard_bounds(int(x.shape[0]), r, world)
+        parts.append(bufs[r][: b - a])
+    return torch.cat(parts, dim=0), (lo, hi)
+
+
+def process_batch_sharded(x, sr: int = 48000, *, gather_to: Optional[int] = 0, **kwargs):
+    """``process_batch`` over the ranks of the default process group (one rank per GPU).  ``x`` is the same
+    CUDA (or CPU) ``[B, n]`` tensor on every rank; each rank renders only its slice."""
+    from .pipeline import process_batch
+    return render_sharded(x, lambda shard: process_batch(shard, sr, **kwargs)[0], gather_to=gather_to)

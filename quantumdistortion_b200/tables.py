@@ -250,7 +250,7 @@ def max_fan_in(target_bins: Optional[np.ndarray], active_mask: Optional[np.ndarr
     return int(np.max(np.bincount(np.asarray(target_bins)[np.asarray(active_mask, dtype=bool)])))
 
 
-def choose_precision(precision: str, n_fft: int, target_bins, active_mask) -> int:
+def choose_precision(precision: str, n_fft: int, target_bins, active_mask, fx_active: bool = False) -> int:
     """0 = float32 kernels, 1 = float64 kernels.  "auto" keeps the fast float32 path for the reference's
     defaults and switches to float64 where float32 cannot hold the 1e-4 parity bound: n_fft 8192
      and quantiser tables whose targets gather more than F64_FAN_IN source bins
@@ -263,7 +263,7 @@ def choose_precision(precision: str, n_fft: int, target_bins, active_mask) -> in
     if precision != "auto":
         raise ValueError("precision must be 'auto', 'float32' or 'float64'")
     if n_fft >= 8192:
-        return 1
+        return 0 if fx_active else 1   # the float64 FX kernels are not built for n_fft 8192
     return 1 if max_fan_in(target_bins, active_mask) > F64_FAN_IN else 0
 
 
@@ -385,6 +385,6 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
     else:
         # still validate key / scale like the reference would on its first quantizer call
         pass
-    p.precision = choose_precision(precision, n_fft, tb, mask)
+    p.precision = choose_precision(precision, n_fft, tb, mask, fx_active=bool(p.fx_mode))
     return Resolved(params=p, tables=tables, keepalive=tuple(keep), target_bins=tb, active_mask=mask,
                     fx_rng=fx_rng, fx_passes=fx_passes, n_frames=n_frames, n_bins=n_fft // 2 + 1)
