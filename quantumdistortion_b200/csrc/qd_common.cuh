@@ -57,6 +57,41 @@ QD_DEV double qd_exp10(double a) { return pow(10.0, a); }
 QD_DEV void qd_sincos(float a, float *s, float *c)    { QD_SINCOSF(a, s, c); }
 QD_DEV void qd_sincos(double a, double *s, double *c) { *s = sin(a); *c = cos(a); }
 
+// ---------------------------------------------------------------- TMA bulk copy + mbarrier (sm_90+)
+// One-dimensional cp.async.bulk global -> shared, completion signalled on an mbarrier with transaction
+// bytes.  The host emulation completes the copy synchronously and bumps a phase counter.
+#ifdef QD_EMU
+QD_DEV void mbar_init(uint64_t *bar, int) { *bar = 0; }
+QD_DEV void mbar_expect_tx(uint64_t *, uint32_t) {}
+QD_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    std::memcpy(dst, src, bytes);
+    __atomic_add_fetch(bar, 1, __ATOMIC_SEQ_CST);
+}
+QD_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while ((__atomic_load_n(bar, __ATOMIC_SEQ_CST) & 1u) == parity) std::this_thread::yield();
+}
+#else
+QD_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+QD_DEV void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+QD_DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+QD_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+QD_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+#endif
+
 // cos(2*pi*k/32), k = 0..8 (quarter wave); everything else by symmetry
 __host__ __device__ constexpr double qd_cos32_q(int k) {
     return k == 0 ? 1.0

@@ -4,10 +4,12 @@
 
 namespace qd_host {
 
+// double-buffered |x| (padded) and group maxima plus the per-warp scan totals of limiter_mix_kernel
 inline size_t limiter_smem_bytes(int lookahead) {
     const int span = 256 * 8 + lookahead + 8;
-    const size_t floats = (size_t)(span + (span >> 5)) + 8 + (size_t)(span / 8 + 2);
-    return floats * sizeof(float) + 16 + 16 * sizeof(double);
+    const size_t abs_stride = ((size_t)(span + (span >> 5)) + 8 + 3) & ~(size_t)3;
+    const size_t gmax_stride = ((size_t)(span / 8) + 2 + 3) & ~(size_t)3;
+    return 2 * (abs_stride + gmax_stride) * sizeof(float) + 16 + 2 * (8 + 2) * sizeof(double);
 }
 
 // A = [[-a1, 1], [-a2, 0]] is the DF2T state matrix of a section; apow[s][l] = A_s^(8 * 2^l)

@@ -222,11 +222,11 @@ QD_DEV void inv_last(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw, int lane) {
     __syncwarp();
 }
 
+// the forward passes AFTER fwd_first (which the kernel calls itself, to release the staging buffer early)
 template <class T, int NC>
 QD_DEV void fft_forward(V2<T> *buf, const float2 *frame, const SpecArgsT<T> &a, const V2<T> *wtab,
                         const V2<T> *tw1, const V2<T> *tw2, int lane) {
     using C = FftCfg<T, NC>;
-    fwd_first<T, NC, C::R1>(buf, frame, wtab, tw1, lane);
     if constexpr (C::R3 > 1) {
         fwd_pass<T, NC, NC / C::R1, C::R2, true>(buf, tw2, lane);
         fwd_pass<T, NC, C::R3, C::R3, false>(buf, nullptr, lane);
@@ -671,6 +671,20 @@ spec_pass_kernel(const SpecArgsT<T> a) {
 
     for (int i = tid; i < 3 * HP; i += nthreads) tail[i] = mk2<T>(0.0f, 0.0f);
 
+    // TMA staging: the samples of the NEXT batch of frames are fetched by one cp.async.bulk while this batch
+    // is still in its quantizer / inverse FFT; `full` (mbarrier, transaction bytes) says when they have landed,
+    // `consumed` counts the warps that are done reading the staging buffer of the current batch.
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::off_flags);
+    int *consumed = reinterpret_cast<int *>(smem + L::off_flags + 8);
+    if (tid == 0) {
+        mbar_init(full, 1);
+        *consumed = 0;
+    }
+    uint32_t full_parity = 0;
+    bool tma_pending = false;
+    constexpr uint32_t STAGE_BYTES = (uint32_t)(L::STAGE * sizeof(float));
+    __syncthreads();
+
     // hot tables: read through L1/L2, or (TS) copied once per CTA into shared memory
     const V2<T> *wtab = a.wtab, *tw1 = a.tw1, *wsplit = a.wsplit;
     QuantDev qq = a.q;
@@ -705,8 +719,13 @@ spec_pass_kernel(const SpecArgsT<T> a) {
 
     for (int tb = t_first; tb < j1; tb += NW) {
         // ---- stage the samples of frames tb .. tb+NW-1 (zero outside the clip)
-        {
-            const long long s0 = (long long)tb * HOP - NC;  // clip index of staging[0]
+        const long long s0 = (long long)tb * HOP - NC;  // clip index of staging[0]
+        const long long s0n = s0 + (long long)NW * HOP;  // the same for the next batch
+        const bool next_by_tma = vec4 && (tb + NW < j1) && s0n >= 0 && s0n + L::STAGE <= a.n;
+        if (tma_pending) {
+            mbar_wait(full, full_parity);  // bulk copy issued during the previous batch
+            full_parity ^= 1u;
+        } else {
             if (vec4 && s0 >= 0 && s0 + L::STAGE <= a.n) {
                 const float4 *src = reinterpret_cast<const float4 *>(x + s0);
                 float4 *dst = reinterpret_cast<float4 *>(stage);
@@ -718,13 +737,29 @@ spec_pass_kernel(const SpecArgsT<T> a) {
                     stage[i] = (s >= 0 && s < a.n) ? x[s] : 0.0f;
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
+        tma_pending = next_by_tma;
         // ---- one frame per warp (a frame outside the clip contributes zeros)
         const int t = tb + warp;
-        if (t >= 0 && t < a.n_frames) {
+        const bool live = t >= 0 && t < a.n_frames;
+        if (live) {
             const float2 *frame = reinterpret_cast<const float2 *>(stage + warp * HOP);
-            fft_forward<T, NC>(buf, frame, a, wtab, tw1, a.tw2, lane);
+            fwd_first<T, NC, FftCfg<T, NC>::R1>(buf, frame, wtab, tw1, lane);
+        }
+        // this warp no longer needs the staging buffer; the last warp to say so starts the next bulk copy
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(consumed, 1) == NW - 1) {
+                *consumed = 0;
+                if (next_by_tma) {
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    bulk_g2s(stage, x + s0n, STAGE_BYTES, full);
+                }
+            }
+        }
+        if (live) {
+            fft_forward<T, NC>(buf, nullptr, a, wtab, tw1, a.tw2, lane);
             real_split<T, NC>(buf, wsplit, lane);
             if (a.quant) {
                 if constexpr (FX) {

@@ -37,74 +37,131 @@ struct LimiterArgs {
     int apply_trim;
 };
 
-// dsp/limiter.py:14-80 then dsp/pipeline.py:894-910, 1096, 1371-1375
-__global__ void __launch_bounds__(QD_TT) limiter_mix_kernel(const LimiterArgs a) {
+// 8 consecutive samples of one clip starting at s (zero past the end); 2 x 16-byte loads when aligned
+QD_DEV void load8(const float *x, long long s, long long n, bool vec, float (&v)[QD_KS]) {
+    if (vec && s + QD_KS <= n) {
+        const float4 lo = *reinterpret_cast<const float4 *>(x + s);
+        const float4 hi = *reinterpret_cast<const float4 *>(x + s + 4);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+        v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < QD_KS; ++k) v[k] = (s + k < n) ? x[s + k] : 0.0f;
+    }
+}
+
+QD_DEV double limiter_e(float peak, double ceiling) {  // dsp/limiter.py:68-72
+    const double p = (double)peak;
+    return (p > ceiling && p > 1e-12) ? 1.0 - ceiling / p : 0.0;
+}
+
+// dsp/limiter.py:14-80 then dsp/pipeline.py:894-910, 1096, 1371-1375.
+// Streaming structure: a thread keeps its 8 samples of the current chunk and of the next one in registers
+// (the next chunk doubles as the lookahead) and prefetches the chunk after that, so no global-memory
+// latency sits on the per-chunk critical path; shared buffers are double-buffered by chunk parity, which
+// leaves two __syncthreads() per chunk.
+__global__ void __launch_bounds__(QD_TT, 3) limiter_mix_kernel(const LimiterArgs a) {
     QD_DYN_SMEM(smem);
-    float *s_abs = reinterpret_cast<float *>(smem);  // padded |x| for [chunk, chunk + CHUNK + L)
     const int L = a.lookahead;
-    const int span = QD_CHUNK + L + 8;
-    float *s_gmax = s_abs + padi(span) + 8;          // max of each group of KS samples
-    double *s_warp = reinterpret_cast<double *>(s_gmax + (span / QD_KS + 2));
-    s_warp = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_warp) + 7) & ~(uintptr_t)7);
+    const int span = QD_CHUNK + L + 8;                // |x| kept per chunk: the chunk and its lookahead
+    const int abs_stride = (padi(span) + 8 + 3) & ~3;
+    const int ngroups = span / QD_KS;
+    const int gmax_stride = (ngroups + 2 + 3) & ~3;
+    float *s_abs0 = reinterpret_cast<float *>(smem);
+    float *s_gmax0 = s_abs0 + 2 * abs_stride;
+    double *s_warp0 = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_gmax0 + 2 * gmax_stride) + 7) & ~(uintptr_t)7);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = QD_TT / 32;
     const size_t base = (size_t)blockIdx.x * (size_t)a.n;
     const float *x = a.x + base;
+    const bool vec = ((a.n & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+    const bool vec_out = ((a.n & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
+    const bool need_dry = a.apply_mix && a.dry_gain != 0.0f;
     const double c = a.c;
     double c_ks = 1.0;
 #pragma unroll
     for (int k = 0; k < QD_KS; ++k) c_ks *= c;
+    double c_32 = c_ks;  // c_ks^32
+#pragma unroll
+    for (int k = 0; k < 5; ++k) c_32 *= c_32;
+    double lanepow = 1.0;  // c_ks^lane
+    {
+        double p = c_ks;
+        int l = lane;
+        while (l) { if (l & 1) lanepow *= p; p *= p; l >>= 1; }
+    }
     double carry = 0.0;  // u at the end of the previous chunk
+    const int look_threads = (L + 8 + QD_KS - 1) / QD_KS;  // threads whose next-chunk samples are lookahead
+    const bool fast = a.limiter_on && L >= QD_KS && L + 8 <= QD_CHUNK;
 
-    for (long long n0 = 0; n0 < a.n; n0 += QD_CHUNK) {
-        float xv[QD_KS];
+    float cur[QD_KS], nxt[QD_KS], nn[QD_KS];
+    load8(x, (long long)tid * QD_KS, a.n, vec, cur);
+    load8(x, (long long)QD_CHUNK + (long long)tid * QD_KS, a.n, vec, nxt);
+    int par = 0;
+    for (long long n0 = 0; n0 < a.n; n0 += QD_CHUNK, par ^= 1) {
+        load8(x, n0 + 2LL * QD_CHUNK + (long long)tid * QD_KS, a.n, vec, nn);  // lands during this chunk
+        float *s_abs = s_abs0 + par * abs_stride;
+        float *s_gmax = s_gmax0 + par * gmax_stride;
+        double *s_warp = s_warp0 + par * (NWARP + 2);
         double u_in = 0.0;
-        double e[QD_KS];
+        float peak[QD_KS];
         if (a.limiter_on) {
-            // |x| for the chunk and its lookahead (zero past the end: the reference window is clipped)
-            for (int i = tid; i < span; i += QD_TT) {
-                const long long s = n0 + i;
-                s_abs[padi(i)] = s < a.n ? fabsf(x[s]) : 0.0f;
-            }
-            __syncthreads();
-            const int ngroups = span / QD_KS;
-            for (int g = tid; g < ngroups; g += QD_TT) {
+            // ---- |x| of the chunk and of its lookahead into shared memory, with per-group maxima
+            if (fast) {
                 float m = 0.0f;
 #pragma unroll
-                for (int k = 0; k < QD_KS; ++k) m = fmaxf(m, s_abs[padi(g * QD_KS + k)]);
-                s_gmax[g] = m;
-            }
-            __syncthreads();
-            // forward-window maxima of this thread's KS samples
-            float own[QD_KS];
+                for (int k = 0; k < QD_KS; ++k) {
+                    const float v = fabsf(cur[k]);
+                    s_abs[padi(tid * QD_KS + k)] = v;
+                    m = fmaxf(m, v);
+                }
+                s_gmax[tid] = m;
+                if (tid < look_threads) {
+                    float m2 = 0.0f;
 #pragma unroll
-            for (int k = 0; k < QD_KS; ++k) own[k] = s_abs[padi(tid * QD_KS + k)];
-            float peak[QD_KS];
+                    for (int k = 0; k < QD_KS; ++k) {
+                        const float v = fabsf(nxt[k]);
+                        s_abs[padi(QD_CHUNK + tid * QD_KS + k)] = v;
+                        m2 = fmaxf(m2, v);
+                    }
+                    s_gmax[QD_TT + tid] = m2;
+                }
+                __syncthreads();
+            } else {  // very short or very long lookahead: generic staging from global memory
+                for (int i = tid; i < span; i += QD_TT) {
+                    const long long s = n0 + i;
+                    s_abs[padi(i)] = s < a.n ? fabsf(x[s]) : 0.0f;
+                }
+                __syncthreads();
+                for (int g = tid; g < ngroups; g += QD_TT) {
+                    float m = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < QD_KS; ++k) m = fmaxf(m, s_abs[padi(g * QD_KS + k)]);
+                    s_gmax[g] = m;
+                }
+                __syncthreads();
+            }
+            // ---- forward-window maxima of this thread's KS samples
             if (L >= QD_KS) {
                 const int q = L / QD_KS, rem = L % QD_KS;
                 float mc = 0.0f;  // groups tid+1 .. tid+q-1 lie inside every window
                 for (int g = tid + 1; g < tid + q; ++g) mc = fmaxf(mc, s_gmax[g]);
-                float ga[QD_KS], gb[QD_KS];
-#pragma unroll
-                for (int k = 0; k < QD_KS; ++k) {
-                    ga[k] = s_abs[padi((tid + q) * QD_KS + k)];
-                    gb[k] = s_abs[padi((tid + q + 1) * QD_KS + k)];
-                }
                 float suf = 0.0f;
                 float sufv[QD_KS];
 #pragma unroll
-                for (int k = QD_KS - 1; k >= 0; --k) { suf = fmaxf(suf, own[k]); sufv[k] = suf; }
-                float pa[QD_KS + 1], pb[QD_KS + 1];  // prefix maxima of length j
-                pa[0] = 0.0f; pb[0] = 0.0f;
+                for (int k = QD_KS - 1; k >= 0; --k) { suf = fmaxf(suf, fabsf(cur[k])); sufv[k] = suf; }
+                // prefix maxima over the two groups after the common ones: pab[j] = max of their first j samples
+                float pab[2 * QD_KS + 1];
+                pab[0] = 0.0f;
 #pragma unroll
-                for (int k = 0; k < QD_KS; ++k) { pa[k + 1] = fmaxf(pa[k], ga[k]); pb[k + 1] = fmaxf(pb[k], gb[k]); }
+                for (int k = 0; k < 2 * QD_KS; ++k) pab[k + 1] = fmaxf(pab[k], s_abs[padi((tid + q) * QD_KS + k)]);
 #pragma unroll
                 for (int r = 0; r < QD_KS; ++r) {
-                    // window [8t+r, 8t+r+L): tail of own group, common groups, head of group t+q (+ t+q+1)
-                    float m = fmaxf(sufv[r], mc);
-                    const int t = r + rem;
-                    if (t < QD_KS) m = fmaxf(m, pa[t]);
-                    else m = fmaxf(m, fmaxf(pa[QD_KS], pb[t - QD_KS]));
-                    peak[r] = m;
+                    // window [8t+r, 8t+r+L): tail of own group, common groups, first r+rem samples after them
+                    float tailmax = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 2 * QD_KS; ++j) tailmax = (j == r + rem) ? pab[j] : tailmax;  // static indices only
+                    peak[r] = fmaxf(fmaxf(sufv[r], mc), tailmax);
                 }
             } else {
 #pragma unroll
@@ -114,19 +171,11 @@ __global__ void __launch_bounds__(QD_TT) limiter_mix_kernel(const LimiterArgs a)
                     peak[r] = m;
                 }
             }
-            // e_n = 1 - ceiling/peak where the limiter engages  (dsp/limiter.py:68-72)
-            double b = 0.0;
-#pragma unroll
-            for (int k = 0; k < QD_KS; ++k) {
-                const double p = (double)peak[k];
-                e[k] = (p > a.ceiling && p > 1e-12) ? 1.0 - a.ceiling / p : 0.0;
-            }
-            // local aggregate from the chunk carry (thread 0) or zero
+            // ---- local aggregate (from the chunk carry for thread 0), then scan across the CTA
             double u = (tid == 0) ? carry : 0.0;
 #pragma unroll
-            for (int k = 0; k < QD_KS; ++k) u = c * fmax(u, e[k]);
-            b = u;
-            // inclusive scan over threads: b_t = max(c_ks^d * b_{t-d}, b_t)
+            for (int k = 0; k < QD_KS; ++k) u = c * fmax(u, limiter_e(peak[k], a.ceiling));
+            double b = u;
             double apow = c_ks;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -135,56 +184,69 @@ __global__ void __launch_bounds__(QD_TT) limiter_mix_kernel(const LimiterArgs a)
                 apow *= apow;
             }
             if (lane == 31) s_warp[warp] = b;
-            __syncthreads();
-            // apow == c_ks^32 here: combine warp totals
-            double wprev = 0.0;  // aggregate of all warps before this one
-            {
-                double acc = 0.0;
-                for (int w = 0; w < warp; ++w) acc = fmax(apow * acc, s_warp[w]);
-                wprev = acc;
-            }
-            // exclusive value for this thread: aggregate of threads < tid
             double excl = __shfl_up_sync(QD_FULL, b, 1);
-            double lanepow = 1.0;  // c_ks^lane
-            {
-                double p = c_ks;
-                int l = lane;
-                while (l) { if (l & 1) lanepow *= p; p *= p; l >>= 1; }
-            }
             if (lane == 0) excl = 0.0;
-            u_in = fmax(lanepow * wprev, excl);
-            if (tid == 0) u_in = carry;
-            // chunk carry for the next iteration = inclusive value of the last thread
-            double total = fmax(apow * wprev, s_warp[warp]);  // valid in the last warp
             __syncthreads();
-            if (tid == QD_TT - 1) s_warp[0] = total;
-            __syncthreads();
-            carry = s_warp[0];
-            __syncthreads();
+            double acc = 0.0, wprev = 0.0;  // aggregates of the warps before this one / of all warps
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) {
+                if (w == warp) wprev = acc;
+                acc = fmax(c_32 * acc, s_warp[w]);
+            }
+            u_in = (tid == 0) ? carry : fmax(lanepow * wprev, excl);
+            carry = acc;  // inclusive value of the last thread = state entering the next chunk
         }
-        // apply: y = float32(x * g), mix, trim, recombine, delta
+        // ---- apply: y = float32(x * g), mix, trim, recombine, delta
         const long long s0 = n0 + (long long)tid * QD_KS;
+        float out[QD_KS];
         double u = u_in;
 #pragma unroll
         for (int k = 0; k < QD_KS; ++k) {
-            const long long s = s0 + k;
-            if (s >= a.n) break;
-            xv[k] = x[s];
-            float w = xv[k];
+            float w = cur[k];
             if (a.limiter_on) {
-                u = c * fmax(u, e[k]);
+                u = c * fmax(u, limiter_e(peak[k], a.ceiling));
                 double g = 1.0 - u;
                 g = fmin(fmax(g, 0.0), 1.0);
-                w = (float)((double)xv[k] * g);
+                w = (float)((double)cur[k] * g);
             }
-            if (a.apply_mix) {
-                w = __fadd_rn(__fmul_rn(a.wet, w), __fmul_rn(a.dry_gain, a.dry[base + s]));
-                if (a.apply_trim) w = __fmul_rn(w, a.trim);
-                if (a.low) w = __fadd_rn(a.low[base + s], w);
-                if (a.orig) w = __fsub_rn(a.orig[base + s], w);
-            }
-            a.y[base + s] = w;
+            out[k] = w;
         }
+        if (a.apply_mix) {
+            float t[QD_KS];
+            if (need_dry) {
+                load8(a.dry + base, s0, a.n, vec && ((reinterpret_cast<uintptr_t>(a.dry) & 15) == 0), t);
+#pragma unroll
+                for (int k = 0; k < QD_KS; ++k) out[k] = __fadd_rn(__fmul_rn(a.wet, out[k]), __fmul_rn(a.dry_gain, t[k]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < QD_KS; ++k) out[k] = __fadd_rn(__fmul_rn(a.wet, out[k]), 0.0f);  // (1-dw) * dry = 0
+            }
+            if (a.apply_trim) {
+#pragma unroll
+                for (int k = 0; k < QD_KS; ++k) out[k] = __fmul_rn(out[k], a.trim);
+            }
+            if (a.low) {
+                load8(a.low + base, s0, a.n, vec && ((reinterpret_cast<uintptr_t>(a.low) & 15) == 0), t);
+#pragma unroll
+                for (int k = 0; k < QD_KS; ++k) out[k] = __fadd_rn(t[k], out[k]);
+            }
+            if (a.orig) {
+                load8(a.orig + base, s0, a.n, vec && ((reinterpret_cast<uintptr_t>(a.orig) & 15) == 0), t);
+#pragma unroll
+                for (int k = 0; k < QD_KS; ++k) out[k] = __fsub_rn(t[k], out[k]);
+            }
+        }
+        float *yo = a.y + base;
+        if (vec_out && s0 + QD_KS <= a.n) {
+            *reinterpret_cast<float4 *>(yo + s0) = make_float4(out[0], out[1], out[2], out[3]);
+            *reinterpret_cast<float4 *>(yo + s0 + 4) = make_float4(out[4], out[5], out[6], out[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < QD_KS; ++k)
+                if (s0 + k < a.n) yo[s0 + k] = out[k];
+        }
+#pragma unroll
+        for (int k = 0; k < QD_KS; ++k) { cur[k] = nxt[k]; nxt[k] = nn[k]; }
     }
 }
 

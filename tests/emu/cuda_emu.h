@@ -143,6 +143,8 @@ static inline float __frcp_rn(float x) { return 1.0f / x; }
 static inline float __fdividef(float a, float b) { return a / b; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 using std::min;
 using std::max;
 static inline void sincospif(float x, float *s, float *c) {

@@ -73,7 +73,10 @@ def test_emu_passthrough(emu_spec, n_fft, nw, n, tile):
 
 
 @pytest.mark.parametrize("n_fft,nw,n,tile,snap,smear,smooth", [
-    (2048, 4, 6000, 64, 1.0, 0.1, True), (2048, 8, 5003, 4, 0.9, 0.3, True), (2048, 16, 9000, 64, 1.0, 0.1, True), (2048, 4, 4000, 64, 0.75, 0.0, False),
+    (2048, 4, 6000, 64, 1.0, 0.1, True), (2048, 8, 5003, 4, 0.9, 0.3, True), (2048, 16, 9000, 64, 1.0, 0.1, True),
+    (2048, 4, 24000, 64, 1.0, 0.1, True),   # long enough for interior batches: staged by the bulk-copy path
+    (2048, 4, 24000, 13, 1.0, 0.1, True),   # the same cut into tiles
+    (512, 4, 24002, 64, 1.0, 0.1, True),    # n % 4 != 0: bulk copies are never used (2048, 4, 4000, 64, 0.75, 0.0, False),
     (512, 4, 1500, 64, 1.0, 0.1, True), (1024, 4, 2100, 6, 1.0, 0.1, True), (4096, 4, 9000, 64, 1.0, 0.1, True)])
 def test_emu_quantized_pass(emu_spec, n_fft, nw, n, tile, snap, smear, smooth):
     x = synth.noise_clip(5, n)
