@@ -175,7 +175,9 @@ def run_ours(args):
 
     import quantumdistortion_b200 as qd
     from quantumdistortion_b200 import synth
+    from quantumdistortion_b200.distributed import bind_to_gpu_numa
 
+    numa_cpus = bind_to_gpu_numa(local)  # pinned host buffers below become node-local to this rank's GPU
     B = args.clips
     x = synth.bass_batch_torch(B, N_SAMPLES, SR, dev, seed=rank)  # each rank renders its own shard
     r = qd.make_renderer(N_SAMPLES, SR)  # reference defaults, quantize_mode="spectral_bins"
@@ -264,7 +266,7 @@ def run_ours(args):
     achieved = alg_bytes / (spec_ms / 1e3) / 1e9
     step_share = {k: v["ms"] / args.steps for k, v in timing.items() if v["launches"]}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "qd::spec_pass_kernel<1024,8>", "ms_per_launch": spec_ms,
+                "traffic": None, "kernel": "qd::spec_pass_kernel<float,1024,16,TS>", "ms_per_launch": spec_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_ms_per_step": step_share,
                 "note": "the pass is FP32-issue/shared-memory bound (about 600 flop per sample), not HBM bound; see DESIGN.md"}
@@ -294,6 +296,7 @@ def run_ours(args):
                    "l2": "inputs (7.9 GB per GPU) are far larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 4 * B * N_SAMPLES * world,
                 "d2h_bytes_per_step": 4 * B * N_SAMPLES * world, "chunk_clips": args.chunk_clips,
+                "host_numa_cpus": numa_cpus,
                 "api": "quantumdistortion_b200.process_batch(pinned host tensor, out=pinned host tensor)"},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
     }))

@@ -13,6 +13,12 @@ def __getattr__(name):  # lazy: importing the package must not need torch or a G
     if name in ("process_audio", "process_batch", "make_renderer", "Renderer", "RenderTiming"):
         from . import pipeline
         return getattr(pipeline, name)
+    if name in ("process_file_to_file", "process_files"):
+        from . import harness
+        return getattr(harness, name)
+    if name in ("load_audio", "save_audio"):
+        from . import audio_io
+        return getattr(audio_io, name)
     if name in ("peak_limiter", "linkwitz_riley_split", "apply_distortion"):
         from . import stages
         return getattr(stages, name)

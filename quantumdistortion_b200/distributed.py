@@ -58,3 +58,33 @@ def process_batch_sharded(x, sr: int = 48000, *, gather_to: Optional[int] = 0, *
     CUDA (or CPU) ``[B, n]`` tensor on every rank; each rank renders only its slice."""
     from .pipeline import process_batch
     return render_sharded(x, lambda shard: process_batch(shard, sr, **kwargs)[0], gather_to=gather_to)
+
+
+def bind_to_gpu_numa(device_index: int) -> Optional[str]:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs ``local_cpulist`` of its PCI
+    function), so that pinned host buffers allocated afterwards are node-local (first touch) and the
+    host<->device copies do not cross the socket interconnect.  Returns the cpulist used, or None when the
+    topology is not visible (containers without sysfs PCI nodes) -- in which case nothing is changed."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        dom = getattr(pr, "pci_domain_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        with open(path) as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpulist
+    except Exception:  # noqa: BLE001
+        return None

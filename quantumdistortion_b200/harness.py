@@ -1,0 +1,65 @@
+"""File-to-file front end (reference: quantum_distortion/dsp/harness.py:24-63), plus a batched variant that
+renders many files of equal length in one GPU call."""
+from __future__ import annotations
+
+from dataclasses import asdict
+from pathlib import Path
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .audio_io import load_audio, save_audio
+from .config import PipelineConfig, ensure_mono_float32
+
+
+def _config(preset: Optional[str], extra_params: Optional[Dict[str, Any]]) -> PipelineConfig:
+    cfg = PipelineConfig.from_preset(preset) if preset is not None else PipelineConfig()
+    if extra_params is not None:  # dsp/harness.py:56-60: unknown keys are ignored
+        known = asdict(cfg)
+        for k, v in extra_params.items():
+            if k in known:
+                setattr(cfg, k, v)
+    return cfg
+
+
+def process_file_to_file(infile: Path, outfile: Path, preset: Optional[str] = None,
+                         extra_params: Optional[Dict[str, Any]] = None) -> None:
+    """dsp/harness.py:24-63.  (This package's PipelineConfig defaults to the STFT path, see config.py.)"""
+    from .pipeline import process_audio
+    infile, outfile = Path(infile), Path(outfile)
+    if not infile.exists():
+        raise FileNotFoundError(f"Input file not found: {infile}")
+    audio, sr = load_audio(infile)
+    x = ensure_mono_float32(audio)
+    cfg = _config(preset, extra_params)
+    processed, _taps = process_audio(x, sr=sr, pipeline_config=cfg)
+    save_audio(outfile, processed, sr)
+
+
+def process_files(pairs: Iterable[Tuple[Path, Path]], preset: Optional[str] = None,
+                  extra_params: Optional[Dict[str, Any]] = None, seeds=None) -> int:
+    """Render many (infile, outfile) pairs with one parameter set.  Files sharing (length, sample rate) are
+    stacked and rendered as one batch (`process_batch`).  Returns the number of files written."""
+    from .pipeline import process_batch
+    cfg = _config(preset, extra_params)
+    groups: Dict[Tuple[int, int], List[Tuple[Path, np.ndarray]]] = {}
+    for infile, outfile in pairs:
+        infile = Path(infile)
+        if not infile.exists():
+            raise FileNotFoundError(f"Input file not found: {infile}")
+        audio, sr = load_audio(infile)
+        x = ensure_mono_float32(audio)
+        groups.setdefault((x.shape[0], sr), []).append((Path(outfile), x))
+    written = 0
+    for (n, sr), items in groups.items():
+        if n == 0:
+            for out, x in items:
+                save_audio(out, x, sr)
+                written += 1
+            continue
+        batch = np.stack([x for _, x in items])
+        y, _ = process_batch(batch, sr, pipeline_config=cfg, seeds=seeds)
+        for (out, _), row in zip(items, y):
+            save_audio(out, row, sr)
+            written += 1
+    return written

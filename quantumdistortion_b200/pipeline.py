@@ -164,14 +164,54 @@ def _renderer_for(resolved: tables.Resolved) -> Renderer:
     return r
 
 
+def _parse_ui_config(config: Dict[str, Any], kw: Dict[str, Any]) -> Dict[str, Any]:
+    """dsp/pipeline.py:923-1008: the Streamlit V2 UI dict -> keyword overrides.  A UI dict always means a
+    multiband render; in "high_band" the first non-zero of bin_scrambling / phase_dispersal / mag_decimation
+    (defaults 0.2 / 0.3 / 0.5) selects the single active spectral FX."""
+    out: Dict[str, Any] = {"use_multiband": True, "low_trim_db": 0.0}
+    if "quantization" in config:
+        q = config["quantization"]
+        out["key"] = str(q.get("key", kw.get("key", DEFAULT_KEY)))
+        out["scale"] = str(q.get("scale", kw.get("scale", DEFAULT_SCALE)))
+        out["quantize_mode"] = str(q.get("mode", kw.get("quantize_mode", DEFAULT_QUANTIZE_MODE)))
+        out["sub_cut_hz"] = float(q.get("sub_cut_hz", kw.get("sub_cut_hz", DEFAULT_SUB_CUT_HZ)))
+        out["air_cut_hz"] = float(q.get("air_cut_hz", kw.get("air_cut_hz", DEFAULT_AIR_CUT_HZ)))
+    if "crossover_freq" in config:
+        out["crossover_hz"] = float(config["crossover_freq"])
+    if "low_band" in config:
+        lb = config["low_band"]
+        out["lowband_drive"] = 1.0 + (lb.get("saturation_amount", 0.3) * 4.0)
+        out["mono_strength"] = float(lb.get("mono_strength", kw.get("mono_strength", 1.0)))
+        out["low_trim_db"] = float(lb.get("output_trim_db", 0.0))
+    if "high_band" in config:
+        hb = config["high_band"]
+        scr, dis, dec = hb.get("bin_scrambling", 0.2), hb.get("phase_dispersal", 0.3), hb.get("mag_decimation", 0.5)
+        if scr > 0.0:
+            out["spectral_fx_mode"], out["spectral_fx_strength"] = "bin_scramble", scr
+        elif dis > 0.0:
+            out["spectral_fx_mode"], out["spectral_fx_strength"] = "phase_dispersal", dis
+        elif dec > 0.0:
+            out["spectral_fx_mode"], out["spectral_fx_strength"] = "bitcrush", dec
+        out["output_trim_db"] = float(hb.get("output_trim_db", kw.get("output_trim_db", 0.0)))
+    if "quantum_fx" in config:
+        qf = config["quantum_fx"]
+        out["spectral_freeze"] = bool(qf.get("spectral_freeze", kw.get("spectral_freeze", False)))
+        out["formant_shift"] = float(qf.get("formant_shift", kw.get("formant_shift", 0.0)))
+        out["harmonic_lock_hz"] = float(qf.get("fundamental_hz", kw.get("harmonic_lock_hz", 0.0)))
+    if "delta_listen" in config:
+        out["delta_listen"] = bool(config["delta_listen"])
+    return out
+
+
 def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> Tuple[tables.Resolved, Dict[str, Any]]:
     """Apply the reference's argument rules (dsp/pipeline.py:1201-1327) and build the C structs."""
     pc = kw.pop("pipeline_config", None)
     if pc is not None:  # overrides every individual keyword (:1201-1238)
         for f in _PC_FIELDS:
             kw[f] = getattr(pc, f)
-    if kw.pop("config", None) is not None:
-        raise NotImplementedError("the Streamlit UI dict (config=) is outside the STFT hot path (SURVEY.md 8(f) rank 2)")
+    ui = kw.pop("config", None)
+    if ui is not None:  # Streamlit V2 nested dict: overrides a subset of the keywords (:1264-1300)
+        kw.update(_parse_ui_config(ui, kw))
     g = lambda k, d: kw.pop(k, d)  # noqa: E731
     key, scale = g("key", DEFAULT_KEY), g("scale", DEFAULT_SCALE)
     quantize_mode = g("quantize_mode", DEFAULT_QUANTIZE_MODE)

@@ -142,9 +142,21 @@ def gen_stages():
     print("stages:", len(out))
 
 
+def gen_frontend():
+    out = {}
+    for name, (kind, seed, n, sr, rng_seed, cfg, kw) in qd_cases.UI_CASES.items():
+        x = qd_cases.make_signal(kind, seed, n, sr)
+        np.random.seed(rng_seed)
+        y, taps = quiet(ref_pipeline.process_audio, x, sr, quantize_mode="spectral_bins", config=cfg, **kw)
+        out[f"{name}/x"], out[f"{name}/y"] = x, y
+        print(f"ui {name}: peak={np.max(np.abs(y)):.4f}")
+    np.savez_compressed(os.path.join(HERE, "frontend.npz"), **out)
+
+
 if __name__ == "__main__":
+    gen_frontend()
     gen_tables()
     gen_stages()
     gen_pipeline()
-    for f in ("tables.npz", "stages.npz", "pipeline.npz"):
+    for f in ("tables.npz", "stages.npz", "pipeline.npz", "frontend.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

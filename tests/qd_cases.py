@@ -78,3 +78,18 @@ def make_signal(kind: str, seed: int, n: int, sr: int):
     if kind == "loud":
         return signals.loud_clip(seed, n, sr)
     raise KeyError(kind)
+
+
+# Streamlit V2 UI dicts (dsp/pipeline.py:923-1008): name -> (kind, seed, n, sr, rng_seed, config dict, extra kwargs)
+UI_CASES = {
+    "ui_full": ("loud", 50, N, 48000, 77,
+                {"quantization": {"key": "E", "scale": "dorian", "sub_cut_hz": 90.0, "air_cut_hz": 6000.0},
+                 "crossover_freq": 250.0,
+                 "low_band": {"saturation_amount": 0.5, "mono_strength": 0.6, "output_trim_db": -1.5},
+                 "high_band": {"bin_scrambling": 0.0, "phase_dispersal": 0.45, "mag_decimation": 0.7, "output_trim_db": -2.0},
+                 "delta_listen": False}, {"snap_strength": 0.8}),
+    "ui_defaults_scramble": ("bass", 51, N, 48000, 78, {"high_band": {}, "quantum_fx": {"fundamental_hz": 0.0}}, {}),
+    "ui_bitcrush_delta": ("loud", 52, N, 48000, 79,
+                          {"high_band": {"bin_scrambling": 0.0, "phase_dispersal": 0.0, "mag_decimation": 0.6},
+                           "delta_listen": True}, {}),
+}

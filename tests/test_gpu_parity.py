@@ -209,3 +209,41 @@ def test_auto_precision_rule():
     assert _resolve_kwargs(1000, 48000, 8192, {})[0].params.precision == 1
     assert _resolve_kwargs(1000, 48000, 2048, {"sub_cut_hz": 0.0, "air_cut_hz": 0.0})[0].params.precision == 1
     assert _resolve_kwargs(1000, 48000, 2048, {"precision": "float64"})[0].params.precision == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(qd_cases.UI_CASES))
+def test_ui_config_dict_vs_reference_fixtures(qd, name):
+    """Streamlit V2 nested config dict (dsp/pipeline.py:923-1008) through process_audio(config=...)."""
+    g = np.load(os.path.join(G, "frontend.npz"))
+    kind, seed, n, sr, rng_seed, cfg, kw = qd_cases.UI_CASES[name]
+    np.random.seed(rng_seed)
+    y, _ = qd.process_audio(g[f"{name}/x"], sr, config=cfg, **kw)
+    _check(y, g[f"{name}/y"], name)
+
+
+@pytest.mark.gpu
+def test_file_harness_single_and_batched(qd, tmp_path):
+    """process_file_to_file / process_files (dsp/harness.py:24-63): WAV in -> GPU render -> PCM16 WAV out."""
+    from quantumdistortion_b200.audio_io import float_to_pcm16, load_audio, save_audio
+    sr = 44100
+    ins, outs = [], []
+    for i in range(3):
+        p = tmp_path / f"in{i}.wav"
+        save_audio(p, synth.bass_clip(80 + i, 22050 if i < 2 else 11025, sr), sr)
+        ins.append(p)
+        outs.append(tmp_path / "out" / f"o{i}.wav")
+    qd.process_file_to_file(ins[0], outs[0], preset="Perc To Tonal Clang", extra_params={"dry_wet": 0.8})
+    assert qd.process_files(list(zip(ins, outs))[1:], preset="Perc To Tonal Clang", extra_params={"dry_wet": 0.8}) == 2
+    from quantumdistortion_b200 import PipelineConfig
+    for i in range(3):
+        x, _ = load_audio(ins[i])
+        pc = PipelineConfig.from_preset("Perc To Tonal Clang")
+        kw = dict(key=pc.key, scale=pc.scale, snap_strength=pc.snap_strength, smear=pc.smear,
+                  distortion_mode=pc.distortion_mode, distortion_params=pc.distortion_params,
+                  limiter_ceiling_db=pc.limiter_ceiling_db, dry_wet=0.8)
+        ref, _ = orc.process_audio(x, sr, **kw)
+        got, sr2 = load_audio(outs[i])
+        assert sr2 == sr
+        lsb = np.abs(np.rint(got * 32768.0) - float_to_pcm16(ref).astype(np.float64))
+        assert lsb.max() <= 4, lsb.max()   # 1e-4 parity bound = 3.3 LSB of 16-bit PCM

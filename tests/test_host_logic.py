@@ -131,3 +131,36 @@ def test_params_struct_layout_matches_header():
         got = [int(v) for v in subprocess.check_output([exe]).split()]
     P = qlib.QdParams
     assert got == [ctypes.sizeof(P), P.ceiling_lin.offset, P.sos_low.offset, P.low_norm.offset, P.fx_a.offset]
+
+
+def test_ui_config_dict_mapping_matches_reference_rules():
+    from quantumdistortion_b200.pipeline import _parse_ui_config
+    out = _parse_ui_config({"high_band": {}}, {})
+    assert out["use_multiband"] is True and out["spectral_fx_mode"] == "bin_scramble" and out["spectral_fx_strength"] == 0.2
+    out = _parse_ui_config({"high_band": {"bin_scrambling": 0.0}}, {})
+    assert out["spectral_fx_mode"] == "phase_dispersal" and out["spectral_fx_strength"] == 0.3
+    out = _parse_ui_config({"high_band": {"bin_scrambling": 0.0, "phase_dispersal": 0.0, "output_trim_db": -3.0}}, {})
+    assert out["spectral_fx_mode"] == "bitcrush" and out["spectral_fx_strength"] == 0.5 and out["output_trim_db"] == -3.0
+    out = _parse_ui_config({"low_band": {"saturation_amount": 0.5}, "crossover_freq": 250}, {"mono_strength": 0.9})
+    assert out["lowband_drive"] == 3.0 and out["mono_strength"] == 0.9 and out["crossover_hz"] == 250.0
+    r, _ = _resolve_kwargs(12000, 48000, 2048, {"config": {"quantization": {"key": "E", "scale": "dorian"},
+                                                          "high_band": {"bin_scrambling": 0.0, "phase_dispersal": 0.0}}})
+    assert r.params.multiband == 1 and r.params.fx_mode == qlib.QD_FX["bitcrush_log"]
+
+
+def test_wav_io_roundtrip_and_pcm_rules(tmp_path):
+    from quantumdistortion_b200.audio_io import float_to_pcm16, load_audio, save_audio
+    x = np.array([0.0, 0.5, -0.5, 1.0, -1.0, 1.5, 0.25], dtype=np.float32)
+    pcm = float_to_pcm16(x)
+    assert list(pcm) == [0, 16384, -16384, 32767, -32767, 32767, 8192]   # lrint(x * 0x7FFF) half-to-even, clipped
+    p = tmp_path / "a" / "t.wav"
+    save_audio(p, x, 44100)
+    y, sr = load_audio(p)
+    assert sr == 44100 and y.dtype == np.float32 and np.array_equal(y, pcm.astype(np.float32) / 32768.0)
+    from quantumdistortion_b200 import harness
+    with pytest.raises(FileNotFoundError):
+        harness.process_file_to_file(tmp_path / "missing.wav", tmp_path / "o.wav")
+    cfg = harness._config("Subtle Tube Glue", {"dry_wet": 0.25, "not_a_field": 1})
+    assert cfg.dry_wet == 0.25 and cfg.distortion_mode == "tube" and not hasattr(cfg, "not_a_field")
+    with pytest.raises(KeyError):
+        harness._config("nope", None)
