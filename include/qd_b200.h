@@ -108,7 +108,7 @@ typedef struct qd_params {
     int32_t  precision;          /* QD_PRECISION_F32: float32 FFT/quantizer (fast path);
                                     QD_PRECISION_F64: the same kernels instantiated in float64 -- the parity path
                                     for ill-conditioned configurations (band mask wide open, n_fft 8192) */
-    int32_t  reserved0;
+    int32_t  spectral_freeze;    /* dsp/pipeline.py:285-287, 303-304: every frame takes the magnitudes of frame 0 */
 } qd_params;
 
 #define QD_PRECISION_F32 0

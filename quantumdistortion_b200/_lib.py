@@ -27,7 +27,7 @@ class QdParams(C.Structure):
         ("apply_mono_blend", C.c_int32),
         ("fx_mode", C.c_int32), ("fx_a", C.c_double), ("fx_b", C.c_double), ("fx_c", C.c_double),
         ("fx_table_frames", C.c_int32), ("fx_table_per_clip", C.c_int32),
-        ("precision", C.c_int32), ("reserved0", C.c_int32),
+        ("precision", C.c_int32), ("spectral_freeze", C.c_int32),
     ]
 
 

@@ -69,6 +69,7 @@ struct qd_plan {
     HostPipe pipe;
     int sm_count = 148;
     int clip_offset = 0;       // first clip of the current render inside a per-clip FX table
+    void *frozen_ws = nullptr; // slice of the render workspace: frame-0 magnitudes (spectral freeze)
     // optional per-kernel device timing (qd_plan_enable_timing)
     bool timing = false;
     struct Stamp { cudaEvent_t a, b; int cls; };
@@ -174,6 +175,32 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
     return fail(QD_ERR_UNSUPPORTED, "n_fft not supported");
 }
 
+template <class T, int NC>
+int launch_freeze_t(const qd::SpecArgsT<T> &a, T *out, int64_t batch, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = qd::freeze_mag_kernel<T, NC>;
+    const size_t smem = (size_t)qd::buf_slots<NC>() * sizeof(qd::V2<T>) + (size_t)2 * NC * sizeof(float) + 16;
+    if (!attr_set) {
+        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    kern<<<(unsigned)batch, 32, smem, st>>>(a, out);
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+template <class T>
+int launch_freeze(int nc, const qd::SpecArgsT<T> &a, T *out, int64_t batch, cudaStream_t st) {
+    switch (nc) {
+        case 256:  return launch_freeze_t<T, 256>(a, out, batch, st);
+        case 512:  return launch_freeze_t<T, 512>(a, out, batch, st);
+        case 1024: return launch_freeze_t<T, 1024>(a, out, batch, st);
+        case 2048: return launch_freeze_t<T, 2048>(a, out, batch, st);
+        case 4096: return launch_freeze_t<T, 4096>(a, out, batch, st);
+    }
+    return fail(QD_ERR_UNSUPPORTED, "n_fft not supported");
+}
+
 template <class T>
 int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *dst, float *tap, int quant,
                      int epilogue, int64_t batch, cudaStream_t st, int fx_pass, int clip_offset) {
@@ -182,7 +209,7 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
     a.tap = tap;
     a.quant = quant;
     a.epilogue = epilogue;
-    const bool fx = quant && pl->p.fx_mode != QD_FX_NONE;
+    const bool fx = quant && (pl->p.fx_mode != QD_FX_NONE || pl->p.spectral_freeze);
     a.fx.pass = fx_pass;
     a.fx.clip_offset = clip_offset;
     a.fx.table = pl->fx_table;
@@ -205,6 +232,14 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
     if (tile < 1) tile = 1;
     a.tile_blocks = tile;
     const int tiles = (total_blocks + tile - 1) / tile;
+    a.frozen = nullptr;
+    if (fx && pl->p.spectral_freeze) {
+        // frame-0 magnitudes of THIS pass's input (each quantised pass freezes its own first frame)
+        T *frozen = reinterpret_cast<T *>(pl->frozen_ws);
+        int rc = launch_freeze<T>(pl->nc, a, frozen, batch, st);
+        if (rc != QD_OK) return rc;
+        a.frozen = frozen;
+    }
     if (fx) return dispatch_spec<T, true>(pl->nc, nw, false, a, tiles, batch, st);
     return dispatch_spec<T, false>(pl->nc, nw, ts, a, tiles, batch, st);
 }
@@ -328,9 +363,9 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         qdev.smoothing = p.bin_smoothing ? 1 : 0;
         n_slots = qt.n_slots;
     }
-    const bool fx = need_quant && p.fx_mode != QD_FX_NONE;
+    const bool fx = need_quant && (p.fx_mode != QD_FX_NONE || p.spectral_freeze);
     qd::FxDev fxd{};
-    fxd.mode = fx ? p.fx_mode : 0;
+    fxd.mode = (need_quant && p.fx_mode != QD_FX_NONE) ? p.fx_mode : 0;
     fxd.a = (float)p.fx_a; fxd.b = (float)p.fx_b; fxd.c = (float)p.fx_c;
     fxd.step = p.fx_a;
     fxd.table_frames = p.fx_table_frames > 0 ? p.fx_table_frames : 1;
@@ -418,7 +453,8 @@ size_t qd_plan_workspace_bytes(const qd_plan *pl, int64_t batch) {
     if (!pl || batch <= 0) return 0;
     const size_t clip = (size_t)pl->p.n_samples * sizeof(float);
     const size_t bufs = pl->p.multiband ? 3 : 1;  // [x_dist] (+ [low][high])
-    return bufs * clip * (size_t)batch + 256;
+    const size_t frozen = pl->p.spectral_freeze ? (size_t)batch * (size_t)(pl->nc + pl->nc / 32) * sizeof(double) + 256 : 0;
+    return bufs * clip * (size_t)batch + 256 + frozen;
 }
 
 int qd_plan_launches_per_render(const qd_plan *pl) {
@@ -489,6 +525,7 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
     float *w_a = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     float *w_low = w_a + count;
     float *w_high = w_low + count;
+    pl->frozen_ws = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(w_a + (p.multiband ? 3 : 1) * count) + 255) & ~(uintptr_t)255);
     int rc;
 
     const float *src = x;   // what the single-band chain sees (dsp/pipeline.py:1076: the high band)

@@ -37,7 +37,7 @@ template <class T> struct FftCfg<T, 4096> { static constexpr int R1 = 16, R2 = 1
 // conflict-free (stride 33); slot 32 is never produced by pidx() and holds the Nyquist bin.
 QD_DEV int pidx(int a) { return a + (a >> 5); }
 constexpr int QD_NYQ_SLOT = 32;
-template <int NC> constexpr int buf_slots() { return NC + NC / 32; }
+template <int NC> __host__ __device__ constexpr int buf_slots() { return NC + NC / 32; }
 
 // position of spectrum bin k (0..NC) inside the warp buffer after the in-place DIF passes
 template <class T, int NC>
@@ -115,6 +115,7 @@ struct SpecArgsT {
     const T *invw;         // [16][hop]: 1/max(sum_{sl=a..b} w^2[sl*hop+c], 1e-10) at [(a*4+b)*hop + c]
     QuantDev q;
     FxDev fx;
+    const T *frozen;       // optional [batch][BUF]: |X| of frame 0 by buffer position (spectral freeze)
 };
 using SpecArgs = SpecArgsT<float>;
 
@@ -363,7 +364,7 @@ QD_DEV T warp_sum(T v) {
 // mags[pos] the (processed) magnitudes, both indexed by buffer position, so that a bin whose magnitude
 // becomes 0 keeps its phase for the smoothing that follows.
 template <class T, int NC>
-QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long tab_base) {
+QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long tab_base, const T *frozen) {
     constexpr int NBINS = NC + 1;
     constexpr int ROWS = (NBINS + 31) / 32;
     T mx = 0.0f, sm = 0.0f;
@@ -375,6 +376,7 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
             V2<T> u;
             mag_phasor<T>(buf[p], m, u);
             buf[p] = u;
+            if (frozen) m = frozen[p];  // dsp/pipeline.py:285-287, 303-304: first-frame magnitudes, own phases
             mags[p] = m;
             mx = qd_max(mx, m);
             sm += m;
@@ -768,7 +770,8 @@ spec_pass_kernel(const SpecArgsT<T> a) {
                     const int tf = t < a.fx.table_frames ? t : a.fx.table_frames - 1;
                     const long long tab_base =
                         (((long long)(a.fx.table_per_clip ? a.fx.clip_offset + clip : 0) * 2 + a.fx.pass) * a.fx.table_frames + tf) * (NC + 1);
-                    fx_frame<T, NC>(buf, mags, a.fx, lane, tab_base);
+                    fx_frame<T, NC>(buf, mags, a.fx, lane, tab_base,
+                                    a.frozen ? a.frozen + (size_t)clip * L::BUF : nullptr);
                     quantize_frame<T, NC, TS, true>(buf, mags, slotG, slotP, qq, lane);
                 } else {
                     quantize_frame<T, NC, TS, false>(buf, nullptr, slotG, slotP, qq, lane);
@@ -826,6 +829,34 @@ spec_pass_kernel(const SpecArgsT<T> a) {
             }
         }
         __syncthreads();
+    }
+}
+
+// |X| of frame 0 of every clip, by buffer position (input of the spectral-freeze variant of the pass).
+// One warp per clip; frame 0 = n_fft/2 zeros of centre padding followed by the first n_fft/2 samples.
+template <class T, int NC>
+__global__ void __launch_bounds__(32)
+freeze_mag_kernel(const SpecArgsT<T> a, T *out) {
+    constexpr int BUF = buf_slots<NC>();
+    QD_DYN_SMEM(smem);
+    V2<T> *buf = reinterpret_cast<V2<T> *>(smem);
+    float *stage = reinterpret_cast<float *>(smem + (size_t)BUF * sizeof(V2<T>));
+    const int lane = threadIdx.x;
+    const int clip = blockIdx.x;
+    const float *x = a.x + (size_t)clip * a.n;
+    for (int i = lane; i < 2 * NC; i += 32) {
+        const long long s = (long long)i - NC;
+        stage[i] = (s >= 0 && s < a.n) ? x[s] : 0.0f;
+    }
+    __syncwarp();
+    fwd_first<T, NC, FftCfg<T, NC>::R1>(buf, reinterpret_cast<const float2 *>(stage), a.wtab, a.tw1, lane);
+    fft_forward<T, NC>(buf, nullptr, a, a.wtab, a.tw1, a.tw2, lane);
+    real_split<T, NC>(buf, a.wsplit, lane);
+    T *o = out + (size_t)clip * BUF;
+    for (int p = lane; p < BUF; p += 32) {
+        const V2<T> v = buf[p];
+        const T m2 = v.x * v.x + v.y * v.y;
+        o[p] = m2 > (T)QD_TINY2 ? m2 * rsqrt_fast(m2) : (T)0;
     }
 }
 

@@ -297,7 +297,8 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
             passthrough_test: bool, harmonic_lock_hz: float, delta_listen: bool, mono_strength: float,
             output_trim_db: float, low_trim_db: float, sub_cut_hz: float, air_cut_hz: float,
             spectral_fx_mode: Optional[str] = None, spectral_fx_strength: float = 0.0,
-            spectral_fx_params: Optional[Dict[str, Any]] = None, precision: str = "auto") -> Resolved:
+            spectral_fx_params: Optional[Dict[str, Any]] = None, precision: str = "auto",
+            spectral_freeze: bool = False) -> Resolved:
     """Turn the reference's keyword arguments into qd_params / qd_tables.  Raises the reference's
     exceptions (SURVEY.md section 8(b) "Errors") before anything is launched."""
     if n_fft not in SUPPORTED_N_FFT:
@@ -385,6 +386,7 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
     else:
         # still validate key / scale like the reference would on its first quantizer call
         pass
-    p.precision = choose_precision(precision, n_fft, tb, mask, fx_active=bool(p.fx_mode))
+    p.spectral_freeze = int(bool(spectral_freeze) and quant_on)   # dsp/pipeline.py:285-287 (any band)
+    p.precision = choose_precision(precision, n_fft, tb, mask, fx_active=bool(p.fx_mode) or bool(p.spectral_freeze))
     return Resolved(params=p, tables=tables, keepalive=tuple(keep), target_bins=tb, active_mask=mask,
                     fx_rng=fx_rng, fx_passes=fx_passes, n_frames=n_frames, n_bins=n_fft // 2 + 1)

@@ -62,6 +62,10 @@ CASES = {
     "mb_growl_scramble_swap": ("bass", 27, N, 48000, 2048, 1234,
                                dict(GROWL, use_multiband=True, spectral_fx_mode="bin_scramble",
                                     spectral_fx_strength=0.3)),
+    "sb_freeze": ("bass", 28, N, 48000, 2048, None, {"spectral_freeze": True}),
+    "mb_freeze_bitcrush": ("loud", 29, N, 48000, 2048, 1234,
+                           dict(GROWL, use_multiband=True, spectral_freeze=True, spectral_fx_mode="bitcrush",
+                                spectral_fx_strength=0.5)),
     "nfft512": ("bass", 30, 6000, 48000, 512, None, {}),
     "nfft1024": ("bass", 31, 6000, 48000, 1024, None, {}),
     "nfft4096": ("bass", 32, N, 48000, 4096, None, {}),
