@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(QD_TT, 3) limiter_mix_kernel(const LimiterArgs
         double *s_warp = s_warp0 + par * (NWARP + 2);
         double u_in = 0.0;
         float peak[QD_KS];
+        bool lim_active = false;
         if (a.limiter_on) {
             // ---- |x| of the chunk and of its lookahead into shared memory, with per-group maxima
             if (fast) {
@@ -171,6 +172,18 @@ __global__ void __launch_bounds__(QD_TT, 3) limiter_mix_kernel(const LimiterArgs
                     peak[r] = m;
                 }
             }
+            // ---- nothing above the ceiling in this chunk and no release in progress: the gain is exactly 1
+            //      (dsp/limiter.py:68-76 leaves g = 1 - (1 - 1) * c = 1), so the float64 scan is skipped.
+            float pk = 0.0f;
+#pragma unroll
+            for (int k = 0; k < QD_KS; ++k) pk = fmaxf(pk, peak[k]);
+            // a release tail below 2^-54 no longer changes g = 1 - u in float64: treat it as finished
+            const int engaged = __syncthreads_or((double)pk > a.ceiling && pk > 1e-12f) || carry > 5e-17;
+            if (!engaged) {
+                carry = 0.0;
+#pragma unroll
+                for (int k = 0; k < QD_KS; ++k) peak[k] = 0.0f;  // e = 0 everywhere, u stays 0
+            } else {
             // ---- local aggregate (from the chunk carry for thread 0), then scan across the CTA
             double u = (tid == 0) ? carry : 0.0;
 #pragma unroll
@@ -195,6 +208,8 @@ __global__ void __launch_bounds__(QD_TT, 3) limiter_mix_kernel(const LimiterArgs
             }
             u_in = (tid == 0) ? carry : fmax(lanepow * wprev, excl);
             carry = acc;  // inclusive value of the last thread = state entering the next chunk
+            }
+            lim_active = engaged != 0;
         }
         // ---- apply: y = float32(x * g), mix, trim, recombine, delta
         const long long s0 = n0 + (long long)tid * QD_KS;
@@ -203,11 +218,9 @@ __global__ void __launch_bounds__(QD_TT, 3) limiter_mix_kernel(const LimiterArgs
 #pragma unroll
         for (int k = 0; k < QD_KS; ++k) {
             float w = cur[k];
-            if (a.limiter_on) {
-                u = c * fmax(u, limiter_e(peak[k], a.ceiling));
-                double g = 1.0 - u;
-                g = fmin(fmax(g, 0.0), 1.0);
-                w = (float)((double)cur[k] * g);
+            if (lim_active) {
+                u = c * fmax(u, limiter_e(peak[k], a.ceiling));  // 0 <= u < 1, so the reference's clip is a no-op
+                w = (float)((double)cur[k] * (1.0 - u));
             }
             out[k] = w;
         }

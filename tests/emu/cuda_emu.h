@@ -114,6 +114,20 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
 #define gridDim (qd_emu::g_blk->grid)
 
 static inline void __syncthreads() { pthread_barrier_wait(&qd_emu::g_blk->bar); }
+static inline int __syncthreads_or(int pred) {
+    static int flag[2];
+    static thread_local int phase = 0;
+    // blocks run one at a time; two alternating slots so a fast thread cannot clobber a slot still being read
+    int *f = &flag[phase & 1];
+    phase++;
+    pthread_barrier_wait(&qd_emu::g_blk->bar);
+    if (pred) __atomic_store_n(f, 1, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&qd_emu::g_blk->bar);
+    const int r = __atomic_load_n(f, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&qd_emu::g_blk->bar);
+    if (qd_emu::g_tid.x == 0) *f = 0;
+    return r;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) {
     pthread_barrier_wait(&qd_emu::g_blk->warp_bar[qd_emu::warp()]);
 }
