@@ -139,7 +139,7 @@ int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStrea
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const size_t smem = qd::SpecSmem<T, NC, NW>::bytes(a.q.n_slots, TS, a.q.n_src, a.q.n_aff, FX);
+    const size_t smem = qd::SpecSmem<T, NC, NW>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX);
     for (int64_t b0 = 0; b0 < batch; b0 += 65535) {  // gridDim.y limit
         const int64_t nb = std::min<int64_t>(65535, batch - b0);
         qd::SpecArgsT<T> c = a;
@@ -342,23 +342,23 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         qd_host::QuantTablesH qt;
         std::string err;
         if (!qd_host::build_quant_tables(*tables, &qt, &err, pl->f64)) return bail(QD_ERR_INVALID_ARG, err);
-        uint16_t *d_rab;
-        uint32_t *d_ra, *d_rf, *d_st;
-        qd_host::AffEntryH *d_aff;
+        uint16_t *d_sb;
+        uint32_t *d_ra, *d_st;
+        float *d_ik, *d_bs;
         QD_UP(qt.src_tab, d_st);
         QD_UP(qt.row_active, d_ra);
-        QD_UP(qt.row_aff, d_rf);
-        QD_UP(qt.row_aff_base, d_rab);
-        QD_UP(qt.aff, d_aff);
+        QD_UP(qt.slot_of_bin, d_sb);
+        QD_UP(qt.slot_invk, d_ik);
+        QD_UP(qt.slot_base, d_bs);
         qdev.n_slots = qt.n_slots;
-        qdev.n_aff = qt.n_aff;
         qdev.n_src = (int)qt.src_tab.size();
         qdev.row_limit = qt.row_limit;
         qdev.src_tab = d_st;
         qdev.row_active = d_ra;
-        qdev.row_aff = d_rf;
-        qdev.row_aff_base = d_rab;
-        qdev.aff = reinterpret_cast<const qd::AffEntry *>(d_aff);
+        qdev.slot_of_bin = d_sb;
+        qdev.slot_invk = d_ik;
+        qdev.slot_base = d_bs;
+        for (int e = 0; e < 5; ++e) qdev.tap[e] = qt.tap[e];
         qdev.keep_active = qt.keep_active;
         qdev.smoothing = p.bin_smoothing ? 1 : 0;
         n_slots = qt.n_slots;
@@ -393,7 +393,7 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         a.fx = fxd;
         pl->nw = pick_nw<double>(pl->nc, fx);
         pl->ts = false;
-        pl->spec_smem = spec_smem_bytes<double>(pl->nc, pl->nw, false, n_slots, qdev.n_src, qdev.n_aff, fx);
+        pl->spec_smem = spec_smem_bytes<double>(pl->nc, pl->nw, false, n_slots, qdev.n_src, 0, fx);
     } else {
         qd_host::F2 *d_wtab, *d_tw1, *d_tw2, *d_wsplit;
         float *d_invw;
@@ -415,11 +415,11 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         a.fx = fxd;
         pl->nw = pick_nw<float>(pl->nc, fx);
         pl->ts = (pl->nc == 1024 && pl->nw == 16);
-        pl->spec_smem = spec_smem_bytes<float>(pl->nc, pl->nw, pl->ts, n_slots, qdev.n_src, qdev.n_aff, fx);
+        pl->spec_smem = spec_smem_bytes<float>(pl->nc, pl->nw, pl->ts, n_slots, qdev.n_src, 0, fx);
         if (pl->ts && pl->spec_smem > 227 * 1024) {  // tables too large for shared memory: 8 warps, tables through L1
             pl->nw = 8;
             pl->ts = false;
-            pl->spec_smem = spec_smem_bytes<float>(pl->nc, 8, false, n_slots, qdev.n_src, qdev.n_aff, fx);
+            pl->spec_smem = spec_smem_bytes<float>(pl->nc, 8, false, n_slots, qdev.n_src, 0, fx);
         }
     }
 #undef QD_UP

@@ -18,13 +18,6 @@ template <class T> struct Pair;
 template <> struct Pair<float>  { using type = F2; };
 template <> struct Pair<double> { using type = D2; };
 
-struct AffEntryH {  // must match qd::AffEntry
-    int16_t slot[5];
-    int16_t pad;
-    float coef[5];
-};
-static_assert(sizeof(AffEntryH) == 32, "AffEntry layout");
-
 struct FftRadices { int r1, r2, r3; };
 // must mirror qd::FftCfg<T, NC>
 inline bool fft_radices(int nc, FftRadices *o, bool is_double = false) {
@@ -111,12 +104,14 @@ inline int host_spos(int nc, int k, bool is_double = false) {
 }
 
 struct QuantTablesH {
-    int n_bins = 0, n_slots = 0, n_aff = 0, rows = 0, row_limit = 0;
+    int n_bins = 0, n_slots = 0, rows = 0, row_limit = 0;
     std::vector<uint32_t> src_tab;  // tail<<31 | off<<26 | slot<<13 | buffer position, grouped by slot
-    std::vector<uint16_t> slot_begin, src_bin, row_aff_base;
+    std::vector<uint16_t> slot_begin, src_bin;
     std::vector<int32_t> slot_bin;
-    std::vector<uint32_t> row_active, row_aff;
-    std::vector<AffEntryH> aff;
+    std::vector<uint32_t> row_active;
+    std::vector<uint16_t> slot_of_bin;  // [32*rows + 4], entry d+2 = slot with target bin d, else n_slots
+    std::vector<float> slot_invk, slot_base;  // [n_slots + 1]
+    float tap[5] = {0, 0, 0, 0, 0};
     float keep_active = 1.0f;
 };
 
@@ -170,49 +165,34 @@ inline bool build_quant_tables(const qd_tables &in, QuantTablesH *q, std::string
     const double snap = in.snap, smear = in.smear;
     const bool do_smear = smear > 0.0 && radius > 0;  // dsp/quantizer.py:458
     q->keep_active = (float)(1.0 - snap);
-    q->row_aff.assign(q->rows, 0u);
-    q->row_aff_base.assign(q->rows, 0);
-    q->aff.clear();
-    for (int d = 0; d < n; ++d) {
-        AffEntryH e;
-        bool any = false;
-        for (int k = 0; k < 5; ++k) { e.slot[k] = (int16_t)q->n_slots; e.coef[k] = 0.0f; }
-        e.pad = 0;
-        for (int k = 0; k < 5; ++k) {
-            const int t = d + (k - 2);
-            if (t < 0 || t >= n || slot_of[t] < 0) continue;
-            double c = 0.0;
-            if (k == 2) c += snap * (1.0 - smear);  // base energy lands on the target itself (:437, :446)
-            const int o = d - t;                      // offset of d inside the target's smear window
-            if (do_smear && o >= -radius && o <= radius) {
-                // local kernel re-normalised over the part of [t-r, t+r] inside [0, n)  (:311-330)
-                const int a = std::max(0, t - radius), b = std::min(n, t + radius + 1);
-                const int k0 = std::max(0, radius - t);
-                double ksum = 0.0;
-                for (int qq = k0; qq < k0 + (b - a); ++qq) ksum += in.smear_w[qq];
-                if (ksum > 0.0) c += snap * smear * (in.smear_w[o + radius] / ksum);
-            }
-            if (c != 0.0) {
-                e.slot[k] = (int16_t)slot_of[t];
-                e.coef[k] = (float)c;
-                any = true;
-            }
-        }
-        if (any) {
-            q->row_aff[d >> 5] |= 1u << (d & 31);
-            q->aff.push_back(e);
-        }
+    // bin d receives from the target at bin t = d+e-2 the tap at offset o = d - t = 2 - e  (kernel index o + radius)
+    for (int e = 0; e < 5; ++e) {
+        const int o = 2 - e;
+        q->tap[e] = (do_smear && o >= -radius && o <= radius) ? (float)(snap * smear * in.smear_w[o + radius]) : 0.0f;
     }
-    q->n_aff = (int)q->aff.size();
+    q->slot_of_bin.assign((size_t)32 * q->rows + 4, (uint16_t)q->n_slots);
+    q->slot_invk.assign((size_t)q->n_slots + 1, 1.0f);
+    q->slot_base.assign((size_t)q->n_slots + 1, 0.0f);
     q->row_limit = 0;
     for (int r = 0; r < q->rows; ++r)
-        if (q->row_active[r] | q->row_aff[r]) q->row_limit = r + 1;
-    int run = 0;
-    for (int r = 0; r < q->rows; ++r) {
-        q->row_aff_base[r] = (uint16_t)run;
-        run += __builtin_popcount(q->row_aff[r]);
+        if (q->row_active[r]) q->row_limit = r + 1;
+    for (int s = 0; s < q->n_slots; ++s) {
+        const int t = q->slot_bin[s];
+        q->slot_of_bin[(size_t)t + 2] = (uint16_t)s;
+        // local kernel re-normalised over the part of [t-r, t+r] inside [0, n)  (dsp/quantizer.py:311-330)
+        double ksum = 1.0;
+        if (do_smear) {
+            const int a = std::max(0, t - radius), b = std::min(n, t + radius + 1);
+            const int k0 = std::max(0, radius - t);
+            ksum = 0.0;
+            for (int qq = k0; qq < k0 + (b - a); ++qq) ksum += in.smear_w[qq];
+            if (!(ksum > 0.0)) ksum = 1.0;
+        }
+        q->slot_invk[s] = (float)(1.0 / ksum);
+        q->slot_base[s] = (float)(snap * (1.0 - smear) * ksum);  // base energy lands on the target itself (:437, :446)
+        const int last_row = std::min(q->rows - 1, (std::min(n - 1, t + (do_smear ? radius : 0))) >> 5);
+        if (last_row + 1 > q->row_limit) q->row_limit = last_row + 1;
     }
-    if (q->aff.empty()) q->aff.push_back(AffEntryH{});
     return true;
 }
 

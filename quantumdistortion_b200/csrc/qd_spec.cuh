@@ -65,22 +65,20 @@ QD_DEV int mpos(int lane, int row) {
 }
 
 // ---------------------------------------------------------------- device-side tables
-struct AffEntry {          // one destination bin that can receive moved energy
-    int16_t slot[5];       // slot of the target at bin d-2..d+2 (n_slots = "none", reads 0)
-    int16_t pad;
-    float   coef[5];       // snap*smear*k_t(d-t) (+ snap*(1-smear) for the own target)
-};
-
+// Gather tables of the quantizer.  A destination bin d receives, from the target at bin d+e-2 (e = 0..4):
+//   tap[e] * H_slot   (smear, tap[e] = snap*smear*kernel[4-e])   and, for its own target (e = 2), base[slot] * H_slot
+// where H_slot = (sum over the slot's sources) / ksum_slot and base[slot] = snap*(1-smear)*ksum_slot; ksum is 1
+// except for targets whose 5-tap window is clipped at the spectrum edges (dsp/quantizer.py:311-330).
 struct QuantDev {
     int n_slots;                    // distinct target bins
-    int n_aff;
     int n_src;
-    int row_limit;                  // rows >= row_limit hold no source and no affected bin
+    int row_limit;                  // rows >= row_limit hold no source and no bin that can receive energy
     const uint32_t *src_tab;        // [n_src] tail<<31 | off<<26 | slot<<13 | buffer position, grouped by slot
     const uint32_t *row_active;     // [rows] bit l: bin 32*row+l gives its energy away
-    const uint32_t *row_aff;        // [rows] bit l: bin 32*row+l is in the affected list
-    const uint16_t *row_aff_base;   // [rows] affected bins before this row
-    const AffEntry *aff;            // [n_aff]
+    const uint16_t *slot_of_bin;    // [32*rows + 4]: entry d+2 = slot whose target is bin d, else n_slots (reads 0)
+    const float *slot_invk;         // [n_slots + 1]  1 / ksum_slot
+    const float *slot_base;         // [n_slots + 1]  snap*(1-smear)*ksum_slot (0 for the sentinel)
+    float tap[5];                   // see above
     float keep_active;              // 1 - snap
     int smoothing;                  // dsp/quantizer.py:523
 };
@@ -473,28 +471,28 @@ QD_DEV void quant_bin(const V2<T> *buf, const T *mags, const T *slotG, const V2<
                       const QuantDev &q, int lane, int row, uint32_t bit, T &nm, V2<T> &u) {
     T m;
     load_bin<T, FX>(buf, mags, rpos<T, NC>(lane, row), m, u);
-    nm = (tld<TS>(q.row_active + row) & bit) ? m * q.keep_active : m;
-    const uint32_t am = tld<TS>(q.row_aff + row);
-    if (am & bit) {
-        const AffEntry &ae = q.aff[tld<TS>(q.row_aff_base + row) + __popc(am & (bit - 1u))];
-        T te = 0.0f;
-        V2<T> ps = mk2<T>(0.0f, 0.0f);
+    nm = (tld<TS>(q.row_active + row) & bit) ? m * (T)q.keep_active : m;
+    // energy arriving from the (at most five) targets within two bins; non-targets read the zero sentinel
+    const uint16_t *sb = q.slot_of_bin + 32 * row + lane;
+    T te = (T)0;
+    V2<T> ps = mk2<T>((T)0, (T)0);
 #pragma unroll
-        for (int e = 0; e < 5; ++e) {
-            const int s = ae.slot[e];
-            const T c = ae.coef[e];
-            te += c * slotG[s];
-            const V2<T> pv = slotP[s];
-            ps.x += c * pv.x;
-            ps.y += c * pv.y;
-        }
-        nm += te;
-        if (te > 0.0f) {
-            const T p2 = ps.x * ps.x + ps.y * ps.y;
-            const bool ok = p2 > QD_TINY2;
-            const T r = rsqrt_fast(p2);
-            u = mk2<T>(ok ? ps.x * r : 1.0f, ok ? ps.y * r : 0.0f);
-        }
+    for (int e = 0; e < 5; ++e) {
+        const int s = tld<TS>(sb + e);
+        T c = (T)q.tap[e];
+        if (e == 2) c += (T)tld<TS>(q.slot_base + s);
+        const T g = slotG[s];
+        const V2<T> pv = slotP[s];
+        te += c * g;
+        ps.x += c * pv.x;
+        ps.y += c * pv.y;
+    }
+    nm += te;
+    if (te > (T)0) {
+        const T p2 = ps.x * ps.x + ps.y * ps.y;
+        const bool ok = p2 > (T)QD_TINY2;
+        const T r = rsqrt_fast(p2);
+        u = mk2<T>(ok ? ps.x * r : (T)1, ok ? ps.y * r : (T)0);
     }
 }
 
@@ -542,6 +540,14 @@ QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, co
         }
         __syncwarp();
     }
+
+    for (int sl = lane; sl < q.n_slots; sl += 32) {  // H = sum / ksum (ksum = 1 except at the spectrum edges)
+        const T ik = (T)tld<TS>(q.slot_invk + sl);
+        slotG[sl] *= ik;
+        const V2<T> t = slotP[sl];
+        slotP[sl] = mk2<T>(t.x * ik, t.y * ik);
+    }
+    __syncwarp();
 
     // Q3: rows of 32 bins with a rolling window of three rows for the smoothing.  Rows below
     // q.row_limit may give energy away or receive it; the rows above only need |X|, the phasor and the
@@ -609,17 +615,18 @@ struct SpecSmem {
     }
     // shared-memory copies of the hot tables (TS kernels): window, pass-1 twiddles, split twiddles,
     // then the quantizer tables (gather list, row masks, affected-bin entries)
-    static size_t table_bytes(int n_src, int n_aff) {
+    static size_t table_bytes(int n_src, int n_slots) {
         const int rows = (NC + 1 + 31) / 32;
         size_t b = (size_t)(NC + NC + NC / 2 + 2) * sizeof(V2<T>);
-        b += ((size_t)n_src * 4 + 15) & ~(size_t)15;
-        b += ((size_t)rows * (4 + 4 + 2) + 15 + 16) & ~(size_t)15;
-        b += (size_t)(n_aff > 0 ? n_aff : 1) * 32;
+        b += ((size_t)n_src * 4 + 15) & ~(size_t)15;                   // src_tab
+        b += ((size_t)rows * 4 + 15) & ~(size_t)15;                    // row_active
+        b += ((size_t)(32 * rows + 4) * 2 + 15) & ~(size_t)15;         // slot_of_bin
+        b += 2 * (((size_t)(n_slots + 1) * 4 + 15) & ~(size_t)15);     // slot_invk, slot_base
         return b + 64;
     }
-    static size_t bytes(int n_slots, bool tables_in_smem = false, int n_src = 0, int n_aff = 0, bool fx = false) {
-        // FX kernels append one magnitude plane (BUF floats) per warp
-        return off_tables(n_slots) + (tables_in_smem ? table_bytes(n_src, n_aff) : 16) +
+    static size_t bytes(int n_slots, bool tables_in_smem = false, int n_src = 0, int /*unused*/ = 0, bool fx = false) {
+        // FX kernels append one magnitude plane (BUF values of T) per warp
+        return off_tables(n_slots) + (tables_in_smem ? table_bytes(n_src, n_slots) : 16) +
                (fx ? (size_t)NW * BUF * sizeof(T) : 0);
     }
 };
@@ -703,18 +710,17 @@ spec_pass_kernel(const SpecArgsT<T> a) {
             uint32_t *s_src = reinterpret_cast<uint32_t *>(qb);
             qb += ((size_t)a.q.n_src * 4 + 15) & ~(size_t)15;
             uint32_t *s_ra = reinterpret_cast<uint32_t *>(qb);
-            uint32_t *s_rf = s_ra + ROWS;
-            uint16_t *s_rb = reinterpret_cast<uint16_t *>(s_rf + ROWS);
-            qb += ((size_t)ROWS * 10 + 15 + 16) & ~(size_t)15;
-            uint4 *s_aff = reinterpret_cast<uint4 *>(qb);
+            qb += ((size_t)ROWS * 4 + 15) & ~(size_t)15;
+            uint16_t *s_sb = reinterpret_cast<uint16_t *>(qb);
+            qb += ((size_t)(32 * ROWS + 4) * 2 + 15) & ~(size_t)15;
+            float *s_ik = reinterpret_cast<float *>(qb);
+            qb += ((size_t)(a.q.n_slots + 1) * 4 + 15) & ~(size_t)15;
+            float *s_bs = reinterpret_cast<float *>(qb);
             for (int i = tid; i < a.q.n_src; i += nthreads) s_src[i] = a.q.src_tab[i];
-            for (int i = tid; i < ROWS; i += nthreads) {
-                s_ra[i] = a.q.row_active[i]; s_rf[i] = a.q.row_aff[i]; s_rb[i] = a.q.row_aff_base[i];
-            }
-            const uint4 *g_aff = reinterpret_cast<const uint4 *>(a.q.aff);
-            for (int i = tid; i < 2 * a.q.n_aff; i += nthreads) s_aff[i] = g_aff[i];
-            qq.src_tab = s_src; qq.row_active = s_ra; qq.row_aff = s_rf; qq.row_aff_base = s_rb;
-            qq.aff = reinterpret_cast<const AffEntry *>(s_aff);
+            for (int i = tid; i < ROWS; i += nthreads) s_ra[i] = a.q.row_active[i];
+            for (int i = tid; i < 32 * ROWS + 4; i += nthreads) s_sb[i] = a.q.slot_of_bin[i];
+            for (int i = tid; i <= a.q.n_slots; i += nthreads) { s_ik[i] = a.q.slot_invk[i]; s_bs[i] = a.q.slot_base[i]; }
+            qq.src_tab = s_src; qq.row_active = s_ra; qq.slot_of_bin = s_sb; qq.slot_invk = s_ik; qq.slot_base = s_bs;
         }
         __syncthreads();
     }

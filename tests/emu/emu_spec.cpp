@@ -85,14 +85,14 @@ static int go(Cli &c) {
     a.wsplit = reinterpret_cast<const T2 *>(st.wsplit.data());
     a.invw = st.invw.data();
     a.q.n_slots = qt.n_slots;
-    a.q.n_aff = qt.n_aff;
     a.q.n_src = (int)qt.src_tab.size();
     a.q.row_limit = qt.row_limit;
     a.q.src_tab = qt.src_tab.data();
     a.q.row_active = qt.row_active.data();
-    a.q.row_aff = qt.row_aff.data();
-    a.q.row_aff_base = qt.row_aff_base.data();
-    a.q.aff = reinterpret_cast<const qd::AffEntry *>(qt.aff.data());
+    a.q.slot_of_bin = qt.slot_of_bin.data();
+    a.q.slot_invk = qt.slot_invk.data();
+    a.q.slot_base = qt.slot_base.data();
+    for (int e = 0; e < 5; ++e) a.q.tap[e] = qt.tap[e];
     a.q.keep_active = qt.keep_active;
     a.q.smoothing = c.smoothing;
     a.fx.mode = c.fx_mode;
@@ -117,7 +117,7 @@ static int go(Cli &c) {
     QD_CASE(256, 4) QD_CASE(512, 4) QD_CASE(1024, 4) QD_CASE(1024, 8) QD_CASE(2048, 4) QD_CASE(4096, 4) QD_CASE(4096, 2)
     if constexpr (!is_double) {
         if (nc == 1024 && nw == 16) {  // the shared-memory-table variant used for n_fft 2048 on the GPU
-            run<T, 1024, 16, true>(a, n_tiles, qd::SpecSmem<T, 1024, 16>::bytes(qt.n_slots, true, a.q.n_src, a.q.n_aff));
+            run<T, 1024, 16, true>(a, n_tiles, qd::SpecSmem<T, 1024, 16>::bytes(qt.n_slots, true, a.q.n_src, 0));
             return 0;
         }
     }
