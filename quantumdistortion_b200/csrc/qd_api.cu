@@ -106,7 +106,7 @@ template <class T> int pick_nw(int nc, bool fx) {
     if (sizeof(T) == 8 && fx) return nc <= 512 ? 8 : nc == 1024 ? 4 : nc == 2048 ? 2 : 0;  // n_fft 8192: not built
     if (sizeof(T) == 8) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 2;
     if (fx) return nc <= 1024 ? 8 : 4;
-    return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4;
+    return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4;  // 16 = two independent groups of 8 warps per CTA
 }
 
 template <class T, int NC, int NW>
@@ -120,7 +120,7 @@ size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int n_af
         case 256:  return nw == 8 ? smem_of<T, 256, 8>(n_slots, false, 0, 0, fx) : 0;
         case 512:  return nw == 8 ? smem_of<T, 512, 8>(n_slots, false, 0, 0, fx) : 0;
         case 1024:
-            if (nw == 16) return smem_of<T, 1024, 16>(n_slots, ts, n_src, n_aff, fx);
+            if (nw == 16) return qd::SpecSmem<T, 1024, 8, 2>::bytes(n_slots, ts, n_src, n_aff, fx);
             return nw == 8 ? smem_of<T, 1024, 8>(n_slots, false, 0, 0, fx)
                  : nw == 4 ? smem_of<T, 1024, 4>(n_slots, false, 0, 0, fx) : 0;
         case 2048: return nw == 4 ? smem_of<T, 2048, 4>(n_slots, false, 0, 0, fx)
@@ -131,23 +131,24 @@ size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int n_af
     return 0;
 }
 
-template <class T, int NC, int NW, bool TS, bool FX>
+template <class T, int NC, int NW, bool TS, bool FX, int NG = 1>
 int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st) {
     static bool attr_set = false;  // per instantiation; plans are single-threaded per the ABI contract
-    auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX>;
+    auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX, NG>;
     if (!attr_set) {
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const size_t smem = qd::SpecSmem<T, NC, NW>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX);
-    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {  // gridDim.y limit
-        const int64_t nb = std::min<int64_t>(65535, batch - b0);
+    const size_t smem = qd::SpecSmem<T, NC, NW, NG>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX);
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535 * NG) {  // gridDim.y limit
+        const int64_t nb = std::min<int64_t>(65535 * NG, batch - b0);
         qd::SpecArgsT<T> c = a;
+        c.batch = (int)nb;
         c.x = a.x + (size_t)b0 * a.n;
         c.y = a.y + (size_t)b0 * a.n;
         if (a.tap) c.tap = a.tap + (size_t)b0 * a.n;
         c.fx.clip_offset = a.fx.clip_offset + (int)b0;
-        kern<<<dim3((unsigned)tiles, (unsigned)nb, 1), 32 * NW, smem, st>>>(c);
+        kern<<<dim3((unsigned)tiles, (unsigned)((nb + NG - 1) / NG), 1), 32 * NW * NG, smem, st>>>(c);
     }
     QD_CUDA(cudaGetLastError());
     return QD_OK;
@@ -160,7 +161,7 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
         case 512:  return launch_spec_t<T, 512, 8, false, FX>(a, tiles, batch, st);
         case 1024:
             if constexpr (sizeof(T) == 4 && !FX) {
-                if (nw == 16 && ts) return launch_spec_t<T, 1024, 16, true, false>(a, tiles, batch, st);
+                if (nw == 16 && ts) return launch_spec_t<T, 1024, 8, true, false, 2>(a, tiles, batch, st);
             }
             if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 1024, 4, false, true>(a, tiles, batch, st);
             else return launch_spec_t<T, 1024, 8, false, FX>(a, tiles, batch, st);
@@ -214,19 +215,21 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
     a.fx.clip_offset = clip_offset;
     a.fx.table = pl->fx_table;
     // a pass that does not run the FX uses the plain kernel of the same warp count
-    const int nw = fx ? pl->nw : pick_nw<T>(pl->nc, false) == 16 && !pl->ts ? 8 : pick_nw<T>(pl->nc, false);
+    int nw = fx ? pl->nw : pick_nw<T>(pl->nc, false) == 16 && !pl->ts ? 8 : pick_nw<T>(pl->nc, false);
     const bool ts = pl->ts && !fx;
+    const int ng = (nw == 16) ? 2 : 1;   // clips per CTA
     // tiling: whole clips when the batch alone fills the GPU, else cut clips along time
     const int total_blocks = (a.n + pl->hop - 1) / pl->hop;
     const int ctas_per_sm = std::max<int>(1, (int)((227 * 1024) / (pl->spec_smem + 1024)));
-    const int64_t want = (int64_t)pl->sm_count * ctas_per_sm * 2;
+    const int64_t want = (int64_t)pl->sm_count * ctas_per_sm * 2 * ng;
+    const int wpg = nw / ng;  // warps (= frames per batch) of one clip group
     int tile = total_blocks;
     if (batch < want) {
         const int64_t per_clip = (want + batch - 1) / batch;
         tile = (int)((total_blocks + per_clip - 1) / per_clip);
-        const int min_tile = 4 * nw - 3;  // keeps the 3-frame halo recompute below 10 %
+        const int min_tile = 4 * wpg - 3;  // keeps the 3-frame halo recompute below 10 %
         if (tile < min_tile) tile = min_tile;
-        tile = ((tile + 3 + nw - 1) / nw) * nw - 3;  // whole batches of NW frames
+        tile = ((tile + 3 + wpg - 1) / wpg) * wpg - 3;  // whole batches of frames
         if (tile > total_blocks) tile = total_blocks;
     }
     if (tile < 1) tile = 1;
@@ -242,6 +245,7 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
     }
     if (fx) return dispatch_spec<T, true>(pl->nc, nw, false, a, tiles, batch, st);
     return dispatch_spec<T, false>(pl->nc, nw, ts, a, tiles, batch, st);
+    (void)nw;
 }
 
 // One spectral pass over [batch, n]: src -> dst (+ optional tap of the pre-epilogue signal).

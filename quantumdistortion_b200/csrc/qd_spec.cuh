@@ -101,6 +101,7 @@ struct SpecArgsT {
     float *y;              // [batch, n] output (after the epilogue)
     float *tap;            // optional [batch, n]: iSTFT output before the epilogue
     int n;                 // samples per clip
+    int batch;             // clips in this launch (a CTA may hold several clip groups)
     int n_frames;          // T = 1 + n / hop
     int tile_blocks;       // output hops per CTA tile
     int quant;             // run the quantizer (else pure STFT -> iSTFT)
@@ -597,7 +598,9 @@ QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, co
 }
 
 // ---------------------------------------------------------------- the kernel
-template <class T, int NC, int NW>
+// NG independent groups of NW warps share one CTA (and its tables); each group streams its own clip and
+// synchronises only with itself (named barrier), so one group's overlap-add step overlaps the other's FFTs.
+template <class T, int NC, int NW, int NG = 1>
 struct SpecSmem {
     static constexpr int HOP = NC / 2;                       // n_fft / 4 samples
     static constexpr int BUF = buf_slots<NC>();               // V2<T> per warp buffer
@@ -624,10 +627,12 @@ struct SpecSmem {
         b += 2 * (((size_t)(n_slots + 1) * 4 + 15) & ~(size_t)15);     // slot_invk, slot_base
         return b + 64;
     }
+    // layout: NG x [warp buffers | staging | OLA tail | flags | gather scratch], tables, FX magnitude planes
+    __host__ __device__ static size_t group_bytes(int n_slots) { return off_tables(n_slots); }
     static size_t bytes(int n_slots, bool tables_in_smem = false, int n_src = 0, int /*unused*/ = 0, bool fx = false) {
         // FX kernels append one magnitude plane (BUF values of T) per warp
-        return off_tables(n_slots) + (tables_in_smem ? table_bytes(n_src, n_slots) : 16) +
-               (fx ? (size_t)NW * BUF * sizeof(T) : 0);
+        return NG * group_bytes(n_slots) + (tables_in_smem ? table_bytes(n_src, n_slots) : 16) +
+               (fx ? (size_t)NG * NW * BUF * sizeof(T) : 0);
     }
 };
 
@@ -644,28 +649,47 @@ QD_DEV float epilogue_apply(float v, int mode, float fold, float bias, float tg,
     return v;
 }
 
-template <class T, int NC, int NW, bool TS = false, bool FX = false>
-__global__ void __launch_bounds__(32 * NW)
+// barrier among the 32*NW threads of one clip group (barrier 0 stays the CTA-wide __syncthreads)
+template <int NG, int COUNT>
+QD_DEV void group_sync(int g) {
+    if constexpr (NG == 1) {
+        __syncthreads();
+    } else {
+#ifdef QD_EMU
+        qd_emu::named_barrier(g + 1, COUNT);
+#else
+        asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(COUNT) : "memory");
+#endif
+    }
+}
+
+template <class T, int NC, int NW, bool TS = false, bool FX = false, int NG = 1>
+__global__ void __launch_bounds__(32 * NW * NG)
 spec_pass_kernel(const SpecArgsT<T> a) {
-    using L = SpecSmem<T, NC, NW>;
+    using L = SpecSmem<T, NC, NW, NG>;
     constexpr int HOP = L::HOP;
     constexpr int HP = HOP / 2;              // V2<T> pairs per hop
     constexpr int HPP = HP + HP / 32;        // the same span inside a padded warp buffer
     QD_DYN_SMEM(smem);
-    V2<T> *bufs = reinterpret_cast<V2<T> *>(smem + L::off_buf);
-    float *stage = reinterpret_cast<float *>(smem + L::off_stage);
-    V2<T> *tail = reinterpret_cast<V2<T> *>(smem + L::off_tail);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int nthreads = 32 * NW;
+    constexpr int nthreads = 32 * NW;        // threads of one clip group
+    const int grp = NG == 1 ? 0 : (int)threadIdx.x / nthreads;
+    const int tid = NG == 1 ? (int)threadIdx.x : (int)threadIdx.x % nthreads;
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned char *gs = smem + (size_t)grp * L::group_bytes(a.q.n_slots);   // this group's private region
+    unsigned char *tables_base = smem + (size_t)NG * L::group_bytes(a.q.n_slots);
+    V2<T> *bufs = reinterpret_cast<V2<T> *>(gs + L::off_buf);
+    float *stage = reinterpret_cast<float *>(gs + L::off_stage);
+    V2<T> *tail = reinterpret_cast<V2<T> *>(gs + L::off_tail);
     V2<T> *buf = bufs + (size_t)warp * L::BUF;
     const int slot_cap = (a.q.n_slots + 2) & ~1;
-    T *slotG = reinterpret_cast<T *>(smem + L::off_slot) + (size_t)warp * slot_cap * 3;
+    T *slotG = reinterpret_cast<T *>(gs + L::off_slot) + (size_t)warp * slot_cap * 3;
     V2<T> *slotP = reinterpret_cast<V2<T> *>(slotG + slot_cap);
 
-    const int clip = blockIdx.y;
-    const float *x = a.x + (size_t)clip * a.n;
-    float *y = a.y + (size_t)clip * a.n;
-    float *tap = a.tap ? a.tap + (size_t)clip * a.n : nullptr;
+    const int clip = (int)blockIdx.y * NG + grp;
+    const bool group_live = clip < a.batch;   // the last CTA may carry an empty group
+    const float *x = a.x + (size_t)(group_live ? clip : 0) * a.n;
+    float *y = a.y + (size_t)(group_live ? clip : 0) * a.n;
+    float *tap = a.tap ? a.tap + (size_t)(group_live ? clip : 0) * a.n : nullptr;
     // 8-byte vector stores need an even clip length (every row then starts 8-byte aligned)
     const bool vec2 = ((a.n & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 7) == 0) &&
                       (!a.tap || (reinterpret_cast<uintptr_t>(a.tap) & 7) == 0);
@@ -683,8 +707,8 @@ spec_pass_kernel(const SpecArgsT<T> a) {
     // TMA staging: the samples of the NEXT batch of frames are fetched by one cp.async.bulk while this batch
     // is still in its quantizer / inverse FFT; `full` (mbarrier, transaction bytes) says when they have landed,
     // `consumed` counts the warps that are done reading the staging buffer of the current batch.
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::off_flags);
-    int *consumed = reinterpret_cast<int *>(smem + L::off_flags + 8);
+    uint64_t *full = reinterpret_cast<uint64_t *>(gs + L::off_flags);
+    int *consumed = reinterpret_cast<int *>(gs + L::off_flags + 8);
     if (tid == 0) {
         mbar_init(full, 1);
         *consumed = 0;
@@ -698,11 +722,12 @@ spec_pass_kernel(const SpecArgsT<T> a) {
     const V2<T> *wtab = a.wtab, *tw1 = a.tw1, *wsplit = a.wsplit;
     QuantDev qq = a.q;
     if constexpr (TS) {
-        V2<T> *t_w = reinterpret_cast<V2<T> *>(smem + L::off_tables(a.q.n_slots));
+        const int ctid = threadIdx.x, cthreads = nthreads * NG;   // the whole CTA fills the shared tables
+        V2<T> *t_w = reinterpret_cast<V2<T> *>(tables_base);
         V2<T> *t_tw = t_w + NC;
         V2<T> *t_ws = t_tw + NC;
-        for (int i = tid; i < NC; i += nthreads) { t_w[i] = a.wtab[i]; t_tw[i] = a.tw1[i]; }
-        for (int i = tid; i <= NC / 2; i += nthreads) t_ws[i] = a.wsplit[i];
+        for (int i = ctid; i < NC; i += cthreads) { t_w[i] = a.wtab[i]; t_tw[i] = a.tw1[i]; }
+        for (int i = ctid; i <= NC / 2; i += cthreads) t_ws[i] = a.wsplit[i];
         wtab = t_w; tw1 = t_tw; wsplit = t_ws;
         if (a.quant) {
             constexpr int ROWS = (NC + 1 + 31) / 32;
@@ -716,14 +741,15 @@ spec_pass_kernel(const SpecArgsT<T> a) {
             float *s_ik = reinterpret_cast<float *>(qb);
             qb += ((size_t)(a.q.n_slots + 1) * 4 + 15) & ~(size_t)15;
             float *s_bs = reinterpret_cast<float *>(qb);
-            for (int i = tid; i < a.q.n_src; i += nthreads) s_src[i] = a.q.src_tab[i];
-            for (int i = tid; i < ROWS; i += nthreads) s_ra[i] = a.q.row_active[i];
-            for (int i = tid; i < 32 * ROWS + 4; i += nthreads) s_sb[i] = a.q.slot_of_bin[i];
-            for (int i = tid; i <= a.q.n_slots; i += nthreads) { s_ik[i] = a.q.slot_invk[i]; s_bs[i] = a.q.slot_base[i]; }
+            for (int i = ctid; i < a.q.n_src; i += cthreads) s_src[i] = a.q.src_tab[i];
+            for (int i = ctid; i < ROWS; i += cthreads) s_ra[i] = a.q.row_active[i];
+            for (int i = ctid; i < 32 * ROWS + 4; i += cthreads) s_sb[i] = a.q.slot_of_bin[i];
+            for (int i = ctid; i <= a.q.n_slots; i += cthreads) { s_ik[i] = a.q.slot_invk[i]; s_bs[i] = a.q.slot_base[i]; }
             qq.src_tab = s_src; qq.row_active = s_ra; qq.slot_of_bin = s_sb; qq.slot_invk = s_ik; qq.slot_base = s_bs;
         }
         __syncthreads();
     }
+    if (!group_live) return;   // after the last CTA-wide barrier; the other group only uses its named barrier
 
     for (int tb = t_first; tb < j1; tb += NW) {
         // ---- stage the samples of frames tb .. tb+NW-1 (zero outside the clip)
@@ -745,7 +771,7 @@ spec_pass_kernel(const SpecArgsT<T> a) {
                     stage[i] = (s >= 0 && s < a.n) ? x[s] : 0.0f;
                 }
             }
-            __syncthreads();
+            group_sync<NG, 32 * NW>(grp);
         }
         tma_pending = next_by_tma;
         // ---- one frame per warp (a frame outside the clip contributes zeros)
@@ -772,7 +798,7 @@ spec_pass_kernel(const SpecArgsT<T> a) {
             if (a.quant) {
                 if constexpr (FX) {
                     static_assert(!TS, "FX kernels read their tables through L1");
-                    T *mags = reinterpret_cast<T *>(smem + L::off_tables(a.q.n_slots) + 16) + (size_t)warp * L::BUF;
+                    T *mags = reinterpret_cast<T *>(tables_base + 16) + (size_t)(grp * NW + warp) * L::BUF;
                     const int tf = t < a.fx.table_frames ? t : a.fx.table_frames - 1;
                     const long long tab_base =
                         (((long long)(a.fx.table_per_clip ? a.fx.clip_offset + clip : 0) * 2 + a.fx.pass) * a.fx.table_frames + tf) * (NC + 1);
@@ -788,7 +814,7 @@ spec_pass_kernel(const SpecArgsT<T> a) {
         } else {
             for (int i = lane; i < L::BUF; i += 32) buf[i] = mk2<T>(0.0f, 0.0f);
         }
-        __syncthreads();
+        group_sync<NG, 32 * NW>(grp);
         // ---- overlap-add in frame order; blocks tb .. tb+NW-1 are now complete.  A thread owns one
         //      column of sample pairs: slice sl of warp w's frame sits at bufs[w][sl*HPP + pidx(c)].
         for (int c = tid; c < HP; c += nthreads) {
@@ -834,7 +860,7 @@ spec_pass_kernel(const SpecArgsT<T> a) {
                 }
             }
         }
-        __syncthreads();
+        group_sync<NG, 32 * NW>(grp);
     }
 }
 

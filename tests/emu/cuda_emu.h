@@ -51,6 +51,9 @@ struct Block {
     pthread_barrier_t bar;
     std::vector<pthread_barrier_t> warp_bar;
     std::vector<uint64_t> xchg;  // [warps][32]
+    pthread_barrier_t named[16];
+    int named_count[16] = {0};
+    pthread_mutex_t named_mu = PTHREAD_MUTEX_INITIALIZER;
     std::vector<unsigned char> smem;
 };
 extern thread_local Block *g_blk;
@@ -72,6 +75,18 @@ inline T shfl_idx(T v, int src) {
     T out;
     std::memcpy(&out, &got, sizeof(T));
     return out;
+}
+
+// bar.sync id, count: the first caller fixes the participant count of that barrier id for the block
+inline void named_barrier(int id, int count) {
+    Block *b = g_blk;
+    pthread_mutex_lock(&b->named_mu);
+    if (b->named_count[id] == 0) {
+        pthread_barrier_init(&b->named[id], nullptr, (unsigned)count);
+        b->named_count[id] = count;
+    }
+    pthread_mutex_unlock(&b->named_mu);
+    pthread_barrier_wait(&b->named[id]);
 }
 
 // Run `body` once per CUDA thread of every block of the grid (blocks sequentially).

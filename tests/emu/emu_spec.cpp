@@ -30,13 +30,14 @@ static std::vector<T> read_all(const char *path) {
     return v;
 }
 
-template <class T, int NC, int NW, bool TS = false, bool FX = false>
+template <class T, int NC, int NW, bool TS = false, bool FX = false, int NG = 1>
 static void run(qd::SpecArgsT<T> a, int n_tiles, size_t smem) {
-    qd_emu::launch(dim3(n_tiles, 1, 1), dim3(32 * NW, 1, 1), smem, [&] { qd::spec_pass_kernel<T, NC, NW, TS, FX>(a); });
+    qd_emu::launch(dim3(n_tiles, (a.batch + NG - 1) / NG, 1), dim3(32 * NW * NG, 1, 1), smem,
+                   [&] { qd::spec_pass_kernel<T, NC, NW, TS, FX, NG>(a); });
 }
 
 struct Cli {
-    int n_fft, nw, n, tile_blocks, quant, smoothing, epilogue, fx_mode = 0, fx_pass = 0;
+    int n_fft, nw, n, tile_blocks, quant, smoothing, epilogue, fx_mode = 0, fx_pass = 0, batch = 1;
     double snap, smear, fx_a = 0, fx_b = 0, fx_c = 0;
     float fold, bias, tg, tn;
     std::vector<float> x;
@@ -67,13 +68,14 @@ static int go(Cli &c) {
     std::string err;
     if (!qd_host::build_quant_tables(ht, &qt, &err, is_double)) { std::cerr << err << "\n"; return 2; }
     const int n = c.n;
-    c.y.assign(n, -777.0f);
-    c.tap.assign(n, -777.0f);
+    c.y.assign((size_t)n * c.batch, -777.0f);
+    c.tap.assign((size_t)n * c.batch, -777.0f);
     qd::SpecArgsT<T> a{};
     a.x = c.x.data();
     a.y = c.y.data();
     a.tap = c.tap.data();
     a.n = n;
+    a.batch = c.batch;
     a.n_frames = 1 + n / st.hop;
     a.tile_blocks = c.tile_blocks;
     a.quant = c.quant;
@@ -117,7 +119,7 @@ static int go(Cli &c) {
     QD_CASE(256, 4) QD_CASE(512, 4) QD_CASE(1024, 4) QD_CASE(1024, 8) QD_CASE(2048, 4) QD_CASE(4096, 4) QD_CASE(4096, 2)
     if constexpr (!is_double) {
         if (nc == 1024 && nw == 16) {  // the shared-memory-table variant used for n_fft 2048 on the GPU
-            run<T, 1024, 16, true>(a, n_tiles, qd::SpecSmem<T, 1024, 16>::bytes(qt.n_slots, true, a.q.n_src, 0));
+            run<T, 1024, 8, true, false, 2>(a, n_tiles, qd::SpecSmem<T, 1024, 8, 2>::bytes(qt.n_slots, true, a.q.n_src, 0));
             return 0;
         }
     }
@@ -151,7 +153,8 @@ int main(int argc, char **argv) {
     c.mask = read_all<uint8_t>(argv[ai++]);
     const char *y_path = argv[ai++];
     const char *tap_path = argv[ai++];
-    if ((int)c.x.size() != c.n) { std::cerr << "x size\n"; return 2; }
+    if (c.n <= 0 || c.x.size() % (size_t)c.n != 0) { std::cerr << "x size\n"; return 2; }
+    c.batch = (int)(c.x.size() / (size_t)c.n);   // several clips of n samples each
     if (argc == 26) {
         c.fx_mode = std::atoi(argv[ai++]);
         c.fx_a = std::atof(argv[ai++]); c.fx_b = std::atof(argv[ai++]); c.fx_c = std::atof(argv[ai++]);
@@ -161,7 +164,7 @@ int main(int argc, char **argv) {
     }
     const int rc = prec == "f64" ? go<double>(c) : go<float>(c);
     if (rc) return rc;
-    std::ofstream(y_path, std::ios::binary).write(reinterpret_cast<const char *>(c.y.data()), (std::streamsize)(c.n * sizeof(float)));
-    std::ofstream(tap_path, std::ios::binary).write(reinterpret_cast<const char *>(c.tap.data()), (std::streamsize)(c.n * sizeof(float)));
+    std::ofstream(y_path, std::ios::binary).write(reinterpret_cast<const char *>(c.y.data()), (std::streamsize)(c.y.size() * sizeof(float)));
+    std::ofstream(tap_path, std::ios::binary).write(reinterpret_cast<const char *>(c.tap.data()), (std::streamsize)(c.tap.size() * sizeof(float)));
     return 0;
 }

@@ -38,7 +38,8 @@ def run_emu(exe, x, sr, n_fft, nw, tile_blocks, quant, smoothing, snap, smear, e
         x.astype(np.float32).tofile(p("x"))
         tb.tofile(p("tb"))
         mask.tofile(p("mask"))
-        cmd = [exe, prec, str(n_fft), str(nw), str(len(x)), str(tile_blocks), str(int(quant)),
+        n_per_clip = x.shape[-1]   # x may be [clips, n]: the grouped kernel renders several clips per CTA
+        cmd = [exe, prec, str(n_fft), str(nw), str(n_per_clip), str(tile_blocks), str(int(quant)),
                str(int(smoothing)), repr(float(snap)), repr(float(smear)), str(epilogue),
                repr(float(fold)), repr(float(bias)), repr(float(tg)), repr(float(tn)),
                p("x"), p("tb"), p("mask"), p("y"), p("tap")]
@@ -183,3 +184,16 @@ def test_emu_float64_wide_mask_second_pass(emu_spec):
     y64, _ = run_emu(emu_spec, xd, 48000, 2048, 4, 64, True, True, 1.0, 0.1, prec="f64", **kw)
     ref = oracle_pass(xd, 48000, 2048, True, True, 1.0, 0.1, **kw)
     assert float(np.max(np.abs(y64 - ref))) <= 2e-7
+
+
+def test_emu_two_clip_groups_per_cta(emu_spec):
+    """n_fft 2048 production variant: two independent 8-warp groups per CTA, one clip each, odd batch (the
+    last CTA carries an empty group), clips cut into tiles."""
+    n = 9000
+    x = np.stack([synth.noise_clip(20 + i, n) for i in range(3)])
+    y, tap = run_emu(emu_spec, x, 48000, 2048, 16, 16, True, True, 1.0, 0.1, epilogue=1, fold=2.0, bias=0.05)
+    y, tap = y.reshape(3, n), tap.reshape(3, n)
+    for i in range(3):
+        ref_tap = oracle_pass(x[i], 48000, 2048, True, True, 1.0, 0.1)
+        assert float(np.max(np.abs(tap[i] - ref_tap))) < 1e-5
+        assert float(np.max(np.abs(y[i] - orc.apply_distortion(tap[i], "wavefold", fold_amount=2.0, bias=0.05)))) < 1e-5
