@@ -266,7 +266,7 @@ def run_ours(args):
     achieved = alg_bytes / (spec_ms / 1e3) / 1e9
     step_share = {k: v["ms"] / args.steps for k, v in timing.items() if v["launches"]}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "qd::spec_pass_kernel<float,1024,16,TS>", "ms_per_launch": spec_ms,
+                "traffic": None, "kernel": "qd::spec_pass_kernel<float,1024,8,TS,noFX,NG=2>", "ms_per_launch": spec_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_ms_per_step": step_share,
                 "note": "the pass is FP32-issue/shared-memory bound (about 600 flop per sample), not HBM bound; see DESIGN.md"}
