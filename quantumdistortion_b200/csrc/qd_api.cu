@@ -1,6 +1,7 @@
 // qd_api.cu -- C ABI of libqd_b200.so (see include/qd_b200.h).  sm_100a only; no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -133,11 +134,11 @@ size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int n_af
 
 template <class T, int NC, int NW, bool TS, bool FX, int NG = 1>
 int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st) {
-    static bool attr_set = false;  // per instantiation; plans are single-threaded per the ABI contract
+    static std::atomic<bool> attr_set{false};  // per instantiation; setting the attribute twice is harmless
     auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX, NG>;
-    if (!attr_set) {
+    if (!attr_set.load(std::memory_order_acquire)) {
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     const size_t smem = qd::SpecSmem<T, NC, NW, NG>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX);
     for (int64_t b0 = 0; b0 < batch; b0 += 65535 * NG) {  // gridDim.y limit
@@ -178,12 +179,12 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
 
 template <class T, int NC>
 int launch_freeze_t(const qd::SpecArgsT<T> &a, T *out, int64_t batch, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set{false};
     auto kern = qd::freeze_mag_kernel<T, NC>;
     const size_t smem = (size_t)qd::buf_slots<NC>() * sizeof(qd::V2<T>) + (size_t)2 * NC * sizeof(float) + 16;
-    if (!attr_set) {
+    if (!attr_set.load(std::memory_order_acquire)) {
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     kern<<<(unsigned)batch, 32, smem, st>>>(a, out);
     QD_CUDA(cudaGetLastError());
@@ -257,12 +258,12 @@ int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant
 }
 
 int launch_limiter(const qd::LimiterArgs &a, int64_t batch, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set{false};
     const size_t smem = qd_host::limiter_smem_bytes(a.lookahead);
     if (smem > 200 * 1024) return fail(QD_ERR_UNSUPPORTED, "limiter lookahead too long");
-    if (!attr_set) {
+    if (!attr_set.load(std::memory_order_acquire)) {
         QD_CUDA(cudaFuncSetAttribute(qd::limiter_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     for (int64_t b0 = 0; b0 < batch; b0 += (1 << 30)) {
         const int64_t nb = std::min<int64_t>(1 << 30, batch - b0);

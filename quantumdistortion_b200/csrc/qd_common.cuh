@@ -52,6 +52,10 @@ QD_DEV float  qd_rint(float a)  { return rintf(a); }
 QD_DEV double qd_rint(double a) { return rint(a); }
 QD_DEV float  qd_log10(float a)  { return log10f(a); }
 QD_DEV double qd_log10(double a) { return log10(a); }
+QD_DEV float  qd_log2(float a)  { return log2f(a); }
+QD_DEV double qd_log2(double a) { return log2(a); }
+QD_DEV float  qd_exp2(float a)  { return exp2f(a); }
+QD_DEV double qd_exp2(double a) { return exp2(a); }
 QD_DEV float  qd_exp10(float a)  { return QD_EXP10F(a); }
 QD_DEV double qd_exp10(double a) { return pow(10.0, a); }
 QD_DEV void qd_sincos(float a, float *s, float *c)    { QD_SINCOSF(a, s, c); }

@@ -88,7 +88,8 @@ inline bool build_spec_tables(int n_fft, SpecTablesT<T> *t) {
                     const double w = hann_periodic(sl * hop + c, n_fft);
                     s += w * w;
                 }
-                t->invw[(size_t)(a * 4 + b) * hop + c] = (T)(1.0 / std::max(s, 1e-10));
+                // x 1/n_fft: the inverse FFT in the kernel is unnormalised
+                t->invw[(size_t)(a * 4 + b) * hop + c] = (T)(1.0 / std::max(s, 1e-10) / (double)n_fft);
             }
     return true;
 }

@@ -194,13 +194,13 @@ QD_DEV void fwd_first(V2<T> *buf, const float2 *frame, const V2<T> *wtab, const 
     __syncwarp();
 }
 
-// last inverse pass: synthesis window and 1/n_fft, leaves the time-domain frame in buf
+// last inverse pass: synthesis window (the 1/n_fft of the inverse FFT is folded into the host's 1/sum(w^2) table),
+// leaves the time-domain frame in buf
 template <class T, int NC, int R>
 QD_DEV void inv_last(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw, int lane) {
     constexpr int S = NC / R;
     constexpr int NB = NC / R / 32;
     constexpr int LG = qd_log2(R);
-    const T scale = (T)1 / (T)(2 * NC);
 #pragma unroll 1
     for (int i = 0; i < NB; ++i) {
         const int a0 = lane + 32 * i;
@@ -216,7 +216,7 @@ QD_DEV void inv_last(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw, int lane) {
         for (int r = 0; r < R; ++r) {
             const int n = a0 + qd_bitrev(r, LG) * S;
             const V2<T> w = wtab[n];
-            buf[pidx(n)] = mk2<T>(v[r].x * (w.x * scale), v[r].y * (w.y * scale));
+            buf[pidx(n)] = mk2<T>(v[r].x * w.x, v[r].y * w.y);
         }
     }
     __syncwarp();
@@ -393,11 +393,11 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
                 if (fx.step > 0.0) {
                     if (fx.mode == 1) {
                         const T mm = qd_max(m, 1e-12f);
-                        const T q = 20.0f * qd_log10(mm) / (T)fx.step;
+                        const T q = qd_log2(mm) * (T)(6.020599913279624 / fx.step);  // 20 log10(m) / step_db
                         T rq = qd_rint(q);
                         if (qd_abs(qd_abs(q - rq) - 0.5f) < 0.02f)  // close to a rounding boundary: decide in double
                             rq = (T)rint(20.0 * log10((double)mm) / fx.step);
-                        m = qd_exp10((T)((double)rq * fx.step / 20.0));
+                        m = qd_exp2(rq * (T)(fx.step * 0.16609640474436813));       // 10^(q step / 20)
                     } else {
                         m = qd_max((T)(rint((double)m / fx.step) * fx.step), 0.0f);
                     }

@@ -247,3 +247,21 @@ def test_file_harness_single_and_batched(qd, tmp_path):
         assert sr2 == sr
         lsb = np.abs(np.rint(got * 32768.0) - float_to_pcm16(ref).astype(np.float64))
         assert lsb.max() <= 4, lsb.max()   # 1e-4 parity bound = 3.3 LSB of 16-bit PCM
+
+
+@pytest.mark.gpu
+def test_host_pipeline_odd_batch_small_chunks(qd):
+    """qd_render_host with a batch that is not a multiple of the chunk, chunks of 1 / 2 / > batch clips, multiband
+    with a per-clip FX table (clip offsets inside the table follow the chunks)."""
+    import torch
+    n, sr = 9000, 48000
+    x = np.stack([synth.loud_clip(90 + i, n, sr) for i in range(5)])
+    kw = dict(qd_cases.GROWL, use_multiband=True, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.55)
+    ref, _ = qd.process_batch(torch.from_numpy(x).cuda(), sr, seeds=[1, 2, 3, 4, 5], **kw)
+    ref = ref.cpu().numpy()
+    for chunk in (1, 2, 64):
+        y, _ = qd.process_batch(x, sr, seeds=[1, 2, 3, 4, 5], chunk_clips=chunk, **kw)
+        assert np.array_equal(y, ref), chunk
+    np.random.seed(3)
+    o, _ = orc.process_audio(x[2], sr, **kw)
+    _check(ref[2], o, "per-clip seeded scramble, clip 2")
