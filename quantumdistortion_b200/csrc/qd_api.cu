@@ -106,7 +106,7 @@ namespace {
 template <class T> int pick_nw(int nc, bool fx) {
     if (sizeof(T) == 8 && fx) return nc <= 512 ? 8 : nc == 1024 ? 4 : nc == 2048 ? 2 : 0;  // n_fft 8192: not built
     if (sizeof(T) == 8) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 2;
-    if (fx) return nc <= 1024 ? 8 : 4;
+    if (fx) return nc == 1024 ? 12 : nc < 1024 ? 8 : 4;   // 12 warps: what fits beside the FX magnitude planes
     return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4;  // 16 = two independent groups of 8 warps per CTA
 }
 
@@ -123,6 +123,7 @@ size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int n_af
         case 1024:
             if (nw == 16) return qd::SpecSmem<T, 1024, 8, 2>::bytes(n_slots, ts, n_src, n_aff, fx);
             return nw == 8 ? smem_of<T, 1024, 8>(n_slots, false, 0, 0, fx)
+                 : nw == 12 ? smem_of<T, 1024, 12>(n_slots, false, 0, 0, fx)
                  : nw == 4 ? smem_of<T, 1024, 4>(n_slots, false, 0, 0, fx) : 0;
         case 2048: return nw == 4 ? smem_of<T, 2048, 4>(n_slots, false, 0, 0, fx)
                         : nw == 2 ? smem_of<T, 2048, 2>(n_slots, false, 0, 0, fx) : 0;
@@ -165,7 +166,8 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
                 if (nw == 16 && ts) return launch_spec_t<T, 1024, 8, true, false, 2>(a, tiles, batch, st);
             }
             if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 1024, 4, false, true>(a, tiles, batch, st);
-            else return launch_spec_t<T, 1024, 8, false, FX>(a, tiles, batch, st);
+            else if constexpr (FX) return launch_spec_t<T, 1024, 12, false, true>(a, tiles, batch, st);
+            else return launch_spec_t<T, 1024, 8, false, false>(a, tiles, batch, st);
         case 2048:
             if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 2048, 2, false, true>(a, tiles, batch, st);
             else return launch_spec_t<T, 2048, 4, false, FX>(a, tiles, batch, st);

@@ -110,7 +110,7 @@ static int go(Cli &c) {
         run<T, NC_, NW_, false, true>(a, n_tiles, qd::SpecSmem<T, NC_, NW_>::bytes(qt.n_slots, false, 0, 0, true)); \
         return 0;                                                                                                 \
     }
-    QD_FXCASE(1024, 8) QD_FXCASE(256, 4) QD_FXCASE(2048, 4)
+    QD_FXCASE(1024, 8) QD_FXCASE(1024, 12) QD_FXCASE(256, 4) QD_FXCASE(2048, 4)
 #define QD_CASE(NC_, NW_)                                                                 \
     if (nc == NC_ && nw == NW_) {                                                         \
         run<T, NC_, NW_>(a, n_tiles, qd::SpecSmem<T, NC_, NW_>::bytes(qt.n_slots));       \

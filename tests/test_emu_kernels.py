@@ -154,7 +154,8 @@ def test_emu_spectral_fx_pass(emu_spec, mode, strength, seed):
     if fxr["rng"]:
         np.random.seed(seed)
         tab = tables.replay_fx_table(fxr["rng"], 1, 1 + n // (n_fft // 4), n_fft // 2 + 1)
-    y, _ = run_emu(emu_spec, x, sr, n_fft, 8, 64, True, True, 0.9, 0.3, key="F",
+    nw = 12 if mode == "bin_scramble" else 8   # 12 warps per CTA is the production FX variant for n_fft 2048
+    y, _ = run_emu(emu_spec, x, sr, n_fft, nw, 64, True, True, 0.9, 0.3, key="F",
                    fx=(fxr["fx_mode"], fxr["a"], fxr["b"], fxr["c"], tab, 0))
     S, freqs = orc.stft(x, sr, n_fft)
     if seed is not None:
