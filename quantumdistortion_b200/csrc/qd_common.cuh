@@ -34,12 +34,71 @@ template <class T> QD_DEV V2<T> mk2(T a, T b);
 template <> QD_DEV float2  mk2<float>(float a, float b)    { return make_float2(a, b); }
 template <> QD_DEV double2 mk2<double>(double a, double b) { return make_double2(a, b); }
 
+// ---------------------------------------------------------------- packed float2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2)
+// Blackwell issues one instruction for both halves of a 64-bit register pair (add/sub/mul/fma.rn.f32x2).  The
+// spectral pass is issue bound, and complex data already lives in float2 pairs, so every complex add/sub
+// is one FADD2 and a twiddle multiply is FMUL2 + FFMA2.  ptxas folds scalar broadcasts (`R.F32`) and half swaps
+// (`.LO_HI`) of the operands into the instruction, so splat()/swap() below cost nothing.  Each half rounds
+// exactly like the scalar .rn instruction.  double2 (parity path) and the host emulation use scalar code.
+#ifdef QD_EMU
+QD_DEV float2 padd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+QD_DEV float2 psub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+QD_DEV float2 pmul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+QD_DEV float2 pfma(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#else
+QD_DEV unsigned long long f2_bits(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+QD_DEV float2 bits_f2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+QD_DEV float2 padd(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+QD_DEV float2 psub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+QD_DEV float2 pmul(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+QD_DEV float2 pfma(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(r);
+}
+#endif
+QD_DEV double2 padd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+QD_DEV double2 psub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+QD_DEV double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
+QD_DEV double2 pfma(double2 a, double2 b, double2 c) { return make_double2(a.x * b.x + c.x, a.y * b.y + c.y); }
+QD_DEV float2  splat(float a)  { return make_float2(a, a); }
+QD_DEV double2 splat(double a) { return make_double2(a, a); }
+QD_DEV float2  pswap(float2 a)  { return make_float2(a.y, a.x); }
+QD_DEV double2 pswap(double2 a) { return make_double2(a.y, a.x); }
+
 #define QD_COMPLEX_OPS(T2, MK)                                                                         \
-    QD_DEV T2 cadd(T2 a, T2 b) { return MK(a.x + b.x, a.y + b.y); }                                    \
-    QD_DEV T2 csub(T2 a, T2 b) { return MK(a.x - b.x, a.y - b.y); }                                    \
-    QD_DEV T2 cmul(T2 a, T2 b) { return MK(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }            \
+    QD_DEV T2 cadd(T2 a, T2 b) { return padd(a, b); }                                                  \
+    QD_DEV T2 csub(T2 a, T2 b) { return psub(a, b); }                                                  \
+    /* a * b = a * splat(b.x) + (-a.y, a.x) * b.y */                                                   \
+    QD_DEV T2 cmul(T2 a, T2 b) {                                                                       \
+        const T2 t = pmul(a, splat(b.x));                                                              \
+        return MK(t.x - a.y * b.y, t.y + a.x * b.y);                                                   \
+    }                                                                                                  \
     /* a * conj(b) */                                                                                  \
-    QD_DEV T2 cmulc(T2 a, T2 b) { return MK(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }           \
+    QD_DEV T2 cmulc(T2 a, T2 b) {                                                                      \
+        const T2 t = pmul(a, splat(b.x));                                                              \
+        return MK(t.x + a.y * b.y, t.y - a.x * b.y);                                                   \
+    }                                                                                                  \
     QD_DEV T2 cconj(T2 a) { return MK(a.x, -a.y); }
 QD_COMPLEX_OPS(float2, make_float2)
 QD_COMPLEX_OPS(double2, make_double2)
@@ -123,10 +182,12 @@ QD_DEV V2<T> mul_w32(V2<T> d, int k) {
     if (k == 24) return DIR > 0 ? mk2<T>(d.y, -d.x) : mk2<T>(-d.y, d.x);
     const T c = (T)qd_cos32(k);
     const T s = (T)(DIR > 0 ? qd_sin32(k) : -qd_sin32(k));
-    return mk2<T>(d.x * c - d.y * s, d.x * s + d.y * c);
+    // (x c - y s, y c + x s) = d * (c, c) + swap(d) * (-s, s): FMUL2 + FFMA2
+    return pfma(pswap(d), mk2<T>(-s, s), pmul(d, splat(c)));
 }
 
 __host__ __device__ constexpr int qd_log2(int r) { return r <= 1 ? 0 : 1 + qd_log2(r >> 1); }
+__host__ __device__ constexpr int qd_ctz(int v) { return (v & 1) ? 0 : 1 + qd_ctz(v >> 1); }  // v > 0
 __host__ __device__ constexpr int qd_bitrev(int v, int bits) {
     int o = 0;
     for (int i = 0; i < bits; ++i) o |= ((v >> i) & 1) << (bits - 1 - i);
@@ -147,7 +208,10 @@ QD_DEV void dft_reg(V2<T> (&v)[R]) {
                 const V2<T> a = v[base + i];
                 const V2<T> b = v[base + i + half];
                 v[base + i] = cadd(a, b);
-                v[base + i + half] = mul_w32<DIR, T>(csub(a, b), i * (16 / half));
+                if (i * (16 / half) == 8)   // (a - b) * (-/+ i) without forming a - b as a pair
+                    v[base + i + half] = DIR > 0 ? mk2<T>(b.y - a.y, a.x - b.x) : mk2<T>(a.y - b.y, b.x - a.x);
+                else
+                    v[base + i + half] = mul_w32<DIR, T>(csub(a, b), i * (16 / half));
             }
         }
     }

@@ -52,9 +52,19 @@ inline bool build_spec_tables(int n_fft, SpecTablesT<T> *t) {
     if (!fft_radices(nc, &r, is_double)) return false;
     t->nc = nc;
     t->hop = n_fft / 4;
-    t->wtab.resize(nc);
-    for (int n = 0; n < nc; ++n)
-        t->wtab[n] = F2{(T)hann_periodic(2 * n, n_fft), (T)hann_periodic(2 * n + 1, n_fft)};
+    // Hann window by angle addition: the first-pass butterfly a0 (0 <= a0 < S = nc/R1) touches the sample pairs
+    // 2(a0 + qS), 2(a0 + qS) + 1, q = 0..R1-1, whose window is 0.5 - 0.5 cos(A + 2 pi q / R1), A = 2 pi (2 a0 [+1]) / n_fft.
+    // Entry 2 a0 = -0.5 cos A (even, odd sample), entry 2 a0 + 1 = 0.5 sin A; cos/sin(2 pi q / R1) are compile-time
+    // constants of the kernel, so the window costs two FFMA2 instead of a shared-memory read per sample pair.
+    {
+        const int S = nc / r.r1;
+        t->wtab.resize((size_t)2 * S);
+        for (int a0 = 0; a0 < S; ++a0) {
+            const double ae = 2.0 * M_PI * (double)(2 * a0) / (double)n_fft, ao = 2.0 * M_PI * (double)(2 * a0 + 1) / (double)n_fft;
+            t->wtab[2 * a0] = F2{(T)(-0.5 * std::cos(ae)), (T)(-0.5 * std::cos(ao))};
+            t->wtab[2 * a0 + 1] = F2{(T)(0.5 * std::sin(ae)), (T)(0.5 * std::sin(ao))};
+        }
+    }
     // access-ordered twiddles: entry [(i*R + k)*32 + lane] = exp(-2 pi i j k / M),
     // butterfly u = lane + 32 i of a pass with sub-size M, radix R, stride S = M/R, j = u % S
     auto fill = [&](std::vector<F2> &tw, int M, int R) {
@@ -74,8 +84,12 @@ inline bool build_spec_tables(int n_fft, SpecTablesT<T> *t) {
     t->wsplit.resize(nc / 2 + 1);
     for (int k = 0; k <= nc / 2; ++k) {
         const double ang = -2.0 * M_PI * (double)k / (double)n_fft;
-        t->wsplit[k] = F2{(T)std::cos(ang), (T)std::sin(ang)};
+        // V_k = -i/2 * exp(-2 pi i k / n_fft): the factor of the odd part in the real split (and, conjugated
+        // and doubled, in the Hermitian merge) with the 1/(2i) already folded in
+        t->wsplit[k] = F2{(T)(0.5 * std::sin(ang)), (T)(-0.5 * std::cos(ang))};
     }
+    t->wsplit[0] = F2{(T)0, (T)-0.5};         // exact quarter turns
+    t->wsplit[nc / 2] = F2{(T)-0.5, (T)0};
     // 1 / max(sum of w^2 over the frames covering a hop-block, 1e-10)  (dsp/stft_utils.py:174-186, 214)
     // frames are added in ascending t = descending slice index.
     const int hop = t->hop;
@@ -106,7 +120,7 @@ inline int host_spos(int nc, int k, bool is_double = false) {
 
 struct QuantTablesH {
     int n_bins = 0, n_slots = 0, rows = 0, row_limit = 0;
-    std::vector<uint32_t> src_tab;  // tail<<31 | off<<26 | slot<<13 | buffer position, grouped by slot
+    std::vector<uint32_t> src_tab;  // tail<<31 | off<<26 | slot<<13 | source bin, grouped by slot
     std::vector<uint16_t> slot_begin, src_bin;
     std::vector<int32_t> slot_bin;
     std::vector<uint32_t> row_active;
@@ -158,7 +172,8 @@ inline bool build_quant_tables(const qd_tables &in, QuantTablesH *q, std::string
             int off = 0;
             for (int j = i - 1; j >= (i / 32) * 32 && slot_of_src[j] == slot_of_src[i]; --j) ++off;
             const bool tail = (i % 32 == 31) || (i == ns - 1) || (slot_of_src[i + 1] != slot_of_src[i]);
-            const uint32_t pos = (uint32_t)host_spos(n - 1, q->src_bin[i], is_double);
+            const uint32_t pos = (uint32_t)q->src_bin[i];
+            (void)is_double;
             q->src_tab.push_back(((uint32_t)tail << 31) | ((uint32_t)off << 26) | ((uint32_t)slot_of_src[i] << 13) | pos);
         }
     }

@@ -44,10 +44,20 @@ template <class T, int NC>
 QD_DEV int spos(int k) {
     using C = FftCfg<T, NC>;
     if (k >= NC) return QD_NYQ_SLOT;
-    const int k1 = k & (C::R1 - 1);
-    const int k2 = (k / C::R1) & (C::R2 - 1);
-    const int k3 = k / (C::R1 * C::R2);
-    return pidx(k1 * (NC / C::R1) + k2 * (NC / (C::R1 * C::R2)) + k3);
+    const unsigned uk = (unsigned)k;
+    if constexpr (C::R1 == 32 && NC == 1024) return (int)(33u * (uk & 31u) + (uk >> 5));
+    const unsigned k1 = uk & (unsigned)(C::R1 - 1);
+    const unsigned k2 = (uk / (unsigned)C::R1) & (unsigned)(C::R2 - 1);
+    const unsigned k3 = uk / (unsigned)(C::R1 * C::R2);
+    return pidx((int)(k1 * (unsigned)(NC / C::R1) + k2 * (unsigned)(NC / (C::R1 * C::R2)) + k3));
+}
+// the same for a bin known to be below NC (no Nyquist test)
+template <class T, int NC>
+QD_DEV int spos_lt(int k) {
+    using C = FftCfg<T, NC>;
+    const unsigned uk = (unsigned)k;
+    if constexpr (C::R1 == 32 && NC == 1024) return (int)(33u * (uk & 31u) + (uk >> 5));
+    else return spos<T, NC>(k);
 }
 
 // position of bin 32*row + lane.  For the 32x32 plan this is 33*lane + row for every bin including the
@@ -73,7 +83,7 @@ struct QuantDev {
     int n_slots;                    // distinct target bins
     int n_src;
     int row_limit;                  // rows >= row_limit hold no source and no bin that can receive energy
-    const uint32_t *src_tab;        // [n_src] tail<<31 | off<<26 | slot<<13 | buffer position, grouped by slot
+    const uint32_t *src_tab;        // [n_src] tail<<31 | off<<26 | slot<<13 | source bin, grouped by slot
     const uint32_t *row_active;     // [rows] bit l: bin 32*row+l gives its energy away
     const uint16_t *slot_of_bin;    // [32*rows + 4]: entry d+2 = slot whose target is bin d, else n_slots (reads 0)
     const float *slot_invk;         // [n_slots + 1]  1 / ksum_slot
@@ -107,10 +117,10 @@ struct SpecArgsT {
     int quant;             // run the quantizer (else pure STFT -> iSTFT)
     int epilogue;          // 0 none, 1 wavefold, 2 tube
     float fold, bias, tube_gain, tube_norm;
-    const V2<T> *wtab;     // [NC] Hann window as pairs (w[2n], w[2n+1])
+    const V2<T> *wtab;     // [2 NC/R1] Hann window factors (-0.5 cos A, 0.5 sin A) per first-pass butterfly (host builder)
     const V2<T> *tw1;      // access-ordered twiddles of pass 1 / pass 2 (see host builder)
     const V2<T> *tw2;
-    const V2<T> *wsplit;   // [NC/2+1] exp(-2 pi i k / n_fft)
+    const V2<T> *wsplit;   // [NC/2+1] V_k = -i/2 exp(-2 pi i k / n_fft)
     const T *invw;         // [16][hop]: 1/max(sum_{sl=a..b} w^2[sl*hop+c], 1e-10) at [(a*4+b)*hop + c]
     QuantDev q;
     FxDev fx;
@@ -166,6 +176,46 @@ QD_DEV void inv_pass(V2<T> *buf, const V2<T> *tw, int lane) {
     __syncwarp();
 }
 
+// Hann window of the sample pair q of a first-pass butterfly: 0.5 - 0.5 cos(A + 2 pi q / R) by angle addition from the
+// butterfly's (-0.5 cos A, 0.5 sin A) pairs (wtab, see the host builder); q is a compile-time constant after unrolling
+template <class T, int R>
+QD_DEV V2<T> hann_pair(V2<T> wc, V2<T> ws, int q) {
+    const int k = q * (32 / R);   // angle in 32nds of a turn
+    if (k == 0) return padd(splat((T)0.5), wc);
+    if (k == 8) return padd(splat((T)0.5), ws);
+    if (k == 16) return psub(splat((T)0.5), wc);
+    if (k == 24) return psub(splat((T)0.5), ws);
+    return pfma(splat((T)qd_cos32(k)), wc, pfma(splat((T)qd_sin32(k)), ws, splat((T)0.5)));
+}
+
+// Twiddles exp(-2 pi i j k / NC), k = 1..R-1, of a first-pass butterfly: only the powers of two are read from the table,
+// the others are products w_k = w_{k - lowbit(k)} w_{lowbit(k)} (at most log2(R) - 1 multiplications deep), because the
+// pass is bound by shared-memory wavefronts, not by arithmetic.  `cur[j]` = latest w whose index has >= j trailing zeros.
+template <int K> struct KConst { static constexpr int value = K; };
+template <class T, int R, int K, class F>
+QD_DEV void twiddle_step(const V2<T> (&pw)[qd_log2(R)], V2<T> (&cur)[qd_log2(R) + 1], F &body) {
+    if constexpr (K < R) {
+        constexpr int z = qd_ctz(K);
+        V2<T> w;
+        if constexpr (K == (1 << z)) w = pw[z];
+        else w = cmul(cur[z + 1], pw[z]);
+#pragma unroll
+        for (int j = 0; j <= z; ++j) cur[j] = w;
+        body(KConst<K>{}, w);
+        twiddle_step<T, R, K + 1, F>(pw, cur, body);
+    }
+}
+template <class T, int R, class F>
+QD_DEV void twiddle_walk(const V2<T> *twp, F &&body) {   // twp = &tw[(i * R) * 32 + lane]
+    constexpr int LG = qd_log2(R);
+    V2<T> pw[LG], cur[LG + 1];
+#pragma unroll
+    for (int z = 0; z < LG; ++z) pw[z] = twp[(1 << z) * 32];
+#pragma unroll
+    for (int z = 0; z <= LG; ++z) cur[z] = mk2<T>((T)1, (T)0);
+    twiddle_step<T, R, 1, F>(pw, cur, body);
+}
+
 // first forward pass: reads the frame from the staging buffer, applies the analysis window
 template <class T, int NC, int R>
 QD_DEV void fwd_first(V2<T> *buf, const float2 *frame, const V2<T> *wtab, const V2<T> *tw, int lane) {
@@ -175,21 +225,20 @@ QD_DEV void fwd_first(V2<T> *buf, const float2 *frame, const V2<T> *wtab, const 
 #pragma unroll 1
     for (int i = 0; i < NB; ++i) {
         const int a0 = lane + 32 * i;
+        const V2<T> wc = wtab[2 * a0], ws = wtab[2 * a0 + 1];
         V2<T> v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const float2 s = frame[a0 + q * S];
-            const V2<T> w = wtab[a0 + q * S];
-            v[q] = mk2<T>((T)s.x * w.x, (T)s.y * w.y);
+            v[q] = pmul(mk2<T>((T)s.x, (T)s.y), hann_pair<T, R>(wc, ws, q));
         }
         dft_reg<R, -1, T>(v);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int k = qd_bitrev(r, LG);
-            V2<T> t = v[r];
-            if (k > 0) t = cmul(t, tw[(i * R + k) * 32 + lane]);
-            buf[pidx(a0 + k * S)] = t;
-        }
+        buf[pidx(a0)] = v[0];
+        twiddle_walk<T, R>(tw + (i * R) * 32 + lane,
+                           [&](auto kc, V2<T> w) {
+                               constexpr int k = decltype(kc)::value;
+                               buf[pidx(a0 + k * S)] = cmul(v[qd_bitrev(k, LG)], w);
+                           });
     }
     __syncwarp();
 }
@@ -205,18 +254,17 @@ QD_DEV void inv_last(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw, int lane) {
     for (int i = 0; i < NB; ++i) {
         const int a0 = lane + 32 * i;
         V2<T> v[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            V2<T> t = buf[pidx(a0 + k * S)];
-            if (k > 0) t = cmulc(t, tw[(i * R + k) * 32 + lane]);
-            v[k] = t;
-        }
+        v[0] = buf[pidx(a0)];
+        twiddle_walk<T, R>(tw + (i * R) * 32 + lane, [&](auto kc, V2<T> w) {
+            constexpr int k = decltype(kc)::value;
+            v[k] = cmulc(buf[pidx(a0 + k * S)], w);
+        });
         dft_reg<R, +1, T>(v);
+        const V2<T> wc = wtab[2 * a0], ws = wtab[2 * a0 + 1];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int n = a0 + qd_bitrev(r, LG) * S;
-            const V2<T> w = wtab[n];
-            buf[pidx(n)] = mk2<T>(v[r].x * w.x, v[r].y * w.y);
+            const int q = qd_bitrev(r, LG);
+            buf[pidx(a0 + q * S)] = pmul(v[r], hann_pair<T, R>(wc, ws, q));
         }
     }
     __syncwarp();
@@ -250,8 +298,8 @@ QD_DEV void fft_inverse(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw1, const V
 
 // ---------------------------------------------------------------- real <-> complex packing
 // Z = FFT_NC(x[2n] + i x[2n+1])  ->  X[k], k = 0..NC   (in place, Nyquist in the pad slot)
-//   E = (Z[k] + conj Z[NC-k]) / 2,  T = W_N^k (Z[k] - conj Z[NC-k]) / (2i)
-//   X[k] = E + T,  X[NC-k] = conj(E - T)
+//   E = Z[k] + conj Z[NC-k],  T = V_k (Z[k] - conj Z[NC-k]),  V_k = W_N^k / (2i)   (host table)
+//   X[k] = E/2 + T,  X[NC-k] = conj(E/2 - T)
 template <class T, int NC>
 QD_DEV void real_split(V2<T> *buf, const V2<T> *wsplit, int lane) {
 #pragma unroll 4
@@ -265,19 +313,18 @@ QD_DEV void real_split(V2<T> *buf, const V2<T> *wsplit, int lane) {
             buf[pm] = cconj(buf[pm]);
         } else {
             const int pa = rpos<T, NC>(lane, row), pb = mpos<T, NC>(lane, row);
-            const V2<T> za = buf[pa], zb = buf[pb];
-            const V2<T> e = mk2<T>(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
-            const V2<T> o = mk2<T>(0.5f * (za.y + zb.y), -0.5f * (za.x - zb.x));  // (za - conj zb)/(2i)
-            const V2<T> t = cmul(o, wsplit[k]);
-            buf[pa] = cadd(e, t);
-            buf[pb] = cconj(csub(e, t));
+            const V2<T> za = buf[pa], zb = cconj(buf[pb]);
+            const V2<T> e = cadd(za, zb);
+            const V2<T> t = cmul(csub(za, zb), wsplit[k]);
+            buf[pa] = pfma(e, splat((T)0.5), t);
+            buf[pb] = cconj(pfma(e, splat((T)0.5), mk2<T>(-t.x, -t.y)));
         }
     }
     __syncwarp();
 }
 
 // X'[k] (only Re of DC / Nyquist used, like pocketfft c2r) -> Z' with z = IFFT_NC(Z') * 1/(2 NC)
-//   E2 = X'[k] + conj X'[NC-k],  T2 = X'[k] - conj X'[NC-k],  O2 = conj(W_N^k) T2
+//   E2 = X'[k] + conj X'[NC-k],  T2 = X'[k] - conj X'[NC-k],  i O2 = i conj(W_N^k) T2 = 2 conj(V_k) T2
 //   Z'[k] = E2 + i O2,  Z'[NC-k] = conj(E2 - i O2)
 template <class T, int NC>
 QD_DEV void real_merge(V2<T> *buf, const V2<T> *wsplit, int lane) {
@@ -292,12 +339,11 @@ QD_DEV void real_merge(V2<T> *buf, const V2<T> *wsplit, int lane) {
             buf[pm] = mk2<T>(2.0f * xm.x, -2.0f * xm.y);
         } else {
             const int pa = rpos<T, NC>(lane, row), pb = mpos<T, NC>(lane, row);
-            const V2<T> xa = buf[pa], xb = buf[pb];
-            const V2<T> e = mk2<T>(xa.x + xb.x, xa.y - xb.y);
-            const V2<T> t = mk2<T>(xa.x - xb.x, xa.y + xb.y);
-            const V2<T> o = cmulc(t, wsplit[k]);
-            buf[pa] = mk2<T>(e.x - o.y, e.y + o.x);   // E2 + i O2
-            buf[pb] = mk2<T>(e.x + o.y, o.x - e.y);   // conj(E2 - i O2)
+            const V2<T> xa = buf[pa], xb = cconj(buf[pb]);
+            const V2<T> e = cadd(xa, xb);
+            const V2<T> h = cmulc(csub(xa, xb), wsplit[k]);             // i O2 / 2
+            buf[pa] = pfma(h, splat((T)2), e);                          // E2 + i O2
+            buf[pb] = cconj(pfma(h, splat((T)-2), e));                  // conj(E2 - i O2)
         }
     }
     __syncwarp();
@@ -329,13 +375,19 @@ QD_DEV void mag_phasor(V2<T> xv, T &m, V2<T> &u) {
     const bool ok = m2 > QD_TINY2;
     const T r = rsqrt_fast(m2);
     m = ok ? m2 * r : 0.0f;
-    u.x = ok ? xv.x * r : 1.0f;
-    u.y = ok ? xv.y * r : 0.0f;
+    u = ok ? pmul(xv, splat(r)) : mk2<T>(1.0f, 0.0f);
 }
 
 // [1/4,1/2,1/4] smoothing of row `cur` with two shuffles: lane 31 lends its previous-row value to lane 0,
 // lane 0 lends its next-row value to lane 31 (nobody else needs those two lanes' own m_cur as a neighbour
 // on that side).
+// the same with the lane tests hoisted by the caller (is31 / is0) and no edge handling
+template <class T>
+QD_DEV T smooth_mid(T m_prev, T m_cur, T m_next, bool is0, bool is31, int lane_m1, int lane_p1) {
+    const T left = __shfl_sync(QD_FULL, is31 ? m_prev : m_cur, lane_m1);
+    const T right = __shfl_sync(QD_FULL, is0 ? m_next : m_cur, lane_p1);
+    return 0.5f * m_cur + 0.25f * (left + right);
+}
 template <class T>
 QD_DEV T smooth_row(T m_prev, T m_cur, T m_next, int lane, bool first_bin, bool last_bin) {
     T left = __shfl_sync(QD_FULL, lane == 31 ? m_prev : m_cur, (lane + 31) & 31);
@@ -485,16 +537,34 @@ QD_DEV void quant_bin(const V2<T> *buf, const T *mags, const T *slotG, const V2<
         const T g = slotG[s];
         const V2<T> pv = slotP[s];
         te += c * g;
-        ps.x += c * pv.x;
-        ps.y += c * pv.y;
+        ps = pfma(splat(c), pv, ps);
     }
     nm += te;
     if (te > (T)0) {
         const T p2 = ps.x * ps.x + ps.y * ps.y;
         const bool ok = p2 > (T)QD_TINY2;
         const T r = rsqrt_fast(p2);
-        u = mk2<T>(ok ? ps.x * r : (T)1, ok ? ps.y * r : (T)0);
+        u = ok ? pmul(ps, splat(r)) : mk2<T>((T)1, (T)0);
     }
+}
+
+// one step of the segmented warp scan of Q1: add the values shuffled up by d when the lane has at least d
+// same-slot sources below it (one ISETP + three predicated FADD)
+template <class T>
+QD_DEV void seg_scan_step(T &g, V2<T> &p, int off, int d) {
+    const T go = __shfl_up_sync(QD_FULL, g, d);
+    const T pxo = __shfl_up_sync(QD_FULL, p.x, d);
+    const T pyo = __shfl_up_sync(QD_FULL, p.y, d);
+#ifdef QD_EMU
+    if (off >= d) { g += go; p.x += pxo; p.y += pyo; }
+#else
+    if constexpr (sizeof(T) == 4) {
+        asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %6, %7;\n\t@q add.f32 %0, %0, %3;\n\t@q add.f32 %1, %1, %4;\n\t@q add.f32 %2, %2, %5;\n\t}"
+            : "+f"(g), "+f"(p.x), "+f"(p.y) : "f"(go), "f"(pxo), "f"(pyo), "r"(off), "r"(d));
+    } else {
+        if (off >= d) { g += go; p.x += pxo; p.y += pyo; }
+    }
+#endif
 }
 
 template <class T, int NC, bool TS, bool FX>
@@ -516,10 +586,11 @@ QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, co
         V2<T> p = mk2<T>(0.0f, 0.0f);
         if (i < q.n_src) {
             e = tld<TS>(q.src_tab + i);
-            p = buf[e & 0x1fffu];
+            const int pos = spos<T, NC>((int)(e & 0x1fffu));
+            p = buf[pos];
             if constexpr (FX) {
-                g = mags[e & 0x1fffu];
-                p = mk2<T>(g * p.x, g * p.y);
+                g = mags[pos];
+                p = pmul(p, splat(g));
             } else {
                 const T m2 = p.x * p.x + p.y * p.y;
                 g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
@@ -527,17 +598,12 @@ QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, co
         }
         const int off = (int)((e >> 26) & 31u);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const T go = __shfl_up_sync(QD_FULL, g, d);
-            const T pxo = __shfl_up_sync(QD_FULL, p.x, d);
-            const T pyo = __shfl_up_sync(QD_FULL, p.y, d);
-            if (off >= d) { g += go; p.x += pxo; p.y += pyo; }
-        }
+        for (int d = 1; d < 32; d <<= 1) seg_scan_step<T>(g, p, off, d);
         if (e >> 31) {
             const int sid = (int)((e >> 13) & 0x1fffu);
             slotG[sid] += g;
             const V2<T> t = slotP[sid];
-            slotP[sid] = mk2<T>(t.x + p.x, t.y + p.y);
+            slotP[sid] = padd(t, p);
         }
         __syncwarp();
     }
@@ -546,7 +612,7 @@ QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, co
         const T ik = (T)tld<TS>(q.slot_invk + sl);
         slotG[sl] *= ik;
         const V2<T> t = slotP[sl];
-        slotP[sl] = mk2<T>(t.x * ik, t.y * ik);
+        slotP[sl] = pmul(t, splat(ik));
     }
     __syncwarp();
 
@@ -566,7 +632,7 @@ QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, co
         quant_bin<T, NC, TS, FX>(buf, mags, slotG, slotP, q, lane, row, bit, m_next, u_next);
         if (row > 0) {
             const T out = smooth ? smooth_row<T>(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
-            buf[rpos<T, NC>(lane, row - 1)] = mk2<T>(out * u_cur.x, out * u_cur.y);
+            buf[rpos<T, NC>(lane, row - 1)] = pmul(u_cur, splat(out));
         }
         m_prev = m_cur; m_cur = m_next; u_cur = u_next;
     }
@@ -576,7 +642,7 @@ QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, co
         load_bin<T, FX>(buf, mags, rpos<T, NC>(lane, row), m_next, u_next);
         if (row > 0) {
             const T out = smooth ? smooth_row<T>(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
-            buf[rpos<T, NC>(lane, row - 1)] = mk2<T>(out * u_cur.x, out * u_cur.y);
+            buf[rpos<T, NC>(lane, row - 1)] = pmul(u_cur, splat(out));
         }
         m_prev = m_cur; m_cur = m_next; u_cur = u_next;
     }
@@ -589,10 +655,170 @@ QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, co
             else load_bin<T, FX>(buf, mags, rpos<T, NC>(0, ROWS - 1), m_next, u_next);
         }
         const T out = smooth ? smooth_row<T>(m_prev, m_cur, m_next, lane, ROWS == 2 && lane == 0, false) : m_cur;
-        buf[rpos<T, NC>(lane, ROWS - 2)] = mk2<T>(out * u_cur.x, out * u_cur.y);
+        buf[rpos<T, NC>(lane, ROWS - 2)] = pmul(u_cur, splat(out));
         m_prev = m_cur; m_cur = m_next; u_cur = u_next;
         const T outn = smooth ? smooth_row<T>(m_prev, m_cur, 0.0f, lane, false, lane == 0) : m_cur;
-        if (lane == 0) buf[rpos<T, NC>(0, ROWS - 1)] = mk2<T>(outn * u_cur.x, outn * u_cur.y);
+        if (lane == 0) buf[rpos<T, NC>(0, ROWS - 1)] = pmul(u_cur, splat(outn));
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- quantizer fused with the real split / merge
+// The spectral pass is bound by shared-memory wavefronts, so the plain (no-FX) quantizer does not run
+// real_split / real_merge as separate sweeps over the warp buffer: it reads the packed-FFT output Z[k], Z[NC-k]
+// as a pair, forms X[k] and X[NC-k] in registers, quantizes both, and writes Z'[k], Z'[NC-k] back -- one read
+// and one write of the buffer instead of three.  A lane walks bin k = 32 i + lane upwards (low side) and its
+// mirror NC - k downwards (high side); both sides keep the rolling three-row window of the smoothing, and
+// the two walks meet at bin NC/2.
+
+// X[k] for any k in 0..NC straight from Z (Q1 sources).  DC / Nyquist come out of the same formula because
+// Z[NC] = Z[0] and V_0 = -i/2.
+template <class T, int NC>
+QD_DEV V2<T> split_bin(const V2<T> *buf, const V2<T> *wsplit, int k) {
+    const bool hi = 2 * k > NC;
+    const int kk = hi ? NC - k : k;
+    const V2<T> za = buf[spos_lt<T, NC>(kk)];
+    const V2<T> zb = cconj(buf[spos_lt<T, NC>((NC - kk) & (NC - 1))]);
+    const V2<T> t = cmul(csub(za, zb), wsplit[kk]);
+    const V2<T> e = cadd(za, zb);
+    return hi ? cconj(pfma(e, splat((T)0.5), mk2<T>(-t.x, -t.y))) : pfma(e, splat((T)0.5), t);
+}
+
+// quantizer arithmetic of bin d (any lane / row mapping): magnitude after giving away / receiving energy, and
+// the phasor of the arriving sum when energy arrived
+template <class T, bool TS>
+QD_DEV void quant_apply(T m, V2<T> &u, T &nm, int d, const T *slotG, const V2<T> *slotP, const QuantDev &q) {
+    nm = ((tld<TS>(q.row_active + (d >> 5)) >> (d & 31)) & 1u) ? m * (T)q.keep_active : m;
+    const uint16_t *sb = q.slot_of_bin + d;
+    T te = (T)0;
+    V2<T> ps = mk2<T>((T)0, (T)0);
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+        const int s = tld<TS>(sb + e);
+        T c = (T)q.tap[e];
+        if (e == 2) c += (T)tld<TS>(q.slot_base + s);
+        te += c * slotG[s];
+        ps = pfma(splat(c), slotP[s], ps);
+    }
+    nm += te;
+    if (te > (T)0) {
+        const T p2 = ps.x * ps.x + ps.y * ps.y;
+        const bool ok = p2 > (T)QD_TINY2;
+        const T r = rsqrt_fast(p2);
+        u = ok ? pmul(ps, splat(r)) : mk2<T>((T)1, (T)0);
+    }
+}
+
+template <class T, int NC, bool TS>
+QD_DEV void quantize_frame_fused(V2<T> *buf, T *slotG, V2<T> *slotP, const QuantDev &q, const V2<T> *wsplit, int lane) {
+    // Q1: per-target gathers (see quantize_frame), the source bins split on the fly
+    for (int s = lane; s <= q.n_slots; s += 32) {
+        slotG[s] = 0.0f;
+        slotP[s] = mk2<T>(0.0f, 0.0f);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int i0 = 0; i0 < q.n_src; i0 += 32) {
+        const int i = i0 + lane;
+        uint32_t e = 0u;
+        T g = 0.0f;
+        V2<T> p = mk2<T>(0.0f, 0.0f);
+        if (i < q.n_src) {
+            e = tld<TS>(q.src_tab + i);
+            p = split_bin<T, NC>(buf, wsplit, (int)(e & 0x1fffu));
+            const T m2 = p.x * p.x + p.y * p.y;
+            g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
+        }
+        const int off = (int)((e >> 26) & 31u);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) seg_scan_step<T>(g, p, off, d);
+        if (e >> 31) {
+            const int sid = (int)((e >> 13) & 0x1fffu);
+            slotG[sid] += g;
+            slotP[sid] = padd(slotP[sid], p);
+        }
+        __syncwarp();
+    }
+    for (int sl = lane; sl < q.n_slots; sl += 32) {
+        const T ik = (T)tld<TS>(q.slot_invk + sl);
+        slotG[sl] *= ik;
+        slotP[sl] = pmul(slotP[sl], splat(ik));
+    }
+    __syncwarp();
+
+    // Q3: paired walk.  l* = low side (bins ascending), h* = high side (bins descending); *p/*c/*n = previous,
+    // current, next row of the rolling smoothing window; the pair of iteration i-1 is finished in iteration i.
+    constexpr int HR = NC / 64;
+    const bool smooth = q.smoothing != 0;
+    T lp = 0.0f, lc = 0.0f, ln = 0.0f, hp = 0.0f, hc = 0.0f, hn = 0.0f;
+    V2<T> luc = mk2<T>(1.0f, 0.0f), lun = luc, huc = luc, hun = luc, vc = luc, vn = luc;
+    int pac = 0, pbc = 0;
+    const bool is0 = lane == 0, is31 = lane == 31;
+    const int lane_m1 = (lane + 31) & 31, lane_p1 = (lane + 1) & 31;
+    // `edge`: the pair being finished is iteration 0, whose lane 0 holds the two spectrum edges (DC, Nyquist)
+    auto emit = [&](bool edge) {
+        T ol = lc, oh = hc;
+        if (smooth) {
+            if (edge) {
+                ol = smooth_row<T>(lp, lc, ln, lane, is0, false);
+                oh = smooth_row<T>(hp, hc, hn, lane, is0, false);
+            } else {
+                ol = smooth_mid<T>(lp, lc, ln, is0, is31, lane_m1, lane_p1);
+                oh = smooth_mid<T>(hp, hc, hn, is0, is31, lane_m1, lane_p1);
+            }
+        }
+        V2<T> xa = pmul(luc, splat(ol));
+        V2<T> xb = cconj(pmul(huc, splat(oh)));
+        if (edge && is0) { xa.y = 0.0f; xb.y = 0.0f; }   // only Re of DC / Nyquist (pocketfft c2r)
+        // Hermitian merge (see real_merge): Z'[k] = E2 + i O2, Z'[NC-k] = conj(E2 - i O2)
+        const V2<T> e2 = cadd(xa, xb);
+        const V2<T> h = cmulc(csub(xa, xb), vc);
+        buf[pac] = pfma(h, splat((T)2), e2);
+        buf[pbc] = cconj(pfma(h, splat((T)-2), e2));
+    };
+#pragma unroll 2
+    for (int i = 0; i < HR; ++i) {
+        const int k = 32 * i + lane;
+        const int pa = rpos<T, NC>(lane, i);
+        const int pb = k == 0 ? pa : mpos<T, NC>(lane, i);   // Z[NC] = Z[0]
+        vn = wsplit[k];
+        const V2<T> za = buf[pa], zb = cconj(buf[pb]);
+        const V2<T> e = cadd(za, zb);
+        const V2<T> t = cmul(csub(za, zb), vn);
+        const V2<T> xl = pfma(e, splat((T)0.5), t);                            // X[k]
+        const V2<T> xh = cconj(pfma(e, splat((T)0.5), mk2<T>(-t.x, -t.y)));    // X[NC-k]
+        T ml, mh;
+        mag_phasor<T>(xl, ml, lun);
+        mag_phasor<T>(xh, mh, hun);
+        if (i < q.row_limit) quant_apply<T, TS>(ml, lun, ln, k, slotG, slotP, q);
+        else ln = ml;
+        if (NC - 32 * i - 31 < 32 * q.row_limit) quant_apply<T, TS>(mh, hun, hn, NC - k, slotG, slotP, q);
+        else hn = mh;
+        if (i > 1) emit(false);
+        else if (i == 1) emit(true);
+        lp = lc; lc = ln; luc = lun;
+        hp = hc; hc = hn; huc = hun;
+        vc = vn; pac = pa; pbc = pb;
+    }
+    // the two walks meet at bin NC/2 (lane 0)
+    {
+        const int pm = spos<T, NC>(NC / 2);
+        T mm = 0.0f;
+        V2<T> um = mk2<T>(1.0f, 0.0f);
+        if (lane == 0) {
+            T m0;
+            mag_phasor<T>(cconj(buf[pm]), m0, um);
+            if ((NC / 64) < q.row_limit) quant_apply<T, TS>(m0, um, mm, NC / 2, slotG, slotP, q);
+            else mm = m0;
+        }
+        ln = mm; hn = mm;
+        emit(HR == 1);
+        const T left = __shfl_sync(QD_FULL, lc, 31);    // bin NC/2 - 1
+        const T right = __shfl_sync(QD_FULL, hc, 31);   // bin NC/2 + 1
+        if (lane == 0) {
+            const T om = smooth ? 0.5f * mm + 0.25f * (left + right) : mm;
+            buf[pm] = mk2<T>(2.0f * om * um.x, -2.0f * om * um.y);
+        }
     }
     __syncwarp();
 }
@@ -726,7 +952,8 @@ spec_pass_kernel(const SpecArgsT<T> a) {
         V2<T> *t_w = reinterpret_cast<V2<T> *>(tables_base);
         V2<T> *t_tw = t_w + NC;
         V2<T> *t_ws = t_tw + NC;
-        for (int i = ctid; i < NC; i += cthreads) { t_w[i] = a.wtab[i]; t_tw[i] = a.tw1[i]; }
+        for (int i = ctid; i < NC; i += cthreads) t_tw[i] = a.tw1[i];
+        for (int i = ctid; i < 2 * (NC / FftCfg<T, NC>::R1); i += cthreads) t_w[i] = a.wtab[i];
         for (int i = ctid; i <= NC / 2; i += cthreads) t_ws[i] = a.wsplit[i];
         wtab = t_w; tw1 = t_tw; wsplit = t_ws;
         if (a.quant) {
@@ -794,7 +1021,7 @@ spec_pass_kernel(const SpecArgsT<T> a) {
         }
         if (live) {
             fft_forward<T, NC>(buf, nullptr, a, wtab, tw1, a.tw2, lane);
-            real_split<T, NC>(buf, wsplit, lane);
+            if (FX || !a.quant) real_split<T, NC>(buf, wsplit, lane);
             if (a.quant) {
                 if constexpr (FX) {
                     static_assert(!TS, "FX kernels read their tables through L1");
@@ -806,10 +1033,10 @@ spec_pass_kernel(const SpecArgsT<T> a) {
                                     a.frozen ? a.frozen + (size_t)clip * L::BUF : nullptr);
                     quantize_frame<T, NC, TS, true>(buf, mags, slotG, slotP, qq, lane);
                 } else {
-                    quantize_frame<T, NC, TS, false>(buf, nullptr, slotG, slotP, qq, lane);
+                    quantize_frame_fused<T, NC, TS>(buf, slotG, slotP, qq, wsplit, lane);
                 }
             }
-            real_merge<T, NC>(buf, wsplit, lane);
+            if (FX || !a.quant) real_merge<T, NC>(buf, wsplit, lane);
             fft_inverse<T, NC>(buf, wtab, tw1, a.tw2, lane);
         } else {
             for (int i = lane; i < L::BUF; i += 32) buf[i] = mk2<T>(0.0f, 0.0f);
@@ -828,8 +1055,7 @@ spec_pass_kernel(const SpecArgsT<T> a) {
 #pragma unroll
                 for (int w = (h - 3 > 0 ? h - 3 : 0); w <= (h < NW - 1 ? h : NW - 1); ++w) {
                     const V2<T> f = bufs[(size_t)w * L::BUF + (h - w) * HPP + pc];
-                    v.x += f.x;
-                    v.y += f.y;
+                    v = padd(v, f);
                 }
                 if (h >= NW) {
                     tail[(h - NW) * HP + c] = v;  // partial sums of the next three blocks
@@ -844,7 +1070,8 @@ spec_pass_kernel(const SpecArgsT<T> a) {
                 const int sl_b = j < 3 ? j : 3;
                 V2<T> inv = mk2<T>(0.0f, 0.0f);
                 if (sl_a <= sl_b) inv = __ldg(reinterpret_cast<const V2<T> *>(a.invw + (sl_a * 4 + sl_b) * HOP) + c);
-                const float2 o = make_float2((float)(v.x * inv.x), (float)(v.y * inv.y));  // float32 like istft_mono
+                const V2<T> vi = pmul(v, inv);
+                const float2 o = make_float2((float)vi.x, (float)vi.y);  // float32 like istft_mono
                 const float2 r = make_float2(epilogue_apply(o.x, a.epilogue, a.fold, a.bias, a.tube_gain, a.tube_norm),
                                              epilogue_apply(o.y, a.epilogue, a.fold, a.bias, a.tube_gain, a.tube_norm));
                 if (vec2) {  // nidx is even and n is even, so nidx + 1 < n
