@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 2
+#define QD_ABI_VERSION 3
 
 typedef enum qd_status {
     QD_OK = 0,
@@ -109,6 +109,10 @@ typedef struct qd_params {
                                     QD_PRECISION_F64: the same kernels instantiated in float64 -- the parity path
                                     for ill-conditioned configurations (band mask wide open, n_fft 8192) */
     int32_t  spectral_freeze;    /* dsp/pipeline.py:285-287, 303-304: every frame takes the magnitudes of frame 0 */
+    double   formant_ratio;      /* 2^(formant_shift/12), dsp/spectral_fx.py:173; 0 = off (dsp/pipeline.py:306-310).
+                                    float32 kernels, n_fft <= 4096 */
+    int32_t  formant_order;      /* cepstral lifter order, dsp/spectral_fx.py:120 (30) */
+    int32_t  reserved0;
 } qd_params;
 
 #define QD_PRECISION_F32 0

@@ -386,12 +386,38 @@ def apply_spectral_fx(mag, phase, mode, s, params):
     return mag, phase
 
 
+def formant_shift_frame(mag, shift_semitones: float, lifter_order: int = 30):
+    """dsp/spectral_fx.py:116-195: cepstral envelope (low-quefrency lifter) moved along the bin axis by
+    2**(semitones/12), fine structure kept, total energy preserved."""
+    mag = np.asarray(mag, dtype=float)
+    if len(mag) < 4 or shift_semitones == 0.0:  # :146-147
+        return mag.copy()
+    eps = 1e-12
+    n_bins = len(mag)
+    log_mag = np.log(np.clip(mag, eps, None))  # :153
+    cep = np.fft.irfft(log_mag, n=2 * (n_bins - 1))  # :156
+    lifter = np.zeros_like(cep)  # :159-162
+    order = min(lifter_order, len(lifter) // 2)
+    lifter[:order] = 1.0
+    lifter[-order + 1:] = 1.0
+    log_env = np.fft.rfft(cep * lifter)[:n_bins].real  # :168
+    log_fine = np.fft.rfft(cep * (1.0 - lifter))[:n_bins].real  # :169
+    ratio = 2.0 ** (shift_semitones / 12.0)  # :173
+    idx = np.arange(n_bins, dtype=float)
+    env_s = np.interp(idx / ratio, idx, log_env, left=log_env[0], right=log_env[-1])  # :176-183
+    out = np.exp(env_s + log_fine)  # :186-187
+    e0, e1 = np.sum(mag ** 2), np.sum(out ** 2)  # :190-193
+    if e1 > eps:
+        out *= np.sqrt(e0 / e1)
+    return out
+
+
 # --------------------------------------------------------------------------- spectral stage on an STFT matrix
 def spectral_quantize_stft(S, freqs, key, scale, snap_strength, smear, bin_smoothing, *,
                            is_high_band=False, spectral_fx_mode=None, spectral_fx_strength=0.0,
                            spectral_fx_params=None, spectral_freeze=False, harmonic_lock_hz=0.0,
-                           quantize_min_hz=110.0, quantize_max_hz=5000.0):
-    """dsp/pipeline.py:228-342 (formant_shift is outside the graded path and unsupported)."""
+                           quantize_min_hz=110.0, quantize_max_hz=5000.0, formant_shift=0.0):
+    """dsp/pipeline.py:228-342."""
     mags = np.abs(S).T.copy()  # [frames, bins]   :269
     phases = np.angle(S).T.copy()  # :270
     tb = (harmonic_target_bins(freqs, harmonic_lock_hz) if harmonic_lock_hz > 0.0
@@ -399,6 +425,9 @@ def spectral_quantize_stft(S, freqs, key, scale, snap_strength, smear, bin_smoot
     am = quantize_band_mask(freqs, quantize_min_hz, quantize_max_hz)  # :282
     if spectral_freeze and mags.shape[0] > 0:  # :285-287, :303-304
         mags[:] = mags[0][None, :]
+    if formant_shift != 0.0:  # :306-310, any band, after the freeze and before the FX
+        for t in range(mags.shape[0]):
+            mags[t] = formant_shift_frame(mags[t], formant_shift)
     if is_high_band and spectral_fx_mode is not None:  # :291, :313-314 -- per frame, RNG order preserved
         for t in range(mags.shape[0]):
             mags[t], phases[t] = apply_spectral_fx(mags[t], phases[t], spectral_fx_mode,
@@ -522,7 +551,7 @@ def process_single_band(x_in, sr, *, key, scale, snap_strength, smear, bin_smoot
                         dry_wet, tap_input, passthrough_test=False, is_high_band=False,
                         spectral_fx_mode=None, spectral_fx_strength=0.0, spectral_fx_params=None,
                         spectral_freeze=False, harmonic_lock_hz=0.0, output_trim_db=0.0,
-                        sub_cut_hz=110.0, air_cut_hz=5000.0, n_fft=N_FFT_DEFAULT):
+                        sub_cut_hz=110.0, air_cut_hz=5000.0, n_fft=N_FFT_DEFAULT, formant_shift=0.0):
     """dsp/pipeline.py:419-920 without the autotune branch (:537-601)."""
     n = x_in.shape[0]
     if passthrough_test:  # :477-535
@@ -535,7 +564,8 @@ def process_single_band(x_in, sr, *, key, scale, snap_strength, smear, bin_smoot
             S, freqs, key, scale, snap_strength, smear, bin_smoothing, is_high_band=is_high_band,
             spectral_fx_mode=spectral_fx_mode, spectral_fx_strength=spectral_fx_strength,
             spectral_fx_params=spectral_fx_params, spectral_freeze=spectral_freeze,
-            harmonic_lock_hz=harmonic_lock_hz, quantize_min_hz=sub_cut_hz, quantize_max_hz=air_cut_hz)
+            harmonic_lock_hz=harmonic_lock_hz, quantize_min_hz=sub_cut_hz, quantize_max_hz=air_cut_hz,
+            formant_shift=formant_shift)
 
     pre = bool(pre_quant and snap_strength > 0.0)  # :635
     post = bool(post_quant and snap_strength > 0.0)  # :728
@@ -579,7 +609,7 @@ def process_audio(audio, sr=48000, key="D", scale="minor", quantize_mode="spectr
                   spectral_fx_strength=0.0, spectral_fx_params=None, spectral_freeze=False,
                   harmonic_lock_hz=0.0, delta_listen=False, mono_strength=1.0, output_trim_db=0.0,
                   sub_cut_hz=110.0, air_cut_hz=5000.0, low_trim_db=0.0,
-                  n_fft=N_FFT_DEFAULT) -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
+                  n_fft=N_FFT_DEFAULT, formant_shift=0.0) -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
     """
     dsp/pipeline.py:1113-1407 for the STFT path.  ``quantize_mode`` must resolve to
     "spectral_bins" (the reference's default "autotune_v1" is a different, out-of-scope
@@ -587,7 +617,7 @@ def process_audio(audio, sr=48000, key="D", scale="minor", quantize_mode="spectr
     :1315-1324).  ``n_fft`` restates the module global N_FFT_DEFAULT (:149).
     """
     if quantize_mode == "autotune_v1" and (spectral_fx_mode is not None or spectral_freeze
-                                            or harmonic_lock_hz > 0.0):
+                                            or formant_shift != 0.0 or harmonic_lock_hz > 0.0):
         quantize_mode = "spectral_bins"
     if quantize_mode != "spectral_bins":
         raise NotImplementedError("oracle covers quantize_mode='spectral_bins' only")
@@ -604,7 +634,7 @@ def process_audio(audio, sr=48000, key="D", scale="minor", quantize_mode="spectr
         spectral_fx_mode=spectral_fx_mode, spectral_fx_strength=spectral_fx_strength,
         spectral_fx_params=spectral_fx_params or {}, spectral_freeze=spectral_freeze,
         harmonic_lock_hz=harmonic_lock_hz, output_trim_db=output_trim_db, sub_cut_hz=sub_cut_hz,
-        air_cut_hz=air_cut_hz, n_fft=n_fft)
+        air_cut_hz=air_cut_hz, n_fft=n_fft, formant_shift=formant_shift)
     if use_multiband:  # dsp/pipeline.py:1011-1110
         low, high = linkwitz_riley_split(x, sr, crossover_hz)
         d = n_fft // 2  # :1056, filter-delay term cancels (:380-386)

@@ -103,7 +103,8 @@ namespace {
 // ---- kernel selection.  float32: n_fft 2048 (the headline size) runs 16 warps per CTA with its tables in
 //      shared memory (falls back to 8 warps + L1 tables when they do not fit); float64 (parity path) and the
 //      FX variants read tables through L1.  Must stay in sync with the switch in dispatch_spec().
-template <class T> int pick_nw(int nc, bool fx) {
+template <class T> int pick_nw(int nc, bool fx, bool formant = false) {
+    if (sizeof(T) == 4 && formant) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 0;   // scratch buffer per warp; n_fft 8192: not built
     if (sizeof(T) == 8 && fx) return nc <= 512 ? 8 : nc == 1024 ? 4 : nc == 2048 ? 2 : 0;  // n_fft 8192: not built
     if (sizeof(T) == 8) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 2;
     if (fx) return nc == 1024 ? 12 : nc < 1024 ? 8 : 4;   // 12 warps: what fits beside the FX magnitude planes
@@ -111,24 +112,25 @@ template <class T> int pick_nw(int nc, bool fx) {
 }
 
 template <class T, int NC, int NW>
-size_t smem_of(int n_slots, bool ts, int n_src, int n_aff, bool fx) {
-    return qd::SpecSmem<T, NC, NW>::bytes(n_slots, ts, n_src, n_aff, fx);
+size_t smem_of(int n_slots, bool ts, int n_src, int formant, bool fx) {
+    return qd::SpecSmem<T, NC, NW>::bytes(n_slots, ts, n_src, 0, fx, formant != 0);
 }
 
 template <class T>
-size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int n_aff, bool fx) {
+size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int formant, bool fx) {
+    const int fm = formant;
     switch (nc) {
-        case 256:  return nw == 8 ? smem_of<T, 256, 8>(n_slots, false, 0, 0, fx) : 0;
-        case 512:  return nw == 8 ? smem_of<T, 512, 8>(n_slots, false, 0, 0, fx) : 0;
+        case 256:  return nw == 8 ? smem_of<T, 256, 8>(n_slots, false, 0, fm, fx) : 0;
+        case 512:  return nw == 8 ? smem_of<T, 512, 8>(n_slots, false, 0, fm, fx) : 0;
         case 1024:
-            if (nw == 16) return qd::SpecSmem<T, 1024, 8, 2>::bytes(n_slots, ts, n_src, n_aff, fx);
-            return nw == 8 ? smem_of<T, 1024, 8>(n_slots, false, 0, 0, fx)
-                 : nw == 12 ? smem_of<T, 1024, 12>(n_slots, false, 0, 0, fx)
-                 : nw == 4 ? smem_of<T, 1024, 4>(n_slots, false, 0, 0, fx) : 0;
-        case 2048: return nw == 4 ? smem_of<T, 2048, 4>(n_slots, false, 0, 0, fx)
-                        : nw == 2 ? smem_of<T, 2048, 2>(n_slots, false, 0, 0, fx) : 0;
-        case 4096: return nw == 4 ? smem_of<T, 4096, 4>(n_slots, false, 0, 0, fx)
-                        : nw == 2 ? smem_of<T, 4096, 2>(n_slots, false, 0, 0, fx) : 0;
+            if (nw == 16) return qd::SpecSmem<T, 1024, 8, 2>::bytes(n_slots, ts, n_src, 0, fx);
+            return nw == 8 ? smem_of<T, 1024, 8>(n_slots, false, 0, fm, fx)
+                 : nw == 12 ? smem_of<T, 1024, 12>(n_slots, false, 0, fm, fx)
+                 : nw == 4 ? smem_of<T, 1024, 4>(n_slots, false, 0, fm, fx) : 0;
+        case 2048: return nw == 4 ? smem_of<T, 2048, 4>(n_slots, false, 0, fm, fx)
+                        : nw == 2 ? smem_of<T, 2048, 2>(n_slots, false, 0, fm, fx) : 0;
+        case 4096: return nw == 4 ? smem_of<T, 4096, 4>(n_slots, false, 0, fm, fx)
+                        : nw == 2 ? smem_of<T, 4096, 2>(n_slots, false, 0, fm, fx) : 0;
     }
     return 0;
 }
@@ -141,7 +143,7 @@ int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStrea
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set.store(true, std::memory_order_release);
     }
-    const size_t smem = qd::SpecSmem<T, NC, NW, NG>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX);
+    const size_t smem = qd::SpecSmem<T, NC, NW, NG>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX, FX && a.formant_idx != nullptr);
     for (int64_t b0 = 0; b0 < batch; b0 += 65535 * NG) {  // gridDim.y limit
         const int64_t nb = std::min<int64_t>(65535 * NG, batch - b0);
         qd::SpecArgsT<T> c = a;
@@ -166,7 +168,8 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
                 if (nw == 16 && ts) return launch_spec_t<T, 1024, 8, true, false, 2>(a, tiles, batch, st);
             }
             if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 1024, 4, false, true>(a, tiles, batch, st);
-            else if constexpr (FX) return launch_spec_t<T, 1024, 12, false, true>(a, tiles, batch, st);
+            else if constexpr (FX) return nw == 8 ? launch_spec_t<T, 1024, 8, false, true>(a, tiles, batch, st)
+                                                  : launch_spec_t<T, 1024, 12, false, true>(a, tiles, batch, st);
             else return launch_spec_t<T, 1024, 8, false, false>(a, tiles, batch, st);
         case 2048:
             if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 2048, 2, false, true>(a, tiles, batch, st);
@@ -213,7 +216,7 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
     a.tap = tap;
     a.quant = quant;
     a.epilogue = epilogue;
-    const bool fx = quant && (pl->p.fx_mode != QD_FX_NONE || pl->p.spectral_freeze);
+    const bool fx = quant && (pl->p.fx_mode != QD_FX_NONE || pl->p.spectral_freeze || pl->p.formant_ratio > 0.0);
     a.fx.pass = fx_pass;
     a.fx.clip_offset = clip_offset;
     a.fx.table = pl->fx_table;
@@ -370,7 +373,11 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         qdev.smoothing = p.bin_smoothing ? 1 : 0;
         n_slots = qt.n_slots;
     }
-    const bool fx = need_quant && (p.fx_mode != QD_FX_NONE || p.spectral_freeze);
+    const bool formant = need_quant && p.formant_ratio > 0.0;
+    if (formant && p.precision != QD_PRECISION_F32) return bail(QD_ERR_UNSUPPORTED, "formant shift is built for the float32 kernels");
+    if (formant && p.n_fft > 4096) return bail(QD_ERR_UNSUPPORTED, "formant shift is built for n_fft <= 4096");
+    if (formant && p.formant_order < 2) return bail(QD_ERR_INVALID_ARG, "formant_order must be >= 2");
+    const bool fx = need_quant && (p.fx_mode != QD_FX_NONE || p.spectral_freeze || formant);
     qd::FxDev fxd{};
     fxd.mode = (need_quant && p.fx_mode != QD_FX_NONE) ? p.fx_mode : 0;
     fxd.a = (float)p.fx_a; fxd.b = (float)p.fx_b; fxd.c = (float)p.fx_c;
@@ -420,9 +427,27 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         a.invw = d_invw;
         a.q = qdev;
         a.fx = fxd;
-        pl->nw = pick_nw<float>(pl->nc, fx);
+        if (formant) {
+            // np.interp(k / ratio, arange(n_bins), env): segment index and fraction per bin in float64
+            // (dsp/spectral_fx.py:173-183); beyond the last bin the envelope is held (right = env[-1])
+            const int nb = st.nc + 1;
+            std::vector<int16_t> fi((size_t)nb);
+            std::vector<float> ff((size_t)nb);
+            for (int k = 0; k < nb; ++k) {
+                const double x = (double)k / p.formant_ratio;
+                if (x >= (double)(nb - 1)) { fi[k] = (int16_t)(nb - 1); ff[k] = 0.0f; }
+                else { const double fl = std::floor(x); fi[k] = (int16_t)fl; ff[k] = (float)(x - fl); }
+            }
+            int16_t *d_fi; float *d_ff;
+            QD_UP(fi, d_fi);
+            QD_UP(ff, d_ff);
+            a.formant_idx = d_fi;
+            a.formant_frac = d_ff;
+            a.formant_order = p.formant_order;
+        }
+        pl->nw = pick_nw<float>(pl->nc, fx, formant);
         pl->ts = (pl->nc == 1024 && pl->nw == 16);
-        pl->spec_smem = spec_smem_bytes<float>(pl->nc, pl->nw, pl->ts, n_slots, qdev.n_src, 0, fx);
+        pl->spec_smem = spec_smem_bytes<float>(pl->nc, pl->nw, pl->ts, n_slots, qdev.n_src, formant ? 1 : 0, fx);
         if (pl->ts && pl->spec_smem > 227 * 1024) {  // tables too large for shared memory: 8 warps, tables through L1
             pl->nw = 8;
             pl->ts = false;

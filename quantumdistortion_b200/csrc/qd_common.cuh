@@ -113,6 +113,10 @@ QD_DEV float  qd_log10(float a)  { return log10f(a); }
 QD_DEV double qd_log10(double a) { return log10(a); }
 QD_DEV float  qd_log2(float a)  { return log2f(a); }
 QD_DEV double qd_log2(double a) { return log2(a); }
+QD_DEV float  qd_log(float a)  { return logf(a); }
+QD_DEV double qd_log(double a) { return log(a); }
+QD_DEV float  qd_exp(float a)  { return expf(a); }
+QD_DEV double qd_exp(double a) { return exp(a); }
 QD_DEV float  qd_exp2(float a)  { return exp2f(a); }
 QD_DEV double qd_exp2(double a) { return exp2(a); }
 QD_DEV float  qd_exp10(float a)  { return QD_EXP10F(a); }

@@ -125,6 +125,10 @@ struct SpecArgsT {
     QuantDev q;
     FxDev fx;
     const T *frozen;       // optional [batch][BUF]: |X| of frame 0 by buffer position (spectral freeze)
+    // formant shift (dsp/spectral_fx.py:116-195), float32 FX kernels only; null = off
+    const int16_t *formant_idx;   // [NC+1] floor(k / ratio) clamped to NC        (np.interp segment, host float64)
+    const float *formant_frac;    // [NC+1] k / ratio - floor(k / ratio), 0 when clamped
+    int formant_order;            // lifter order (30)
 };
 using SpecArgs = SpecArgsT<float>;
 
@@ -243,9 +247,33 @@ QD_DEV void fwd_first(V2<T> *buf, const float2 *frame, const V2<T> *wtab, const 
     __syncwarp();
 }
 
-// last inverse pass: synthesis window (the 1/n_fft of the inverse FFT is folded into the host's 1/sum(w^2) table),
-// leaves the time-domain frame in buf
+// first forward pass of a sequence that already sits in the warp buffer (pidx layout), no window: the forward real
+// FFT of the liftered cepstrum (formant shift)
 template <class T, int NC, int R>
+QD_DEV void fwd_first_buf(V2<T> *buf, const V2<T> *tw, int lane) {
+    constexpr int S = NC / R;
+    constexpr int NB = NC / R / 32;
+    constexpr int LG = qd_log2(R);
+#pragma unroll 1
+    for (int i = 0; i < NB; ++i) {
+        const int a0 = lane + 32 * i;
+        V2<T> v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = buf[pidx(a0 + q * S)];
+        dft_reg<R, -1, T>(v);
+        buf[pidx(a0)] = v[0];
+        twiddle_walk<T, R>(tw + (i * R) * 32 + lane,
+                           [&](auto kc, V2<T> w) {
+                               constexpr int k = decltype(kc)::value;
+                               buf[pidx(a0 + k * S)] = cmul(v[qd_bitrev(k, LG)], w);
+                           });
+    }
+    __syncwarp();
+}
+
+// last inverse pass: synthesis window (the 1/n_fft of the inverse FFT is folded into the host's 1/sum(w^2) table),
+// leaves the time-domain frame in buf.  WIN = false: no window (inverse real FFT of the log spectrum, formant shift)
+template <class T, int NC, int R, bool WIN = true>
 QD_DEV void inv_last(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw, int lane) {
     constexpr int S = NC / R;
     constexpr int NB = NC / R / 32;
@@ -260,11 +288,16 @@ QD_DEV void inv_last(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw, int lane) {
             v[k] = cmulc(buf[pidx(a0 + k * S)], w);
         });
         dft_reg<R, +1, T>(v);
-        const V2<T> wc = wtab[2 * a0], ws = wtab[2 * a0 + 1];
+        if constexpr (WIN) {
+            const V2<T> wc = wtab[2 * a0], ws = wtab[2 * a0 + 1];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int q = qd_bitrev(r, LG);
-            buf[pidx(a0 + q * S)] = pmul(v[r], hann_pair<T, R>(wc, ws, q));
+            for (int r = 0; r < R; ++r) {
+                const int q = qd_bitrev(r, LG);
+                buf[pidx(a0 + q * S)] = pmul(v[r], hann_pair<T, R>(wc, ws, q));
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) buf[pidx(a0 + qd_bitrev(r, LG) * S)] = v[r];
         }
     }
     __syncwarp();
@@ -284,7 +317,7 @@ QD_DEV void fft_forward(V2<T> *buf, const float2 *frame, const SpecArgsT<T> &a, 
     (void)a;
 }
 
-template <class T, int NC>
+template <class T, int NC, bool WIN = true>
 QD_DEV void fft_inverse(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw1, const V2<T> *tw2, int lane) {
     using C = FftCfg<T, NC>;
     if constexpr (C::R3 > 1) {
@@ -293,7 +326,7 @@ QD_DEV void fft_inverse(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw1, const V
     } else {
         inv_pass<T, NC, NC / C::R1, C::R2, false>(buf, nullptr, lane);
     }
-    inv_last<T, NC, C::R1>(buf, wtab, tw1, lane);
+    inv_last<T, NC, C::R1, WIN>(buf, wtab, tw1, lane);
 }
 
 // ---------------------------------------------------------------- real <-> complex packing
@@ -411,11 +444,76 @@ QD_DEV T warp_sum(T v) {
     return v;
 }
 
+// Formant shift of one frame (dsp/spectral_fx.py:116-195) on the magnitude plane `mags`; `scr` is a second
+// warp-private buffer.  The spectral envelope is the low-quefrency part of the real cepstrum:
+//   L = log(max(m, 1e-12));  c = irfft(L);  c *= lifter (|q| < order);  env = Re rfft(c)
+// and, because rfft(irfft(L)) = L, the reference's fine structure rfft(c (1 - lifter)) is L - env, so
+//   m' = max(m, 1e-12) exp(env_shifted - env),  env_shifted[k] = np.interp(k / ratio, bins, env)
+// followed by the energy renormalisation sqrt(sum m^2 / sum m'^2).  The two FFTs are the warp's own n_fft-point
+// real FFT (merge + inverse passes, forward passes + split) without the Hann window; the interpolation segment and
+// fraction of every bin come from the host (float64, so the segment index is the reference's).
+template <class T, int NC>
+QD_DEV void formant_frame(T *mags, V2<T> *scr, const SpecArgsT<T> &a, const V2<T> *tw1, const V2<T> *wsplit, int lane) {
+    constexpr int NBINS = NC + 1;
+    constexpr int ROWS = (NBINS + 31) / 32;
+    T e0 = 0.0f;
+    for (int row = 0; row < ROWS; ++row) {
+        if (row < ROWS - 1 || lane == 0) {
+            const int p = rpos<T, NC>(lane, row);
+            const T m = mags[p];
+            e0 += m * m;
+            scr[p] = mk2<T>(qd_log(qd_max(m, (T)1e-12)), (T)0);
+        }
+    }
+    __syncwarp();
+    real_merge<T, NC>(scr, wsplit, lane);
+    fft_inverse<T, NC, false>(scr, nullptr, tw1, a.tw2, lane);       // scr[pidx(j)] = n_fft * (c[2j], c[2j+1])
+    {
+        const int n = 2 * NC;
+        const int order = a.formant_order < NC ? a.formant_order : NC;   // min(lifter_order, len // 2)
+        const T inv_n = (T)1 / (T)n;
+        for (int j = lane; j < NC; j += 32) {                             // lifter[:order] = lifter[-order+1:] = 1
+            const V2<T> v = scr[pidx(j)];
+            const int q0 = 2 * j, q1 = 2 * j + 1;
+            scr[pidx(j)] = mk2<T>((q0 < order || q0 > n - order) ? v.x * inv_n : (T)0,
+                                  (q1 < order || q1 > n - order) ? v.y * inv_n : (T)0);
+        }
+    }
+    __syncwarp();
+    fwd_first_buf<T, NC, FftCfg<T, NC>::R1>(scr, tw1, lane);
+    fft_forward<T, NC>(scr, nullptr, a, nullptr, tw1, a.tw2, lane);
+    real_split<T, NC>(scr, wsplit, lane);                             // Re scr[pos(k)] = env[k]
+    T e1 = 0.0f;
+    for (int row = 0; row < ROWS; ++row) {
+        if (row < ROWS - 1 || lane == 0) {
+            const int p = rpos<T, NC>(lane, row);
+            const int k = 32 * row + lane;
+            const int j = (int)__ldg(a.formant_idx + k);
+            const T fr = (T)__ldg(a.formant_frac + k);
+            const T f0 = scr[spos<T, NC>(j)].x;
+            const T f1 = scr[spos<T, NC>(j < NC ? j + 1 : NC)].x;
+            const T es = (f1 - f0) * fr + f0;                             // np.interp: slope * (x - xp[j]) + fp[j]
+            const T m = qd_max(mags[p], (T)1e-12) * qd_exp(es - scr[p].x);
+            mags[p] = m;
+            e1 += m * m;
+        }
+    }
+    e0 = warp_sum(e0);
+    e1 = warp_sum(e1);
+    if (e1 > (T)1e-12) {
+        const T sc = sqrt(e0 / e1);
+        for (int row = 0; row < ROWS; ++row)
+            if (row < ROWS - 1 || lane == 0) mags[rpos<T, NC>(lane, row)] *= sc;
+    }
+    __syncwarp();
+}
+
 // Spectral FX on one frame (high band only).  On entry buf holds X; on exit buf holds the unit phasors and
 // mags[pos] the (processed) magnitudes, both indexed by buffer position, so that a bin whose magnitude
 // becomes 0 keeps its phase for the smoothing that follows.
 template <class T, int NC>
-QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long tab_base, const T *frozen) {
+QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long tab_base, const T *frozen,
+                     V2<T> *scr, const SpecArgsT<T> &a, const V2<T> *tw1, const V2<T> *wsplit) {
     constexpr int NBINS = NC + 1;
     constexpr int ROWS = (NBINS + 31) / 32;
     T mx = 0.0f, sm = 0.0f;
@@ -433,8 +531,22 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
             sm += m;
         }
     }
-    mx = warp_max(mx);  // max / sum of the magnitudes BEFORE the effect (dsp/pipeline.py:90,105; spectral_fx.py:387)
     __syncwarp();
+    if constexpr (sizeof(T) == 4) {
+        if (a.formant_idx) {   // dsp/pipeline.py:306-310: after the freeze, before the FX
+            formant_frame<T, NC>(mags, scr, a, tw1, wsplit, lane);
+            mx = 0.0f;
+            sm = 0.0f;
+            for (int row = 0; row < ROWS; ++row) {
+                if (row < ROWS - 1 || lane == 0) {
+                    const T m = mags[rpos<T, NC>(lane, row)];
+                    mx = qd_max(mx, m);
+                    sm += m;
+                }
+            }
+        }
+    }
+    mx = warp_max(mx);  // max / sum of the magnitudes BEFORE the effect (dsp/pipeline.py:90,105; spectral_fx.py:387)
     if (fx.mode == 1 || fx.mode == 2) {
         // bitcrush (dsp/spectral_fx.py:198-260); np.round is half-to-even = rint
         const T thr = fx.c > 0.0f ? fx.c : fx.b * mx;
@@ -855,10 +967,11 @@ struct SpecSmem {
     }
     // layout: NG x [warp buffers | staging | OLA tail | flags | gather scratch], tables, FX magnitude planes
     __host__ __device__ static size_t group_bytes(int n_slots) { return off_tables(n_slots); }
-    static size_t bytes(int n_slots, bool tables_in_smem = false, int n_src = 0, int /*unused*/ = 0, bool fx = false) {
-        // FX kernels append one magnitude plane (BUF values of T) per warp
+    static size_t bytes(int n_slots, bool tables_in_smem = false, int n_src = 0, int /*unused*/ = 0, bool fx = false,
+                        bool formant = false) {
+        // FX kernels append one magnitude plane (BUF values of T) per warp, the formant shift a scratch buffer
         return NG * group_bytes(n_slots) + (tables_in_smem ? table_bytes(n_src, n_slots) : 16) +
-               (fx ? (size_t)NG * NW * BUF * sizeof(T) : 0);
+               (fx ? (size_t)NG * NW * BUF * sizeof(T) : 0) + (formant ? (size_t)NG * NW * BUF * sizeof(V2<T>) : 0);
     }
 };
 
@@ -1029,8 +1142,10 @@ spec_pass_kernel(const SpecArgsT<T> a) {
                     const int tf = t < a.fx.table_frames ? t : a.fx.table_frames - 1;
                     const long long tab_base =
                         (((long long)(a.fx.table_per_clip ? a.fx.clip_offset + clip : 0) * 2 + a.fx.pass) * a.fx.table_frames + tf) * (NC + 1);
+                    V2<T> *scr = reinterpret_cast<V2<T> *>(tables_base + 16 + (size_t)NG * NW * L::BUF * sizeof(T)) +
+                                 (size_t)(grp * NW + warp) * L::BUF;   // only there when the formant shift is on
                     fx_frame<T, NC>(buf, mags, a.fx, lane, tab_base,
-                                    a.frozen ? a.frozen + (size_t)clip * L::BUF : nullptr);
+                                    a.frozen ? a.frozen + (size_t)clip * L::BUF : nullptr, scr, a, tw1, wsplit);
                     quantize_frame<T, NC, TS, true>(buf, mags, slotG, slotP, qq, lane);
                 } else {
                     quantize_frame_fused<T, NC, TS>(buf, slotG, slotP, qq, wsplit, lane);

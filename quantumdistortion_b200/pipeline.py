@@ -243,8 +243,6 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
     if quantize_mode != "spectral_bins":
         raise NotImplementedError("only quantize_mode='spectral_bins' (the STFT path) is implemented; "
                                   "autotune_v1 is a different algorithm (SURVEY.md 8(f) rank 3)")
-    if formant != 0.0:
-        raise NotImplementedError("formant_shift is not built yet (SURVEY.md 8(f) rank 1)")
     res = tables.resolve(sr=sr, n_samples=n_samples, n_fft=n_fft, key=key, scale=scale, snap_strength=snap,
                          smear=smear, bin_smoothing=bin_smoothing, pre_quant=pre_quant, post_quant=post_quant,
                          distortion_mode=distortion_mode, distortion_params=distortion_params,
@@ -254,7 +252,7 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
                          mono_strength=mono_strength, output_trim_db=trim_db, low_trim_db=low_trim_db,
                          sub_cut_hz=sub_cut, air_cut_hz=air_cut, spectral_fx_mode=fx_mode,
                          spectral_fx_strength=fx_strength, spectral_fx_params=fx_params, precision=precision,
-                         spectral_freeze=bool(freeze))
+                         spectral_freeze=bool(freeze), formant_shift=float(formant))
     return res, {"fx_params": fx_params}
 
 

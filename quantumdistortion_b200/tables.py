@@ -250,7 +250,8 @@ def max_fan_in(target_bins: Optional[np.ndarray], active_mask: Optional[np.ndarr
     return int(np.max(np.bincount(np.asarray(target_bins)[np.asarray(active_mask, dtype=bool)])))
 
 
-def choose_precision(precision: str, n_fft: int, target_bins, active_mask, fx_active: bool = False) -> int:
+def choose_precision(precision: str, n_fft: int, target_bins, active_mask, fx_active: bool = False,
+                     formant_active: bool = False) -> int:
     """0 = float32 kernels, 1 = float64 kernels.  "auto" keeps the fast float32 path for the reference's
     defaults and switches to float64 where float32 cannot hold the 1e-4 parity bound: n_fft 8192
      and quantiser tables whose targets gather more than F64_FAN_IN source bins
@@ -262,6 +263,8 @@ def choose_precision(precision: str, n_fft: int, target_bins, active_mask, fx_ac
         return 1
     if precision != "auto":
         raise ValueError("precision must be 'auto', 'float32' or 'float64'")
+    if formant_active:
+        return 0                       # the formant shift is built for the float32 kernels
     if n_fft >= 8192:
         return 0 if fx_active else 1   # the float64 FX kernels are not built for n_fft 8192
     return 1 if max_fan_in(target_bins, active_mask) > F64_FAN_IN else 0
@@ -298,7 +301,7 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
             output_trim_db: float, low_trim_db: float, sub_cut_hz: float, air_cut_hz: float,
             spectral_fx_mode: Optional[str] = None, spectral_fx_strength: float = 0.0,
             spectral_fx_params: Optional[Dict[str, Any]] = None, precision: str = "auto",
-            spectral_freeze: bool = False) -> Resolved:
+            spectral_freeze: bool = False, formant_shift: float = 0.0) -> Resolved:
     """Turn the reference's keyword arguments into qd_params / qd_tables.  Raises the reference's
     exceptions (SURVEY.md section 8(b) "Errors") before anything is launched."""
     if n_fft not in SUPPORTED_N_FFT:
@@ -387,6 +390,12 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
         # still validate key / scale like the reference would on its first quantizer call
         pass
     p.spectral_freeze = int(bool(spectral_freeze) and quant_on)   # dsp/pipeline.py:285-287 (any band)
-    p.precision = choose_precision(precision, n_fft, tb, mask, fx_active=bool(p.fx_mode) or bool(p.spectral_freeze))
+    formant_on = bool(quant_on and float(formant_shift) != 0.0)  # dsp/pipeline.py:306-310 (any band)
+    if formant_on and n_fft > 4096:
+        raise NotImplementedError("formant_shift is built for n_fft <= 4096")
+    p.formant_ratio = float(2.0 ** (float(formant_shift) / 12.0)) if formant_on else 0.0  # dsp/spectral_fx.py:173
+    p.formant_order = 30                                                                  # dsp/spectral_fx.py:120
+    p.precision = choose_precision(precision, n_fft, tb, mask, fx_active=bool(p.fx_mode) or bool(p.spectral_freeze),
+                                   formant_active=formant_on)
     return Resolved(params=p, tables=tables, keepalive=tuple(keep), target_bins=tb, active_mask=mask,
                     fx_rng=fx_rng, fx_passes=fx_passes, n_frames=n_frames, n_bins=n_fft // 2 + 1)

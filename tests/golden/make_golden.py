@@ -125,6 +125,16 @@ def gen_stages():
         out[f"fx/{tag}/mag"], out[f"fx/{tag}/phase"] = np.array(frames_m), np.array(frames_p)
     a, b = ref_fx.bitcrush(fm, fp, method="uniform", step=0.07, threshold=0.01)
     out["fx/uniform/mag"] = a
+    # --- formant shift (cepstral lifter), incl. a frame with exact zeros and a 257-bin frame
+    fz = fm.copy()
+    fz[::5] = 0.0
+    out["fx/formant/zeros_in"] = fz
+    f257 = np.abs(rng.standard_normal(257)) * np.exp(-np.arange(257) / 40.0)
+    out["fx/formant/in257"] = f257
+    for st in (3.0, -5.0, 12.0, -0.5):
+        out[f"fx/formant/{st}"] = ref_fx.formant_shift_frame(fm, freqs, st)
+        out[f"fx/formant/zeros/{st}"] = ref_fx.formant_shift_frame(fz, freqs, st)
+        out[f"fx/formant/257/{st}"] = ref_fx.formant_shift_frame(f257, np.fft.rfftfreq(512, d=1.0 / sr), st)
     # --- time-domain stages
     xl = qd_cases.make_signal("loud", 41, 6000, sr)
     out["td/x"] = xl

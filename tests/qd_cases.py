@@ -66,6 +66,13 @@ CASES = {
     "mb_freeze_bitcrush": ("loud", 29, N, 48000, 2048, 1234,
                            dict(GROWL, use_multiband=True, spectral_freeze=True, spectral_fx_mode="bitcrush",
                                 spectral_fx_strength=0.5)),
+    "sb_formant_up": ("bass", 34, N, 48000, 2048, None, {"formant_shift": 3.0}),
+    "sb_formant_down_growl": ("loud", 35, N, 48000, 2048, None, dict(GROWL, formant_shift=-5.0)),
+    "mb_formant_bitcrush": ("loud", 36, N, 48000, 2048, 1234,
+                            dict(GROWL, use_multiband=True, formant_shift=2.0, spectral_fx_mode="bitcrush",
+                                 spectral_fx_strength=0.5)),
+    "sb_formant_freeze": ("bass", 37, N, 48000, 2048, None, {"formant_shift": 7.0, "spectral_freeze": True}),
+    "nfft1024_formant": ("bass", 38, 6000, 48000, 1024, None, {"formant_shift": -2.0}),
     "nfft512": ("bass", 30, 6000, 48000, 512, None, {}),
     "nfft1024": ("bass", 31, 6000, 48000, 1024, None, {}),
     "nfft4096": ("bass", 32, N, 48000, 4096, None, {}),

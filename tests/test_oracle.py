@@ -105,6 +105,15 @@ def test_spectral_fx_matches_reference(stages):
     assert np.array_equal(a, stages["fx/uniform/mag"])
 
 
+def test_formant_shift_matches_reference(stages):
+    fm = stages["fx/mag"]
+    for st in (3.0, -5.0, 12.0, -0.5):
+        assert np.array_equal(orc.formant_shift_frame(fm, st), stages[f"fx/formant/{st}"]), st
+        assert np.array_equal(orc.formant_shift_frame(stages["fx/formant/zeros_in"], st), stages[f"fx/formant/zeros/{st}"]), st
+        assert np.array_equal(orc.formant_shift_frame(stages["fx/formant/in257"], st), stages[f"fx/formant/257/{st}"]), st
+    assert np.array_equal(orc.formant_shift_frame(fm, 0.0), fm)
+
+
 def test_time_domain_stages_match_reference(stages):
     x = stages["td/x"]
     assert np.array_equal(orc.apply_distortion(x, "wavefold", fold_amount=5.0, bias=0.1), stages["td/wavefold"])
