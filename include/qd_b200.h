@@ -206,6 +206,16 @@ int qd_crossover_device(const float *x, float *low, float *high, int64_t batch, 
 int qd_distort_device(const float *x, float *y, int64_t count, int32_t mode, float fold_amount,
                       float bias, float tube_gain, float tube_norm, void *stream);
 
+/*
+ * Device half of the scale-alignment metric avg_cents_offset_from_scale (dsp/analyses.py:53-142):
+ * the STFT of every clip (dsp/stft_utils.py:11-97, n_fft = frame_length, hop n_fft/4, centre padded) and, per
+ * frame, the `topn` (<= 8) strongest bins in descending magnitude among bins 1..n_fft/2 whose magnitude is
+ * >= min_mag = 10^(min_db/20); bins [batch][1 + n/hop][topn] int16, -1 where fewer qualify.  The caller maps
+ * bins to cents with its float64 table (quantumdistortion_b200/analyses.py).  precision: QD_PRECISION_*.
+ */
+int qd_spectral_peaks_device(const float *x, int64_t batch, int32_t n_samples, int32_t n_fft, int32_t topn,
+                             double min_mag, int32_t precision, int16_t *bins, void *stream);
+
 /* pinned host memory helpers for qd_render_host callers */
 void *qd_host_alloc(size_t bytes);
 void  qd_host_free(void *p);

@@ -539,6 +539,68 @@ def null_test_db(a, b) -> float:
     return float(20.0 * np.log10(max(float(np.sqrt(np.mean(r ** 2))) if n else 0.0, 1e-10)))
 
 
+# --------------------------------------------------------------------------- QA metric
+def _nearest_scale_midi(midi_value: float, key: str, scale: str) -> float:
+    """dsp/analyses.py:18-50."""
+    if not np.isfinite(midi_value):
+        return np.nan
+    freq = 440.0 * (2.0 ** ((midi_value - 69.0) / 12.0))
+    fmin, fmax = float(max(20.0, freq / 4.0)), float(min(20000.0, freq * 4.0))
+    root = note_name_to_pitch_class(key)
+    intervals = SCALE_INTERVALS[scale]
+    lo = int(np.floor(_freq_to_midi(max(fmin, 20.0)))) - 12
+    hi = int(np.ceil(_freq_to_midi(min(fmax, 22050.0)))) + 12
+    midis = []
+    for midi in range(lo, hi + 1):  # dsp/quantizer.py:113-123
+        if (midi % 12 - root) % 12 in intervals:
+            f = 440.0 * (2.0 ** ((float(midi) - 69.0) / 12.0))
+            if f < fmin * 0.5 or f > fmax * 2.0:
+                continue
+            midis.append(midi)
+    if not midis:
+        return np.nan
+    m = np.array(midis, dtype=float)
+    return float(m[int(np.argmin(np.abs(m - midi_value)))])
+
+
+def avg_cents_offset_from_scale(audio, sr, key, scale, frame_length=2048, hop_length=None, topn_peaks=3,
+                                min_db=-60.0, return_bins=False):
+    """dsp/analyses.py:53-142.  ``return_bins`` additionally returns the chosen bins [frames, topn] (-1 = none),
+    which is what the CUDA kernel is compared with."""
+    x = np.asarray(audio, dtype=float)
+    if x.ndim != 1:
+        raise ValueError("avg_cents_offset_from_scale expects mono (1D) audio")
+    S, freqs = stft(x, sr, n_fft=frame_length)  # :90-96 (hop_length is unused by the reference)
+    mags_db = 20.0 * np.log10(np.maximum(np.abs(S), 1e-12))  # :97-101
+    per_peak = []
+    bins = np.full((mags_db.shape[1], topn_peaks), -1, dtype=np.int16)
+    for t in range(mags_db.shape[1]):
+        frame_db = mags_db[:, t]
+        if np.max(frame_db) < min_db:  # :108-110
+            continue
+        count = 0
+        for idx in np.argsort(frame_db)[::-1]:  # :113
+            if frame_db[idx] < min_db:
+                break
+            freq = float(freqs[idx])
+            if freq <= 0.0:
+                continue
+            midi_est = _freq_to_midi(freq)
+            if not np.isfinite(midi_est):
+                continue
+            scale_midi = _nearest_scale_midi(midi_est, key, scale)
+            if not np.isfinite(scale_midi):
+                continue
+            per_peak.append(abs(float(100.0 * (midi_est - scale_midi))))
+            bins[t, count] = idx
+            count += 1
+            if count >= topn_peaks:
+                break
+    arr = np.array(per_peak, dtype=float)
+    avg = float(np.mean(arr)) if arr.size else float("nan")
+    return (avg, arr, bins) if return_bins else (avg, arr)
+
+
 # --------------------------------------------------------------------------- pipeline
 def _fit(x: np.ndarray, n: int) -> np.ndarray:
     if x.shape[0] == n:

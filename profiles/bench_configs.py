@@ -24,6 +24,8 @@ CONFIGS = [
     ("config4 growl + multiband + bitcrush 0.5", dict(GROWL, use_multiband=True, spectral_fx_mode="bitcrush", spectral_fx_strength=0.5), 2048, 1234),
     ("config4 growl + multiband + phase_dispersal 0.6", dict(GROWL, use_multiband=True, spectral_fx_mode="phase_dispersal", spectral_fx_strength=0.6), 2048, 1234),
     ("config4 growl + multiband + bin_scramble 0.55", dict(GROWL, use_multiband=True, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.55), 2048, 1234),
+    ("next(f1) single-band + formant_shift +3 st", dict(formant_shift=3.0), 2048, None),
+    ("next(f1) single-band + spectral_freeze", dict(spectral_freeze=True), 2048, None),
     ("config5 n_fft 512", {}, 512, None),
     ("config5 n_fft 1024", {}, 1024, None),
     ("config5 n_fft 4096", {}, 4096, None),

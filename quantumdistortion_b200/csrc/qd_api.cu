@@ -2,6 +2,9 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -11,6 +14,7 @@
 #include "qd_host_tables.hpp"
 #include "qd_host_time.hpp"
 #include "qd_spec.cuh"
+#include "qd_peaks.cuh"
 #include "qd_time.cuh"
 
 #ifndef QD_NW_1024
@@ -291,6 +295,81 @@ int ew_grid(int64_t count, int sm_count) {
 
 }  // namespace
 
+namespace {
+// FFT tables of the peaks kernel, built once per (device, n_fft, precision) and kept for the process lifetime
+struct PeakTables { void *wtab = nullptr, *tw1 = nullptr, *tw2 = nullptr, *wsplit = nullptr; };
+std::mutex g_peak_mu;
+std::map<std::tuple<int, int, int>, PeakTables> g_peak_tables;
+
+template <class T>
+int peak_tables(int dev, int n_fft, PeakTables *out) {
+    std::lock_guard<std::mutex> lk(g_peak_mu);
+    const auto key = std::make_tuple(dev, n_fft, (int)sizeof(T));
+    auto it = g_peak_tables.find(key);
+    if (it == g_peak_tables.end()) {
+        qd_host::SpecTablesT<T> st;
+        if (!qd_host::build_spec_tables<T>(n_fft, &st)) return fail(QD_ERR_UNSUPPORTED, "n_fft must be one of 512, 1024, 2048, 4096, 8192");
+        PeakTables pt;
+        typename qd_host::Pair<T>::type *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr;
+        QD_CUDA(upload(st.wtab, &a));
+        QD_CUDA(upload(st.tw1, &b));
+        QD_CUDA(upload(st.tw2, &c));
+        QD_CUDA(upload(st.wsplit, &d));
+        pt.wtab = a; pt.tw1 = b; pt.tw2 = c; pt.wsplit = d;
+        it = g_peak_tables.emplace(key, pt).first;
+    }
+    *out = it->second;
+    return QD_OK;
+}
+
+template <class T, int NC>
+int launch_peaks_t(qd::PeaksArgsT<T> a, int64_t batch, cudaStream_t st) {
+    static std::atomic<bool> attr_set{false};
+    auto kern = qd::peaks_kernel<T, NC>;
+    if (!attr_set.load(std::memory_order_acquire)) {
+        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set.store(true, std::memory_order_release);
+    }
+    const size_t per_warp = (size_t)qd::buf_slots<NC>() * sizeof(qd::V2<T>) + (size_t)2 * NC * sizeof(float);
+    const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
+    const unsigned gx = (unsigned)((a.n_frames + nw - 1) / nw);
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+        const int64_t nb = std::min<int64_t>(65535, batch - b0);
+        qd::PeaksArgsT<T> c = a;
+        c.x = a.x + (size_t)b0 * a.n;
+        c.bins = a.bins + (size_t)b0 * a.n_frames * a.topn;
+        kern<<<dim3(gx, (unsigned)nb, 1), 32 * nw, per_warp * nw, st>>>(c);
+    }
+    QD_CUDA(cudaGetLastError());
+    return QD_OK;
+}
+
+template <class T>
+int launch_peaks(const float *x, int64_t batch, int n, int n_fft, int topn, double min_mag, int16_t *bins, cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(QD_ERR_NO_DEVICE, "no CUDA device: libqd_b200 has no CPU path"); }
+    PeakTables pt;
+    int rc = peak_tables<T>(dev, n_fft, &pt);
+    if (rc != QD_OK) return rc;
+    qd::PeaksArgsT<T> a{};
+    a.x = x; a.bins = bins; a.n = n; a.topn = topn;
+    a.n_frames = 1 + n / (n_fft / 4);
+    a.min_mag2 = (T)(min_mag * min_mag);
+    a.wtab = reinterpret_cast<const qd::V2<T> *>(pt.wtab);
+    a.tw1 = reinterpret_cast<const qd::V2<T> *>(pt.tw1);
+    a.tw2 = reinterpret_cast<const qd::V2<T> *>(pt.tw2);
+    a.wsplit = reinterpret_cast<const qd::V2<T> *>(pt.wsplit);
+    switch (n_fft / 2) {
+        case 256:  return launch_peaks_t<T, 256>(a, batch, st);
+        case 512:  return launch_peaks_t<T, 512>(a, batch, st);
+        case 1024: return launch_peaks_t<T, 1024>(a, batch, st);
+        case 2048: return launch_peaks_t<T, 2048>(a, batch, st);
+        case 4096: return launch_peaks_t<T, 4096>(a, batch, st);
+    }
+    return fail(QD_ERR_UNSUPPORTED, "n_fft must be one of 512, 1024, 2048, 4096, 8192");
+}
+}  // namespace
+
 extern "C" {
 
 int qd_abi_version(void) { return QD_ABI_VERSION; }
@@ -306,6 +385,17 @@ int qd_device_count(void) {
         if (cudaGetDeviceProperties(&pr, i) == cudaSuccess && pr.major == 10) ++ok;
     }
     return ok;
+}
+
+int qd_spectral_peaks_device(const float *x, int64_t batch, int32_t n_samples, int32_t n_fft, int32_t topn,
+                             double min_mag, int32_t precision, int16_t *bins, void *stream) {
+    if (!x || !bins || batch < 0 || n_samples < 0) return fail(QD_ERR_INVALID_ARG, "null / negative argument");
+    if (topn < 1 || topn > qd::QD_PEAKS_MAX) return fail(QD_ERR_INVALID_ARG, "topn must be 1..8");
+    if (batch == 0) return QD_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (precision == QD_PRECISION_F64) return launch_peaks<double>(x, batch, n_samples, n_fft, topn, min_mag, bins, st);
+    if (precision == QD_PRECISION_F32) return launch_peaks<float>(x, batch, n_samples, n_fft, topn, min_mag, bins, st);
+    return fail(QD_ERR_INVALID_ARG, "bad precision");
 }
 
 int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **out) {

@@ -77,6 +77,18 @@ def gen_tables():
     print("tables:", len(out))
 
 
+def gen_analysis():
+    """avg_cents_offset_from_scale (dsp/analyses.py:53-142) on a few clips, raw and rendered."""
+    from quantum_distortion.dsp.analyses import avg_cents_offset_from_scale
+    out = {}
+    for name, (kind, seed, n, sr, key, scale, kw) in qd_cases.ANALYSIS_CASES.items():
+        x = qd_cases.make_signal(kind, seed, n, sr)
+        avg, per = avg_cents_offset_from_scale(x, sr, key, scale, **kw)
+        out[f"{name}/x"], out[f"{name}/avg"], out[f"{name}/per_peak"] = x, np.float64(avg), per
+        print(f"analysis {name}: avg {avg:.3f} cents over {len(per)} peaks")
+    np.savez_compressed(os.path.join(HERE, "analysis.npz"), **out)
+
+
 def gen_stages():
     out = {}
     rng = np.random.default_rng(7)
@@ -164,9 +176,13 @@ def gen_frontend():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["analysis"]:   # only the newest file
+        gen_analysis()
+        sys.exit(0)
+    gen_analysis()
     gen_frontend()
     gen_tables()
     gen_stages()
     gen_pipeline()
-    for f in ("tables.npz", "stages.npz", "pipeline.npz", "frontend.npz"):
+    for f in ("tables.npz", "stages.npz", "pipeline.npz", "frontend.npz", "analysis.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

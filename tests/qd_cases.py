@@ -91,6 +91,14 @@ def make_signal(kind: str, seed: int, n: int, sr: int):
     raise KeyError(kind)
 
 
+# avg_cents_offset_from_scale (dsp/analyses.py:53-142): name -> (kind, seed, n, sr, key, scale, kwargs)
+ANALYSIS_CASES = {
+    "an_bass_dminor": ("bass", 60, N, 48000, "D", "minor", {}),
+    "an_noise_top5": ("noise", 61, 6000, 48000, "A", "pentatonic", {"topn_peaks": 5, "min_db": -20.0}),
+    "an_loud_1024": ("loud", 62, 9000, 44100, "F#", "dorian", {"frame_length": 1024}),
+    "an_quiet": ("bass", 63, 6000, 48000, "C", "major", {"min_db": 40.0}),
+}
+
 # Streamlit V2 UI dicts (dsp/pipeline.py:923-1008): name -> (kind, seed, n, sr, rng_seed, config dict, extra kwargs)
 UI_CASES = {
     "ui_full": ("loud", 50, N, 48000, 77,

@@ -265,3 +265,46 @@ def test_host_pipeline_odd_batch_small_chunks(qd):
     np.random.seed(3)
     o, _ = orc.process_audio(x[2], sr, **kw)
     _check(ref[2], o, "per-clip seeded scramble, clip 2")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(qd_cases.ANALYSIS_CASES))
+def test_cents_metric_vs_reference_fixtures(qd, name):
+    """avg_cents_offset_from_scale (dsp/analyses.py:53-142): the peak bins come from the CUDA STFT (float64 kernels
+    by default), the cents from the host table -> the reference's per-peak values bit for bit."""
+    from quantumdistortion_b200 import analyses
+    g = np.load(os.path.join(G, "analysis.npz"))
+    kind, seed, n, sr, key, scale, kw = qd_cases.ANALYSIS_CASES[name]
+    x = g[f"{name}/x"]
+    avg, per = analyses.avg_cents_offset_from_scale(x, sr, key, scale, **kw)
+    assert np.array_equal(per, g[f"{name}/per_peak"]), name
+    assert avg == float(g[f"{name}/avg"])
+    # peak bins vs the oracle, float64 exactly and float32 on all but near-tied bins
+    _, _, ref_bins = orc.avg_cents_offset_from_scale(x, sr, key, scale, return_bins=True, **kw)
+    nf, topn = kw.get("frame_length", 2048), kw.get("topn_peaks", 3)
+    b64 = analyses.spectral_peak_bins(x[None, :], n_fft=nf, topn=topn, min_db=kw.get("min_db", -60.0))
+    assert np.array_equal(b64[0], ref_bins)
+    b32 = analyses.spectral_peak_bins(x[None, :], n_fft=nf, topn=topn, min_db=kw.get("min_db", -60.0), precision="float32")
+    assert np.mean(b32[0] == ref_bins) >= 0.98
+    avg32, _ = analyses.avg_cents_offset_from_scale(x, sr, key, scale, precision="float32", **kw)
+    assert abs(avg32 - avg) <= 0.02 * avg
+
+
+@pytest.mark.gpu
+def test_cents_metric_batch_of_renders(qd):
+    """The metric's purpose (scripts/validate_dsp_metrics.py:59-105): rendering with the scale-snap quantizer moves the
+    strongest bins towards the scale.  Batch API, every clip against the oracle."""
+    from quantumdistortion_b200 import analyses
+    n, sr = 24000, 48000
+    x = np.stack([synth.bass_clip(70 + i, n, sr) for i in range(4)])
+    y, _ = qd.process_batch(x, sr, limiter_on=False)
+    for sig in (x, y):
+        avgs, per = analyses.avg_cents_offset_batch(sig, sr, "D", "minor")
+        for i in range(len(sig)):
+            a, p = orc.avg_cents_offset_from_scale(sig[i], sr, "D", "minor")
+            assert np.array_equal(per[i], p) and avgs[i] == a
+    wet, _ = analyses.avg_cents_offset_batch(y, sr, "D", "minor")
+    dry, _ = analyses.avg_cents_offset_batch(x, sr, "D", "minor")
+    assert np.mean(wet) < np.mean(dry)
+    silent, per0 = analyses.avg_cents_offset_from_scale(np.zeros(5000, dtype=np.float32), sr, "D", "minor")
+    assert np.isnan(silent) and per0.size == 0

@@ -160,3 +160,20 @@ def test_null_test_definition():
     a = np.zeros(100, dtype=np.float32)
     assert orc.null_test_db(a, a) == -200.0
     assert abs(orc.null_test_db(a + 0.1, a) + 20.0) < 1e-4
+
+
+@pytest.mark.parametrize("name", list(qd_cases.ANALYSIS_CASES))
+def test_cents_metric_matches_reference(name):
+    """avg_cents_offset_from_scale (dsp/analyses.py:53-142): oracle and the host cents table vs the live reference."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "analysis.npz"))
+    kind, seed, n, sr, key, scale, kw = qd_cases.ANALYSIS_CASES[name]
+    x = qd_cases.make_signal(kind, seed, n, sr)
+    assert np.array_equal(x, g[f"{name}/x"])
+    avg, per, bins = orc.avg_cents_offset_from_scale(x, sr, key, scale, return_bins=True, **kw)
+    assert np.array_equal(per, g[f"{name}/per_peak"])
+    assert (np.isnan(avg) and np.isnan(g[f"{name}/avg"])) or avg == float(g[f"{name}/avg"])
+    # the product's per-bin table reproduces the per-peak values from the chosen bins
+    from quantumdistortion_b200.analyses import scale_cents_table
+    table = scale_cents_table(np.fft.rfftfreq(kw.get("frame_length", 2048), d=1.0 / sr), key, scale)
+    flat = bins.reshape(-1)
+    assert np.array_equal(table[flat[flat >= 0]], per)
