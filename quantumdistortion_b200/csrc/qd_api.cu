@@ -155,6 +155,7 @@ int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStrea
         c.x = a.x + (size_t)b0 * a.n;
         c.y = a.y + (size_t)b0 * a.n;
         if (a.tap) c.tap = a.tap + (size_t)b0 * a.n;
+        if (a.clip_peak) c.clip_peak = a.clip_peak + b0;
         c.fx.clip_offset = a.fx.clip_offset + (int)b0;
         kern<<<dim3((unsigned)tiles, (unsigned)((nb + NG - 1) / NG), 1), 32 * NW * NG, smem, st>>>(c);
     }
@@ -214,10 +215,12 @@ int launch_freeze(int nc, const qd::SpecArgsT<T> &a, T *out, int64_t batch, cuda
 
 template <class T>
 int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *dst, float *tap, int quant,
-                     int epilogue, int64_t batch, cudaStream_t st, int fx_pass, int clip_offset) {
+                     int epilogue, int64_t batch, cudaStream_t st, int fx_pass, int clip_offset, float *clip_peak) {
     a.x = src;
     a.y = dst;
     a.tap = tap;
+    a.clip_peak = clip_peak;
+    if (clip_peak) QD_CUDA(cudaMemsetAsync(clip_peak, 0, (size_t)batch * sizeof(float), st));
     a.quant = quant;
     a.epilogue = epilogue;
     const bool fx = quant && (pl->p.fx_mode != QD_FX_NONE || pl->p.spectral_freeze || pl->p.formant_ratio > 0.0);
@@ -260,10 +263,10 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
 
 // One spectral pass over [batch, n]: src -> dst (+ optional tap of the pre-epilogue signal).
 int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant, int epilogue,
-                int64_t batch, cudaStream_t st, int fx_pass = 0, int clip_offset = 0) {
+                int64_t batch, cudaStream_t st, int fx_pass = 0, int clip_offset = 0, float *clip_peak = nullptr) {
     TimeScope ts(pl, st, QD_KERNEL_SPECTRAL);
-    if (pl->f64) return launch_spec_prec<double>(pl, pl->spec64, src, dst, tap, quant, epilogue, batch, st, fx_pass, clip_offset);
-    return launch_spec_prec<float>(pl, pl->spec, src, dst, tap, quant, epilogue, batch, st, fx_pass, clip_offset);
+    if (pl->f64) return launch_spec_prec<double>(pl, pl->spec64, src, dst, tap, quant, epilogue, batch, st, fx_pass, clip_offset, clip_peak);
+    return launch_spec_prec<float>(pl, pl->spec, src, dst, tap, quant, epilogue, batch, st, fx_pass, clip_offset, clip_peak);
 }
 
 int launch_limiter(const qd::LimiterArgs &a, int64_t batch, cudaStream_t st) {
@@ -282,6 +285,7 @@ int launch_limiter(const qd::LimiterArgs &a, int64_t batch, cudaStream_t st) {
         if (a.dry) c.dry = a.dry + off;
         if (a.low) c.low = a.low + off;
         if (a.orig) c.orig = a.orig + off;
+        if (a.clip_peak) c.clip_peak = a.clip_peak + b0;
         qd::limiter_mix_kernel<<<(unsigned)nb, qd::QD_TT, smem, st>>>(c);
     }
     QD_CUDA(cudaGetLastError());
@@ -576,7 +580,7 @@ size_t qd_plan_workspace_bytes(const qd_plan *pl, int64_t batch) {
     const size_t clip = (size_t)pl->p.n_samples * sizeof(float);
     const size_t bufs = pl->p.multiband ? 3 : 1;  // [x_dist] (+ [low][high])
     const size_t frozen = pl->p.spectral_freeze ? (size_t)batch * (size_t)(pl->nc + pl->nc / 32) * sizeof(double) + 256 : 0;
-    return bufs * clip * (size_t)batch + 256 + frozen;
+    return bufs * clip * (size_t)batch + 256 + frozen + (size_t)batch * sizeof(float) + 256;   // + per-clip peaks
 }
 
 int qd_plan_launches_per_render(const qd_plan *pl) {
@@ -648,6 +652,10 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
     float *w_low = w_a + count;
     float *w_high = w_low + count;
     pl->frozen_ws = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(w_a + (p.multiband ? 3 : 1) * count) + 255) & ~(uintptr_t)255);
+    // per-clip peak of the limiter input, written by the spectral pass that produces it (behind the freeze scratch)
+    const size_t frozen_bytes = p.spectral_freeze ? (size_t)batch * (size_t)(pl->nc + pl->nc / 32) * sizeof(double) + 256 : 0;
+    float *clip_peak = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(pl->frozen_ws) + frozen_bytes + 255) & ~(uintptr_t)255);
+    if (!p.limiter_on) clip_peak = nullptr;
     int rc;
 
     const float *src = x;   // what the single-band chain sees (dsp/pipeline.py:1076: the high band)
@@ -695,9 +703,10 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
     const float *x_pq = nullptr;  // limiter input
     if (p.pre_quant) {
         // pass A: STFT -> quantize -> iSTFT (= pre_quant tap) -> distortion        (:635-721)
-        if ((rc = launch_spec(pl, src, w_a, tap_pre, 1, epi, batch, st, 0, pl->clip_offset)) != QD_OK) return rc;
+        if ((rc = launch_spec(pl, src, w_a, tap_pre, 1, epi, batch, st, 0, pl->clip_offset,
+                              p.post_quant ? nullptr : clip_peak)) != QD_OK) return rc;
         if (p.post_quant) {  // pass B on the distorted signal                         (:729-801)
-            if ((rc = launch_spec(pl, w_a, y, nullptr, 1, 0, batch, st, 1, pl->clip_offset)) != QD_OK) return rc;
+            if ((rc = launch_spec(pl, w_a, y, nullptr, 1, 0, batch, st, 1, pl->clip_offset, clip_peak)) != QD_OK) return rc;
             x_pq = y;
         } else {
             x_pq = w_a;       // :851-853
@@ -710,7 +719,7 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
                 src, w_a, (long long)count, p.distortion_mode, p.fold_amount, p.bias, p.tube_gain, p.tube_norm);
             QD_CUDA(cudaGetLastError());
         }
-        if ((rc = launch_spec(pl, src, y, nullptr, p.post_quant ? 1 : 0, 0, batch, st, 0, pl->clip_offset)) != QD_OK) return rc;
+        if ((rc = launch_spec(pl, src, y, nullptr, p.post_quant ? 1 : 0, 0, batch, st, 0, pl->clip_offset, clip_peak)) != QD_OK) return rc;
         x_pq = y;
     }
     if (tap_dist) {  // dsp/pipeline.py:916 / :1107 (low band added in multiband mode)
@@ -726,6 +735,7 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
     l.limiter_on = p.limiter_on; l.lookahead = p.lookahead > 0 ? p.lookahead : 1;
     l.ceiling = p.ceiling_lin; l.c = p.release_coeff;
     l.wet = p.wet; l.dry_gain = p.dry; l.trim = p.trim_gain; l.apply_trim = p.apply_trim; l.apply_mix = 1;
+    l.clip_peak = clip_peak;   // written by the spectral pass that produced x_pq
     TimeScope ts(pl, st, QD_KERNEL_LIMITER);
     return launch_limiter(l, batch, st);
 }

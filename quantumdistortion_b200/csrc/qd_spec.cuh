@@ -110,6 +110,8 @@ struct SpecArgsT {
     const float *x;        // [batch, n] input clips
     float *y;              // [batch, n] output (after the epilogue)
     float *tap;            // optional [batch, n]: iSTFT output before the epilogue
+    float *clip_peak;      // optional [batch]: max |y| per clip (atomicMax on the bit pattern; caller zeroes it).
+                           // The limiter skips a clip whose peak never exceeds the ceiling: its gain is exactly 1.
     int n;                 // samples per clip
     int batch;             // clips in this launch (a CTA may hold several clip groups)
     int n_frames;          // T = 1 + n / hop
@@ -1091,6 +1093,7 @@ spec_pass_kernel(const SpecArgsT<T> a) {
     }
     if (!group_live) return;   // after the last CTA-wide barrier; the other group only uses its named barrier
 
+    float out_peak = 0.0f;   // max |y| this thread stored
     for (int tb = t_first; tb < j1; tb += NW) {
         // ---- stage the samples of frames tb .. tb+NW-1 (zero outside the clip)
         const long long s0 = (long long)tb * HOP - NC;  // clip index of staging[0]
@@ -1192,17 +1195,24 @@ spec_pass_kernel(const SpecArgsT<T> a) {
                 if (vec2) {  // nidx is even and n is even, so nidx + 1 < n
                     if (tap) *reinterpret_cast<float2 *>(tap + nidx) = o;
                     *reinterpret_cast<float2 *>(y + nidx) = r;
+                    out_peak = fmaxf(out_peak, fmaxf(fabsf(r.x), fabsf(r.y)));
                 } else {
                     if (tap) tap[nidx] = o.x;
                     y[nidx] = r.x;
+                    out_peak = fmaxf(out_peak, fabsf(r.x));
                     if (nidx + 1 < a.n) {
                         if (tap) tap[nidx + 1] = o.y;
                         y[nidx + 1] = r.y;
+                        out_peak = fmaxf(out_peak, fabsf(r.y));
                     }
                 }
             }
         }
         group_sync<NG, 32 * NW>(grp);
+    }
+    if (a.clip_peak) {   // non-negative floats order like their bit patterns
+        out_peak = warp_max(out_peak);
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned *>(a.clip_peak) + clip, __float_as_uint(out_peak));
     }
 }
 

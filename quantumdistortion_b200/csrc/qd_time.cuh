@@ -35,6 +35,9 @@ struct LimiterArgs {
     float wet, dry_gain, trim;
     int apply_mix;        // 0: y = limited (stage-level entry point)
     int apply_trim;
+    const float *clip_peak;   // optional [batch]: max |x| per clip from the producing spectral pass.  A clip that never
+                              // exceeds the ceiling has gain exactly 1 (dsp/limiter.py:68-76): its limiter is skipped,
+                              // and with an identity mix in place (x == y) the CTA has nothing to do at all.
 };
 
 // 8 consecutive samples of one clip starting at s (zero past the end); 2 x 16-byte loads when aligned
@@ -77,6 +80,10 @@ __global__ void __launch_bounds__(QD_TT, 3) limiter_mix_kernel(const LimiterArgs
     const bool vec = ((a.n & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
     const bool vec_out = ((a.n & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
     const bool need_dry = a.apply_mix && a.dry_gain != 0.0f;
+    const bool clip_quiet = a.clip_peak != nullptr && !((double)a.clip_peak[blockIdx.x] > a.ceiling);
+    const bool limiter_on = a.limiter_on && !clip_quiet;
+    if (!limiter_on && a.x == a.y && !need_dry && !a.low && !a.orig && (!a.apply_mix || (a.wet == 1.0f && !a.apply_trim)))
+        return;   // y = float32(x * 1) in place
     const double c = a.c;
     double c_ks = 1.0;
 #pragma unroll
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(QD_TT, 3) limiter_mix_kernel(const LimiterArgs
     }
     double carry = 0.0;  // u at the end of the previous chunk
     const int look_threads = (L + 8 + QD_KS - 1) / QD_KS;  // threads whose next-chunk samples are lookahead
-    const bool fast = a.limiter_on && L >= QD_KS && L + 8 <= QD_CHUNK;
+    const bool fast = limiter_on && L >= QD_KS && L + 8 <= QD_CHUNK;
 
     float cur[QD_KS], nxt[QD_KS], nn[QD_KS];
     load8(x, (long long)tid * QD_KS, a.n, vec, cur);
@@ -106,7 +113,7 @@ __global__ void __launch_bounds__(QD_TT, 3) limiter_mix_kernel(const LimiterArgs
         double u_in = 0.0;
         float peak[QD_KS];
         bool lim_active = false;
-        if (a.limiter_on) {
+        if (limiter_on) {
             // ---- |x| of the chunk and of its lookahead into shared memory, with per-group maxima
             if (fast) {
                 float m = 0.0f;
