@@ -40,6 +40,24 @@ def loud_clip(seed: int, n: int, sr: int = 48000) -> np.ndarray:
     return np.clip(1.6 * bass_clip(seed, n, sr), -1.5, 1.5).astype(np.float32)
 
 
+def tone_clip(seed: int, n: int, sr: int = 48000) -> np.ndarray:
+    """Pitched clip for the autotune path: two consecutive notes (f0~U(150,420) Hz, usually off the scale), eight
+    harmonics 1/h, 5.5 Hz vibrato of +-12 cents, a short silence in the middle, light noise, peak 0.5."""
+    rng = np.random.default_rng(9000 + seed)
+    t = np.arange(n, dtype=np.float64) / sr
+    f = np.where(t < t[-1] * 0.55, rng.uniform(150.0, 420.0), rng.uniform(150.0, 420.0))
+    f = f * 2.0 ** (0.01 * np.sin(2.0 * np.pi * 5.5 * t))
+    ph = 2.0 * np.pi * np.cumsum(f) / sr
+    x = np.zeros(n)
+    for h in range(1, 9):
+        x += np.sin(h * ph + rng.uniform(0.0, 2.0 * np.pi)) / h
+    gap = (t > t[-1] * 0.5) & (t < t[-1] * 0.55)
+    x[gap] = 0.0
+    x += 0.002 * rng.standard_normal(n)
+    x *= 0.5 / max(np.max(np.abs(x)), 1e-12)
+    return x.astype(np.float32)
+
+
 def bass_batch_torch(batch: int, n: int, sr: int, device, seed: int = 0, rows_per_step: int = 64):
     """Device-side version of ``bass_clip`` for large benchmark batches (same recipe, torch RNG):
     returns float32 ``[batch, n]`` on ``device``.  Built ``rows_per_step`` clips at a time."""

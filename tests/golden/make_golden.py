@@ -89,6 +89,40 @@ def gen_analysis():
     np.savez_compressed(os.path.join(HERE, "analysis.npz"), **out)
 
 
+def gen_autotune():
+    """quantize_mode="autotune_v1": every stage of dsp/autotune.py on one clip, then whole renders."""
+    from quantum_distortion.dsp import autotune as ref_at
+    out = {}
+    sr = 48000
+    x = qd_cases.make_signal("tone", 0, qd_cases.AT_N, sr)
+    cfg = ref_at.AutotuneV1Config(key="D", scale="minor")
+    res = ref_at.apply_autotune_v1(x, sr, cfg)
+    det = ref_at.make_detector_sidechain(res.body_band, sr, cfg.detector_low_hz, cfg.detector_high_hz)
+    out["st/x"], out["st/sub"], out["st/body"], out["st/air"], out["st/det"] = x, res.sub_band, res.body_band, res.air_band, det
+    out["st/ratio_track"], out["st/corrected"], out["st/output"] = res.diagnostics.ratio_track, res.corrected_body, res.output
+    out["st/sub_layer"] = ref_at.generate_sub_layer(x, sr, cfg)
+    out["st/env"] = ref_at.envelope_follow(x, sr)
+    feats = []
+    for start in range(0, len(det), 512):   # the detector's own framing (dsp/autotune.py:217-236)
+        fr = det[start:start + 4096]
+        if len(fr) < 4096:
+            fr = np.pad(fr, (0, 4096 - len(fr)), mode="constant")
+        p, c = ref_at.detect_pitch_yin(fr, sr, min_freq=max(60.0, 110.0 * 0.65), max_freq=3000.0)
+        feats.append([float(np.sqrt(np.mean(fr * fr))), ref_at._spectral_flatness(fr), p, c])
+    out["st/features"] = np.array(feats)
+    # a hand-made ratio track exercises the shifter away from 1 (both directions, wraps of both taps)
+    rt = (1.0 + 0.2 * np.sin(2.0 * np.pi * 3.0 * np.arange(len(x)) / sr)).astype(np.float32)
+    out["st/ratio_manual"], out["st/shift_manual"] = rt, ref_at.granular_pitch_shift(res.body_band, rt)
+    out["st/nearest"] = np.array([ref_at.nearest_scale_freq(f, "D", "minor") for f in (97.3, 233.1, 440.0, 1234.5)])
+    for name, (kind, seed, n, srr, kw) in qd_cases.AUTOTUNE_CASES.items():
+        xx = qd_cases.make_signal(kind, seed, n, srr)
+        y, taps = quiet(ref_pipeline.process_audio, xx, srr, quantize_mode="autotune_v1", **kw)
+        out[f"{name}/x"], out[f"{name}/y"] = xx, y
+        out[f"{name}/pre_quant"], out[f"{name}/post_dist"] = taps["pre_quant"].astype(np.float32), taps["post_dist"].astype(np.float32)
+        print(f"autotune {name}: n={n} peak={np.max(np.abs(y)):.4f} moved={np.max(np.abs(y - xx)):.4f}")
+    np.savez_compressed(os.path.join(HERE, "autotune.npz"), **out)
+
+
 def gen_stages():
     out = {}
     rng = np.random.default_rng(7)
@@ -176,9 +210,13 @@ def gen_frontend():
 
 
 if __name__ == "__main__":
-    if sys.argv[1:] == ["analysis"]:   # only the newest file
+    if sys.argv[1:] == ["analysis"]:   # only that file
         gen_analysis()
         sys.exit(0)
+    if sys.argv[1:] == ["autotune"]:
+        gen_autotune()
+        sys.exit(0)
+    gen_autotune()
     gen_analysis()
     gen_frontend()
     gen_tables()

@@ -88,8 +88,24 @@ def make_signal(kind: str, seed: int, n: int, sr: int):
         return signals.noise_clip(seed, n)
     if kind == "loud":
         return signals.loud_clip(seed, n, sr)
+    if kind == "tone":
+        return signals.tone_clip(seed, n, sr)
     raise KeyError(kind)
 
+
+# quantize_mode="autotune_v1" (dsp/autotune.py, dsp/pipeline.py:537-601): name -> (kind, seed, n, sr, kwargs)
+AT_N = 24000  # 0.5 s @ 48 kHz -> 47 detector frames
+AUTOTUNE_CASES = {
+    "at_tone_default": ("tone", 0, AT_N, 48000, {}),
+    "at_tone_half_strength_441": ("tone", 1, 22050, 44100, {"snap_strength": 0.5, "key": "F", "scale": "major"}),
+    "at_bass_growl_nosub": ("bass", 80, AT_N, 48000, dict(GROWL, sub_enabled=False)),
+    "at_tone_tube_drywet": ("tone", 2, AT_N, 48000, dict(CLANG, dry_wet=0.6, sub_source="scale_degree",
+                                                          sub_scale_degree=4, sub_octave=1, sub_level=0.5,
+                                                          air_mix=0.5, output_trim_db=-2.0)),
+    "at_noise": ("noise", 81, 9000, 48000, {"sub_source": "manual", "sub_note": "G", "delta_listen": True}),
+    "at_no_prequant": ("tone", 3, 9000, 48000, {"pre_quant": False}),
+    "at_ragged_short": ("tone", 4, 5003, 48000, {"sub_cut_hz": 0.0, "air_cut_hz": 8000.0}),
+}
 
 # avg_cents_offset_from_scale (dsp/analyses.py:53-142): name -> (kind, seed, n, sr, key, scale, kwargs)
 ANALYSIS_CASES = {
