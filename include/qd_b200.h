@@ -216,6 +216,65 @@ int qd_distort_device(const float *x, float *y, int64_t count, int32_t mode, flo
 int qd_spectral_peaks_device(const float *x, int64_t batch, int32_t n_samples, int32_t n_fft, int32_t topn,
                              double min_mag, int32_t precision, int16_t *bins, void *stream);
 
+/*
+ * quantize_mode = "autotune_v1", the reference's default mode (dsp/autotune.py:426-447 behind dsp/pipeline.py:537-601):
+ * zero-phase band split -> YIN pitch track -> note hold -> granular pitch shifter -> sub layer, then the same
+ * distortion / limiter / mix tail as the STFT path.  Everything the reference derives on the CPU (Butterworth
+ * sections and sosfilt_zi from scipy, sample counts, key / scale tables) arrives resolved in this struct
+ * (quantumdistortion_b200/autotune.py builds it).
+ */
+typedef struct qd_autotune_params {
+    uint32_t struct_size;
+    int32_t  sample_rate;
+    int32_t  n_samples;
+    int32_t  apply;              /* pre_quant and snap_strength > 0 (dsp/pipeline.py:538); 0: x_pre = x */
+    /* zero-phase 4th-order Butterworth filters, dsp/autotune.py:88-127: [0] sub low-pass, [1] air high-pass,
+       [2] detector high-pass, [3] detector low-pass; filt_on = 0 when the cutoff is <= 0 */
+    int32_t  filt_on[4];
+    double   sos[4][2][6];
+    double   zi[4][2][2];        /* scipy.signal.sosfilt_zi */
+    /* detector, dsp/autotune.py:140-236 */
+    int32_t  frame_size;         /* 4096 */
+    int32_t  hop;                /* 512 */
+    int32_t  min_tau, max_tau;   /* dsp/autotune.py:153-154 */
+    double   min_freq, max_freq, yin_threshold;
+    double   rms_thr, flat_thr, conf_thr;
+    /* note hold, dsp/autotune.py:65-85, 238-277 */
+    int32_t  root_pc, n_intervals, intervals[8];
+    double   strength, change_cents;
+    int32_t  confirm_frames, release_frames;
+    /* granular shifter, dsp/autotune.py:301-360 */
+    int32_t  max_delay;          /* max(256, grain_size) */
+    int32_t  buffer_size;        /* power of two >= 2 * max_delay */
+    /* sub layer and mix, dsp/autotune.py:363-437 */
+    int32_t  sub_enabled;
+    int32_t  layer_on;           /* sub_enabled and sub_level > 0 and sub frequency > 0 */
+    float    env_attack, env_release;   /* float32(exp(-1 / max(1, ms * sr / 1000))) */
+    float    sub_level, sub_preserve, air_mix;
+    float    phase_k;            /* float32(2 pi f_sub) */
+    /* shared tail, same meaning as in qd_params */
+    int32_t  distortion_mode;
+    float    fold_amount, bias, tube_gain, tube_norm;
+    int32_t  limiter_on, lookahead;
+    double   ceiling_lin, release_coeff;
+    float    wet, dry, trim_gain;
+    int32_t  apply_trim, delta_listen;
+} qd_autotune_params;
+
+/* optional device outputs of the intermediate stages (parity ladder); NULL members are skipped */
+typedef struct qd_autotune_debug {
+    float  *sub, *body, *air, *det;     /* [batch, n] bands and detector side chain */
+    float  *ratio_track;                /* [batch, n] */
+    float  *corrected;                  /* [batch, n] shifted body */
+    float  *sub_layer;                  /* [batch, n] */
+    double *features;                   /* [batch, ceil(n / hop), 4]: rms, flatness, pitch, confidence */
+} qd_autotune_debug;
+
+size_t qd_autotune_workspace_bytes(const qd_autotune_params *params, int64_t batch);
+int    qd_autotune_render_device(const qd_autotune_params *params, const float *x, float *y, int64_t batch,
+                                 const qd_taps *taps, const qd_autotune_debug *debug, void *workspace,
+                                 size_t workspace_bytes, void *stream);
+
 /* pinned host memory helpers for qd_render_host callers */
 void *qd_host_alloc(size_t bytes);
 void  qd_host_free(void *p);

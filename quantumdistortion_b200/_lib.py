@@ -83,6 +83,9 @@ def load() -> C.CDLL:
     lib.qd_crossover_device.argtypes = [vp, vp, vp, i64, i64, C.POINTER((dbl * 6) * 2), C.POINTER((dbl * 6) * 2), vp]
     lib.qd_distort_device.argtypes = [vp, vp, i64, i32, flt, flt, flt, flt, vp]
     lib.qd_spectral_peaks_device.argtypes = [vp, i64, i32, i32, i32, dbl, i32, vp, vp]
+    lib.qd_autotune_workspace_bytes.argtypes = [vp, i64]
+    lib.qd_autotune_workspace_bytes.restype = C.c_size_t
+    lib.qd_autotune_render_device.argtypes = [vp, vp, vp, i64, vp, vp, vp, C.c_size_t, vp]
     lib.qd_host_alloc.argtypes = [C.c_size_t]
     lib.qd_host_alloc.restype = vp
     lib.qd_host_free.argtypes = [vp]

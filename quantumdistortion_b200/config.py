@@ -21,9 +21,9 @@ DEFAULT_DISTORTION_MODE = "wavefold"
 DEFAULT_LIMITER_ON = True
 DEFAULT_LIMITER_CEILING_DB = -1.0
 DEFAULT_DRY_WET = 1.0
-# The reference defaults to "autotune_v1" (config.py:44), a pitch-tracking algorithm outside the
-# STFT path.  This package implements the STFT path only, so its default is "spectral_bins";
-# passing quantize_mode="autotune_v1" without an FX/freeze/lock option raises NotImplementedError.
+# The reference defaults to "autotune_v1" (config.py:44), a time-domain pitch-tracking mode outside the STFT
+# path.  This package's headline is the STFT path, so its default is "spectral_bins"; quantize_mode="autotune_v1"
+# selects the other mode (quantumdistortion_b200/autotune.py).
 DEFAULT_QUANTIZE_MODE = "spectral_bins"
 DEFAULT_SUB_CUT_HZ = 110.0
 DEFAULT_AIR_CUT_HZ = 5000.0
@@ -42,8 +42,8 @@ def ensure_mono_float32(audio: np.ndarray) -> np.ndarray:
 
 @dataclass
 class PipelineConfig:
-    """Same fields and defaults as the reference's PipelineConfig (config.py:64-130); the
-    autotune-only ``sub_*`` / ``air_mix`` fields are accepted and ignored by the STFT path."""
+    """Same fields and defaults as the reference's PipelineConfig (config.py:64-130); the ``sub_*`` / ``air_mix``
+    fields only matter for quantize_mode="autotune_v1"."""
     key: str = DEFAULT_KEY
     scale: str = DEFAULT_SCALE
     quantize_mode: str = DEFAULT_QUANTIZE_MODE

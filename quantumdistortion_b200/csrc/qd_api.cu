@@ -15,6 +15,7 @@
 #include "qd_host_time.hpp"
 #include "qd_spec.cuh"
 #include "qd_peaks.cuh"
+#include "qd_autotune.cuh"
 #include "qd_time.cuh"
 
 #ifndef QD_NW_1024
@@ -841,3 +842,5 @@ void qd_host_free(void *p) {
 }
 
 }  // extern "C"
+
+#include "qd_autotune_api.inc"

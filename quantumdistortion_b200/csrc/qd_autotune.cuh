@@ -1,0 +1,463 @@
+// qd_autotune.cuh -- the reference's default mode "autotune_v1" (dsp/autotune.py, dsp/pipeline.py:537-601):
+//
+//   zero-phase band split (sosfiltfilt x4)  ->  YIN pitch track on the detector band  ->  note-hold state machine
+//   ->  per-sample ratio track  ->  granular two-tap pitch shifter  ->  envelope-followed sub oscillator  ->  mix
+//
+// First CUDA version: correctness first.  The strictly sequential recurrences (IIR sweeps, note hold, tap positions,
+// envelope follower) run one thread per clip in the reference's own operation order and precision, with explicit
+// round-to-nearest intrinsics so that nothing is contracted into an FMA the reference does not have; everything
+// per-sample-independent (band arithmetic, shifter read-out, oscillator, mix) and the per-frame detector run wide.
+// The detector's difference function is float64 like the reference: the shifter integrates 1 - ratio, so the pitch
+// has to match to ~1e-9 for the output to stay inside the 1e-4 parity bound.
+#pragma once
+#include "qd_spec.cuh"
+
+namespace qd {
+
+struct AtFilter {         // one zero-phase 4th-order Butterworth (two second-order sections), dsp/autotune.py:88-100
+    int on;               // 0: cutoff <= 0 -> identity (astype float32)
+    double sos[2][6];
+    double zi[2][2];      // scipy.signal.sosfilt_zi
+};
+
+constexpr int AT_EDGE = 15;   // sosfiltfilt default padlen = 3 * ntaps, ntaps = 5
+
+// ---------------------------------------------------------------- zero-phase filter, one thread per (clip, job)
+// scipy.signal.sosfiltfilt(sos, x_float32).astype(float32): odd extension by 15 samples formed in float32, forward sweep
+// from the state zi * ext[0], backward sweep from zi * y[-1], float64 in between (oracle/qd_autotune.py
+// sosfiltfilt_restated).  `scratch` holds the forward result: [jobs][batch][n + 30] doubles.
+struct AtFiltArgs {
+    const float *x[2];    // input per job, [batch, n]
+    float *y[2];          // output per job
+    AtFilter f[2];
+    int jobs;
+    double *scratch;
+    long long n;
+    int batch;
+};
+
+QD_DEV double at_section(const double *c, double v, double &z0, double &z1) {
+    const double o = __dadd_rn(__dmul_rn(c[0], v), z0);
+    z0 = __dadd_rn(__dsub_rn(__dmul_rn(c[1], v), __dmul_rn(c[4], o)), z1);
+    z1 = __dsub_rn(__dmul_rn(c[2], v), __dmul_rn(c[5], o));
+    return o;
+}
+
+__global__ void at_filtfilt_kernel(const AtFiltArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.batch * a.jobs) return;
+    const int job = t / a.batch, clip = t % a.batch;
+    const float *x = a.x[job] + (size_t)clip * a.n;
+    float *y = a.y[job] + (size_t)clip * a.n;
+    const AtFilter &f = a.f[job];
+    const long long n = a.n;
+    if (!f.on) {
+        for (long long i = 0; i < n; ++i) y[i] = x[i];
+        return;
+    }
+    const long long m = n + 2 * AT_EDGE;
+    double *s = a.scratch + (size_t)t * (size_t)m;
+    auto ext = [&](long long i) -> double {   // odd extension in float32
+        if (i < AT_EDGE) return (double)__fsub_rn(__fmul_rn(2.0f, x[0]), x[AT_EDGE - i]);
+        if (i >= n + AT_EDGE) return (double)__fsub_rn(__fmul_rn(2.0f, x[n - 1]), x[n - 2 - (i - n - AT_EDGE)]);
+        return (double)x[i - AT_EDGE];
+    };
+    const double x0 = ext(0);
+    double z[2][2] = {{f.zi[0][0] * x0, f.zi[0][1] * x0}, {f.zi[1][0] * x0, f.zi[1][1] * x0}};
+    double last = 0.0;
+    for (long long i = 0; i < m; ++i) {
+        double v = ext(i);
+        v = at_section(f.sos[0], v, z[0][0], z[0][1]);
+        v = at_section(f.sos[1], v, z[1][0], z[1][1]);
+        s[i] = v;
+        last = v;
+    }
+    z[0][0] = f.zi[0][0] * last; z[0][1] = f.zi[0][1] * last;
+    z[1][0] = f.zi[1][0] * last; z[1][1] = f.zi[1][1] * last;
+    for (long long i = m - 1; i >= 0; --i) {
+        double v = s[i];
+        v = at_section(f.sos[0], v, z[0][0], z[0][1]);
+        v = at_section(f.sos[1], v, z[1][0], z[1][1]);
+        if (i >= AT_EDGE && i < n + AT_EDGE) y[i - AT_EDGE] = (float)v;
+    }
+}
+
+// body = (audio - sub - air) in float32 (dsp/autotune.py:112)
+__global__ void at_body_kernel(const float *__restrict__ x, const float *__restrict__ sub, const float *__restrict__ air,
+                               float *__restrict__ body, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        body[i] = __fsub_rn(__fsub_rn(x[i], sub[i]), air[i]);
+}
+
+// ---------------------------------------------------------------- detector: one CTA per frame
+// dsp/autotune.py:217-236: rms, spectral flatness (symmetric Hann, float32 warp FFT), YIN (float64).
+struct AtDetArgs {
+    const float *det;        // [batch, n] detector side chain
+    double *feat;            // [batch, frames, 4]: rms, flatness, pitch, confidence
+    long long n;
+    int frames, frame_size, hop;
+    int min_tau, max_tau;
+    double sr, min_freq, max_freq, threshold;
+    const float *hann;       // [frame_size] np.hanning (symmetric), float32
+    const float2 *tw1, *tw2, *wsplit;   // float32 FFT tables of n_fft = frame_size
+};
+
+template <int NC>   // NC = frame_size / 2
+__global__ void __launch_bounds__(256) at_detector_kernel(const AtDetArgs a) {
+    constexpr int FS = 2 * NC;
+    constexpr int BUF = buf_slots<NC>();
+    QD_DYN_SMEM(smem);
+    double *c = reinterpret_cast<double *>(smem);                  // [FS] centred frame (float64)
+    double *diff = c + FS;                                         // [max_tau + 2]
+    float2 *buf = reinterpret_cast<float2 *>(diff + ((a.max_tau + 2 + 1) & ~1));   // warp FFT buffer
+    __shared__ double s_red[16];
+    __shared__ float s_redf[8];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x, clip = blockIdx.y;
+    const float *x = a.det + (size_t)clip * a.n;
+    const long long start = (long long)frame * a.hop;
+    // ---- load, mean, sum of squares, max |x|
+    double sum = 0.0;
+    float sq = 0.0f, mx = 0.0f;
+    for (int i = tid; i < FS; i += 256) {
+        const long long s = start + i;
+        const float v = s < a.n ? x[s] : 0.0f;
+        c[i] = (double)v;
+        sum += (double)v;
+        sq += v * v;
+        mx = fmaxf(mx, fabsf(v));
+    }
+    sum = warp_sum(sum); sq = warp_sum(sq); mx = warp_max(mx);
+    if (lane == 0) { s_red[warp] = sum; s_redf[warp] = sq; s_red[8 + warp] = (double)mx; }
+    __syncthreads();
+    double tot = 0.0, peak = 0.0;
+    float sqt = 0.0f;
+    for (int w = 0; w < 8; ++w) { tot += s_red[w]; sqt += s_redf[w]; peak = fmax(peak, s_red[8 + w]); }
+    const double mean = tot / (double)FS;
+    const float rms = sqrtf(sqt / (float)FS);
+    // ---- warp 0: spectral flatness of the Hann-windowed frame (dsp/autotune.py:130-137)
+    double flat = 1.0;
+    if (warp == 0) {
+        for (int j = lane; j < NC; j += 32)
+            buf[pidx(j)] = make_float2((float)c[2 * j] * a.hann[2 * j], (float)c[2 * j + 1] * a.hann[2 * j + 1]);
+        __syncwarp();
+        SpecArgsT<float> sa{};
+        sa.tw2 = a.tw2;
+        fwd_first_buf<float, NC, FftCfg<float, NC>::R1>(buf, a.tw1, lane);
+        fft_forward<float, NC>(buf, nullptr, sa, nullptr, a.tw1, a.tw2, lane);
+        real_split<float, NC>(buf, a.wsplit, lane);
+        constexpr int ROWS = (NC + 1 + 31) / 32;
+        double lg = 0.0, ar = 0.0;
+        for (int row = 0; row < ROWS; ++row) {
+            if (row < ROWS - 1 || lane == 0) {
+                const float2 v = buf[rpos<float, NC>(lane, row)];
+                const double m = sqrt((double)v.x * (double)v.x + (double)v.y * (double)v.y) + 1e-8;
+                lg += log(m);
+                ar += m;
+            }
+        }
+        lg = warp_sum(lg); ar = warp_sum(ar);
+        const double geo = exp(lg / (double)(NC + 1)), ari = ar / (double)(NC + 1);
+        flat = ari <= 1e-8 ? 1.0 : geo / ari;
+    }
+    __syncthreads();
+    // ---- YIN (dsp/autotune.py:140-198), float64.  centred frame, difference function in ascending blocks of tau with
+    //      an early exit once the first dip below the threshold and its local minimum are known
+    for (int i = tid; i < FS; i += 256) c[i] -= mean;
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    double pitch = 0.0, conf = 0.0;
+    const bool usable = !(peak < 1e-6) && a.max_tau > a.min_tau;
+    if (usable) {
+        int done_tau = 0;        // diff[1..done_tau] are valid
+        double run = 0.0;        // thread 0: cumulative sum, cmnd overwrites diff in place
+        int scan_tau = 0;        // thread 0: cmnd[1..scan_tau] valid
+        while (done_tau < a.max_tau) {
+            const int tau = done_tau + 1 + tid;
+            if (tau <= a.max_tau) {
+                double acc = 0.0;
+                const int cnt = FS - tau;
+                for (int j = 0; j < cnt; ++j) {
+                    const double d = c[j] - c[j + tau];
+                    acc = fma(d, d, acc);
+                }
+                diff[tau] = acc;
+            }
+            done_tau = min(done_tau + 256, a.max_tau);
+            __syncthreads();
+            if (tid == 0) {
+                for (int t2 = scan_tau + 1; t2 <= done_tau; ++t2) {
+                    run += diff[t2];
+                    diff[t2] = run > 0.0 ? diff[t2] * (double)t2 / run : 1.0;
+                }
+                scan_tau = done_tau;
+                // first tau >= min_tau with cmnd < threshold, walked to its local minimum
+                int est = -1;
+                for (int t2 = a.min_tau; t2 <= scan_tau; ++t2) {
+                    if (diff[t2] < a.threshold) {
+                        while (t2 + 1 <= scan_tau && diff[t2 + 1] < diff[t2]) ++t2;
+                        est = t2;
+                        break;
+                    }
+                }
+                // final when the walk stopped inside the computed range (which also gives the parabola its right
+                // neighbour) or when every tau is known; otherwise the next block decides
+                if (est >= 0 && (est < scan_tau || scan_tau >= a.max_tau)) s_flag = est + 1;
+                else if (scan_tau >= a.max_tau) s_flag = -1;
+            }
+            __syncthreads();
+            if (s_flag != 0) break;
+        }
+        if (tid == 0 && s_flag > 0) {
+            const int est = s_flag - 1;
+            double better = (double)est;
+            if (a.min_tau < est && est < a.max_tau) {
+                const double s0 = diff[est - 1], s1 = diff[est], s2 = diff[est + 1];
+                const double den = 2.0 * (s0 - 2.0 * s1 + s2);
+                if (fabs(den) > 1e-12) better = (double)est + (s0 - s2) / den;
+            }
+            const double p = better > 0.0 ? a.sr / better : 0.0;
+            if (!(p < a.min_freq || p > a.max_freq)) {
+                pitch = p;
+                conf = fmin(fmax(1.0 - diff[est], 0.0), 1.0);
+            }
+        }
+    }
+    if (tid == 0) {
+        double *o = a.feat + ((size_t)clip * a.frames + frame) * 4;
+        o[0] = (double)rms; o[1] = flat; o[2] = pitch; o[3] = conf;
+    }
+}
+
+// ---------------------------------------------------------------- note-hold state machine, one thread per clip
+struct AtHoldArgs {
+    const double *feat;      // [batch, frames, 4]
+    double *ratio;           // [batch, frames]
+    int batch, frames;
+    int root_pc, n_intervals;
+    int intervals[8];
+    double strength, rms_thr, flat_thr, conf_thr, change_cents;
+    int confirm_frames, release_frames;
+};
+
+QD_DEV double at_pymod(double v, double w) {   // Python's float %, w > 0
+    double m = fmod(v, w);
+    if (m != 0.0 && m < 0.0) m += w;
+    return m;
+}
+
+QD_DEV double at_nearest_scale_freq(double freq, const AtHoldArgs &a) {   // dsp/autotune.py:65-85
+    if (freq <= 0.0) return freq;
+    const double midi = 69.0 + 12.0 * log2(freq / 440.0);
+    const double in_oct = at_pymod(at_pymod(midi - (double)a.root_pc, 12.0) + 12.0, 12.0);
+    const double base = midi - in_oct;
+    double best = rint(midi), best_d = INFINITY;
+    for (int o = -1; o <= 1; ++o)
+        for (int k = 0; k < a.n_intervals; ++k) {
+            const double cand = base + (double)a.intervals[k] + (double)o * 12.0;
+            const double d = fabs(midi - cand);
+            if (d < best_d) { best_d = d; best = cand; }
+        }
+    return 440.0 * exp2((best - 69.0) / 12.0);
+}
+
+__global__ void at_hold_kernel(const AtHoldArgs a) {
+    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (clip >= a.batch) return;
+    const double *f = a.feat + (size_t)clip * a.frames * 4;
+    double *out = a.ratio + (size_t)clip * a.frames;
+    double held = 0.0, cand = 0.0, last = 1.0;
+    int cand_n = 0, rel = a.release_frames + 1;
+    for (int i = 0; i < a.frames; ++i) {
+        const double rms = f[4 * i], flat = f[4 * i + 1], p = f[4 * i + 2], conf = f[4 * i + 3];
+        const bool voiced = p > 0.0 && rms >= a.rms_thr && flat <= a.flat_thr && conf >= a.conf_thr;
+        double r;
+        if (voiced) {
+            const double tgt = at_nearest_scale_freq(p, a);
+            if (held <= 0.0) {
+                held = tgt; cand = 0.0; cand_n = 0;
+            } else {
+                const double dc = fabs(1200.0 * log2(fmax(tgt, 1e-6) / fmax(held, 1e-6)));
+                if (dc >= a.change_cents) {
+                    const double cd = cand > 0.0 ? fabs(1200.0 * log2(fmax(tgt, 1e-6) / fmax(cand, 1e-6))) : INFINITY;
+                    if (cand > 0.0 && cd < 20.0) ++cand_n;
+                    else { cand = tgt; cand_n = 1; }
+                    if (cand_n >= a.confirm_frames) { held = cand; cand = 0.0; cand_n = 0; }
+                } else {
+                    cand = 0.0; cand_n = 0;
+                }
+            }
+            r = fmin(fmax(1.0 + a.strength * ((held / p) - 1.0), 0.5), 2.0);
+            rel = 0;
+            last = r;
+        } else {
+            ++rel;
+            if (held > 0.0 && rel <= a.release_frames) {
+                r = last;
+            } else {
+                held = 0.0; cand = 0.0; cand_n = 0;
+                r = 1.0; last = 1.0;
+            }
+        }
+        out[i] = r;
+    }
+}
+
+// np.interp(arange(n), centers, ratio) as float32 (dsp/autotune.py:293-294): centers[k] = min(n-1, k*hop + fs/2)
+QD_DEV float at_ratio_at(const double *ratio, int frames, long long n, int hop, int half, long long s) {
+    const double x = (double)s;
+    auto cen = [&](int k) -> double { const long long c = (long long)k * hop + half; return (double)(c < n - 1 ? c : n - 1); };
+    if (x < cen(0)) return (float)ratio[0];
+    if (x > cen(frames - 1)) return (float)ratio[frames - 1];
+    // largest j with centers[j] <= x (duplicates at the end resolve to the last one)
+    long long j = (s - half) / hop;
+    if (j < 0) j = 0;
+    if (j > frames - 1) j = frames - 1;
+    while (j + 1 <= frames - 1 && cen((int)j + 1) <= x) ++j;
+    while (j > 0 && cen((int)j) > x) --j;
+    if (j == frames - 1) return (float)ratio[j];
+    const double x0 = cen((int)j), x1 = cen((int)j + 1);
+    if (x0 == x) return (float)ratio[j];
+    const double slope = (ratio[j + 1] - ratio[j]) / (x1 - x0);
+    return (float)(slope * (x - x0) + ratio[j]);
+}
+
+// ---------------------------------------------------------------- granular shifter
+// Pass 1 (one thread per clip): the two delay taps, exactly the reference's sequential float64 accumulation with wraps
+// (dsp/autotune.py:327-337), plus the np.allclose(ratio, 1, atol=1e-3) early-out flag.  Pass 2 (wide): read-out.
+struct AtShiftArgs {
+    const float *body;       // [batch, n]
+    const double *ratio;     // [batch, frames]
+    double *taps;            // [batch, n, 2]
+    float *ratio_track;      // optional [batch, n]
+    int *flat_flag;          // [batch] 1: ratio track allclose to 1 -> output = body
+    float *raw;              // [batch, n] shifter output before the latency trim
+    float *out;              // [batch, n] corrected body
+    long long n;
+    int batch, frames, hop, half;
+    int max_delay, buf_size;
+};
+
+__global__ void at_taps_kernel(const AtShiftArgs a) {
+    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (clip >= a.batch) return;
+    const double *ratio = a.ratio + (size_t)clip * a.frames;
+    double *taps = a.taps + (size_t)clip * a.n * 2;
+    float *rt = a.ratio_track ? a.ratio_track + (size_t)clip * a.n : nullptr;
+    const double md = (double)a.max_delay;
+    double t0 = 0.25 * md, t1 = 0.75 * md;
+    bool flat = true;
+    for (long long i = 0; i < a.n; ++i) {
+        const float r = at_ratio_at(ratio, a.frames, a.n, a.hop, a.half, i);
+        if (rt) rt[i] = r;
+        if (!(fabs((double)r - 1.0) <= 1e-3 + 1e-5)) flat = false;   // np.allclose(r, 1.0, atol=1e-3): rtol 1e-5 * |1.0|
+        const double slope = 1.0 - (double)fminf(fmaxf(r, 0.5f), 2.0f);
+        t0 += slope;
+        while (t0 < 0.0) t0 += md;
+        while (t0 >= md) t0 -= md;
+        t1 += slope;
+        while (t1 < 0.0) t1 += md;
+        while (t1 >= md) t1 -= md;
+        taps[2 * i] = t0;
+        taps[2 * i + 1] = t1;
+    }
+    a.flat_flag[clip] = flat ? 1 : 0;
+}
+
+__global__ void at_shift_kernel(const AtShiftArgs a) {
+    const int clip = blockIdx.y;
+    const float *x = a.body + (size_t)clip * a.n;
+    const double *taps = a.taps + (size_t)clip * a.n * 2;
+    float *raw = a.raw + (size_t)clip * a.n;
+    const bool flat = a.flat_flag[clip] != 0;
+    const double md = (double)a.max_delay, size = (double)a.buf_size;
+    const int mask = a.buf_size - 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        if (flat) { raw[i] = x[i]; continue; }
+        const int w = (int)(i & mask);
+        double mixed = 0.0, wsum = 0.0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const double d = taps[2 * i + t];
+            const double phase = d / md;
+            const double weight = 0.5 * (1.0 - cos(2.0 * 3.141592653589793 * phase));
+            const double rp = fmod(((double)w - d) + size, size);
+            const int b = ((int)rp) & mask;
+            const int nx = (b + 1) & mask;
+            const double fr = rp - (double)(int)rp;
+            const long long j0 = i - ((w - b) & mask), j1 = i - ((w - nx) & mask);
+            const float s0 = j0 >= 0 ? x[j0] : 0.0f, s1 = j1 >= 0 ? x[j1] : 0.0f;
+            const float smp = __fadd_rn(__fmul_rn(s0, (float)(1.0 - fr)), __fmul_rn(s1, (float)fr));   // float32 (NEP 50)
+            mixed += (double)smp * weight;
+            wsum += weight;
+        }
+        raw[i] = wsum > 1e-6 ? (float)(mixed / wsum) : 0.0f;
+    }
+}
+
+// latency trim: out = raw[lat:] ++ zeros(lat) unless the early-out copied the body (dsp/autotune.py:355-358)
+__global__ void at_trim_kernel(const AtShiftArgs a) {
+    const int clip = blockIdx.y;
+    const float *raw = a.raw + (size_t)clip * a.n;
+    float *out = a.out + (size_t)clip * a.n;
+    const bool flat = a.flat_flag[clip] != 0;
+    const long long lat = (!flat && a.n > a.max_delay / 2) ? a.max_delay / 2 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (i + lat < a.n) ? raw[i + lat] : 0.0f;
+}
+
+// ---------------------------------------------------------------- sub layer and final mix
+struct AtMixArgs {
+    const float *x, *sub, *air, *corrected;
+    float *env;              // [batch, n] scratch
+    float *env_max;          // [batch]
+    float *sub_layer;        // optional [batch, n]
+    float *y;                // [batch, n] autotune output
+    long long n;
+    int batch;
+    int sub_enabled;         // cfg.sub_enabled
+    int layer_on;            // sub_enabled and sub_level > 0 and freq > 0
+    float att, rel;          // float32(exp(-1/(ms*sr/1000)))
+    float level, preserve, air_mix;
+    float phase_k, sr_f;     // float32(2 pi f), float32(sr): phase = f32(f32(k * i) / sr)
+};
+
+// envelope follower, float32 sequential per clip (dsp/autotune.py:363-377 with NEP-50 scalar types)
+__global__ void at_env_kernel(const AtMixArgs a) {
+    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (clip >= a.batch) return;
+    const float *x = a.x + (size_t)clip * a.n;
+    float *env = a.env + (size_t)clip * a.n;
+    float cur = 0.0f, top = 0.0f;
+    for (long long i = 0; i < a.n; ++i) {
+        const float s = fabsf(x[i]);
+        const float k = s > cur ? a.att : a.rel;
+        cur = __fadd_rn(s, __fmul_rn(k, __fsub_rn(cur, s)));
+        env[i] = cur;
+        top = fmaxf(top, cur);
+    }
+    a.env_max[clip] = top;
+}
+
+__global__ void at_mix_kernel(const AtMixArgs a) {
+    const int clip = blockIdx.y;
+    const size_t base = (size_t)clip * a.n;
+    const float top = a.layer_on ? a.env_max[clip] : 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        float layer = 0.0f;
+        if (a.layer_on) {
+            float e = a.env[base + i];
+            if ((double)top > 1e-6) e = __fdiv_rn(e, top);
+            const float phase = __fdiv_rn(__fmul_rn(a.phase_k, (float)i), a.sr_f);
+            layer = __fmul_rn(__fmul_rn(a.level, e), sinf(phase));
+        }
+        if (a.sub_layer) a.sub_layer[base + i] = layer;
+        const float sub = a.sub[base + i];
+        const float low = a.sub_enabled ? __fadd_rn(__fmul_rn(a.preserve, sub), layer) : sub;
+        a.y[base + i] = __fadd_rn(__fadd_rn(low, a.corrected[base + i]), __fmul_rn(a.air_mix, a.air[base + i]));
+    }
+}
+
+}  // namespace qd

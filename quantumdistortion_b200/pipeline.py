@@ -16,7 +16,7 @@ from typing import Any, Dict, Optional, Tuple, Union
 
 import numpy as np
 
-from . import _lib, tables
+from . import _lib, autotune, tables
 from .config import (DEFAULT_AIR_CUT_HZ, DEFAULT_BIN_SMOOTHING, DEFAULT_DISTORTION_MODE, DEFAULT_DRY_WET,
                      DEFAULT_KEY, DEFAULT_LIMITER_CEILING_DB, DEFAULT_LIMITER_ON, DEFAULT_QUANTIZE_MODE,
                      DEFAULT_SAMPLE_RATE, DEFAULT_SCALE, DEFAULT_SMEAR, DEFAULT_SNAP_STRENGTH, DEFAULT_SUB_CUT_HZ,
@@ -28,7 +28,8 @@ _PC_FIELDS = ("key", "scale", "quantize_mode", "snap_strength", "smear", "bin_sm
               "limiter_ceiling_db", "dry_wet", "preview_enabled", "use_multiband", "crossover_hz", "lowband_drive",
               "passthrough_test", "spectral_fx_mode", "spectral_fx_strength", "spectral_fx_params",
               "spectral_freeze", "formant_shift", "harmonic_lock_hz", "delta_listen", "mono_strength",
-              "output_trim_db")
+              "output_trim_db", "sub_enabled", "sub_source", "sub_note", "sub_scale_degree", "sub_octave", "sub_level",
+              "air_mix")
 
 
 @dataclass
@@ -148,6 +149,35 @@ class Renderer:
         _lib.check(self._lib.qd_render_host(self._plan, x_host.data_ptr(), y_host.data_ptr(), batch, int(chunk_clips)))
 
 
+class AutotuneRenderer:
+    """``quantize_mode="autotune_v1"`` (the reference's default mode) with the Renderer interface."""
+
+    launches_per_render = 16
+
+    def __init__(self, params: "autotune.QdAutotuneParams"):
+        _lib.load()
+        self.params = params
+        self.n = int(params.n_samples)
+
+    def close(self) -> None:
+        pass
+
+    def set_fx_seeds(self, batch: int, seeds=None) -> None:   # no random stage in this mode
+        pass
+
+    def render_device(self, x, want_taps: bool = False, debug: bool = False, chunk_clips: int = 512):
+        _torch()
+        y, taps, dbg = autotune.render_device(self.params, x, want_taps=want_taps, debug=debug, chunk_clips=chunk_clips)
+        return (y, taps, dbg) if debug else (y, taps)
+
+    def render_host(self, x_host, y_host, chunk_clips: int = 128) -> None:
+        """Chunked H2D -> render -> D2H (no copy/compute overlap in this first version of the mode)."""
+        for b0 in range(0, int(x_host.shape[0]), int(chunk_clips)):
+            xs = x_host[b0:b0 + chunk_clips].cuda(non_blocking=True)
+            y, _ = self.render_device(xs, chunk_clips=chunk_clips)
+            y_host[b0:b0 + chunk_clips].copy_(y)
+
+
 _RENDERERS: Dict[Any, Renderer] = {}
 
 
@@ -234,15 +264,24 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
     low_trim_db = g("low_trim_db", 0.0)
     precision = g("precision", "auto")
     g("preview_enabled", None)
-    for ignored in ("sub_enabled", "sub_source", "sub_note", "sub_scale_degree", "sub_octave", "sub_level", "air_mix"):
-        kw.pop(ignored, None)  # autotune-only fields (config.py:80-89)
+    sub_kw = {k: g(k, d) for k, d in (("sub_enabled", True), ("sub_source", "root"), ("sub_note", "C"),
+                                      ("sub_scale_degree", 0), ("sub_octave", 2), ("sub_level", 0.35),
+                                      ("air_mix", 1.0))}  # autotune-only fields (config.py:80-89)
     if kw:
         raise TypeError(f"process_audio() got unexpected keyword arguments: {sorted(kw)}")
     if quantize_mode == "autotune_v1" and (fx_mode is not None or freeze or formant != 0.0 or lock_hz > 0.0):
         quantize_mode = "spectral_bins"  # :1315-1324
-    if quantize_mode != "spectral_bins":
-        raise NotImplementedError("only quantize_mode='spectral_bins' (the STFT path) is implemented; "
-                                  "autotune_v1 is a different algorithm (SURVEY.md 8(f) rank 3)")
+    if quantize_mode == "autotune_v1" and not passthrough:   # dsp/pipeline.py:537-601 (after the passthrough branch :477)
+        if use_multiband and not snap > 0.0:                 # :1326-1327 only forces single band when snap > 0
+            raise NotImplementedError("autotune_v1 with snap_strength 0 inside a multiband render is not built")
+        ap = autotune.resolve(sr=sr, n_samples=n_samples, key=key, scale=scale, snap_strength=snap,
+                              pre_quant=pre_quant, distortion_mode=distortion_mode,
+                              distortion_params=distortion_params, limiter_on=limiter_on,
+                              limiter_ceiling_db=ceiling_db, dry_wet=dry_wet, output_trim_db=trim_db,
+                              delta_listen=delta_listen, sub_cut_hz=sub_cut, air_cut_hz=air_cut, **sub_kw)
+        return ap, {}
+    if quantize_mode not in ("spectral_bins", "autotune_v1"):
+        raise NotImplementedError(f"unknown quantize_mode {quantize_mode!r}: 'spectral_bins' and 'autotune_v1' are built")
     res = tables.resolve(sr=sr, n_samples=n_samples, n_fft=n_fft, key=key, scale=scale, snap_strength=snap,
                          smear=smear, bin_smoothing=bin_smoothing, pre_quant=pre_quant, post_quant=post_quant,
                          distortion_mode=distortion_mode, distortion_params=distortion_params,
@@ -261,6 +300,9 @@ def make_renderer(n_samples: int, sr: int = DEFAULT_SAMPLE_RATE, n_fft: int = N_
     """Resolve the reference keyword arguments once and return the cached CUDA renderer.  ``seeds`` only
     matters for the random spectral FX (see Renderer.set_fx_seeds): an int selects one shared table."""
     res, _ = _resolve_kwargs(int(n_samples), int(sr), int(n_fft), dict(kwargs))
+    if isinstance(res, autotune.QdAutotuneParams):
+        _torch()
+        return AutotuneRenderer(res)
     if res.fx_rng:
         res.params.fx_table_per_clip = 0 if isinstance(seeds, (int, np.integer)) else 1
     return _renderer_for(res)
@@ -351,7 +393,9 @@ def process_audio(audio: np.ndarray, sr: int = DEFAULT_SAMPLE_RATE, key: str = D
               spectral_fx_params=spectral_fx_params, config=config, spectral_freeze=spectral_freeze,
               formant_shift=formant_shift, harmonic_lock_hz=harmonic_lock_hz, delta_listen=delta_listen,
               mono_strength=mono_strength, output_trim_db=output_trim_db, sub_cut_hz=sub_cut_hz,
-              air_cut_hz=air_cut_hz, pipeline_config=pipeline_config, precision=precision)
+              air_cut_hz=air_cut_hz, pipeline_config=pipeline_config, precision=precision,
+              sub_enabled=sub_enabled, sub_source=sub_source, sub_note=sub_note, sub_scale_degree=sub_scale_degree,
+              sub_octave=sub_octave, sub_level=sub_level, air_mix=air_mix)
     tap_input = x.copy()
     if x.shape[0] == 0:
         _resolve_kwargs(0, int(sr), int(n_fft), dict(kw))  # argument validation only

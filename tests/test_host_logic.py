@@ -84,9 +84,9 @@ def test_resolved_flags_follow_reference_gates():
     assert r.params.post_quant == 0 and r.params.distortion_mode == 1 and abs(r.params.wet - np.float32(0.7)) == 0
     assert r.params.lookahead == 220
     with pytest.raises(NotImplementedError):
-        _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1"})
+        _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "granular_v9"})
     r, _ = _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1", "harmonic_lock_hz": 55.0})
-    assert r.params.pre_quant == 1
+    assert r.params.pre_quant == 1          # an FX / freeze / formant / lock option flips the mode (:1315-1324)
     with pytest.raises(TypeError):
         _resolve_kwargs(1000, 48000, 2048, {"bogus": 1})
     # formant shift (dsp/pipeline.py:306-310): ratio 2^(st/12), float32 kernels, flips autotune_v1 to the STFT path
@@ -96,6 +96,43 @@ def test_resolved_flags_follow_reference_gates():
     assert r.params.formant_ratio == 0.0   # the spectral stage does not run at all (:635, :728)
     with pytest.raises(NotImplementedError):
         _resolve_kwargs(1000, 48000, 8192, {"formant_shift": 3.0})
+
+
+def test_autotune_params_follow_reference_rules():
+    """quantize_mode="autotune_v1" (dsp/pipeline.py:537-601, dsp/autotune.py): host-resolved numbers and struct layout."""
+    import subprocess
+    import tempfile
+    from quantumdistortion_b200 import autotune as host_at
+    from oracle import qd_autotune as at
+    p, _ = _resolve_kwargs(24000, 48000, 2048, {"quantize_mode": "autotune_v1", "key": "F", "scale": "dorian",
+                                                 "snap_strength": 1.7, "sub_source": "scale_degree", "sub_scale_degree": 4,
+                                                 "sub_octave": 1, "use_multiband": True})
+    assert isinstance(p, host_at.QdAutotuneParams) and p.apply == 1 and p.strength == 1.0
+    assert (p.min_tau, p.max_tau, p.frame_size, p.hop) == (16, 671, 4096, 512)
+    assert (p.max_delay, p.buffer_size) == (1024, 4096) and p.root_pc == 5 and list(p.intervals[:7]) == [0, 2, 3, 5, 7, 9, 10]
+    cfg = at.AutotuneConfig(key="F", scale="dorian", sub_source="scale_degree", sub_scale_degree=4, sub_octave=1)
+    assert p.phase_k == float(np.float32(2.0 * np.pi * at.sub_frequency(cfg)))
+    sos = at.butter_sos(48000, 110.0, "low")
+    assert [p.sos[0][1][c] for c in range(6)] == list(sos[1])
+    p44, _ = _resolve_kwargs(100, 44100, 2048, {"quantize_mode": "autotune_v1", "sub_cut_hz": 0.0})
+    assert p44.filt_on[0] == 0 and p44.filt_on[1] == 1 and p44.max_tau == int(44100 / 71.5) and p44.lookahead == 220
+    with pytest.raises(ValueError):     # scipy's sosfiltfilt: input shorter than the padding
+        _resolve_kwargs(12, 48000, 2048, {"quantize_mode": "autotune_v1"})
+    with pytest.raises(NotImplementedError):
+        _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1", "snap_strength": 0.0, "use_multiband": True})
+    r, _ = _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1", "passthrough_test": True})
+    assert r.params.passthrough == 1     # the passthrough branch comes first (:477)
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "qd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", '
+           'sizeof(qd_autotune_params), offsetof(qd_autotune_params, zi), offsetof(qd_autotune_params, strength), '
+           'offsetof(qd_autotune_params, phase_k), offsetof(qd_autotune_params, ceiling_lin));return 0;}\n')
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
+        got = [int(v) for v in subprocess.check_output([exe]).split()]
+    P = host_at.QdAutotuneParams
+    assert got == [ctypes.sizeof(P), P.zi.offset, P.strength.offset, P.phase_k.offset, P.ceiling_lin.offset]
 
 
 def test_presets_mirror_reference():
