@@ -1,0 +1,18 @@
+"""Fixed workload for ncu captures of the autotune_v1 mode: one chunk of 10 s clips.
+    python profiles/ncu_target_autotune.py [clips]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import quantumdistortion_b200 as qd
+from quantumdistortion_b200 import synth
+
+clips = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+x = synth.bass_batch_torch(clips, 480000, 48000, "cuda", seed=0)
+r = qd.make_renderer(480000, 48000, quantize_mode="autotune_v1")
+y, _ = r.render_device(x, chunk_clips=clips)
+torch.cuda.synchronize()
+print("ok", float(y.abs().max()))

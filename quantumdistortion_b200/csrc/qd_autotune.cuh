@@ -43,42 +43,107 @@ QD_DEV double at_section(const double *c, double v, double &z0, double &z1) {
     return o;
 }
 
-__global__ void at_filtfilt_kernel(const AtFiltArgs a) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// The sweeps are sequential per clip and would be bound by memory latency, so a WARP owns one (clip, job): all lanes
+// fetch the next tile of AT_TS samples (coalesced, in flight while lane 0 runs the dependent float64 chain over the
+// current tile out of shared memory) and write the finished tile back with coalesced stores.
+constexpr int AT_BK = 8;      // register block of the one-thread-per-clip kernels below
+constexpr int AT_TS = 512;    // samples per tile
+constexpr int AT_FW = 4;      // warps per CTA
+
+__global__ void __launch_bounds__(32 * AT_FW) at_filtfilt_kernel(const AtFiltArgs a) {
+    __shared__ double s_in[AT_FW][AT_TS];
+    __shared__ double s_out[AT_FW][AT_TS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * AT_FW + warp;
     if (t >= a.batch * a.jobs) return;
     const int job = t / a.batch, clip = t % a.batch;
-    const float *x = a.x[job] + (size_t)clip * a.n;
-    float *y = a.y[job] + (size_t)clip * a.n;
+    const float *__restrict__ x = a.x[job] + (size_t)clip * a.n;
+    float *__restrict__ y = a.y[job] + (size_t)clip * a.n;
     const AtFilter &f = a.f[job];
     const long long n = a.n;
     if (!f.on) {
-        for (long long i = 0; i < n; ++i) y[i] = x[i];
+        for (long long i = lane; i < n; i += 32) y[i] = x[i];
         return;
     }
     const long long m = n + 2 * AT_EDGE;
-    double *s = a.scratch + (size_t)t * (size_t)m;
-    auto ext = [&](long long i) -> double {   // odd extension in float32
+    double *__restrict__ s = a.scratch + (size_t)t * (size_t)m;
+    double *in = s_in[warp], *out = s_out[warp];
+    auto ext = [&](long long i) -> double {   // odd extension in float32; 0 past the end
         if (i < AT_EDGE) return (double)__fsub_rn(__fmul_rn(2.0f, x[0]), x[AT_EDGE - i]);
-        if (i >= n + AT_EDGE) return (double)__fsub_rn(__fmul_rn(2.0f, x[n - 1]), x[n - 2 - (i - n - AT_EDGE)]);
+        if (i >= n + AT_EDGE) return i < m ? (double)__fsub_rn(__fmul_rn(2.0f, x[n - 1]), x[n - 2 - (i - n - AT_EDGE)]) : 0.0;
         return (double)x[i - AT_EDGE];
     };
+    constexpr int PER = AT_TS / 32;
+    double nxt[PER];
     const double x0 = ext(0);
     double z[2][2] = {{f.zi[0][0] * x0, f.zi[0][1] * x0}, {f.zi[1][0] * x0, f.zi[1][1] * x0}};
     double last = 0.0;
-    for (long long i = 0; i < m; ++i) {
-        double v = ext(i);
-        v = at_section(f.sos[0], v, z[0][0], z[0][1]);
-        v = at_section(f.sos[1], v, z[1][0], z[1][1]);
-        s[i] = v;
-        last = v;
+    // ---- forward sweep over ext[0 .. m)
+#pragma unroll
+    for (int k = 0; k < PER; ++k) in[lane + 32 * k] = ext((long long)(lane + 32 * k));
+    __syncwarp();
+    for (long long i0 = 0; i0 < m; i0 += AT_TS) {
+        const bool more = i0 + AT_TS < m;
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < PER; ++k) nxt[k] = ext(i0 + AT_TS + lane + 32 * k);
+        }
+        const int cnt = (int)(m - i0 < AT_TS ? m - i0 : AT_TS);
+        if (lane == 0) {
+            for (int k = 0; k < cnt; ++k) {
+                double v = at_section(f.sos[0], in[k], z[0][0], z[0][1]);
+                v = at_section(f.sos[1], v, z[1][0], z[1][1]);
+                out[k] = v;
+            }
+            last = out[cnt - 1];
+        }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) s[i0 + k] = out[k];
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < PER; ++k) in[lane + 32 * k] = nxt[k];
+        }
+        __syncwarp();
     }
+    last = __shfl_sync(QD_FULL, last, 0);
     z[0][0] = f.zi[0][0] * last; z[0][1] = f.zi[0][1] * last;
     z[1][0] = f.zi[1][0] * last; z[1][1] = f.zi[1][1] * last;
-    for (long long i = m - 1; i >= 0; --i) {
-        double v = s[i];
-        v = at_section(f.sos[0], v, z[0][0], z[0][1]);
-        v = at_section(f.sos[1], v, z[1][0], z[1][1]);
-        if (i >= AT_EDGE && i < n + AT_EDGE) y[i - AT_EDGE] = (float)v;
+    // ---- backward sweep: tiles [lo, lo + cnt) from the end, processed from the top down (the stores of the forward sweep
+    //      were issued by this same warp, so they are visible to its own later loads)
+    const long long tiles = (m + AT_TS - 1) / AT_TS;
+    auto load_tile = [&](long long tl, double (&v)[PER]) {
+        const long long lo = tl * AT_TS;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const long long i = lo + lane + 32 * k;
+            v[k] = i < m ? s[i] : 0.0;
+        }
+    };
+    load_tile(tiles - 1, nxt);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) in[lane + 32 * k] = nxt[k];
+    __syncwarp();
+    for (long long tl = tiles - 1; tl >= 0; --tl) {
+        if (tl > 0) load_tile(tl - 1, nxt);
+        const long long lo = tl * AT_TS;
+        const int cnt = (int)(m - lo < AT_TS ? m - lo : AT_TS);
+        if (lane == 0) {
+            for (int k = cnt - 1; k >= 0; --k) {
+                double v = at_section(f.sos[0], in[k], z[0][0], z[0][1]);
+                v = at_section(f.sos[1], v, z[1][0], z[1][1]);
+                out[k] = v;
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) {
+            const long long i = lo + k;
+            if (i >= AT_EDGE && i < n + AT_EDGE) y[i - AT_EDGE] = (float)out[k];
+        }
+        if (tl > 0) {
+#pragma unroll
+            for (int k = 0; k < PER; ++k) in[lane + 32 * k] = nxt[k];
+        }
+        __syncwarp();
     }
 }
 
@@ -101,6 +166,8 @@ struct AtDetArgs {
     double sr, min_freq, max_freq, threshold;
     const float *hann;       // [frame_size] np.hanning (symmetric), float32
     const float2 *tw1, *tw2, *wsplit;   // float32 FFT tables of n_fft = frame_size
+    int yin_inline;          // 1: YIN inside this kernel (per-frame difference function);
+                             // 0: only rms / flatness / "frame is not silent" (feat[2] = 1 or 0), YIN by the sliding kernels
 };
 
 template <int NC>   // NC = frame_size / 2
@@ -170,7 +237,9 @@ __global__ void __launch_bounds__(256) at_detector_kernel(const AtDetArgs a) {
     __syncthreads();
     double pitch = 0.0, conf = 0.0;
     const bool usable = !(peak < 1e-6) && a.max_tau > a.min_tau;
-    if (usable) {
+    if (!a.yin_inline) {
+        pitch = usable ? 1.0 : 0.0;
+    } else if (usable) {
         int done_tau = 0;        // diff[1..done_tau] are valid
         double run = 0.0;        // thread 0: cumulative sum, cmnd overwrites diff in place
         int scan_tau = 0;        // thread 0: cmnd[1..scan_tau] valid
@@ -228,6 +297,120 @@ __global__ void __launch_bounds__(256) at_detector_kernel(const AtDetArgs a) {
     if (tid == 0) {
         double *o = a.feat + ((size_t)clip * a.frames + frame) * 4;
         o[0] = (double)rms; o[1] = flat; o[2] = pitch; o[3] = conf;
+    }
+}
+
+// ---------------------------------------------------------------- YIN by sliding sums (the fast detector path)
+// The mean of a frame cancels in c[j] - c[j+tau], so the difference function of frame f is a window sum of one
+// per-lag sequence over the (zero-extended) clip:
+//   d_f(tau) = sum_{j = f*hop}^{f*hop + W - tau - 1} e_tau[j],   e_tau[j] = (x[j] - x[j+tau])^2
+// Consecutive frames overlap by 7/8, so one running float64 prefix per lag serves every frame: 8x less arithmetic than
+// frame-by-frame evaluation.  A thread owns one lag and walks the clip hop-block by hop-block; the prefix at each
+// frame start is parked in a 9-deep ring, the frame's value is emitted when the walk reaches f*hop + W - tau.
+struct AtYinArgs {
+    const float *det;        // [batch, n]
+    double *diff;            // [batch, frames, stride] difference function, entry tau
+    double *feat;            // [batch, frames, 4]; feat[2] holds 1 / 0 (frame not silent) on entry of the pick kernel
+    long long n;
+    long long total_frames;  // batch * frames
+    int frames, frame_size, hop, stride;
+    int min_tau, max_tau;
+    double sr, min_freq, max_freq, threshold;
+};
+
+constexpr int AT_YT = 256;   // lags per CTA
+
+__global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
+    QD_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    const int tau0 = 1 + blockIdx.x * AT_YT;            // lags of this CTA: tau0 .. tau0 + AT_YT - 1
+    const int tau = tau0 + tid;
+    const bool live = tau <= a.max_tau;
+    const int span = a.hop + tau0 + AT_YT;             // samples a hop-block needs
+    double *tile = reinterpret_cast<double *>(smem);    // [span]
+    double *ring = tile + ((span + 1) & ~1);            // [9][AT_YT]
+    const float *x = a.det + (size_t)blockIdx.y * a.n;
+    double *out = a.diff + (size_t)blockIdx.y * a.frames * a.stride;
+    const int wlen = a.frame_size - tau;                // window length of this lag
+    const int q = wlen / a.hop, off = wlen % a.hop;     // frame f ends inside hop-block f + q at offset off
+    double S = 0.0;
+    const int blocks = a.frames + a.frame_size / a.hop;
+    for (int b = 0; b < blocks; ++b) {
+        const long long j0 = (long long)b * a.hop;
+        __syncthreads();
+        for (int i = tid; i < span; i += AT_YT) {
+            const long long sidx = j0 + i;
+            tile[i] = sidx < a.n ? (double)x[sidx] : 0.0;
+        }
+        __syncthreads();
+        if (!live) continue;
+        if (b < a.frames) ring[(b % 9) * AT_YT + tid] = S;
+        const double *pa = tile, *pb = tile + tau;
+        for (int jj = 0; jj < off; ++jj) {
+            const double d = pa[jj] - pb[jj];
+            S = fma(d, d, S);
+        }
+        const int f = b - q;
+        if (f >= 0 && f < a.frames) out[(size_t)f * a.stride + tau] = S - ring[(f % 9) * AT_YT + tid];
+        for (int jj = off; jj < a.hop; ++jj) {
+            const double d = pa[jj] - pb[jj];
+            S = fma(d, d, S);
+        }
+    }
+}
+
+// cumulative-mean normalisation and pick (dsp/autotune.py:162-197), one warp per frame
+__global__ void __launch_bounds__(256) at_yin_pick_kernel(const AtYinArgs a) {
+    QD_DYN_SMEM(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long fr = (long long)blockIdx.x * 8 + warp;        // frame index over the whole batch
+    if (fr >= a.total_frames) return;
+    double *cm = reinterpret_cast<double *>(smem) + (size_t)warp * a.stride;
+    double *ft = a.feat + (size_t)fr * 4;
+    const double *d = a.diff + (size_t)fr * a.stride;
+    // running sum over tau by warp scans of 32 lags
+    double run = 0.0;
+    for (int t0 = 1; t0 <= a.max_tau; t0 += 32) {
+        const int t = t0 + lane;
+        const double v = t <= a.max_tau ? d[t] : 0.0;
+        double inc = v;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const double o = __shfl_up_sync(QD_FULL, inc, sft);
+            if (lane >= sft) inc += o;
+        }
+        const double rs = run + inc;                               // running_sum including lag t
+        if (t <= a.max_tau) cm[t] = rs > 0.0 ? v * (double)t / rs : 1.0;
+        run += __shfl_sync(QD_FULL, inc, 31);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double pitch = 0.0, conf = 0.0;
+        if (ft[2] != 0.0 && a.max_tau > a.min_tau) {
+            int est = -1;
+            for (int t = a.min_tau; t <= a.max_tau; ++t) {
+                if (cm[t] < a.threshold) {
+                    while (t + 1 <= a.max_tau && cm[t + 1] < cm[t]) ++t;
+                    est = t;
+                    break;
+                }
+            }
+            if (est >= 0) {
+                double better = (double)est;
+                if (a.min_tau < est && est < a.max_tau) {
+                    const double s0 = cm[est - 1], s1 = cm[est], s2 = cm[est + 1];
+                    const double den = 2.0 * (s0 - 2.0 * s1 + s2);
+                    if (fabs(den) > 1e-12) better = (double)est + (s0 - s2) / den;
+                }
+                const double p = better > 0.0 ? a.sr / better : 0.0;
+                if (!(p < a.min_freq || p > a.max_freq)) {
+                    pitch = p;
+                    conf = fmin(fmax(1.0 - cm[est], 0.0), 1.0);
+                }
+            }
+        }
+        ft[2] = pitch;
+        ft[3] = conf;
     }
 }
 
@@ -321,7 +504,7 @@ QD_DEV float at_ratio_at(const double *ratio, int frames, long long n, int hop, 
     const double x0 = cen((int)j), x1 = cen((int)j + 1);
     if (x0 == x) return (float)ratio[j];
     const double slope = (ratio[j + 1] - ratio[j]) / (x1 - x0);
-    return (float)(slope * (x - x0) + ratio[j]);
+    return (float)__dadd_rn(__dmul_rn(slope, x - x0), ratio[j]);   // NumPy: multiply, then add
 }
 
 // ---------------------------------------------------------------- granular shifter
@@ -340,30 +523,48 @@ struct AtShiftArgs {
     int max_delay, buf_size;
 };
 
-__global__ void at_taps_kernel(const AtShiftArgs a) {
-    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * AT_FW) at_taps_kernel(const AtShiftArgs a) {
+    __shared__ float s_r[AT_FW][AT_TS];
+    __shared__ double2 s_t[AT_FW][AT_TS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int clip = blockIdx.x * AT_FW + warp;
     if (clip >= a.batch) return;
-    const double *ratio = a.ratio + (size_t)clip * a.frames;
-    double *taps = a.taps + (size_t)clip * a.n * 2;
-    float *rt = a.ratio_track ? a.ratio_track + (size_t)clip * a.n : nullptr;
+    const double *__restrict__ ratio = a.ratio + (size_t)clip * a.frames;
+    double2 *__restrict__ taps = reinterpret_cast<double2 *>(a.taps + (size_t)clip * a.n * 2);
+    float *__restrict__ rt = a.ratio_track ? a.ratio_track + (size_t)clip * a.n : nullptr;
+    float *rr = s_r[warp];
+    double2 *tt = s_t[warp];
     const double md = (double)a.max_delay;
     double t0 = 0.25 * md, t1 = 0.75 * md;
     bool flat = true;
-    for (long long i = 0; i < a.n; ++i) {
-        const float r = at_ratio_at(ratio, a.frames, a.n, a.hop, a.half, i);
-        if (rt) rt[i] = r;
-        if (!(fabs((double)r - 1.0) <= 1e-3 + 1e-5)) flat = false;   // np.allclose(r, 1.0, atol=1e-3): rtol 1e-5 * |1.0|
-        const double slope = 1.0 - (double)fminf(fmaxf(r, 0.5f), 2.0f);
-        t0 += slope;
-        while (t0 < 0.0) t0 += md;
-        while (t0 >= md) t0 -= md;
-        t1 += slope;
-        while (t1 < 0.0) t1 += md;
-        while (t1 >= md) t1 -= md;
-        taps[2 * i] = t0;
-        taps[2 * i + 1] = t1;
+    for (long long i0 = 0; i0 < a.n; i0 += AT_TS) {
+        const int cnt = (int)(a.n - i0 < AT_TS ? a.n - i0 : AT_TS);
+        // the ratio track of the tile, all lanes (np.interp per sample, see at_ratio_at)
+        for (int k = lane; k < cnt; k += 32) {
+            const float r = at_ratio_at(ratio, a.frames, a.n, a.hop, a.half, i0 + k);
+            rr[k] = r;
+            if (rt) rt[i0 + k] = r;
+            if (!(fabs((double)r - 1.0) <= 1e-3 + 1e-5)) flat = false;   // np.allclose(r, 1.0, atol=1e-3): rtol 1e-5 * |1.0|
+        }
+        __syncwarp();
+        if (lane == 0) {   // the sequential float64 accumulation with wraps (dsp/autotune.py:327-337)
+            for (int k = 0; k < cnt; ++k) {
+                const double sl = 1.0 - (double)fminf(fmaxf(rr[k], 0.5f), 2.0f);
+                t0 += sl;
+                while (t0 < 0.0) t0 += md;
+                while (t0 >= md) t0 -= md;
+                t1 += sl;
+                while (t1 < 0.0) t1 += md;
+                while (t1 >= md) t1 -= md;
+                tt[k] = make_double2(t0, t1);
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) taps[i0 + k] = tt[k];
+        __syncwarp();
     }
-    a.flat_flag[clip] = flat ? 1 : 0;
+    flat = __all_sync(QD_FULL, flat);
+    if (lane == 0) a.flat_flag[clip] = flat ? 1 : 0;
 }
 
 __global__ void at_shift_kernel(const AtShiftArgs a) {
@@ -425,20 +626,46 @@ struct AtMixArgs {
 };
 
 // envelope follower, float32 sequential per clip (dsp/autotune.py:363-377 with NEP-50 scalar types)
-__global__ void at_env_kernel(const AtMixArgs a) {
-    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * AT_FW) at_env_kernel(const AtMixArgs a) {
+    __shared__ float s_io[AT_FW][AT_TS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int clip = blockIdx.x * AT_FW + warp;
     if (clip >= a.batch) return;
-    const float *x = a.x + (size_t)clip * a.n;
-    float *env = a.env + (size_t)clip * a.n;
+    const float *__restrict__ x = a.x + (size_t)clip * a.n;
+    float *__restrict__ env = a.env + (size_t)clip * a.n;
+    float *io = s_io[warp];
+    constexpr int PER = AT_TS / 32;
+    float nxt[PER];
     float cur = 0.0f, top = 0.0f;
-    for (long long i = 0; i < a.n; ++i) {
-        const float s = fabsf(x[i]);
-        const float k = s > cur ? a.att : a.rel;
-        cur = __fadd_rn(s, __fmul_rn(k, __fsub_rn(cur, s)));
-        env[i] = cur;
-        top = fmaxf(top, cur);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) io[lane + 32 * k] = lane + 32 * k < a.n ? x[lane + 32 * k] : 0.0f;
+    __syncwarp();
+    for (long long i0 = 0; i0 < a.n; i0 += AT_TS) {
+        const bool more = i0 + AT_TS < a.n;
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < PER; ++k) { const long long i = i0 + AT_TS + lane + 32 * k; nxt[k] = i < a.n ? x[i] : 0.0f; }
+        }
+        const int cnt = (int)(a.n - i0 < AT_TS ? a.n - i0 : AT_TS);
+        if (lane == 0) {
+            for (int k = 0; k < cnt; ++k) {
+                const float s = fabsf(io[k]);
+                const float c = s > cur ? a.att : a.rel;
+                cur = __fadd_rn(s, __fmul_rn(c, __fsub_rn(cur, s)));
+                io[k] = cur;
+                top = fmaxf(top, cur);
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) env[i0 + k] = io[k];
+        __syncwarp();
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < PER; ++k) io[lane + 32 * k] = nxt[k];
+        }
+        __syncwarp();
     }
-    a.env_max[clip] = top;
+    if (lane == 0) a.env_max[clip] = top;
 }
 
 __global__ void at_mix_kernel(const AtMixArgs a) {
