@@ -269,7 +269,8 @@ def run_ours(args):
                 "traffic": None, "kernel": "qd::spec_pass_kernel<float,1024,8,TS,noFX,NG=2>", "ms_per_launch": spec_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_ms_per_step": step_share,
-                "note": "the pass is FP32-issue/shared-memory bound (about 600 flop per sample), not HBM bound; see DESIGN.md"}
+                "note": "the pass is bound by instruction issue and shared-memory wavefronts (about 600 flop per sample), "
+                        "not by HBM; the limiter launch skips clips that never exceed the ceiling (gain exactly 1); see DESIGN.md"}
     ncu_traffic = os.path.join(ROOT, "profiles", "spec_traffic_bytes_per_launch.json")
     if os.path.exists(ncu_traffic):
         try:
@@ -280,7 +281,7 @@ def run_ours(args):
             pass
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
         v, cores, n_clips, wall = cpu_baseline(args.cpu_clips_per_core)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
