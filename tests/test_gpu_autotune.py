@@ -91,3 +91,23 @@ def test_autotune_batch_vs_oracle(qd):
     assert np.array_equal(y, y2)
     with pytest.raises(ValueError):
         qd.process_audio(np.zeros(10, dtype=np.float32), sr, quantize_mode="autotune_v1")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [16, 17, 100, 513, 2049, 4097])
+def test_autotune_tiny_and_silent_clips(qd, n):
+    """Lengths around the padding (15), one hop, half a frame and one frame; silence; stereo input."""
+    sr = 48000
+    x = qd_cases.make_signal("tone", 30 + n, max(n, 64), sr)[:n]
+    y, taps = qd.process_audio(x, sr, quantize_mode="autotune_v1")
+    ref, rt = at.process_audio_autotune(x, sr)
+    _check(y, ref, f"n={n}")
+    _check(taps["pre_quant"], rt["pre_quant"], f"n={n} pre_quant")
+    z = np.zeros(n, dtype=np.float32)
+    yz, _ = qd.process_audio(z, sr, quantize_mode="autotune_v1")
+    refz, _ = at.process_audio_autotune(z, sr)
+    assert np.array_equal(yz, refz)
+    st = np.stack([x, 0.5 * x], axis=1)
+    ys, _ = qd.process_audio(st, sr, quantize_mode="autotune_v1")
+    refs, _ = at.process_audio_autotune(st, sr)
+    _check(ys, refs, f"stereo n={n}")
