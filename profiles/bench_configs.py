@@ -39,11 +39,11 @@ for name, kw in (("next(f3) autotune_v1 defaults (bass batch)", {}), ("next(f3) 
     kw = {k: v for k, v in kw.items() if k not in ("smear",)}
     xs = x[:AT_CLIPS]
     r = qd.make_renderer(N, SR, quantize_mode="autotune_v1", **kw)
-    y, _ = r.render_device(xs, chunk_clips=1024)
+    y, _ = r.render_device(xs, chunk_clips=2048)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    y, _ = r.render_device(xs, chunk_clips=1024)
+    y, _ = r.render_device(xs, chunk_clips=2048)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)

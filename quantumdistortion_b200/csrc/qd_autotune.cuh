@@ -318,7 +318,7 @@ struct AtYinArgs {
     double sr, min_freq, max_freq, threshold;
 };
 
-constexpr int AT_YT = 256;   // lags per CTA
+constexpr int AT_YT = 224;   // lags per CTA (671 lags at 48 kHz = 3 CTAs of 7 warps)
 
 __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
     QD_DYN_SMEM(smem);

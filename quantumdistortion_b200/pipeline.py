@@ -165,7 +165,7 @@ class AutotuneRenderer:
     def set_fx_seeds(self, batch: int, seeds=None) -> None:   # no random stage in this mode
         pass
 
-    def render_device(self, x, want_taps: bool = False, debug: bool = False, chunk_clips: int = 512):
+    def render_device(self, x, want_taps: bool = False, debug: bool = False, chunk_clips: int = 2048):
         _torch()
         y, taps, dbg = autotune.render_device(self.params, x, want_taps=want_taps, debug=debug, chunk_clips=chunk_clips)
         return (y, taps, dbg) if debug else (y, taps)
