@@ -146,8 +146,9 @@ def resolve(*, sr: int, n_samples: int, key: str, scale: str, snap_strength: flo
     return p
 
 
-def render_device(p: QdAutotuneParams, x, want_taps: bool = False, debug: bool = False, chunk_clips: int = 2048):
-    """x: CUDA float32 [B, n] -> (y, taps or None, debug dict or None).  Clips are rendered ``chunk_clips`` at a time:
+def render_device(p: QdAutotuneParams, x, want_taps: bool = False, debug: bool = False, chunk_clips: int = 2048,
+                  workspace=None):
+    """x: CUDA float32 [B, n] -> (y, taps or None, debug dict or None, workspace tensor to hand back in next time).  Clips are rendered ``chunk_clips`` at a time:
     the mode keeps its bands in HBM (40 bytes of workspace per sample plus the YIN difference functions, about 24 MB
     per 10 s clip), and the sequential sweeps cost the same for 1 clip as for a few thousand."""
     import torch
@@ -164,9 +165,11 @@ def render_device(p: QdAutotuneParams, x, want_taps: bool = False, debug: bool =
         dbg = {k: torch.zeros_like(x) for k in ("sub", "body", "air", "det", "ratio_track", "corrected", "sub_layer")}
         dbg["features"] = torch.zeros((b, frames, 4), dtype=torch.float64, device=x.device)
     if b == 0 or n == 0:
-        return y, taps, dbg
+        return y, taps, dbg, workspace
     chunk = max(1, min(int(chunk_clips), b))
-    ws = torch.empty(int(lib.qd_autotune_workspace_bytes(C.byref(p), chunk)), dtype=torch.uint8, device=x.device)
+    need = int(lib.qd_autotune_workspace_bytes(C.byref(p), chunk))
+    ws = workspace if workspace is not None and workspace.numel() >= need and workspace.device == x.device else \
+        torch.empty(need, dtype=torch.uint8, device=x.device)
     stream = torch.cuda.current_stream().cuda_stream
     for b0 in range(0, b, chunk):
         nb = min(chunk, b - b0)
@@ -179,4 +182,4 @@ def render_device(p: QdAutotuneParams, x, want_taps: bool = False, debug: bool =
                                                  C.byref(ct) if ct is not None else None,
                                                  C.byref(cd) if cd is not None else None,
                                                  ws.data_ptr(), ws.numel(), stream))
-    return y, taps, dbg
+    return y, taps, dbg, ws

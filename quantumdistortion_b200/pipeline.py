@@ -158,16 +158,18 @@ class AutotuneRenderer:
         _lib.load()
         self.params = params
         self.n = int(params.n_samples)
+        self._ws = None   # device workspace, kept between renders
 
     def close(self) -> None:
-        pass
+        self._ws = None
 
     def set_fx_seeds(self, batch: int, seeds=None) -> None:   # no random stage in this mode
         pass
 
     def render_device(self, x, want_taps: bool = False, debug: bool = False, chunk_clips: int = 2048):
         _torch()
-        y, taps, dbg = autotune.render_device(self.params, x, want_taps=want_taps, debug=debug, chunk_clips=chunk_clips)
+        y, taps, dbg, self._ws = autotune.render_device(self.params, x, want_taps=want_taps, debug=debug,
+                                                        chunk_clips=chunk_clips, workspace=self._ws)
         return (y, taps, dbg) if debug else (y, taps)
 
     def render_host(self, x_host, y_host, chunk_clips: int = 128) -> None:
