@@ -379,6 +379,60 @@ __global__ void __launch_bounds__(256) at_detector_kernel(const AtDetArgs a) {
     }
 }
 
+// rms, spectral flatness and the silence flag with one WARP per frame (the detector path used with the sliding YIN):
+// the lanes load the frame once, accumulate the sums and write the Hann-windowed samples straight into the warp's FFT
+// buffer.  feat = (rms, flatness, 1 or 0 for "not silent", 0).
+template <int NC>
+__global__ void __launch_bounds__(256) at_frame_stats_kernel(const AtDetArgs a, long long total_frames) {
+    constexpr int FS = 2 * NC;
+    constexpr int BUF = buf_slots<NC>();
+    QD_DYN_SMEM(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long fr = (long long)blockIdx.x * 8 + warp;
+    if (fr >= total_frames) return;
+    float2 *buf = reinterpret_cast<float2 *>(smem) + (size_t)warp * BUF;
+    const long long clip = fr / a.frames;
+    const int frame = (int)(fr % a.frames);
+    const float *x = a.det + (size_t)clip * a.n;
+    const long long start = (long long)frame * a.hop;
+    float sq = 0.0f, mx = 0.0f;
+    for (int j = lane; j < NC; j += 32) {
+        const long long s0 = start + 2 * j;
+        const float v0 = s0 < a.n ? x[s0] : 0.0f, v1 = s0 + 1 < a.n ? x[s0 + 1] : 0.0f;
+        sq += v0 * v0 + v1 * v1;
+        mx = fmaxf(mx, fmaxf(fabsf(v0), fabsf(v1)));
+        buf[pidx(j)] = make_float2(v0 * a.hann[2 * j], v1 * a.hann[2 * j + 1]);
+    }
+    sq = warp_sum(sq);
+    mx = warp_max(mx);
+    __syncwarp();
+    SpecArgsT<float> sa{};
+    sa.tw2 = a.tw2;
+    fwd_first_buf<float, NC, FftCfg<float, NC>::R1>(buf, a.tw1, lane);
+    fft_forward<float, NC>(buf, nullptr, sa, nullptr, a.tw1, a.tw2, lane);
+    real_split<float, NC>(buf, a.wsplit, lane);
+    constexpr int ROWS = (NC + 1 + 31) / 32;
+    double lg = 0.0, ar = 0.0;
+    for (int row = 0; row < ROWS; ++row) {
+        if (row < ROWS - 1 || lane == 0) {
+            const float2 v = buf[rpos<float, NC>(lane, row)];
+            const double m = sqrt((double)v.x * (double)v.x + (double)v.y * (double)v.y) + 1e-8;
+            lg += log(m);
+            ar += m;
+        }
+    }
+    lg = warp_sum(lg);
+    ar = warp_sum(ar);
+    if (lane == 0) {
+        const double geo = exp(lg / (double)(NC + 1)), ari = ar / (double)(NC + 1);
+        double *o = a.feat + (size_t)fr * 4;
+        o[0] = (double)sqrtf(sq / (float)FS);
+        o[1] = ari <= 1e-8 ? 1.0 : geo / ari;
+        o[2] = (!((double)mx < 1e-6) && a.max_tau > a.min_tau) ? 1.0 : 0.0;
+        o[3] = 0.0;
+    }
+}
+
 // ---------------------------------------------------------------- YIN by sliding sums (the fast detector path)
 // The mean of a frame cancels in c[j] - c[j+tau], so the difference function of frame f is a window sum of one
 // per-lag sequence over the (zero-extended) clip:
@@ -628,13 +682,14 @@ __global__ void __launch_bounds__(32 * AT_FW) at_taps_kernel(const AtShiftArgs a
         __syncwarp();
         if (lane == 0) {   // the sequential float64 accumulation with wraps (dsp/autotune.py:327-337)
             for (int k = 0; k < cnt; ++k) {
+                // |1 - ratio| <= 1 < max_delay, so each of the reference's two while loops runs at most once: selects
                 const double sl = 1.0 - (double)fminf(fmaxf(rr[k], 0.5f), 2.0f);
                 t0 += sl;
-                while (t0 < 0.0) t0 += md;
-                while (t0 >= md) t0 -= md;
+                t0 = t0 < 0.0 ? t0 + md : t0;
+                t0 = t0 >= md ? t0 - md : t0;
                 t1 += sl;
-                while (t1 < 0.0) t1 += md;
-                while (t1 >= md) t1 -= md;
+                t1 = t1 < 0.0 ? t1 + md : t1;
+                t1 = t1 >= md ? t1 - md : t1;
                 tt[k] = make_double2(t0, t1);
             }
         }

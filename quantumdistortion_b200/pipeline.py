@@ -303,8 +303,14 @@ def make_renderer(n_samples: int, sr: int = DEFAULT_SAMPLE_RATE, n_fft: int = N_
     matters for the random spectral FX (see Renderer.set_fx_seeds): an int selects one shared table."""
     res, _ = _resolve_kwargs(int(n_samples), int(sr), int(n_fft), dict(kwargs))
     if isinstance(res, autotune.QdAutotuneParams):
-        _torch()
-        return AutotuneRenderer(res)
+        torch = _torch()
+        key = ("autotune_v1", torch.cuda.current_device(), bytes(res))
+        r = _RENDERERS.get(key)
+        if r is None:
+            if len(_RENDERERS) > 32:
+                _RENDERERS.pop(next(iter(_RENDERERS))).close()
+            r = _RENDERERS[key] = AutotuneRenderer(res)
+        return r
     if res.fx_rng:
         res.params.fx_table_per_clip = 0 if isinstance(seeds, (int, np.integer)) else 1
     return _renderer_for(res)
