@@ -3,12 +3,13 @@
 //   zero-phase band split (sosfiltfilt x4)  ->  YIN pitch track on the detector band  ->  note-hold state machine
 //   ->  per-sample ratio track  ->  granular two-tap pitch shifter  ->  envelope-followed sub oscillator  ->  mix
 //
-// First CUDA version: correctness first.  The strictly sequential recurrences (IIR sweeps, note hold, tap positions,
-// envelope follower) run one thread per clip in the reference's own operation order and precision, with explicit
-// round-to-nearest intrinsics so that nothing is contracted into an FMA the reference does not have; everything
-// per-sample-independent (band arithmetic, shifter read-out, oscillator, mix) and the per-frame detector run wide.
-// The detector's difference function is float64 like the reference: the shifter integrates 1 - ratio, so the pitch
-// has to match to ~1e-9 for the output to stay inside the 1e-4 parity bound.
+// Where the reference is a per-sample Python loop, the kernels keep its operation order and precision (explicit
+// round-to-nearest intrinsics where an FMA would change a float32 result; NumPy's NEP-50 scalar typing followed operation
+// by operation).  The IIR sweeps are blocked affine scans in float64, YIN's difference function is one running float64
+// prefix per lag shared by all frames, the shifter read-out, oscillator and mix run wide; only the delay-tap accumulation,
+// the envelope follower and the note-hold state machine stay sequential per clip (one lane, warp-staged tiles).
+// The detector is float64 like the reference because the shifter integrates 1 - ratio: the pitch has to match to ~1e-9
+// for the output to stay inside the 1e-4 parity bound.
 #pragma once
 #include "qd_spec.cuh"
 #include "qd_time.cuh"
@@ -23,7 +24,7 @@ struct AtFilter {         // one zero-phase 4th-order Butterworth (two second-or
 
 constexpr int AT_EDGE = 15;   // sosfiltfilt default padlen = 3 * ntaps, ntaps = 5
 
-// ---------------------------------------------------------------- zero-phase filter, one thread per (clip, job)
+// ---------------------------------------------------------------- zero-phase filter
 // scipy.signal.sosfiltfilt(sos, x_float32).astype(float32): odd extension by 15 samples formed in float32, forward sweep
 // from the state zi * ext[0], backward sweep from zi * y[-1], float64 in between (oracle/qd_autotune.py
 // sosfiltfilt_restated).  `scratch` holds the forward result: [jobs][batch][n + 30] doubles.
@@ -37,118 +38,12 @@ struct AtFiltArgs {
     int batch;
 };
 
-QD_DEV double at_section(const double *c, double v, double &z0, double &z1) {
-    const double o = __dadd_rn(__dmul_rn(c[0], v), z0);
-    z0 = __dadd_rn(__dsub_rn(__dmul_rn(c[1], v), __dmul_rn(c[4], o)), z1);
-    z1 = __dsub_rn(__dmul_rn(c[2], v), __dmul_rn(c[5], o));
-    return o;
-}
-
-// The sweeps are sequential per clip and would be bound by memory latency, so a WARP owns one (clip, job): all lanes
-// fetch the next tile of AT_TS samples (coalesced, in flight while lane 0 runs the dependent float64 chain over the
-// current tile out of shared memory) and write the finished tile back with coalesced stores.
-constexpr int AT_BK = 8;      // register block of the one-thread-per-clip kernels below
+// tile / CTA shape of the warp-staged sequential kernels below (delay taps, envelope follower): all lanes move a tile of
+// AT_TS samples (coalesced), lane 0 runs the dependent chain over it out of shared memory
 constexpr int AT_TS = 512;    // samples per tile
 constexpr int AT_FW = 4;      // warps per CTA
 
-__global__ void __launch_bounds__(32 * AT_FW) at_filtfilt_kernel(const AtFiltArgs a) {
-    __shared__ double s_in[AT_FW][AT_TS];
-    __shared__ double s_out[AT_FW][AT_TS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = blockIdx.x * AT_FW + warp;
-    if (t >= a.batch * a.jobs) return;
-    const int job = t / a.batch, clip = t % a.batch;
-    const float *__restrict__ x = a.x[job] + (size_t)clip * a.n;
-    float *__restrict__ y = a.y[job] + (size_t)clip * a.n;
-    const AtFilter &f = a.f[job];
-    const long long n = a.n;
-    if (!f.on) {
-        for (long long i = lane; i < n; i += 32) y[i] = x[i];
-        return;
-    }
-    const long long m = n + 2 * AT_EDGE;
-    double *__restrict__ s = a.scratch + (size_t)t * (size_t)m;
-    double *in = s_in[warp], *out = s_out[warp];
-    auto ext = [&](long long i) -> double {   // odd extension in float32; 0 past the end
-        if (i < AT_EDGE) return (double)__fsub_rn(__fmul_rn(2.0f, x[0]), x[AT_EDGE - i]);
-        if (i >= n + AT_EDGE) return i < m ? (double)__fsub_rn(__fmul_rn(2.0f, x[n - 1]), x[n - 2 - (i - n - AT_EDGE)]) : 0.0;
-        return (double)x[i - AT_EDGE];
-    };
-    constexpr int PER = AT_TS / 32;
-    double nxt[PER];
-    const double x0 = ext(0);
-    double z[2][2] = {{f.zi[0][0] * x0, f.zi[0][1] * x0}, {f.zi[1][0] * x0, f.zi[1][1] * x0}};
-    double last = 0.0;
-    // ---- forward sweep over ext[0 .. m)
-#pragma unroll
-    for (int k = 0; k < PER; ++k) in[lane + 32 * k] = ext((long long)(lane + 32 * k));
-    __syncwarp();
-    for (long long i0 = 0; i0 < m; i0 += AT_TS) {
-        const bool more = i0 + AT_TS < m;
-        if (more) {
-#pragma unroll
-            for (int k = 0; k < PER; ++k) nxt[k] = ext(i0 + AT_TS + lane + 32 * k);
-        }
-        const int cnt = (int)(m - i0 < AT_TS ? m - i0 : AT_TS);
-        if (lane == 0) {
-            for (int k = 0; k < cnt; ++k) {
-                double v = at_section(f.sos[0], in[k], z[0][0], z[0][1]);
-                v = at_section(f.sos[1], v, z[1][0], z[1][1]);
-                out[k] = v;
-            }
-            last = out[cnt - 1];
-        }
-        __syncwarp();
-        for (int k = lane; k < cnt; k += 32) s[i0 + k] = out[k];
-        if (more) {
-#pragma unroll
-            for (int k = 0; k < PER; ++k) in[lane + 32 * k] = nxt[k];
-        }
-        __syncwarp();
-    }
-    last = __shfl_sync(QD_FULL, last, 0);
-    z[0][0] = f.zi[0][0] * last; z[0][1] = f.zi[0][1] * last;
-    z[1][0] = f.zi[1][0] * last; z[1][1] = f.zi[1][1] * last;
-    // ---- backward sweep: tiles [lo, lo + cnt) from the end, processed from the top down (the stores of the forward sweep
-    //      were issued by this same warp, so they are visible to its own later loads)
-    const long long tiles = (m + AT_TS - 1) / AT_TS;
-    auto load_tile = [&](long long tl, double (&v)[PER]) {
-        const long long lo = tl * AT_TS;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const long long i = lo + lane + 32 * k;
-            v[k] = i < m ? s[i] : 0.0;
-        }
-    };
-    load_tile(tiles - 1, nxt);
-#pragma unroll
-    for (int k = 0; k < PER; ++k) in[lane + 32 * k] = nxt[k];
-    __syncwarp();
-    for (long long tl = tiles - 1; tl >= 0; --tl) {
-        if (tl > 0) load_tile(tl - 1, nxt);
-        const long long lo = tl * AT_TS;
-        const int cnt = (int)(m - lo < AT_TS ? m - lo : AT_TS);
-        if (lane == 0) {
-            for (int k = cnt - 1; k >= 0; --k) {
-                double v = at_section(f.sos[0], in[k], z[0][0], z[0][1]);
-                v = at_section(f.sos[1], v, z[1][0], z[1][1]);
-                out[k] = v;
-            }
-        }
-        __syncwarp();
-        for (int k = lane; k < cnt; k += 32) {
-            const long long i = lo + k;
-            if (i >= AT_EDGE && i < n + AT_EDGE) y[i - AT_EDGE] = (float)out[k];
-        }
-        if (tl > 0) {
-#pragma unroll
-            for (int k = 0; k < PER; ++k) in[lane + 32 * k] = nxt[k];
-        }
-        __syncwarp();
-    }
-}
-
-// The same zero-phase filter as a blocked affine scan (the crossover's biquad_scan with an initial state): one CTA per
+// Zero-phase filter as a blocked affine scan (the crossover's biquad_scan with an initial state): one CTA per
 // (clip, job), 2048 samples per step, every thread runs its 8 samples from a zero state, the per-thread aggregates
 // (A^8 powers from the host) are combined across the CTA, and the thread re-runs from its true incoming state.  Rounding
 // differs from the sequential sweep at the 1e-14 level (measured against an 80-bit evaluation), far inside the parity
@@ -234,8 +129,8 @@ __global__ void at_body_kernel(const float *__restrict__ x, const float *__restr
         body[i] = __fsub_rn(__fsub_rn(x[i], sub[i]), air[i]);
 }
 
-// ---------------------------------------------------------------- detector: one CTA per frame
-// dsp/autotune.py:217-236: rms, spectral flatness (symmetric Hann, float32 warp FFT), YIN (float64).
+// ---------------------------------------------------------------- detector (dsp/autotune.py:217-236)
+// rms and spectral flatness (symmetric Hann, float32 warp FFT) per frame here, YIN (float64) by the sliding kernels below.
 struct AtDetArgs {
     const float *det;        // [batch, n] detector side chain
     double *feat;            // [batch, frames, 4]: rms, flatness, pitch, confidence
@@ -245,141 +140,9 @@ struct AtDetArgs {
     double sr, min_freq, max_freq, threshold;
     const float *hann;       // [frame_size] np.hanning (symmetric), float32
     const float2 *tw1, *tw2, *wsplit;   // float32 FFT tables of n_fft = frame_size
-    int yin_inline;          // 1: YIN inside this kernel (per-frame difference function);
-                             // 0: only rms / flatness / "frame is not silent" (feat[2] = 1 or 0), YIN by the sliding kernels
 };
 
-template <int NC>   // NC = frame_size / 2
-__global__ void __launch_bounds__(256) at_detector_kernel(const AtDetArgs a) {
-    constexpr int FS = 2 * NC;
-    constexpr int BUF = buf_slots<NC>();
-    QD_DYN_SMEM(smem);
-    double *c = reinterpret_cast<double *>(smem);                  // [FS] centred frame (float64)
-    double *diff = c + FS;                                         // [max_tau + 2]
-    float2 *buf = reinterpret_cast<float2 *>(diff + ((a.max_tau + 2 + 1) & ~1));   // warp FFT buffer
-    __shared__ double s_red[16];
-    __shared__ float s_redf[8];
-    __shared__ int s_flag;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int frame = blockIdx.x, clip = blockIdx.y;
-    const float *x = a.det + (size_t)clip * a.n;
-    const long long start = (long long)frame * a.hop;
-    // ---- load, mean, sum of squares, max |x|
-    double sum = 0.0;
-    float sq = 0.0f, mx = 0.0f;
-    for (int i = tid; i < FS; i += 256) {
-        const long long s = start + i;
-        const float v = s < a.n ? x[s] : 0.0f;
-        c[i] = (double)v;
-        sum += (double)v;
-        sq += v * v;
-        mx = fmaxf(mx, fabsf(v));
-    }
-    sum = warp_sum(sum); sq = warp_sum(sq); mx = warp_max(mx);
-    if (lane == 0) { s_red[warp] = sum; s_redf[warp] = sq; s_red[8 + warp] = (double)mx; }
-    __syncthreads();
-    double tot = 0.0, peak = 0.0;
-    float sqt = 0.0f;
-    for (int w = 0; w < 8; ++w) { tot += s_red[w]; sqt += s_redf[w]; peak = fmax(peak, s_red[8 + w]); }
-    const double mean = tot / (double)FS;
-    const float rms = sqrtf(sqt / (float)FS);
-    // ---- warp 0: spectral flatness of the Hann-windowed frame (dsp/autotune.py:130-137)
-    double flat = 1.0;
-    if (warp == 0) {
-        for (int j = lane; j < NC; j += 32)
-            buf[pidx(j)] = make_float2((float)c[2 * j] * a.hann[2 * j], (float)c[2 * j + 1] * a.hann[2 * j + 1]);
-        __syncwarp();
-        SpecArgsT<float> sa{};
-        sa.tw2 = a.tw2;
-        fwd_first_buf<float, NC, FftCfg<float, NC>::R1>(buf, a.tw1, lane);
-        fft_forward<float, NC>(buf, nullptr, sa, nullptr, a.tw1, a.tw2, lane);
-        real_split<float, NC>(buf, a.wsplit, lane);
-        constexpr int ROWS = (NC + 1 + 31) / 32;
-        double lg = 0.0, ar = 0.0;
-        for (int row = 0; row < ROWS; ++row) {
-            if (row < ROWS - 1 || lane == 0) {
-                const float2 v = buf[rpos<float, NC>(lane, row)];
-                const double m = sqrt((double)v.x * (double)v.x + (double)v.y * (double)v.y) + 1e-8;
-                lg += log(m);
-                ar += m;
-            }
-        }
-        lg = warp_sum(lg); ar = warp_sum(ar);
-        const double geo = exp(lg / (double)(NC + 1)), ari = ar / (double)(NC + 1);
-        flat = ari <= 1e-8 ? 1.0 : geo / ari;
-    }
-    __syncthreads();
-    // ---- YIN (dsp/autotune.py:140-198), float64.  centred frame, difference function in ascending blocks of tau with
-    //      an early exit once the first dip below the threshold and its local minimum are known
-    for (int i = tid; i < FS; i += 256) c[i] -= mean;
-    if (tid == 0) s_flag = 0;
-    __syncthreads();
-    double pitch = 0.0, conf = 0.0;
-    const bool usable = !(peak < 1e-6) && a.max_tau > a.min_tau;
-    if (!a.yin_inline) {
-        pitch = usable ? 1.0 : 0.0;
-    } else if (usable) {
-        int done_tau = 0;        // diff[1..done_tau] are valid
-        double run = 0.0;        // thread 0: cumulative sum, cmnd overwrites diff in place
-        int scan_tau = 0;        // thread 0: cmnd[1..scan_tau] valid
-        while (done_tau < a.max_tau) {
-            const int tau = done_tau + 1 + tid;
-            if (tau <= a.max_tau) {
-                double acc = 0.0;
-                const int cnt = FS - tau;
-                for (int j = 0; j < cnt; ++j) {
-                    const double d = c[j] - c[j + tau];
-                    acc = fma(d, d, acc);
-                }
-                diff[tau] = acc;
-            }
-            done_tau = min(done_tau + 256, a.max_tau);
-            __syncthreads();
-            if (tid == 0) {
-                for (int t2 = scan_tau + 1; t2 <= done_tau; ++t2) {
-                    run += diff[t2];
-                    diff[t2] = run > 0.0 ? diff[t2] * (double)t2 / run : 1.0;
-                }
-                scan_tau = done_tau;
-                // first tau >= min_tau with cmnd < threshold, walked to its local minimum
-                int est = -1;
-                for (int t2 = a.min_tau; t2 <= scan_tau; ++t2) {
-                    if (diff[t2] < a.threshold) {
-                        while (t2 + 1 <= scan_tau && diff[t2 + 1] < diff[t2]) ++t2;
-                        est = t2;
-                        break;
-                    }
-                }
-                // final when the walk stopped inside the computed range (which also gives the parabola its right
-                // neighbour) or when every tau is known; otherwise the next block decides
-                if (est >= 0 && (est < scan_tau || scan_tau >= a.max_tau)) s_flag = est + 1;
-                else if (scan_tau >= a.max_tau) s_flag = -1;
-            }
-            __syncthreads();
-            if (s_flag != 0) break;
-        }
-        if (tid == 0 && s_flag > 0) {
-            const int est = s_flag - 1;
-            double better = (double)est;
-            if (a.min_tau < est && est < a.max_tau) {
-                const double s0 = diff[est - 1], s1 = diff[est], s2 = diff[est + 1];
-                const double den = 2.0 * (s0 - 2.0 * s1 + s2);
-                if (fabs(den) > 1e-12) better = (double)est + (s0 - s2) / den;
-            }
-            const double p = better > 0.0 ? a.sr / better : 0.0;
-            if (!(p < a.min_freq || p > a.max_freq)) {
-                pitch = p;
-                conf = fmin(fmax(1.0 - diff[est], 0.0), 1.0);
-            }
-        }
-    }
-    if (tid == 0) {
-        double *o = a.feat + ((size_t)clip * a.frames + frame) * 4;
-        o[0] = (double)rms; o[1] = flat; o[2] = pitch; o[3] = conf;
-    }
-}
-
-// rms, spectral flatness and the silence flag with one WARP per frame (the detector path used with the sliding YIN):
+// rms, spectral flatness and the silence flag with one WARP per frame:
 // the lanes load the frame once, accumulate the sums and write the Hann-windowed samples straight into the warp's FFT
 // buffer.  feat = (rms, flatness, 1 or 0 for "not silent", 0).
 template <int NC>
