@@ -38,6 +38,20 @@ int fail(int code, const std::string &msg) {
             return fail(QD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember the devices a kernel was opted in on
+// (a process may render on several GPUs one after the other)
+template <class K>
+int ensure_dyn_smem(K kern, std::atomic<uint64_t> &mask, int bytes) {
+    int dev = 0;
+    QD_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(mask.load(std::memory_order_acquire) & bit)) {
+        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        mask.fetch_or(bit, std::memory_order_release);
+    }
+    return QD_OK;
+}
+
 template <class T>
 cudaError_t upload(const std::vector<T> &h, T **d) {
     *d = nullptr;
@@ -142,12 +156,9 @@ size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int form
 
 template <class T, int NC, int NW, bool TS, bool FX, int NG = 1>
 int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st) {
-    static std::atomic<bool> attr_set{false};  // per instantiation; setting the attribute twice is harmless
+    static std::atomic<uint64_t> attr_mask{0};  // devices this instantiation was opted in on
     auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX, NG>;
-    if (!attr_set.load(std::memory_order_acquire)) {
-        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set.store(true, std::memory_order_release);
-    }
+    if (int rc_ = ensure_dyn_smem(kern, attr_mask, 227 * 1024)) return rc_;
     const size_t smem = qd::SpecSmem<T, NC, NW, NG>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX, FX && a.formant_idx != nullptr);
     for (int64_t b0 = 0; b0 < batch; b0 += 65535 * NG) {  // gridDim.y limit
         const int64_t nb = std::min<int64_t>(65535 * NG, batch - b0);
@@ -190,13 +201,10 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
 
 template <class T, int NC>
 int launch_freeze_t(const qd::SpecArgsT<T> &a, T *out, int64_t batch, cudaStream_t st) {
-    static std::atomic<bool> attr_set{false};
+    static std::atomic<uint64_t> attr_mask{0};  // devices this instantiation was opted in on
     auto kern = qd::freeze_mag_kernel<T, NC>;
     const size_t smem = (size_t)qd::buf_slots<NC>() * sizeof(qd::V2<T>) + (size_t)2 * NC * sizeof(float) + 16;
-    if (!attr_set.load(std::memory_order_acquire)) {
-        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set.store(true, std::memory_order_release);
-    }
+    if (int rc_ = ensure_dyn_smem(kern, attr_mask, 227 * 1024)) return rc_;
     kern<<<(unsigned)batch, 32, smem, st>>>(a, out);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
@@ -271,13 +279,10 @@ int launch_spec(qd_plan *pl, const float *src, float *dst, float *tap, int quant
 }
 
 int launch_limiter(const qd::LimiterArgs &a, int64_t batch, cudaStream_t st) {
-    static std::atomic<bool> attr_set{false};
+    static std::atomic<uint64_t> attr_mask{0};  // devices this instantiation was opted in on
     const size_t smem = qd_host::limiter_smem_bytes(a.lookahead);
     if (smem > 200 * 1024) return fail(QD_ERR_UNSUPPORTED, "limiter lookahead too long");
-    if (!attr_set.load(std::memory_order_acquire)) {
-        QD_CUDA(cudaFuncSetAttribute(qd::limiter_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set.store(true, std::memory_order_release);
-    }
+    if (int rc_ = ensure_dyn_smem(qd::limiter_mix_kernel, attr_mask, 200 * 1024)) return rc_;
     for (int64_t b0 = 0; b0 < batch; b0 += (1 << 30)) {
         const int64_t nb = std::min<int64_t>(1 << 30, batch - b0);
         qd::LimiterArgs c = a;
@@ -329,12 +334,9 @@ int peak_tables(int dev, int n_fft, PeakTables *out) {
 
 template <class T, int NC>
 int launch_peaks_t(qd::PeaksArgsT<T> a, int64_t batch, cudaStream_t st) {
-    static std::atomic<bool> attr_set{false};
+    static std::atomic<uint64_t> attr_mask{0};  // devices this instantiation was opted in on
     auto kern = qd::peaks_kernel<T, NC>;
-    if (!attr_set.load(std::memory_order_acquire)) {
-        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set.store(true, std::memory_order_release);
-    }
+    if (int rc_ = ensure_dyn_smem(kern, attr_mask, 227 * 1024)) return rc_;
     const size_t per_warp = (size_t)qd::buf_slots<NC>() * sizeof(qd::V2<T>) + (size_t)2 * NC * sizeof(float);
     const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
     const unsigned gx = (unsigned)((a.n_frames + nw - 1) / nw);

@@ -214,43 +214,80 @@ struct AtYinArgs {
     double sr, min_freq, max_freq, threshold;
 };
 
-constexpr int AT_YT = 224;   // lags per CTA (671 lags at 48 kHz = 3 CTAs of 7 warps)
+// Register tiling: a thread owns AT_YL = 4 consecutive lags and walks the samples four at a time, so 16 (sample, lag)
+// pairs come from 4 broadcast loads of x[j..j+3] and 7 loads of x[j+tau..j+tau+6]; the tile is stored de-interleaved by four
+// (element i at (i & 3) * Q + (i >> 2)) so that the lanes' stride-4 addresses fall on consecutive words: 1.1 shared-memory
+// wavefronts per pair instead of 3, which brings the walk down to the float64 pipe's rate.
+constexpr int AT_YL = 4;     // lags per thread
+constexpr int AT_YT = 96;    // threads per CTA -> 384 lags per CTA (671 lags at 48 kHz = 2 CTAs per clip)
 
 __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
     QD_DYN_SMEM(smem);
     const int tid = threadIdx.x;
-    const int tau0 = 1 + blockIdx.x * AT_YT;            // lags of this CTA: tau0 .. tau0 + AT_YT - 1
-    const int tau = tau0 + tid;
-    const bool live = tau <= a.max_tau;
-    const int span = a.hop + tau0 + AT_YT;             // samples a hop-block needs
-    double *tile = reinterpret_cast<double *>(smem);    // [span]
-    double *ring = tile + ((span + 1) & ~1);            // [9][AT_YT]
+    const int tau0 = 1 + blockIdx.x * AT_YT * AT_YL;    // lags of this CTA: tau0 .. tau0 + 4 * AT_YT - 1
+    const int taub = tau0 + AT_YL * tid;                 // this thread: taub .. taub + 3
+    const int span = a.hop + tau0 + AT_YL * AT_YT + 8;   // samples a hop-block needs (+ the look-ahead of the last sub-block)
+    const int Q = (span + 3) >> 2;
+    double *tile = reinterpret_cast<double *>(smem);     // [4][Q] de-interleaved
+    double *ring = tile + 4 * Q;                         // [9][AT_YT * AT_YL]
     const float *x = a.det + (size_t)blockIdx.y * a.n;
     double *out = a.diff + (size_t)blockIdx.y * a.frames * a.stride;
-    const int wlen = a.frame_size - tau;                // window length of this lag
-    const int q = wlen / a.hop, off = wlen % a.hop;     // frame f ends inside hop-block f + q at offset off
-    double S = 0.0;
+    int q[AT_YL], off[AT_YL];
+    bool live[AT_YL];
+#pragma unroll
+    for (int u = 0; u < AT_YL; ++u) {
+        const int wlen = a.frame_size - (taub + u);       // window length of the lag
+        live[u] = taub + u <= a.max_tau;
+        q[u] = wlen / a.hop;                              // frame f ends inside hop-block f + q at offset off
+        off[u] = wlen % a.hop;
+    }
+    double S[AT_YL] = {0.0, 0.0, 0.0, 0.0};
     const int blocks = a.frames + a.frame_size / a.hop;
+    const int sh = (tau0 & 3);                            // (taub & 3) is the same for every thread
+    auto emit = [&](int u, int b) {
+        const int f = b - q[u];
+        if (live[u] && f >= 0 && f < a.frames) out[(size_t)f * a.stride + taub + u] = S[u] - ring[(f % 9) * (AT_YT * AT_YL) + AT_YL * tid + u];
+    };
     for (int b = 0; b < blocks; ++b) {
         const long long j0 = (long long)b * a.hop;
         __syncthreads();
         for (int i = tid; i < span; i += AT_YT) {
             const long long sidx = j0 + i;
-            tile[i] = sidx < a.n ? (double)x[sidx] : 0.0;
+            tile[(i & 3) * Q + (i >> 2)] = sidx < a.n ? (double)x[sidx] : 0.0;
         }
         __syncthreads();
-        if (!live) continue;
-        if (b < a.frames) ring[(b % 9) * AT_YT + tid] = S;
-        const double *pa = tile, *pb = tile + tau;
-        for (int jj = 0; jj < off; ++jj) {
-            const double d = pa[jj] - pb[jj];
-            S = fma(d, d, S);
+        if (b < a.frames) {
+#pragma unroll
+            for (int u = 0; u < AT_YL; ++u) ring[(b % 9) * (AT_YT * AT_YL) + AT_YL * tid + u] = S[u];
         }
-        const int f = b - q;
-        if (f >= 0 && f < a.frames) out[(size_t)f * a.stride + tau] = S - ring[(f % 9) * AT_YT + tid];
-        for (int jj = off; jj < a.hop; ++jj) {
-            const double d = pa[jj] - pb[jj];
-            S = fma(d, d, S);
+        for (int jj = 0; jj < a.hop; jj += 4) {
+            // x[j0 + jj + s], s = 0..3 (broadcast) and x[j0 + jj + taub + v], v = 0..6
+            double av[4], bv[7];
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) av[s4] = tile[s4 * Q + (jj >> 2)];
+            const int base = jj + taub;                    // (base & 3) == sh for every thread (jj % 4 == 0)
+#pragma unroll
+            for (int v = 0; v < 7; ++v) bv[v] = tile[((sh + v) & 3) * Q + ((base + v) >> 2)];
+            const int sb = jj >> 2;
+            const bool special = (off[0] >> 2) == sb || (off[1] >> 2) == sb || (off[2] >> 2) == sb || (off[3] >> 2) == sb;
+            if (!special) {
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+                    for (int u = 0; u < AT_YL; ++u) {
+                        const double d = av[s4] - bv[s4 + u];
+                        S[u] = fma(d, d, S[u]);
+                    }
+            } else {   // a window of one of the four lags ends inside this sub-block: emit before the sample at `off`
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+                    for (int u = 0; u < AT_YL; ++u) {
+                        if (jj + s4 == off[u]) emit(u, b);
+                        const double d = av[s4] - bv[s4 + u];
+                        S[u] = fma(d, d, S[u]);
+                    }
+            }
         }
     }
 }
