@@ -111,3 +111,16 @@ def test_autotune_tiny_and_silent_clips(qd, n):
     ys, _ = qd.process_audio(st, sr, quantize_mode="autotune_v1")
     refs, _ = at.process_audio_autotune(st, sr)
     _check(ys, refs, f"stereo n={n}")
+
+
+@pytest.mark.gpu
+def test_autotune_full_length_clip_vs_oracle(qd):
+    """BASELINE clip length (10 s @ 48 kHz): the shifter integrates 1 - ratio over 480 000 samples, so this is where a
+    pitch-track mismatch would show as drift.  One pitched clip, whole render, against the oracle."""
+    n, sr = 480000, 48000
+    x = qd_cases.make_signal("tone", 77, n, sr)
+    y, taps = qd.process_audio(x, sr, quantize_mode="autotune_v1")
+    ref, rt = at.process_audio_autotune(x, sr)
+    err = _check(taps["pre_quant"], rt["pre_quant"], "10 s pre_quant")
+    _check(y, ref, "10 s output")
+    print(f"10 s autotune clip: max abs err {err:.3e}")
