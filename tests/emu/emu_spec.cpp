@@ -15,6 +15,7 @@ thread_local dim3 g_tid, g_bid;
 #include "../../quantumdistortion_b200/csrc/qd_host_tables.hpp"
 #include "../../quantumdistortion_b200/csrc/qd_spec.cuh"
 
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -101,16 +102,37 @@ static int go(Cli &c) {
     a.fx.a = (float)c.fx_a; a.fx.b = (float)c.fx_b; a.fx.c = (float)c.fx_c; a.fx.step = c.fx_a;
     a.fx.table = c.fx_table.empty() ? nullptr : c.fx_table.data();
     a.fx.table_frames = a.n_frames; a.fx.table_per_clip = 0; a.fx.pass = c.fx_pass; a.fx.clip_offset = 0;
+    // formant shift (dsp/spectral_fx.py:116-195): QD_EMU_FORMANT_RATIO=<2^(st/12)> in the environment; same tables as
+    // qd_plan_create builds
+    std::vector<int16_t> fidx;
+    std::vector<float> ffrac;
+    bool formant = false;
+    if (const char *fr = std::getenv("QD_EMU_FORMANT_RATIO")) {
+        const double ratio = std::atof(fr);
+        if (ratio > 0.0 && !is_double) {
+            const int nb = c.n_fft / 2 + 1;
+            fidx.resize(nb); ffrac.resize(nb);
+            for (int k = 0; k < nb; ++k) {
+                const double xk = (double)k / ratio;
+                if (xk >= (double)(nb - 1)) { fidx[k] = (int16_t)(nb - 1); ffrac[k] = 0.0f; }
+                else { const double fl = std::floor(xk); fidx[k] = (int16_t)fl; ffrac[k] = (float)(xk - fl); }
+            }
+            a.formant_idx = fidx.data();
+            a.formant_frac = ffrac.data();
+            a.formant_order = 30;
+            formant = true;
+        }
+    }
     const int blocks_total = (n + st.hop - 1) / st.hop;
     const int n_tiles = (blocks_total + c.tile_blocks - 1) / c.tile_blocks;
     const int nc = c.n_fft / 2, nw = c.nw;
     const int fx_mode = c.fx_mode;
 #define QD_FXCASE(NC_, NW_)                                                                                       \
-    if (fx_mode && nc == NC_ && nw == NW_) {                                                                      \
-        run<T, NC_, NW_, false, true>(a, n_tiles, qd::SpecSmem<T, NC_, NW_>::bytes(qt.n_slots, false, 0, 0, true)); \
+    if ((fx_mode || formant) && nc == NC_ && nw == NW_) {                                                         \
+        run<T, NC_, NW_, false, true>(a, n_tiles, qd::SpecSmem<T, NC_, NW_>::bytes(qt.n_slots, false, 0, 0, true, formant)); \
         return 0;                                                                                                 \
     }
-    QD_FXCASE(1024, 8) QD_FXCASE(1024, 12) QD_FXCASE(256, 4) QD_FXCASE(2048, 4)
+    QD_FXCASE(1024, 8) QD_FXCASE(1024, 12) QD_FXCASE(256, 4) QD_FXCASE(512, 4) QD_FXCASE(2048, 4)
 #define QD_CASE(NC_, NW_)                                                                 \
     if (nc == NC_ && nw == NW_) {                                                         \
         run<T, NC_, NW_>(a, n_tiles, qd::SpecSmem<T, NC_, NW_>::bytes(qt.n_slots));       \

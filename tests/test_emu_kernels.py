@@ -29,7 +29,8 @@ def emu_spec():
 
 
 def run_emu(exe, x, sr, n_fft, nw, tile_blocks, quant, smoothing, snap, smear, epilogue=0, fold=1.0,
-            bias=0.0, tg=1.0, tn=1.0, key="D", scale="minor", lo=110.0, hi=5000.0, fx=None, prec="f32"):
+            bias=0.0, tg=1.0, tn=1.0, key="D", scale="minor", lo=110.0, hi=5000.0, fx=None, prec="f32",
+            formant_ratio=None):
     freqs = np.fft.rfftfreq(n_fft, d=1.0 / sr)
     tb = orc.target_bins_for_freqs(freqs, key, scale).astype(np.int32)
     mask = orc.quantize_band_mask(freqs, lo, hi).astype(np.uint8)
@@ -49,7 +50,11 @@ def run_emu(exe, x, sr, n_fft, nw, tile_blocks, quant, smoothing, snap, smear, e
                 fx[4].tofile(p("fxt"))
                 tab = p("fxt")
             cmd += [str(fx[0]), repr(float(fx[1])), repr(float(fx[2])), repr(float(fx[3])), tab, str(fx[5])]
-        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+        env = dict(os.environ)
+        env.pop("QD_EMU_FORMANT_RATIO", None)
+        if formant_ratio is not None:
+            env["QD_EMU_FORMANT_RATIO"] = repr(float(formant_ratio))
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL, env=env)
         return np.fromfile(p("y"), dtype=np.float32), np.fromfile(p("tap"), dtype=np.float32)
 
 
@@ -198,3 +203,17 @@ def test_emu_two_clip_groups_per_cta(emu_spec):
         ref_tap = oracle_pass(x[i], 48000, 2048, True, True, 1.0, 0.1)
         assert float(np.max(np.abs(tap[i] - ref_tap))) < 1e-5
         assert float(np.max(np.abs(y[i] - orc.apply_distortion(tap[i], "wavefold", fold_amount=2.0, bias=0.05)))) < 1e-5
+
+
+@pytest.mark.parametrize("n_fft,nw,n,semitones", [(2048, 8, 5000, 3.0), (2048, 8, 4100, -5.0), (1024, 4, 2600, 7.0)])
+def test_emu_formant_shift_pass(emu_spec, n_fft, nw, n, semitones):
+    """One quantised pass with the formant shift (cepstral lifter through the warp FFT on the scratch buffer): kernel
+    source (emulated) vs the oracle."""
+    sr = 48000
+    x = synth.bass_clip(21, n)
+    y, _ = run_emu(emu_spec, x, sr, n_fft, nw, 64, True, True, 1.0, 0.1, formant_ratio=2.0 ** (semitones / 12.0))
+    S, freqs = orc.stft(x, sr, n_fft)
+    Sq = orc.spectral_quantize_stft(S, freqs, "D", "minor", 1.0, 0.1, True, formant_shift=semitones)
+    ref = orc.istft(Sq, sr, n_fft, length=n)
+    err = float(np.max(np.abs(y - ref)))
+    assert err < 2e-5, err
