@@ -401,6 +401,28 @@ QD_DEV float rsqrt_fast(float x) {
 #endif
 }
 QD_DEV double rsqrt_fast(double x) { return 1.0 / sqrt(x); }
+// log2 / exp2 as single MUFU operations for the log-domain bitcrush: absolute error of lg2.approx ~1e-6 near the values
+// that matter (decisions closer than 2e-4 to a rounding boundary are re-made in double), relative error of ex2.approx 2e-7
+QD_DEV float log2_fast(float x) {
+#ifdef QD_EMU
+    return std::log2(x);
+#else
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+QD_DEV double log2_fast(double x) { return log2(x); }
+QD_DEV float exp2_fast(float x) {
+#ifdef QD_EMU
+    return std::exp2(x);
+#else
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+QD_DEV double exp2_fast(double x) { return exp2(x); }
 constexpr float QD_TINY2 = 1e-30f;  // |X|^2 below this is treated as an exact zero (|X| < 1e-15)
 
 // magnitude and unit phasor of one bin (np.angle(0) = 0 -> phasor 1)
@@ -559,11 +581,14 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
                 if (fx.step > 0.0) {
                     if (fx.mode == 1) {
                         const T mm = qd_max(m, 1e-12f);
-                        const T q = qd_log2(mm) * (T)(6.020599913279624 / fx.step);  // 20 log10(m) / step_db
+                        const T q = log2_fast(mm) * (T)(6.020599913279624 / fx.step);  // 20 log10(m) / step_db
                         T rq = qd_rint(q);
-                        if (qd_abs(qd_abs(q - rq) - 0.5f) < 0.02f)  // close to a rounding boundary: decide in double
+                        // close to a rounding boundary: decide in double.  The float32 evaluation of q is good to ~1e-5
+                        // (log2f 1 ulp of |log2 m| <= 40, one multiply), so a band of 2e-4 is ample; a wider one sends
+                        // most warps down the float64 log10 (a lane in the band is enough)
+                        if (qd_abs(qd_abs(q - rq) - 0.5f) < 2e-4f)
                             rq = (T)rint(20.0 * log10((double)mm) / fx.step);
-                        m = qd_exp2(rq * (T)(fx.step * 0.16609640474436813));       // 10^(q step / 20)
+                        m = exp2_fast(rq * (T)(fx.step * 0.16609640474436813));      // 10^(q step / 20)
                     } else {
                         m = qd_max((T)(rint((double)m / fx.step) * fx.step), 0.0f);
                     }
