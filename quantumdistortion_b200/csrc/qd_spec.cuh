@@ -423,6 +423,14 @@ QD_DEV float exp2_fast(float x) {
 #endif
 }
 QD_DEV double exp2_fast(double x) { return exp2(x); }
+QD_DEV void sincos_fast(float a, float *s, float *c) {
+#ifdef QD_EMU
+    qd_sincos(a, s, c);
+#else
+    __sincosf(a, s, c);
+#endif
+}
+QD_DEV void sincos_fast(double a, double *s, double *c) { qd_sincos(a, s, c); }
 constexpr float QD_TINY2 = 1e-30f;  // |X|^2 below this is treated as an exact zero (|X| < 1e-15)
 
 // magnitude and unit phasor of one bin (np.angle(0) = 0 -> phasor 1)
@@ -610,7 +618,7 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
                     T rot = fx.a * (m * inv_mx);
                     if (jit) rot += (T)__ldg(jit + tab_base + 32 * row + lane) * (T)fx.b;
                     T sn, cs;
-                    qd_sincos(rot, &sn, &cs);
+                    sincos_fast(rot, &sn, &cs);   // |rot| <= 1.2 pi: the MUFU pair is good to ~1e-6 there
                     const V2<T> u = buf[p];
                     buf[p] = mk2<T>(u.x * cs - u.y * sn, u.x * sn + u.y * cs);
                 }
