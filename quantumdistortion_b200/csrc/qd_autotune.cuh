@@ -456,46 +456,88 @@ struct AtShiftArgs {
     int max_delay, buf_size;
 };
 
+// the np.interp segment that contains sample s: r(i) = (i == x0) ? y0 : slope * (i - x0) + y0 for every i of the segment
+struct AtSeg { double x0, y0, slope; };
+QD_DEV AtSeg at_segment_at(const double *ratio, int frames, long long n, int hop, int half, long long s) {
+    const double x = (double)s;
+    auto cen = [&](int k) -> double { const long long c = (long long)k * hop + half; return (double)(c < n - 1 ? c : n - 1); };
+    if (x < cen(0)) return AtSeg{-1.0, ratio[0], 0.0};
+    long long j = (s - half) / hop;
+    if (j < 0) j = 0;
+    if (j > frames - 1) j = frames - 1;
+    while (j + 1 <= frames - 1 && cen((int)j + 1) <= x) ++j;
+    while (j > 0 && cen((int)j) > x) --j;
+    if (j == frames - 1) return AtSeg{cen((int)j), ratio[j], 0.0};
+    const double x0 = cen((int)j), x1 = cen((int)j + 1);
+    return AtSeg{x0, ratio[j], (ratio[j + 1] - ratio[j]) / (x1 - x0)};
+}
+
+// The tap accumulation is exact integer arithmetic in disguise: the per-sample slope 1 - ratio (ratio a float32 in
+// [0.5, 2]) is a multiple of 2^-24 with |slope| <= 1, the taps start at multiples of 2^-24 and stay below max_delay, so
+// every float64 addition and every wrap of the reference's loop (dsp/autotune.py:327-337) is exact.  In units of 2^-24 the
+// taps are T_n = (T_0 + sum_{k<=n} S_k) mod M -- an int64 prefix sum, associative and bit-exact, so it runs as a scan:
+// one warp per clip, 16 consecutive samples per lane and tile, a warp scan of the lane totals, a carry from tile to tile.
+constexpr int AT_SPL = AT_TS / 32;   // samples per lane and tile
+
 __global__ void __launch_bounds__(32 * AT_FW) at_taps_kernel(const AtShiftArgs a) {
-    __shared__ float s_r[AT_FW][AT_TS];
-    __shared__ double2 s_t[AT_FW][AT_TS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int clip = blockIdx.x * AT_FW + warp;
     if (clip >= a.batch) return;
     const double *__restrict__ ratio = a.ratio + (size_t)clip * a.frames;
     double2 *__restrict__ taps = reinterpret_cast<double2 *>(a.taps + (size_t)clip * a.n * 2);
     float *__restrict__ rt = a.ratio_track ? a.ratio_track + (size_t)clip * a.n : nullptr;
-    float *rr = s_r[warp];
-    double2 *tt = s_t[warp];
-    const double md = (double)a.max_delay;
-    double t0 = 0.25 * md, t1 = 0.75 * md;
+    const long long unit = 1ll << 24;
+    const long long M = (long long)a.max_delay * unit;
+    const long long half_m = M / 2;                      // the second tap runs half a grain behind: 0.75 md = 0.25 md + md / 2
+    long long carry = M / 4;                             // tap 0 starts at 0.25 * max_delay
     bool flat = true;
+    // a tile holds no frame centre strictly inside when hop and frame_size / 2 are multiples of the tile (512 | 512, 2048)
+    const bool aligned = (a.hop % AT_TS) == 0 && (a.half % AT_TS) == 0 && (a.max_delay % 4) == 0;
+    const double r_last = ratio[a.frames - 1];
     for (long long i0 = 0; i0 < a.n; i0 += AT_TS) {
-        const int cnt = (int)(a.n - i0 < AT_TS ? a.n - i0 : AT_TS);
-        // the ratio track of the tile, all lanes (np.interp per sample, see at_ratio_at)
-        for (int k = lane; k < cnt; k += 32) {
-            const float r = at_ratio_at(ratio, a.frames, a.n, a.hop, a.half, i0 + k);
-            rr[k] = r;
-            if (rt) rt[i0 + k] = r;
-            if (!(fabs((double)r - 1.0) <= 1e-3 + 1e-5)) flat = false;   // np.allclose(r, 1.0, atol=1e-3): rtol 1e-5 * |1.0|
+        AtSeg sg{0.0, 1.0, 0.0};
+        if (aligned) sg = at_segment_at(ratio, a.frames, a.n, a.hop, a.half, i0);
+        long long loc[AT_SPL];
+        long long run = 0;
+#pragma unroll
+        for (int k = 0; k < AT_SPL; ++k) {
+            const long long i = i0 + (long long)lane * AT_SPL + k;
+            float r = 1.0f;
+            if (i < a.n) {
+                if (!aligned) r = at_ratio_at(ratio, a.frames, a.n, a.hop, a.half, i);
+                else if (i == a.n - 1) r = (float)r_last;               // the last sample sits on the (repeated) last centre
+                else if ((double)i == sg.x0) r = (float)sg.y0;
+                else r = (float)__dadd_rn(__dmul_rn(sg.slope, (double)i - sg.x0), sg.y0);
+                if (rt) rt[i] = r;
+                if (!(fabs((double)r - 1.0) <= 1e-3 + 1e-5)) flat = false;   // np.allclose(r, 1.0, atol=1e-3)
+                run += (long long)((1.0 - (double)fminf(fmaxf(r, 0.5f), 2.0f)) * (double)unit);   // exact: a multiple of 2^-24
+            }
+            loc[k] = run;
         }
-        __syncwarp();
-        if (lane == 0) {   // the sequential float64 accumulation with wraps (dsp/autotune.py:327-337)
-            for (int k = 0; k < cnt; ++k) {
-                // |1 - ratio| <= 1 < max_delay, so each of the reference's two while loops runs at most once: selects
-                const double sl = 1.0 - (double)fminf(fmaxf(rr[k], 0.5f), 2.0f);
-                t0 += sl;
-                t0 = t0 < 0.0 ? t0 + md : t0;
-                t0 = t0 >= md ? t0 - md : t0;
-                t1 += sl;
-                t1 = t1 < 0.0 ? t1 + md : t1;
-                t1 = t1 >= md ? t1 - md : t1;
-                tt[k] = make_double2(t0, t1);
+        long long incl = run;   // inclusive scan of the lane totals
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(QD_FULL, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const long long before = carry + (incl - run);
+#pragma unroll
+        for (int k = 0; k < AT_SPL; ++k) {
+            const long long i = i0 + (long long)lane * AT_SPL + k;
+            if (i < a.n) {
+                // |tile sum| <= 2^33 < M / 2 steps from a value in [0, M): at most a few wraps, done like the reference's loops
+                long long t0 = before + loc[k];
+                while (t0 < 0) t0 += M;
+                while (t0 >= M) t0 -= M;
+                long long t1 = t0 + half_m;
+                if (t1 >= M) t1 -= M;
+                taps[i] = make_double2((double)t0 * (1.0 / (double)unit), (double)t1 * (1.0 / (double)unit));
             }
         }
-        __syncwarp();
-        for (int k = lane; k < cnt; k += 32) taps[i0 + k] = tt[k];
-        __syncwarp();
+        long long c2 = carry + __shfl_sync(QD_FULL, incl, 31);
+        while (c2 < 0) c2 += M;
+        while (c2 >= M) c2 -= M;
+        carry = c2;
     }
     flat = __all_sync(QD_FULL, flat);
     if (lane == 0) a.flat_flag[clip] = flat ? 1 : 0;
