@@ -494,7 +494,7 @@ QD_DEV void formant_frame(T *mags, V2<T> *scr, const SpecArgsT<T> &a, const V2<T
             const int p = rpos<T, NC>(lane, row);
             const T m = mags[p];
             e0 += m * m;
-            scr[p] = mk2<T>(qd_log(qd_max(m, (T)1e-12)), (T)0);
+            scr[p] = mk2<T>(log2_fast(qd_max(m, (T)1e-12)) * (T)0.6931471805599453, (T)0);   // ln m by MUFU.LG2
         }
     }
     __syncwarp();
@@ -525,7 +525,7 @@ QD_DEV void formant_frame(T *mags, V2<T> *scr, const SpecArgsT<T> &a, const V2<T
             const T f0 = scr[spos<T, NC>(j)].x;
             const T f1 = scr[spos<T, NC>(j < NC ? j + 1 : NC)].x;
             const T es = (f1 - f0) * fr + f0;                             // np.interp: slope * (x - xp[j]) + fp[j]
-            const T m = qd_max(mags[p], (T)1e-12) * qd_exp(es - scr[p].x);
+            const T m = qd_max(mags[p], (T)1e-12) * exp2_fast((es - scr[p].x) * (T)1.4426950408889634);   // MUFU.EX2
             mags[p] = m;
             e1 += m * m;
         }
