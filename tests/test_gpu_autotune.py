@@ -124,3 +124,32 @@ def test_autotune_full_length_clip_vs_oracle(qd):
     err = _check(taps["pre_quant"], rt["pre_quant"], "10 s pre_quant")
     _check(y, ref, "10 s output")
     print(f"10 s autotune clip: max abs err {err:.3e}")
+
+
+@pytest.mark.gpu
+def test_autotune_through_the_file_harness(qd, tmp_path):
+    """process_file_to_file / process_files with quantize_mode="autotune_v1" -- what the reference's harness and
+    render_preset.py run by default (dsp/harness.py:24-63)."""
+    from quantumdistortion_b200.audio_io import float_to_pcm16, load_audio, save_audio
+    sr = 48000
+    ins, outs = [], []
+    for i in range(3):
+        p = tmp_path / f"in{i}.wav"
+        save_audio(p, qd_cases.make_signal("tone", 40 + i, 12000, sr), sr)
+        ins.append(p)
+        outs.append(tmp_path / "out" / f"o{i}.wav")
+    extra = {"quantize_mode": "autotune_v1", "sub_level": 0.2}
+    qd.process_file_to_file(ins[0], outs[0], preset="Subtle Tube Glue", extra_params=extra)
+    assert qd.process_files(list(zip(ins, outs))[1:], preset="Subtle Tube Glue", extra_params=extra) == 2
+    from quantumdistortion_b200 import PipelineConfig
+    pc = PipelineConfig.from_preset("Subtle Tube Glue")
+    for i in range(3):
+        x, _ = load_audio(ins[i])
+        ref, _ = at.process_audio_autotune(x, sr, key=pc.key, scale=pc.scale, snap_strength=pc.snap_strength,
+                                           pre_quant=pc.pre_quant, distortion_mode=pc.distortion_mode,
+                                           distortion_params=pc.distortion_params, limiter_on=pc.limiter_on,
+                                           limiter_ceiling_db=pc.limiter_ceiling_db, dry_wet=pc.dry_wet, sub_level=0.2)
+        got, sr2 = load_audio(outs[i])
+        assert sr2 == sr
+        lsb = np.abs(np.rint(got * 32768.0) - float_to_pcm16(ref).astype(np.float64))
+        assert lsb.max() <= 4, lsb.max()   # 1e-4 parity bound = 3.3 LSB of 16-bit PCM
