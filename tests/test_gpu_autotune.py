@@ -153,3 +153,25 @@ def test_autotune_through_the_file_harness(qd, tmp_path):
         assert sr2 == sr
         lsb = np.abs(np.rint(got * 32768.0) - float_to_pcm16(ref).astype(np.float64))
         assert lsb.max() <= 4, lsb.max()   # 1e-4 parity bound = 3.3 LSB of 16-bit PCM
+
+
+@pytest.mark.gpu
+def test_autotune_random_configs_vs_oracle(qd):
+    """Keys, scales, strengths, band edges and sub settings drawn at random (seeded), 0.5 s clips, against the oracle:
+    exercises the note-hold transitions (confirm / release / candidate reset) on more material than the fixtures."""
+    rng = np.random.default_rng(2026)
+    keys = ["C", "C#", "D", "Eb", "E", "F", "F#", "G", "Ab", "A", "Bb", "B"]
+    scales = ["major", "minor", "pentatonic", "dorian", "mixolydian", "harmonic_minor"]
+    n, sr = 24000, 48000
+    worst = 0.0
+    for i in range(8):
+        kw = dict(key=keys[rng.integers(12)], scale=scales[rng.integers(6)], snap_strength=float(rng.uniform(0.3, 1.0)),
+                  sub_cut_hz=float(rng.choice([0.0, 80.0, 110.0, 150.0])), air_cut_hz=float(rng.choice([4000.0, 5000.0, 9000.0])),
+                  sub_level=float(rng.uniform(0.0, 0.6)), sub_octave=int(rng.integers(0, 4)), air_mix=float(rng.uniform(0.0, 1.0)),
+                  limiter_on=bool(rng.integers(2)), dry_wet=float(rng.uniform(0.5, 1.0)))
+        x = qd_cases.make_signal("tone" if i % 4 else "bass", 200 + i, n, sr)
+        y, taps = qd.process_audio(x, sr, quantize_mode="autotune_v1", **kw)
+        ref, rt = at.process_audio_autotune(x, sr, **kw)
+        worst = max(worst, _check(taps["pre_quant"], rt["pre_quant"], f"case {i} {kw} pre_quant"))
+        _check(y, ref, f"case {i} {kw}")
+    print(f"worst autotune error over the random configs: {worst:.3e}")
