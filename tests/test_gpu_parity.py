@@ -308,3 +308,30 @@ def test_cents_metric_batch_of_renders(qd):
     assert np.mean(wet) < np.mean(dry)
     silent, per0 = analyses.avg_cents_offset_from_scale(np.zeros(5000, dtype=np.float32), sr, "D", "minor")
     assert np.isnan(silent) and per0.size == 0
+
+
+@pytest.mark.gpu
+def test_random_configs_vs_oracle(qd):
+    """Keys, scales, snap / smear, band edges, distortion and mix settings drawn at random (seeded) on the STFT path,
+    precision="auto", every render against the oracle at the north-star tolerance."""
+    rng = np.random.default_rng(77)
+    keys = ["C", "C#", "D", "Eb", "E", "F", "F#", "G", "Ab", "A", "Bb", "B"]
+    scales = ["major", "minor", "pentatonic", "dorian", "mixolydian", "harmonic_minor"]
+    n, sr = 12000, 48000
+    worst = 0.0
+    for i in range(12):
+        kw = dict(key=keys[rng.integers(12)], scale=scales[rng.integers(6)], snap_strength=float(rng.uniform(0.2, 1.0)),
+                  smear=float(rng.uniform(0.0, 0.6)), bin_smoothing=bool(rng.integers(2)),
+                  sub_cut_hz=float(rng.choice([60.0, 110.0, 200.0])), air_cut_hz=float(rng.choice([3000.0, 5000.0, 8000.0])),
+                  distortion_mode=str(rng.choice(["wavefold", "tube"])),
+                  distortion_params={"fold_amount": float(rng.uniform(1.0, 4.0)), "bias": float(rng.uniform(-0.1, 0.1)),
+                                     "drive": float(rng.uniform(0.5, 3.0)), "warmth": float(rng.uniform(0.0, 1.0))},
+                  limiter_ceiling_db=float(rng.choice([-0.5, -1.0, -3.0])), dry_wet=float(rng.uniform(0.4, 1.0)),
+                  use_multiband=bool(rng.integers(2)), crossover_hz=float(rng.choice([200.0, 300.0, 500.0])),
+                  lowband_drive=float(rng.uniform(0.5, 2.0)), harmonic_lock_hz=float(rng.choice([0.0, 0.0, 55.0])))
+        x = qd_cases.make_signal(["bass", "loud", "noise"][i % 3], 300 + i, n, sr)
+        y, taps = qd.process_audio(x, sr, **kw)
+        ref, rt = orc.process_audio(x, sr, **kw)
+        worst = max(worst, _check(y, ref, f"case {i} {kw}"))
+        _check(taps["pre_quant"], rt["pre_quant"], f"case {i} pre_quant")
+    print(f"worst error over the random STFT-path configs: {worst:.3e}")
