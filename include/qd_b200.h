@@ -110,7 +110,7 @@ typedef struct qd_params {
                                     for ill-conditioned configurations (band mask wide open, n_fft 8192) */
     int32_t  spectral_freeze;    /* dsp/pipeline.py:285-287, 303-304: every frame takes the magnitudes of frame 0 */
     double   formant_ratio;      /* 2^(formant_shift/12), dsp/spectral_fx.py:173; 0 = off (dsp/pipeline.py:306-310).
-                                    float32 kernels, n_fft <= 4096 */
+                                    n_fft <= 4096 */
     int32_t  formant_order;      /* cepstral lifter order, dsp/spectral_fx.py:120 (30) */
     int32_t  reserved0;
 } qd_params;

@@ -471,7 +471,6 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         n_slots = qt.n_slots;
     }
     const bool formant = need_quant && p.formant_ratio > 0.0;
-    if (formant && p.precision != QD_PRECISION_F32) return bail(QD_ERR_UNSUPPORTED, "formant shift is built for the float32 kernels");
     if (formant && p.n_fft > 4096) return bail(QD_ERR_UNSUPPORTED, "formant shift is built for n_fft <= 4096");
     if (formant && p.formant_order < 2) return bail(QD_ERR_INVALID_ARG, "formant_order must be >= 2");
     const bool fx = need_quant && (p.fx_mode != QD_FX_NONE || p.spectral_freeze || formant);
@@ -481,6 +480,22 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
     fxd.step = p.fx_a;
     fxd.table_frames = p.fx_table_frames > 0 ? p.fx_table_frames : 1;
     fxd.table_per_clip = p.fx_table_per_clip;
+    // formant shift: np.interp(k / ratio, arange(n_bins), env) as segment index and fraction per bin, in float64
+    // (dsp/spectral_fx.py:173-183); beyond the last bin the envelope is held (right = env[-1])
+    int16_t *d_fi = nullptr;
+    float *d_ff = nullptr;
+    if (formant) {
+        const int nb = st.nc + 1;
+        std::vector<int16_t> fi((size_t)nb);
+        std::vector<float> ff((size_t)nb);
+        for (int k = 0; k < nb; ++k) {
+            const double x = (double)k / p.formant_ratio;
+            if (x >= (double)(nb - 1)) { fi[k] = (int16_t)(nb - 1); ff[k] = 0.0f; }
+            else { const double fl = std::floor(x); fi[k] = (int16_t)fl; ff[k] = (float)(x - fl); }
+        }
+        QD_UP(fi, d_fi);
+        QD_UP(ff, d_ff);
+    }
     if (pl->f64) {
         qd_host::SpecTablesT<double> sd;
         qd_host::build_spec_tables<double>(p.n_fft, &sd);
@@ -502,9 +517,10 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         a.invw = d_invw;
         a.q = qdev;
         a.fx = fxd;
+        a.formant_idx = d_fi; a.formant_frac = d_ff; a.formant_order = p.formant_order;
         pl->nw = pick_nw<double>(pl->nc, fx);
         pl->ts = false;
-        pl->spec_smem = spec_smem_bytes<double>(pl->nc, pl->nw, false, n_slots, qdev.n_src, 0, fx);
+        pl->spec_smem = spec_smem_bytes<double>(pl->nc, pl->nw, false, n_slots, qdev.n_src, formant ? 1 : 0, fx);
     } else {
         qd_host::F2 *d_wtab, *d_tw1, *d_tw2, *d_wsplit;
         float *d_invw;
@@ -524,24 +540,7 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         a.invw = d_invw;
         a.q = qdev;
         a.fx = fxd;
-        if (formant) {
-            // np.interp(k / ratio, arange(n_bins), env): segment index and fraction per bin in float64
-            // (dsp/spectral_fx.py:173-183); beyond the last bin the envelope is held (right = env[-1])
-            const int nb = st.nc + 1;
-            std::vector<int16_t> fi((size_t)nb);
-            std::vector<float> ff((size_t)nb);
-            for (int k = 0; k < nb; ++k) {
-                const double x = (double)k / p.formant_ratio;
-                if (x >= (double)(nb - 1)) { fi[k] = (int16_t)(nb - 1); ff[k] = 0.0f; }
-                else { const double fl = std::floor(x); fi[k] = (int16_t)fl; ff[k] = (float)(x - fl); }
-            }
-            int16_t *d_fi; float *d_ff;
-            QD_UP(fi, d_fi);
-            QD_UP(ff, d_ff);
-            a.formant_idx = d_fi;
-            a.formant_frac = d_ff;
-            a.formant_order = p.formant_order;
-        }
+        a.formant_idx = d_fi; a.formant_frac = d_ff; a.formant_order = p.formant_order;
         pl->nw = pick_nw<float>(pl->nc, fx, formant);
         pl->ts = (pl->nc == 1024 && pl->nw == 16);
         pl->spec_smem = spec_smem_bytes<float>(pl->nc, pl->nw, pl->ts, n_slots, qdev.n_src, formant ? 1 : 0, fx);

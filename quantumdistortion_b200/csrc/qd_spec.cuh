@@ -127,7 +127,7 @@ struct SpecArgsT {
     QuantDev q;
     FxDev fx;
     const T *frozen;       // optional [batch][BUF]: |X| of frame 0 by buffer position (spectral freeze)
-    // formant shift (dsp/spectral_fx.py:116-195), float32 FX kernels only; null = off
+    // formant shift (dsp/spectral_fx.py:116-195), FX kernels; null = off
     const int16_t *formant_idx;   // [NC+1] floor(k / ratio) clamped to NC        (np.interp segment, host float64)
     const float *formant_frac;    // [NC+1] k / ratio - floor(k / ratio), 0 when clamped
     int formant_order;            // lifter order (30)
@@ -564,7 +564,7 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
         }
     }
     __syncwarp();
-    if constexpr (sizeof(T) == 4) {
+    {
         if (a.formant_idx) {   // dsp/pipeline.py:306-310: after the freeze, before the FX
             formant_frame<T, NC>(mags, scr, a, tw1, wsplit, lane);
             mx = 0.0f;

@@ -264,7 +264,7 @@ def choose_precision(precision: str, n_fft: int, target_bins, active_mask, fx_ac
     if precision != "auto":
         raise ValueError("precision must be 'auto', 'float32' or 'float64'")
     if formant_active:
-        return 0                       # the formant shift is built for the float32 kernels
+        return 0   # float32 kernels; precision="float64" runs the cepstral FFTs in float64 as well
     if n_fft >= 8192:
         return 0 if fx_active else 1   # the float64 FX kernels are not built for n_fft 8192
     return 1 if max_fan_in(target_bins, active_mask) > F64_FAN_IN else 0

@@ -311,6 +311,18 @@ def test_cents_metric_batch_of_renders(qd):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sb_formant_up", "mb_formant_bitcrush", "nfft1024_formant"])
+def test_formant_shift_float64_kernels(qd, pipe, name):
+    """precision="float64": the cepstral FFTs of the formant shift run in float64 like the rest of the pass."""
+    kind, seed, n, sr, n_fft, rng_seed, kw = qd_cases.CASES[name]
+    x = pipe[f"{name}/x"]
+    if rng_seed is not None:
+        np.random.seed(rng_seed)
+    y, _ = qd.process_audio(x, sr, n_fft=n_fft, precision="float64", **kw)
+    _check(y, pipe[f"{name}/y"], f"{name}/y float64", 5e-6)
+
+
+@pytest.mark.gpu
 def test_random_configs_vs_oracle(qd):
     """Keys, scales, snap / smear, band edges, distortion and mix settings drawn at random (seeded) on the STFT path,
     precision="auto", every render against the oracle at the north-star tolerance."""
