@@ -28,6 +28,9 @@ SR = 48000
 CLIP_SECONDS = 10
 N_SAMPLES = SR * CLIP_SECONDS
 WORKLOAD = "configs[1]: 4096 synthetic 10 s mono clips/GPU, single-band STFT pre-quant->wavefold->post-quant->limiter, n_fft 2048 hop 512, spectral_bins defaults"
+# --workload multiband: BASELINE configs[2] (not the default bench line; for the record in profiles/)
+WORKLOAD_MB = "configs[2]: 4096 synthetic 10 s mono clips/GPU, multiband: LR4 crossover @300 Hz, low-band saturation, high-band STFT chain + lookahead limiter, n_fft 2048 hop 512"
+RENDER_KW = {}   # extra process_audio keyword arguments of the selected workload
 METRIC = "audio-seconds/sec for batched STFT quantize+distort pipeline"
 UNIT = "audio-s/s"
 
@@ -44,7 +47,7 @@ def _peaks():
 
 # ------------------------------------------------------------------------------------ CPU arm
 def _cpu_worker(args):
-    seed, n, sr = args
+    seed, n, sr, kw = args   # kw travels explicitly: the pool's workers are spawned and do not see RENDER_KW
     import contextlib
     import io
 
@@ -54,7 +57,7 @@ def _cpu_worker(args):
     x = synth.bass_clip(seed, n, sr)
     t0 = time.perf_counter()
     with contextlib.redirect_stdout(io.StringIO()):
-        y, _ = orc.process_audio(x, sr)
+        y, _ = orc.process_audio(x, sr, **kw)
     return time.perf_counter() - t0, float(abs(y).max())
 
 
@@ -68,9 +71,9 @@ def cpu_baseline(clips_per_core: int, pool=None):
     if own:
         pool = mp.get_context("spawn").Pool(cores)
     try:
-        pool.map(_cpu_worker, [(10_000 + i, 4800, SR) for i in range(cores)])  # import + warm-up, untimed
+        pool.map(_cpu_worker, [(10_000 + i, 4800, SR, dict(RENDER_KW)) for i in range(cores)])  # import + warm-up, untimed
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(i, N_SAMPLES, SR) for i in range(n_clips)], chunksize=1)
+        pool.map(_cpu_worker, [(i, N_SAMPLES, SR, dict(RENDER_KW)) for i in range(n_clips)], chunksize=1)
         wall = time.perf_counter() - t0
     finally:
         if own:
@@ -180,7 +183,7 @@ def run_ours(args):
     numa_cpus = bind_to_gpu_numa(local)  # pinned host buffers below become node-local to this rank's GPU
     B = args.clips
     x = synth.bass_batch_torch(B, N_SAMPLES, SR, dev, seed=rank)  # each rank renders its own shard
-    r = qd.make_renderer(N_SAMPLES, SR)  # reference defaults, quantize_mode="spectral_bins"
+    r = qd.make_renderer(N_SAMPLES, SR, **RENDER_KW)  # reference defaults, quantize_mode="spectral_bins"
     r.enable_timing(True)
 
     def barrier():
@@ -224,7 +227,7 @@ def run_ours(args):
         errs, nulls = [], []
         for i in range(args.check_clips):
             idx = (i * 997) % B
-            ref, _ = orc.process_audio(x[idx].cpu().numpy(), SR)
+            ref, _ = orc.process_audio(x[idx].cpu().numpy(), SR, **RENDER_KW)
             got = y[idx].cpu().numpy()
             errs.append(float(np.max(np.abs(got.astype(np.float64) - ref))))
             nulls.append(orc.null_test_db(got, ref))
@@ -241,11 +244,11 @@ def run_ours(args):
     x_host.copy_(x)
     torch.cuda.synchronize()
     for _ in range(max(1, args.warmup - 1)):
-        qd.process_batch(x_host, SR, out=y_host, chunk_clips=args.chunk_clips)
+        qd.process_batch(x_host, SR, out=y_host, chunk_clips=args.chunk_clips, **RENDER_KW)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        qd.process_batch(x_host, SR, out=y_host, chunk_clips=args.chunk_clips)
+        qd.process_batch(x_host, SR, out=y_host, chunk_clips=args.chunk_clips, **RENDER_KW)
     torch.cuda.synchronize()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     barrier()
@@ -316,7 +319,13 @@ def main():
     ap.add_argument("--check-clips", type=int, default=2)
     ap.add_argument("--cpu-clips-per-core", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="single_band", choices=["single_band", "multiband"],
+                    help="single_band = BASELINE configs[1] (the bench line); multiband = configs[2], for the record")
     args = ap.parse_args()
+    if args.workload == "multiband":
+        global WORKLOAD
+        WORKLOAD = WORKLOAD_MB
+        RENDER_KW.update(use_multiband=True, crossover_hz=300.0, lowband_drive=1.0)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
