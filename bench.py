@@ -30,7 +30,7 @@ N_SAMPLES = SR * CLIP_SECONDS
 WORKLOAD = "configs[1]: 4096 synthetic 10 s mono clips/GPU, single-band STFT pre-quant->wavefold->post-quant->limiter, n_fft 2048 hop 512, spectral_bins defaults"
 # --workload multiband: BASELINE configs[2] (not the default bench line; for the record in profiles/)
 WORKLOAD_MB = "configs[2]: 4096 synthetic 10 s mono clips/GPU, multiband: LR4 crossover @300 Hz, low-band saturation, high-band STFT chain + lookahead limiter, n_fft 2048 hop 512"
-RENDER_KW = {}   # extra process_audio keyword arguments of the selected workload
+RENDER_KW = {"quantize_mode": "spectral_bins"}   # process_audio keyword arguments of the selected workload (the STFT path)
 METRIC = "audio-seconds/sec for batched STFT quantize+distort pipeline"
 UNIT = "audio-s/s"
 

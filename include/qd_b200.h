@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 3
+#define QD_ABI_VERSION 4
 
 typedef enum qd_status {
     QD_OK = 0,
@@ -112,7 +112,10 @@ typedef struct qd_params {
     double   formant_ratio;      /* 2^(formant_shift/12), dsp/spectral_fx.py:173; 0 = off (dsp/pipeline.py:306-310).
                                     n_fft <= 4096 */
     int32_t  formant_order;      /* cepstral lifter order, dsp/spectral_fx.py:120 (30) */
-    int32_t  reserved0;
+    int32_t  no_spectral;        /* 1: no STFT pass at all -- x_pre = band, distortion, limiter, mix.  What
+                                    quantize_mode="autotune_v1" does when its pitch stage is gated off (pre_quant off or
+                                    snap_strength <= 0, dsp/pipeline.py:537-601), the only form in which that mode
+                                    survives inside a multiband render (:1326-1327, :1076) */
 } qd_params;
 
 #define QD_PRECISION_F32 0

@@ -613,8 +613,11 @@ def process_single_band(x_in, sr, *, key, scale, snap_strength, smear, bin_smoot
                         dry_wet, tap_input, passthrough_test=False, is_high_band=False,
                         spectral_fx_mode=None, spectral_fx_strength=0.0, spectral_fx_params=None,
                         spectral_freeze=False, harmonic_lock_hz=0.0, output_trim_db=0.0,
-                        sub_cut_hz=110.0, air_cut_hz=5000.0, n_fft=N_FFT_DEFAULT, formant_shift=0.0):
-    """dsp/pipeline.py:419-920 without the autotune branch (:537-601)."""
+                        sub_cut_hz=110.0, air_cut_hz=5000.0, n_fft=N_FFT_DEFAULT, formant_shift=0.0,
+                        no_spectral=False):
+    """dsp/pipeline.py:419-920.  Of the autotune branch (:537-601) only the form with its pitch stage gated off
+    (``no_spectral``: x_pre = x_in, distortion, limiter, mix) is restated here; the pitch stage itself is
+    oracle/qd_autotune.py."""
     n = x_in.shape[0]
     if passthrough_test:  # :477-535
         S, _ = stft(x_in, sr, n_fft)
@@ -629,9 +632,9 @@ def process_single_band(x_in, sr, *, key, scale, snap_strength, smear, bin_smoot
             harmonic_lock_hz=harmonic_lock_hz, quantize_min_hz=sub_cut_hz, quantize_max_hz=air_cut_hz,
             formant_shift=formant_shift)
 
-    pre = bool(pre_quant and snap_strength > 0.0)  # :635
-    post = bool(post_quant and snap_strength > 0.0)  # :728
-    S, freqs = stft(x_in, sr, n_fft)  # :615
+    pre = bool(pre_quant and snap_strength > 0.0) and not no_spectral  # :635
+    post = bool(post_quant and snap_strength > 0.0) and not no_spectral  # :728
+    S, freqs = (None, None) if no_spectral else stft(x_in, sr, n_fft)  # :615
     if pre:
         S = spec(S, freqs)
         x_pre = istft(S, sr, n_fft, length=n).astype(np.float32)  # :668 / :690
@@ -650,7 +653,7 @@ def process_single_band(x_in, sr, *, key, scale, snap_strength, smear, bin_smoot
         else:  # :802-848 -- post-quant of the UNDISTORTED spectrum
             x_pq = istft(spec(S, freqs), sr, n_fft, length=n).astype(np.float32)
     else:
-        x_pq = x_dist.copy() if pre else istft(S, sr, n_fft, length=n).astype(np.float32)  # :849-879
+        x_pq = x_dist.copy() if (pre or no_spectral) else istft(S, sr, n_fft, length=n).astype(np.float32)  # :849-879, :591
     if limiter_on:  # :882-891
         x_lim, _ = peak_limiter(x_pq, sr, ceiling_db=limiter_ceiling_db, lookahead_ms=5.0, release_ms=30.0)
     else:
@@ -681,8 +684,11 @@ def process_audio(audio, sr=48000, key="D", scale="minor", quantize_mode="spectr
     if quantize_mode == "autotune_v1" and (spectral_fx_mode is not None or spectral_freeze
                                             or formant_shift != 0.0 or harmonic_lock_hz > 0.0):
         quantize_mode = "spectral_bins"
-    if quantize_mode != "spectral_bins":
-        raise NotImplementedError("oracle covers quantize_mode='spectral_bins' only")
+    # autotune_v1 survives inside a multiband render only with snap_strength <= 0 (:1326-1327), where its pitch stage
+    # is gated off (:538): the high band is distorted, limited and mixed without any STFT
+    no_spectral = quantize_mode == "autotune_v1" and use_multiband and not snap_strength > 0.0 and not passthrough_test
+    if quantize_mode != "spectral_bins" and not no_spectral:
+        raise NotImplementedError("this oracle covers quantize_mode='spectral_bins'; autotune_v1 is oracle/qd_autotune.py")
     x = np.asarray(audio, dtype=np.float32)  # config.py:19-24
     if x.ndim == 2:
         x = x.mean(axis=1).astype(np.float32)
@@ -696,7 +702,7 @@ def process_audio(audio, sr=48000, key="D", scale="minor", quantize_mode="spectr
         spectral_fx_mode=spectral_fx_mode, spectral_fx_strength=spectral_fx_strength,
         spectral_fx_params=spectral_fx_params or {}, spectral_freeze=spectral_freeze,
         harmonic_lock_hz=harmonic_lock_hz, output_trim_db=output_trim_db, sub_cut_hz=sub_cut_hz,
-        air_cut_hz=air_cut_hz, n_fft=n_fft, formant_shift=formant_shift)
+        air_cut_hz=air_cut_hz, n_fft=n_fft, formant_shift=formant_shift, no_spectral=no_spectral)
     if use_multiband:  # dsp/pipeline.py:1011-1110
         low, high = linkwitz_riley_split(x, sr, crossover_hz)
         d = n_fft // 2  # :1056, filter-delay term cancels (:380-386)

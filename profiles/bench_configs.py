@@ -53,7 +53,7 @@ for name, kw in (("next(f3) autotune_v1 defaults (bass batch)", {}), ("next(f3) 
 for name, kw, n_fft, seed in CONFIGS:
     b = clips if n_fft <= 4096 and kw.get("precision") != "float64" else max(64, clips // 4)
     xs = x[:b]
-    r = qd.make_renderer(N, SR, n_fft, seeds=seed, **kw)
+    r = qd.make_renderer(N, SR, n_fft, seeds=seed, quantize_mode="spectral_bins", **kw)
     r.set_fx_seeds(b, seed)
     for _ in range(3):
         y, _ = r.render_device(xs)

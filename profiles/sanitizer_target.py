@@ -19,11 +19,11 @@ cases = [({}, 2048), (dict(use_multiband=True), 2048), (dict(GROWL, use_multiban
          (dict(spectral_freeze=True), 2048), (dict(formant_shift=3.0), 2048), (dict(formant_shift=-4.0, spectral_freeze=True), 1024),
          (dict(GROWL, use_multiband=True, formant_shift=2.0, spectral_fx_mode="phase_dispersal", spectral_fx_strength=0.6), 2048), ({}, 512), ({}, 8192), (dict(precision="float64"), 2048), (dict(passthrough_test=True), 1024)]
 for kw, n_fft in cases:
-    y, _ = qd.process_batch(x, sr, n_fft=n_fft, seeds=7, **kw)
+    y, _ = qd.process_batch(x, sr, n_fft=n_fft, seeds=7, quantize_mode="spectral_bins", **kw)
     torch.cuda.synchronize()
     print(n_fft, sorted(kw)[:3], float(y.abs().max()))
 xo = torch.from_numpy(np.stack([synth.loud_clip(9, 5003, sr)])).cuda()   # ragged length: scalar load/store paths
-y, _ = qd.process_batch(xo, sr)
+y, _ = qd.process_batch(xo, sr, quantize_mode="spectral_bins")
 torch.cuda.synchronize()
 from quantumdistortion_b200 import analyses
 for prec in ("float64", "float32"):

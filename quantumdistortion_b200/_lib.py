@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libqd_b200.so")
 
-QD_ABI_VERSION = 3
+QD_ABI_VERSION = 4
 QD_FX = {"none": 0, "bitcrush_log": 1, "bitcrush_uniform": 2, "phase_dispersal": 3,
          "scramble_pick": 4, "scramble_swap": 5}
 
@@ -28,7 +28,7 @@ class QdParams(C.Structure):
         ("fx_mode", C.c_int32), ("fx_a", C.c_double), ("fx_b", C.c_double), ("fx_c", C.c_double),
         ("fx_table_frames", C.c_int32), ("fx_table_per_clip", C.c_int32),
         ("precision", C.c_int32), ("spectral_freeze", C.c_int32),
-        ("formant_ratio", C.c_double), ("formant_order", C.c_int32), ("reserved0", C.c_int32),
+        ("formant_ratio", C.c_double), ("formant_order", C.c_int32), ("no_spectral", C.c_int32),
     ]
 
 

@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2",
     "-shared", "-cudart", "static",
+    "--split-compile", "0",   # optimise the kernels of the one translation unit on every host core
 ]
 
 

@@ -21,10 +21,11 @@ DEFAULT_DISTORTION_MODE = "wavefold"
 DEFAULT_LIMITER_ON = True
 DEFAULT_LIMITER_CEILING_DB = -1.0
 DEFAULT_DRY_WET = 1.0
-# The reference defaults to "autotune_v1" (config.py:44), a time-domain pitch-tracking mode outside the STFT
-# path.  This package's headline is the STFT path, so its default is "spectral_bins"; quantize_mode="autotune_v1"
-# selects the other mode (quantumdistortion_b200/autotune.py).
-DEFAULT_QUANTIZE_MODE = "spectral_bins"
+# config.py:44 -- the reference's default is the time-domain pitch-tracking mode (quantumdistortion_b200/autotune.py);
+# the STFT path (this package's headline) is quantize_mode="spectral_bins", or any spectral FX / freeze / formant /
+# harmonic-lock option (dsp/pipeline.py:1315-1324).  Same default here, so a bare process_audio(x, sr),
+# PipelineConfig() and PipelineConfig.from_preset() run what the same call runs on the reference.
+DEFAULT_QUANTIZE_MODE = "autotune_v1"
 DEFAULT_SUB_CUT_HZ = 110.0
 DEFAULT_AIR_CUT_HZ = 5000.0
 PREVIEW_ENABLED_DEFAULT = False
@@ -42,8 +43,8 @@ def ensure_mono_float32(audio: np.ndarray) -> np.ndarray:
 
 @dataclass
 class PipelineConfig:
-    """Same fields and defaults as the reference's PipelineConfig (config.py:64-130); the ``sub_*`` / ``air_mix``
-    fields only matter for quantize_mode="autotune_v1"."""
+    """Same fields and defaults as the reference's PipelineConfig (config.py:64-130), quantize_mode="autotune_v1"
+    included (:77); the ``sub_*`` / ``air_mix`` fields only matter for that mode."""
     key: str = DEFAULT_KEY
     scale: str = DEFAULT_SCALE
     quantize_mode: str = DEFAULT_QUANTIZE_MODE
@@ -83,7 +84,7 @@ class PipelineConfig:
 
     @classmethod
     def from_preset(cls, preset_name: str) -> "PipelineConfig":
-        """config.py:132-151."""
+        """config.py:132-151 (quantize_mode stays the default "autotune_v1", :140)."""
         from .presets import get_preset
         p = get_preset(preset_name)
         return cls(key=str(p["key"]), scale=str(p["scale"]), quantize_mode=DEFAULT_QUANTIZE_MODE,

@@ -591,6 +591,7 @@ int qd_plan_launches_per_render(const qd_plan *pl) {
     int n = 0;
     if (p.multiband) n += 1;                        // crossover
     if (p.passthrough) return n + 1 + (p.multiband ? 1 : 0);
+    if (p.no_spectral) return n + 2;                // distortion, limiter + mix
     if (p.pre_quant) n += 1;                        // pass A
     if (p.post_quant || !p.pre_quant) n += 1;       // pass B (or the bare STFT->iSTFT)
     n += 1;                                         // limiter + mix
@@ -703,7 +704,16 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
 
     const int epi = p.distortion_mode == QD_DIST_TUBE ? 2 : 1;
     const float *x_pq = nullptr;  // limiter input
-    if (p.pre_quant) {
+    if (p.no_spectral) {
+        // dsp/pipeline.py:537-601 with the pitch stage gated off: x_pre = band (:570), distortion (:580-588), no
+        // spectral post-quantisation (:591), then the common tail (_finalize_single_band_output, :180-223)
+        if (tap_pre) QD_CUDA(cudaMemcpyAsync(tap_pre, src, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        qd::distort_kernel<<<ew_grid((int64_t)count, pl->sm_count), 256, 0, st>>>(
+            src, w_a, (long long)count, p.distortion_mode, p.fold_amount, p.bias, p.tube_gain, p.tube_norm);
+        QD_CUDA(cudaGetLastError());
+        x_pq = w_a;
+        clip_peak = nullptr;   // no spectral pass measured the limiter input
+    } else if (p.pre_quant) {
         // pass A: STFT -> quantize -> iSTFT (= pre_quant tap) -> distortion        (:635-721)
         if ((rc = launch_spec(pl, src, w_a, tap_pre, 1, epi, batch, st, 0, pl->clip_offset,
                               p.post_quant ? nullptr : clip_peak)) != QD_OK) return rc;

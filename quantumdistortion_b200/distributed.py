@@ -55,9 +55,17 @@ def render_sharded(x, render: Callable, *, gather_to: Optional[int] = 0, group=N
 
 def process_batch_sharded(x, sr: int = 48000, *, gather_to: Optional[int] = 0, **kwargs):
     """``process_batch`` over the ranks of the default process group (one rank per GPU).  ``x`` is the same
-    CUDA (or CPU) ``[B, n]`` tensor on every rank; each rank renders only its slice."""
+    CUDA (or CPU) ``[B, n]`` tensor on every rank; each rank renders only its slice.  ``seeds`` (random spectral
+    FX) keeps its single-process meaning: a per-clip list is sliced per rank, and with ``seeds=None`` every rank
+    steps its np.random state past the clips of the lower ranks first (``process_batch(shard=...)``), so the result
+    equals the unsharded ``process_batch`` call made from the same np.random state."""
+    import torch.distributed as dist
     from .pipeline import process_batch
-    return render_sharded(x, lambda shard: process_batch(shard, sr, **kwargs)[0], gather_to=gather_to)
+    total = int(x.shape[0])
+    lo, hi = 0, total
+    if dist.is_available() and dist.is_initialized():
+        lo, hi = shard_bounds(total, dist.get_rank(), dist.get_world_size())
+    return render_sharded(x, lambda part: process_batch(part, sr, shard=(lo, hi, total), **kwargs)[0], gather_to=gather_to)
 
 
 def bind_to_gpu_numa(device_index: int) -> Optional[str]:

@@ -24,7 +24,7 @@ def _config(preset: Optional[str], extra_params: Optional[Dict[str, Any]]) -> Pi
 
 def process_file_to_file(infile: Path, outfile: Path, preset: Optional[str] = None,
                          extra_params: Optional[Dict[str, Any]] = None) -> None:
-    """dsp/harness.py:24-63.  (This package's PipelineConfig defaults to the STFT path, see config.py.)"""
+    """dsp/harness.py:24-63 (PipelineConfig defaults to quantize_mode="autotune_v1" like the reference's)."""
     from .pipeline import process_audio
     infile, outfile = Path(infile), Path(outfile)
     if not infile.exists():
@@ -38,28 +38,34 @@ def process_file_to_file(infile: Path, outfile: Path, preset: Optional[str] = No
 
 def process_files(pairs: Iterable[Tuple[Path, Path]], preset: Optional[str] = None,
                   extra_params: Optional[Dict[str, Any]] = None, seeds=None) -> int:
-    """Render many (infile, outfile) pairs with one parameter set.  Files sharing (length, sample rate) are
-    stacked and rendered as one batch (`process_batch`).  Returns the number of files written."""
-    from .pipeline import process_batch
+    """Render many (infile, outfile) pairs with one parameter set -- the same files ``process_file_to_file`` would
+    write one by one.  Files sharing (length, sample rate) are stacked and rendered as one batch (`process_batch`).
+    ``seeds`` (random spectral FX): None, one int for every file, or one seed per file in the order of ``pairs``.
+    Returns the number of files written."""
+    from .pipeline import preview_truncate, process_batch
     cfg = _config(preset, extra_params)
-    groups: Dict[Tuple[int, int], List[Tuple[Path, np.ndarray]]] = {}
-    for infile, outfile in pairs:
+    pairs = list(pairs)
+    per_file = seeds is not None and not isinstance(seeds, (int, np.integer))
+    if per_file and len(seeds) != len(pairs):
+        raise ValueError("need one seed per file")
+    groups: Dict[Tuple[int, int], List[Tuple[Path, np.ndarray, Any]]] = {}
+    for i, (infile, outfile) in enumerate(pairs):
         infile = Path(infile)
         if not infile.exists():
             raise FileNotFoundError(f"Input file not found: {infile}")
         audio, sr = load_audio(infile)
-        x = ensure_mono_float32(audio)
-        groups.setdefault((x.shape[0], sr), []).append((Path(outfile), x))
+        x = ensure_mono_float32(preview_truncate(audio, sr, None, cfg))   # process_audio truncates before the mono mix
+        groups.setdefault((x.shape[0], sr), []).append((Path(outfile), x, seeds[i] if per_file else None))
     written = 0
     for (n, sr), items in groups.items():
         if n == 0:
-            for out, x in items:
+            for out, x, _ in items:
                 save_audio(out, x, sr)
                 written += 1
             continue
-        batch = np.stack([x for _, x in items])
-        y, _ = process_batch(batch, sr, pipeline_config=cfg, seeds=seeds)
-        for (out, _), row in zip(items, y):
+        batch = np.stack([x for _, x, _ in items])
+        y, _ = process_batch(batch, sr, pipeline_config=cfg, seeds=[s for _, _, s in items] if per_file else seeds)
+        for (out, _, _), row in zip(items, y):
             save_audio(out, row, sr)
             written += 1
     return written

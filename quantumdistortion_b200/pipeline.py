@@ -47,6 +47,41 @@ def _torch():
     return torch
 
 
+def fx_tables(r: "tables.Resolved", batch: int, seeds=None, shard=None):
+    """np.random replay tables (tables.replay_fx_table) of the random spectral FX for `batch` clips.
+
+    seeds=None : draw from the current global np.random state, clip after clip -- what a loop of reference
+                 ``process_audio`` calls would consume;
+    seeds=int  : ``np.random.seed(s)`` before EVERY clip -> one table shared by the whole batch;
+    seeds=[..] : one seed per clip.
+    ``shard=(lo, hi, total)`` says the batch is clips lo..hi of a larger batch of `total` clips rendered elsewhere
+    (multi-GPU sharding): a seed list may then cover the whole batch (it is sliced), and with seeds=None the draws of
+    the clips before the shard are consumed first and those of the clips after it afterwards, so every clip gets
+    the draws it would get in an unsharded render and the global state ends where that render would leave it."""
+    one = lambda: tables.replay_fx_table(r.fx_rng, r.fx_passes, r.n_frames, r.n_bins)  # noqa: E731
+    lo, total = (int(shard[0]), int(shard[2])) if shard is not None else (0, batch)
+    if seeds is None:
+        for _ in range(lo):
+            one()
+        tabs = [one() for _ in range(batch)]
+        for _ in range(total - lo - batch):
+            one()
+        return tabs
+    if isinstance(seeds, (int, np.integer)):
+        np.random.seed(int(seeds))
+        return [one()]
+    seeds = list(seeds)
+    if shard is not None and len(seeds) == total:
+        seeds = seeds[lo:lo + batch]
+    if len(seeds) != batch:
+        raise ValueError("need one seed per clip")
+    tabs = []
+    for sd in seeds:
+        np.random.seed(int(sd))
+        tabs.append(one())
+    return tabs
+
+
 class Renderer:
     """One resolved parameter set bound to a CUDA plan on the current device."""
 
@@ -91,29 +126,13 @@ class Renderer:
             self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
         return self._ws, need
 
-    def set_fx_seeds(self, batch: int, seeds=None) -> None:
-        """Replay the reference's np.random draws for the spectral FX (tables.replay_fx_table) and upload them.
-
-        seeds=None : draw from the current global np.random state, clip after clip -- what a loop of reference
-                     ``process_audio`` calls would consume;
-        seeds=int  : ``np.random.seed(s)`` before EVERY clip -> one table shared by the whole batch;
-        seeds=[..] : one seed per clip."""
+    def set_fx_seeds(self, batch: int, seeds=None, shard=None) -> None:
+        """Replay the reference's np.random draws for the spectral FX (fx_tables) and upload them."""
         r = self.resolved
         if not r.fx_rng:
             return
         torch = _torch()
-        if seeds is None:
-            tabs = [tables.replay_fx_table(r.fx_rng, r.fx_passes, r.n_frames, r.n_bins) for _ in range(batch)]
-        elif isinstance(seeds, (int, np.integer)):
-            np.random.seed(int(seeds))
-            tabs = [tables.replay_fx_table(r.fx_rng, r.fx_passes, r.n_frames, r.n_bins)]
-        else:
-            if len(seeds) != batch:
-                raise ValueError("need one seed per clip")
-            tabs = []
-            for sd in seeds:
-                np.random.seed(int(sd))
-                tabs.append(tables.replay_fx_table(r.fx_rng, r.fx_passes, r.n_frames, r.n_bins))
+        tabs = fx_tables(r, batch, seeds, shard)
         shared = isinstance(seeds, (int, np.integer))
         if bool(r.params.fx_table_per_clip) == shared:
             raise ValueError("renderer built for %s FX tables; use make_renderer(..., seeds=...) with the same kind of seeds"
@@ -163,7 +182,7 @@ class AutotuneRenderer:
     def close(self) -> None:
         self._ws = None
 
-    def set_fx_seeds(self, batch: int, seeds=None) -> None:   # no random stage in this mode
+    def set_fx_seeds(self, batch: int, seeds=None, shard=None) -> None:   # no random stage in this mode
         pass
 
     def render_device(self, x, want_taps: bool = False, debug: bool = False, chunk_clips: int = 2048):
@@ -206,8 +225,15 @@ def _parse_ui_config(config: Dict[str, Any], kw: Dict[str, Any]) -> Dict[str, An
         out["key"] = str(q.get("key", kw.get("key", DEFAULT_KEY)))
         out["scale"] = str(q.get("scale", kw.get("scale", DEFAULT_SCALE)))
         out["quantize_mode"] = str(q.get("mode", kw.get("quantize_mode", DEFAULT_QUANTIZE_MODE)))
+        out["sub_enabled"] = bool(q.get("sub_enabled", kw.get("sub_enabled", True)))          # :966-974: the
+        out["sub_source"] = str(q.get("sub_source", kw.get("sub_source", "root")))            # autotune_v1 sub layer
+        out["sub_note"] = str(q.get("sub_note", kw.get("sub_note", "C")))
+        out["sub_scale_degree"] = int(q.get("sub_scale_degree", kw.get("sub_scale_degree", 0)))
+        out["sub_octave"] = int(q.get("sub_octave", kw.get("sub_octave", 2)))
+        out["sub_level"] = float(q.get("sub_level", kw.get("sub_level", 0.35)))
         out["sub_cut_hz"] = float(q.get("sub_cut_hz", kw.get("sub_cut_hz", DEFAULT_SUB_CUT_HZ)))
         out["air_cut_hz"] = float(q.get("air_cut_hz", kw.get("air_cut_hz", DEFAULT_AIR_CUT_HZ)))
+        out["air_mix"] = float(q.get("air_mix", kw.get("air_mix", 1.0)))
     if "crossover_freq" in config:
         out["crossover_hz"] = float(config["crossover_freq"])
     if "low_band" in config:
@@ -273,9 +299,12 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
         raise TypeError(f"process_audio() got unexpected keyword arguments: {sorted(kw)}")
     if quantize_mode == "autotune_v1" and (fx_mode is not None or freeze or formant != 0.0 or lock_hz > 0.0):
         quantize_mode = "spectral_bins"  # :1315-1324
-    if quantize_mode == "autotune_v1" and not passthrough:   # dsp/pipeline.py:537-601 (after the passthrough branch :477)
-        if use_multiband and not snap > 0.0:                 # :1326-1327 only forces single band when snap > 0
-            raise NotImplementedError("autotune_v1 with snap_strength 0 inside a multiband render is not built")
+    no_spectral = False
+    if quantize_mode == "autotune_v1" and not passthrough and use_multiband and not snap > 0.0:
+        # :1326-1327 only forces single band when snap > 0; with snap <= 0 the high band of the multiband render goes
+        # through the autotune branch with its pitch stage gated off (:538, :570): band -> distortion -> limiter -> mix
+        no_spectral = True
+    elif quantize_mode == "autotune_v1" and not passthrough:   # dsp/pipeline.py:537-601 (after the passthrough branch :477)
         ap = autotune.resolve(sr=sr, n_samples=n_samples, key=key, scale=scale, snap_strength=snap,
                               pre_quant=pre_quant, distortion_mode=distortion_mode,
                               distortion_params=distortion_params, limiter_on=limiter_on,
@@ -293,7 +322,7 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
                          mono_strength=mono_strength, output_trim_db=trim_db, low_trim_db=low_trim_db,
                          sub_cut_hz=sub_cut, air_cut_hz=air_cut, spectral_fx_mode=fx_mode,
                          spectral_fx_strength=fx_strength, spectral_fx_params=fx_params, precision=precision,
-                         spectral_freeze=bool(freeze), formant_shift=float(formant))
+                         spectral_freeze=bool(freeze), formant_shift=float(formant), no_spectral=no_spectral)
     return res, {"fx_params": fx_params}
 
 
@@ -317,11 +346,12 @@ def make_renderer(n_samples: int, sr: int = DEFAULT_SAMPLE_RATE, n_fft: int = N_
 
 
 def process_batch(x, sr: int = DEFAULT_SAMPLE_RATE, *, n_fft: int = N_FFT_DEFAULT, return_taps: bool = False,
-                  chunk_clips: int = 128, out=None, seeds=None, **kwargs):
+                  chunk_clips: int = 128, out=None, seeds=None, shard=None, **kwargs):
     """Render a batch of mono clips ``x[B, n]`` with one parameter set.
 
     ``seeds`` controls the np.random replay of the random spectral FX (None: consume the global state clip by
-    clip like a loop of reference calls; int: reseed before every clip; list: one seed per clip).
+    clip like a loop of reference calls; int: reseed before every clip; list: one seed per clip); ``shard=(lo, hi,
+    total)`` marks ``x`` as clips lo..hi of a larger batch rendered across several processes (see fx_tables).
     ``x`` may be a CUDA tensor (returns CUDA tensors, asynchronous), a CPU tensor or a NumPy array
     (returns the same kind; the copy/compute pipeline of ``qd_render_host`` is used when no taps are
     requested).  ``out`` (CPU tensor, ideally pinned like ``x``) receives the result of the host path
@@ -333,7 +363,7 @@ def process_batch(x, sr: int = DEFAULT_SAMPLE_RATE, *, n_fft: int = N_FFT_DEFAUL
     if xt.dim() != 2:
         raise ValueError("process_batch expects [batch, samples]")
     r = make_renderer(xt.shape[1], sr, n_fft, seeds=seeds, **kwargs)
-    r.set_fx_seeds(int(xt.shape[0]), seeds)  # no-op unless a random spectral FX is active
+    r.set_fx_seeds(int(xt.shape[0]), seeds, shard)  # no-op unless a random spectral FX is active
     if xt.is_cuda:
         return r.render_device(xt.float(), want_taps=return_taps)
     if return_taps:
@@ -354,6 +384,22 @@ def process_batch(x, sr: int = DEFAULT_SAMPLE_RATE, *, n_fft: int = N_FFT_DEFAUL
     return y, taps
 
 
+def preview_truncate(audio: np.ndarray, sr: int, preview_enabled: Optional[bool] = None,
+                     pipeline_config: Optional[PipelineConfig] = None) -> np.ndarray:
+    """dsp/pipeline.py:1241-1249, :1303-1310: preview mode (argument, else PipelineConfig, else the DSP_PREVIEW_MODE
+    environment variable) keeps the first PREVIEW_MAX_SECONDS of the clip."""
+    if preview_enabled is None and pipeline_config is not None:
+        preview_enabled = pipeline_config.preview_enabled
+    if preview_enabled is None:
+        env = os.getenv("DSP_PREVIEW_MODE", "").strip().lower()
+        preview_enabled = True if env in ("1", "true", "yes", "on") else PREVIEW_ENABLED_DEFAULT
+    if preview_enabled:
+        max_samples = int(sr * PREVIEW_MAX_SECONDS)
+        if audio.shape[0] > max_samples:
+            audio = audio[:max_samples]
+    return audio
+
+
 def process_audio(audio: np.ndarray, sr: int = DEFAULT_SAMPLE_RATE, key: str = DEFAULT_KEY, scale: str = DEFAULT_SCALE,
                   quantize_mode: str = DEFAULT_QUANTIZE_MODE, snap_strength: float = DEFAULT_SNAP_STRENGTH,
                   smear: float = DEFAULT_SMEAR, bin_smoothing: bool = DEFAULT_BIN_SMOOTHING, pre_quant: bool = True,
@@ -371,24 +417,16 @@ def process_audio(audio: np.ndarray, sr: int = DEFAULT_SAMPLE_RATE, key: str = D
                   sub_cut_hz: float = DEFAULT_SUB_CUT_HZ, air_cut_hz: float = DEFAULT_AIR_CUT_HZ,
                   air_mix: float = 1.0, *, pipeline_config: Optional[PipelineConfig] = None,
                   n_fft: int = N_FFT_DEFAULT, precision: str = "auto") -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
-    """Drop-in for the reference's ``process_audio`` on the STFT path (one clip).
+    """Drop-in for the reference's ``process_audio`` (one clip).
 
-    Same positional/keyword arguments and defaults as dsp/pipeline.py:1113-1155, except that
-    ``quantize_mode`` defaults to "spectral_bins" (see config.py) and ``n_fft`` exposes the
+    Same positional/keyword arguments and defaults as dsp/pipeline.py:1113-1155 -- ``quantize_mode`` defaults to
+    "autotune_v1" like the reference (config.py:44), the STFT path is ``quantize_mode="spectral_bins"`` or any spectral
+    FX / freeze / formant / harmonic-lock option (:1315-1324).  Two extra keyword-only arguments: ``n_fft`` exposes the
     reference's module global N_FFT_DEFAULT (:149); ``precision`` ("auto" | "float32" | "float64") selects the
     arithmetic of the spectral pass (tables.choose_precision).  Returns ``(float32[n], taps)`` with taps
     ``input / pre_quant / post_dist / output`` (:1368, :1104-1109).
     """
-    if preview_enabled is None and pipeline_config is not None:
-        preview_enabled = pipeline_config.preview_enabled
-    if preview_enabled is None:  # :1241-1249
-        env = os.getenv("DSP_PREVIEW_MODE", "").strip().lower()
-        preview_enabled = True if env in ("1", "true", "yes", "on") else PREVIEW_ENABLED_DEFAULT
-    audio = np.asarray(audio)
-    if preview_enabled:  # :1303-1310
-        max_samples = int(sr * PREVIEW_MAX_SECONDS)
-        if audio.shape[0] > max_samples:
-            audio = audio[:max_samples]
+    audio = preview_truncate(np.asarray(audio), sr, preview_enabled, pipeline_config)
     x = ensure_mono_float32(audio)  # :1312
     if x.ndim != 1:
         raise ValueError("stft_mono expects mono (1D) audio")  # dsp/stft_utils.py:47

@@ -301,7 +301,7 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
             output_trim_db: float, low_trim_db: float, sub_cut_hz: float, air_cut_hz: float,
             spectral_fx_mode: Optional[str] = None, spectral_fx_strength: float = 0.0,
             spectral_fx_params: Optional[Dict[str, Any]] = None, precision: str = "auto",
-            spectral_freeze: bool = False, formant_shift: float = 0.0) -> Resolved:
+            spectral_freeze: bool = False, formant_shift: float = 0.0, no_spectral: bool = False) -> Resolved:
     """Turn the reference's keyword arguments into qd_params / qd_tables.  Raises the reference's
     exceptions (SURVEY.md section 8(b) "Errors") before anything is launched."""
     if n_fft not in SUPPORTED_N_FFT:
@@ -312,6 +312,8 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
     p.passthrough = int(bool(passthrough_test))
     p.pre_quant = int(bool(pre_quant and snap_strength > 0.0))    # dsp/pipeline.py:635 (unclipped gate)
     p.post_quant = int(bool(post_quant and snap_strength > 0.0))  # :728
+    if no_spectral and not passthrough_test:   # autotune_v1 with its pitch stage gated off: no STFT at all (:537-601)
+        p.no_spectral, p.pre_quant, p.post_quant = 1, 0, 0
     p.bin_smoothing = int(bool(bin_smoothing))
     # distortion (dsp/pipeline.py:705-710, dsp/distortion.py:93-114)
     mode = distortion_mode or "wavefold"

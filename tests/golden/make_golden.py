@@ -209,7 +209,108 @@ def gen_frontend():
     np.savez_compressed(os.path.join(HERE, "frontend.npz"), **out)
 
 
+def _run_case(x, sr, n_fft, rng_seed, kw, mode="spectral_bins"):
+    ref_pipeline.N_FFT_DEFAULT = n_fft
+    try:
+        if rng_seed is not None:
+            np.random.seed(rng_seed)
+        return quiet(ref_pipeline.process_audio, x, sr, quantize_mode=mode, **kw)
+    finally:
+        ref_pipeline.N_FFT_DEFAULT = 2048
+
+
+def _scramble_indices(n_bins: int, window: int, mode: str, seed: int, frames: int = 3) -> np.ndarray:
+    """Source-bin indices of `frames` consecutive reference bin_scramble calls (dsp/spectral_fx.py:326-390),
+    recovered from its OUTPUT on mags = 1..n_bins: out = mags[idx] * sum(mags) / (sum(mags[idx]) + 1e-12), so the
+    smallest gap between distinct output values is the scale and out / scale - 1 is idx.  The recovered table is
+    only accepted if it reproduces the reference's output bit for bit."""
+    a = np.arange(1, n_bins + 1, dtype=np.float64)
+    np.random.seed(seed)
+    rows = []
+    for _ in range(frames):
+        out, _ph = ref_fx.bin_scramble(a, np.zeros(n_bins), window=window, mode=mode)
+        u = np.unique(out)
+        scale = float(np.min(np.diff(u)))
+        idx = np.rint(out / scale).astype(np.int64) - 1
+        assert idx.min() >= 0 and idx.max() < n_bins
+        again = a[idx] * (np.sum(a) / (np.sum(a[idx]) + 1e-12))
+        assert np.array_equal(again, out), "index recovery failed"
+        rows.append(idx)
+    return np.array(rows)
+
+
+def gen_round2():
+    """Round-2 fixtures: FX parameter overrides and FX at other n_fft (CASES_R2), autotune_v1 kept inside a
+    multiband render, UI dicts that stay in autotune_v1, and integer scramble-index tables."""
+    out = {}
+    for name, (kind, seed, n, sr, n_fft, rng_seed, kw) in qd_cases.CASES_R2.items():
+        x = qd_cases.make_signal(kind, seed, n, sr)
+        y, taps = _run_case(x, sr, n_fft, rng_seed, kw)
+        out[f"{name}/x"], out[f"{name}/y"] = x, y
+        out[f"{name}/pre_quant"] = taps["pre_quant"].astype(np.float32)
+        out[f"{name}/post_dist"] = taps["post_dist"].astype(np.float32)
+        print(f"r2 {name}: n={n} n_fft={n_fft} peak={np.max(np.abs(y)):.4f}")
+    for name, (kind, seed, n, sr, kw) in qd_cases.AT_MB_CASES.items():
+        x = qd_cases.make_signal(kind, seed, n, sr)
+        y, taps = quiet(ref_pipeline.process_audio, x, sr, **kw)     # quantize_mode left at the reference default
+        out[f"{name}/x"], out[f"{name}/y"] = x, y
+        out[f"{name}/pre_quant"] = taps["pre_quant"].astype(np.float32)
+        out[f"{name}/post_dist"] = taps["post_dist"].astype(np.float32)
+        print(f"r2 {name}: peak={np.max(np.abs(y)):.4f}")
+    for name, (kind, seed, n, sr, rng_seed, cfg, kw) in qd_cases.UI_AT_CASES.items():
+        x = qd_cases.make_signal(kind, seed, n, sr)
+        y, taps = quiet(ref_pipeline.process_audio, x, sr, config=cfg, **kw)   # default mode unless the dict says otherwise
+        out[f"{name}/x"], out[f"{name}/y"] = x, y
+        print(f"r2 {name}: peak={np.max(np.abs(y)):.4f} moved={np.max(np.abs(y - x)):.4f}")
+    # integer gate of the north-star: "scramble permutations must be bit-exact"
+    for n_bins in (1025, 257):
+        for tag, (window, mode) in {"pick_w9": (9, "random_pick"), "pick_w3": (3, "random_pick"),
+                                    "pick_w15": (15, "random_pick"), "swap": (5, "swap")}.items():
+            out[f"scr/{n_bins}/{tag}"] = _scramble_indices(n_bins, window, mode, seed=4321).astype(np.int16)
+    # the draw of a randomized phase_dispersal frame, recovered the same way: phase_out - phase = jitter * rand_amt
+    np.random.seed(4321)
+    jit = []
+    for _ in range(3):
+        m, ph = ref_fx.phase_dispersal(np.ones(1025), np.zeros(1025), thresh=0.0, amount=0.0, randomized=True, rand_amt=1.0)
+        jit.append(ph)
+    out["scr/1025/jitter"] = np.array(jit)
+    np.savez_compressed(os.path.join(HERE, "round2.npz"), **out)
+    print("round2:", len(out), os.path.getsize(os.path.join(HERE, "round2.npz")) // 1024, "KiB")
+
+
+def gen_refwav():
+    """The reference's own audio files (BASELINE configs[0] = examples/example_bass.wav through scripts/render_cli.py:32,
+    plus tests/data/*.wav): input samples, the literal default render (quantize_mode="autotune_v1"), the STFT-path
+    render (quantize_mode="spectral_bins"), and the reference's committed renders tests/data/processed/
+    *_multiband(.|_bitcrush).wav as a secondary known-answer test."""
+    from scipy.io import wavfile
+    out = {}
+    for name, rel in qd_cases.REF_WAVS.items():
+        sr, d = wavfile.read(os.path.join("/root/reference", rel))
+        assert d.dtype == np.int16 and d.ndim == 1
+        x = d.astype(np.float32) / 32768.0          # io/audio_io.py:10-17 (libsndfile PCM16 -> float)
+        out[f"{name}/x16"], out[f"{name}/sr"] = d, np.int64(sr)
+        y_def, _ = quiet(ref_pipeline.process_audio, x, sr)                                   # scripts/render_cli.py:32
+        y_sb, _ = quiet(ref_pipeline.process_audio, x, sr, quantize_mode="spectral_bins")
+        out[f"{name}/y_default"], out[f"{name}/y_spectral_bins"] = y_def, y_sb
+        print(f"refwav {name}: sr={sr} n={len(d)} default peak {np.max(np.abs(y_def)):.4f}, spectral_bins peak {np.max(np.abs(y_sb)):.4f}")
+        for suffix in ("multiband", "multiband_bitcrush"):
+            pth = os.path.join("/root/reference/tests/data/processed", f"{name}_{suffix}.wav")
+            if os.path.exists(pth):
+                sr2, k = wavfile.read(pth)
+                assert sr2 == sr and k.dtype == np.int16
+                out[f"{name}/kat_{suffix}"] = k
+    np.savez_compressed(os.path.join(HERE, "refwav.npz"), **out)
+    print("refwav:", len(out), os.path.getsize(os.path.join(HERE, "refwav.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["round2"]:
+        gen_round2()
+        sys.exit(0)
+    if sys.argv[1:] == ["refwav"]:
+        gen_refwav()
+        sys.exit(0)
     if sys.argv[1:] == ["analysis"]:   # only that file
         gen_analysis()
         sys.exit(0)
@@ -222,5 +323,7 @@ if __name__ == "__main__":
     gen_tables()
     gen_stages()
     gen_pipeline()
+    gen_round2()
+    gen_refwav()
     for f in ("tables.npz", "stages.npz", "pipeline.npz", "frontend.npz", "analysis.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -79,6 +79,88 @@ CASES = {
     "nfft8192": ("bass", 33, 20000, 48000, 8192, None, {}),
 }
 
+# Round-2 additions (fixtures in tests/golden/round2.npz; same tuple layout plus an optional `precision`):
+# spectral_fx_params overrides, uniform bitcrush, spectral FX away from n_fft 2048, the float64 FX kernels,
+# n_fft 8192 with every option, and autotune_v1 kept on the high band of a multiband render (snap_strength = 0).
+_MB = dict(GROWL, use_multiband=True)
+CASES_R2 = {
+    "mb_bitcrush_uniform": ("loud", 100, N, 48000, 2048, 1234,
+                            dict(_MB, spectral_fx_mode="bitcrush", spectral_fx_strength=0.5,
+                                 spectral_fx_params={"method": "uniform"})),
+    "mb_bitcrush_uniform_step_thr": ("bass", 101, N, 48000, 2048, 1234,
+                                     dict(_MB, spectral_fx_mode="bitcrush", spectral_fx_strength=0.3,
+                                          spectral_fx_params={"method": "uniform", "step": 0.004, "threshold": 0.003})),
+    "mb_bitcrush_log_stepdb_thr": ("loud", 102, N, 48000, 2048, 1234,
+                                   dict(_MB, spectral_fx_mode="bitcrush", spectral_fx_strength=0.7,
+                                        spectral_fx_params={"step_db": 3.0, "threshold": 0.02})),
+    "mb_bitcrush_unknown_method": ("bass", 103, N, 48000, 2048, 1234,
+                                   dict(_MB, spectral_fx_mode="bitcrush", spectral_fx_strength=0.6,
+                                        spectral_fx_params={"method": "cubic"})),
+    "mb_dispersal_thresh_det": ("loud", 104, N, 48000, 2048, 1234,
+                                dict(_MB, spectral_fx_mode="phase_dispersal", spectral_fx_strength=0.6,
+                                     spectral_fx_params={"thresh": 0.05, "randomized": False})),
+    "mb_dispersal_forced_random": ("bass", 105, N, 48000, 2048, 1234,
+                                   dict(_MB, spectral_fx_mode="phase_dispersal", spectral_fx_strength=0.2,
+                                        spectral_fx_params={"randomized": True, "rand_amt": 0.4, "amount": 1.1,
+                                                            "thresh": 0.0})),
+    "mb_scramble_window_swap": ("loud", 106, N, 48000, 2048, 1234,
+                                dict(_MB, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.7,
+                                     spectral_fx_params={"window": 9, "mode": "swap"})),
+    "mb_scramble_window_pick": ("bass", 107, N, 48000, 2048, 1234,
+                                dict(_MB, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.2,
+                                     spectral_fx_params={"window": 4, "mode": "random_pick"})),
+    "mb_scramble_unknown_mode": ("bass", 108, N, 48000, 2048, 1234,
+                                 dict(_MB, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.5,
+                                      spectral_fx_params={"mode": "shuffle"})),
+    "nfft512_bitcrush": ("loud", 110, 6000, 48000, 512, 1234,
+                         dict(_MB, spectral_fx_mode="bitcrush", spectral_fx_strength=0.5)),
+    "nfft512_scramble_pick": ("bass", 111, 6000, 48000, 512, 1234,
+                              dict(_MB, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.55)),
+    "nfft1024_dispersal": ("loud", 112, 6000, 48000, 1024, 1234,
+                           dict(_MB, spectral_fx_mode="phase_dispersal", spectral_fx_strength=0.6)),
+    "nfft4096_bitcrush": ("loud", 113, N, 48000, 4096, 1234,
+                          dict(_MB, spectral_fx_mode="bitcrush", spectral_fx_strength=0.5)),
+    "nfft4096_dispersal": ("bass", 114, N, 48000, 4096, 1234,
+                           dict(_MB, spectral_fx_mode="phase_dispersal", spectral_fx_strength=0.6)),
+    "nfft4096_scramble_pick": ("loud", 115, N, 48000, 4096, 1234,
+                               dict(_MB, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.55)),
+    "nfft4096_scramble_swap": ("bass", 116, N, 48000, 4096, 1234,
+                               dict(_MB, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.3)),
+    "nfft4096_formant": ("bass", 117, N, 48000, 4096, None, {"formant_shift": 4.0}),
+    "nfft8192_bitcrush": ("loud", 120, 20000, 48000, 8192, 1234,
+                          dict(_MB, spectral_fx_mode="bitcrush", spectral_fx_strength=0.5)),
+    "nfft8192_dispersal": ("bass", 121, 20000, 48000, 8192, 1234,
+                           dict(_MB, spectral_fx_mode="phase_dispersal", spectral_fx_strength=0.6)),
+    "nfft8192_scramble_pick": ("loud", 122, 20000, 48000, 8192, 1234,
+                               dict(_MB, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.55)),
+    "nfft8192_scramble_swap": ("bass", 123, 20000, 48000, 8192, 1234,
+                               dict(_MB, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.3)),
+    "nfft8192_freeze": ("bass", 124, 20000, 48000, 8192, None, {"spectral_freeze": True}),
+    "nfft8192_formant": ("bass", 125, 20000, 48000, 8192, None, {"formant_shift": 3.0}),
+    "nfft8192_multiband": ("loud", 126, 20000, 48000, 8192, None, {"use_multiband": True}),
+}
+# cases of CASES / CASES_R2 that are ALSO rendered with precision="float64" against the same fixture
+F64_CASES = ("mb_growl_bitcrush", "mb_growl_dispersal", "mb_growl_scramble_pick", "nfft4096_bitcrush",
+             "nfft4096_dispersal", "nfft4096_scramble_pick", "nfft4096_scramble_swap", "nfft4096_formant",
+             "nfft512_scramble_pick")
+
+# quantize_mode left at the reference default ("autotune_v1") with snap_strength = 0 inside a multiband render:
+# the only combination that keeps both (dsp/pipeline.py:1326-1327, :1076, :537-601)
+AT_MB_CASES = {
+    "at_mb_snap0": ("loud", 130, N, 48000, {"snap_strength": 0.0, "use_multiband": True, "lowband_drive": 1.7}),
+    "at_mb_snap0_tube": ("bass", 131, 11025, 44100, dict(CLANG, snap_strength=0.0, use_multiband=True, crossover_hz=180.0,
+                                                          dry_wet=0.6, output_trim_db=-1.5, delta_listen=True)),
+}
+
+# the reference's own audio files (BASELINE configs[0]): name -> path below /root/reference
+REF_WAVS = {
+    "example_bass": "examples/example_bass.wav",
+    "sub_sweep": "tests/data/sub_sweep.wav",
+    "wobble_bass": "tests/data/wobble_bass.wav",
+    "kick_sub_combo": "tests/data/kick_sub_combo.wav",
+    "midrange_growl_like": "tests/data/midrange_growl_like.wav",
+}
+
 
 def make_signal(kind: str, seed: int, n: int, sr: int):
     from quantumdistortion_b200 import synth as signals
@@ -127,4 +209,16 @@ UI_CASES = {
     "ui_bitcrush_delta": ("loud", 52, N, 48000, 79,
                           {"high_band": {"bin_scrambling": 0.0, "phase_dispersal": 0.0, "mag_decimation": 0.6},
                            "delta_listen": True}, {}),
+}
+# UI dicts that keep quantize_mode="autotune_v1" (no high_band / quantum_fx section, so no FX switches the mode):
+# the quantization.* sub-layer keys must reach the autotune render (dsp/pipeline.py:964-977)
+UI_AT_CASES = {
+    "ui_at_sub_keys": ("tone", 53, AT_N, 48000, None,
+                       {"quantization": {"mode": "autotune_v1", "key": "G", "scale": "major", "sub_enabled": True,
+                                         "sub_source": "scale_degree", "sub_scale_degree": 2, "sub_octave": 1,
+                                         "sub_level": 0.6, "sub_cut_hz": 95.0, "air_cut_hz": 7000.0, "air_mix": 0.4},
+                        "crossover_freq": 200.0}, {}),
+    "ui_at_manual_sub": ("tone", 54, AT_N, 48000, None,
+                         {"quantization": {"sub_source": "manual", "sub_note": "A", "sub_level": 0.8},
+                          "low_band": {"saturation_amount": 0.2}}, {"snap_strength": 0.7}),
 }

@@ -17,6 +17,7 @@ from quantumdistortion_b200 import synth
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MAX_ABS = 1e-4
 NULL_DB = -80.0
+SB = {"quantize_mode": "spectral_bins"}   # the STFT path; the default mode is the reference's "autotune_v1" (config.py:44)
 
 
 @pytest.fixture(scope="module")
@@ -52,7 +53,7 @@ def test_pipeline_vs_reference_fixtures(qd, pipe, name):
     x = pipe[f"{name}/x"]
     if rng_seed is not None:
         np.random.seed(rng_seed)  # the random spectral FX replay the global np.random state like the reference
-    y, taps = qd.process_audio(x, sr, n_fft=n_fft, **kw)
+    y, taps = qd.process_audio(x, sr, n_fft=n_fft, **SB, **kw)
     # precision="auto": float32 kernels, except sb_wide_mask (fan-in > 64) and nfft8192, which run in float64
     _check(y, pipe[f"{name}/y"], f"{name}/y")
     _check(taps["pre_quant"], pipe[f"{name}/pre_quant"], f"{name}/pre_quant")
@@ -65,7 +66,7 @@ def test_batch_vs_oracle_default_config(qd):
     """Config #2 shape (single-band defaults) on a small seeded batch, every clip against the oracle."""
     n, sr, b = 48000, 48000, 6
     x = np.stack([synth.bass_clip(i, n, sr) if i % 2 == 0 else synth.noise_clip(i, n) for i in range(b)])
-    y, taps = qd.process_batch(x, sr, return_taps=True)
+    y, taps = qd.process_batch(x, sr, return_taps=True, **SB)
     worst = 0.0
     for i in range(b):
         ref, rt = orc.process_audio(x[i], sr)
@@ -73,7 +74,7 @@ def test_batch_vs_oracle_default_config(qd):
         _check(taps["pre_quant"][i], rt["pre_quant"], f"clip {i} pre_quant")
         _check(taps["post_dist"][i], rt["post_dist"], f"clip {i} post_dist")
     print(f"worst max-abs error vs oracle: {worst:.3e}")
-    y2, _ = qd.process_batch(x, sr)  # host pipeline path (qd_render_host) must agree bit for bit
+    y2, _ = qd.process_batch(x, sr, **SB)  # host pipeline path (qd_render_host) must agree bit for bit
     assert np.array_equal(y, y2)
 
 
@@ -82,7 +83,7 @@ def test_multiband_batch_vs_oracle(qd):
     n, sr = 30000, 48000
     x = np.stack([synth.loud_clip(40 + i, n, sr) for i in range(3)])
     kw = dict(use_multiband=True, crossover_hz=300.0, lowband_drive=1.5, dry_wet=0.9)
-    y, taps = qd.process_batch(x, sr, return_taps=True, **kw)
+    y, taps = qd.process_batch(x, sr, return_taps=True, **SB, **kw)
     for i in range(3):
         ref, rt = orc.process_audio(x[i], sr, **kw)
         _check(y[i], ref, f"mb clip {i}")
@@ -96,9 +97,9 @@ def test_tiling_and_batch_size_do_not_change_bits(qd):
     import torch
     n, sr = 100000, 48000
     clip = synth.bass_clip(77, n, sr)
-    y1, _ = qd.process_batch(torch.from_numpy(clip[None, :]).cuda(), sr)
+    y1, _ = qd.process_batch(torch.from_numpy(clip[None, :]).cuda(), sr, **SB)
     big = torch.from_numpy(np.repeat(clip[None, :], 700, axis=0)).cuda()
-    y700, _ = qd.process_batch(big, sr)
+    y700, _ = qd.process_batch(big, sr, **SB)
     assert torch.equal(y700[0], y1[0]) and torch.equal(y700[699], y1[0]) and torch.equal(y700[350], y1[0])
 
 
@@ -108,17 +109,17 @@ def test_full_size_properties(qd):
     import torch
     n, sr, b = 480000, 48000, 24
     x = synth.bass_batch_torch(b, n, sr, "cuda", seed=5)
-    y, _ = qd.process_batch(x, sr, passthrough_test=True)
+    y, _ = qd.process_batch(x, sr, passthrough_test=True, **SB)
     d = (y - x).double()
     null = 20.0 * torch.log10(torch.sqrt((d * d).mean()).clamp_min(1e-10)).item()
     assert null < -110.0, null  # reference test bar is -80 dB (tests/test_passthrough_null.py:56-148)
     loud = (x * 3.0).clamp(-1.5, 1.5)
     kw = dict(distortion_params={"fold_amount": 3.0})
-    y, _ = qd.process_batch(loud, sr, **kw)
+    y, _ = qd.process_batch(loud, sr, **SB, **kw)
     ceiling = 10.0 ** (-1.0 / 20.0)
     assert float(y.abs().max()) <= ceiling * 1.01  # reference tests/test_limiter.py:7-58 bound
     assert torch.isfinite(y).all()
-    y_again, _ = qd.process_batch(loud, sr, **kw)
+    y_again, _ = qd.process_batch(loud, sr, **SB, **kw)
     assert torch.equal(y, y_again)
     # one clip of the batch against the oracle at full length
     ref, _ = orc.process_audio(loud[3].cpu().numpy(), sr, **kw)
@@ -151,22 +152,22 @@ def test_stage_limiter_and_crossover_and_distortion(qd):
 
 @pytest.mark.gpu
 def test_edge_cases(qd):
-    y, taps = qd.process_audio(np.zeros(0, dtype=np.float32), 48000)
+    y, taps = qd.process_audio(np.zeros(0, dtype=np.float32), 48000, **SB)
     assert y.shape == (0,) and set(taps) == {"input", "pre_quant", "post_dist", "output"}
     # n = 1 is an impulse: every bin has |X| = 1 with alternating sign, the per-target phasor sums cancel to
     # rounding noise and the reference's own phase there is arbitrary -- only shape/finiteness is checked.
-    y, _ = qd.process_audio(np.array([0.4], dtype=np.float32), 48000)
+    y, _ = qd.process_audio(np.array([0.4], dtype=np.float32), 48000, **SB)
     assert y.shape == (1,) and np.isfinite(y).all()
     for n in (5, 511, 512, 513, 2047):
         x = synth.noise_clip(n, n)
-        y, _ = qd.process_audio(x, 48000)
+        y, _ = qd.process_audio(x, 48000, **SB)
         ref, _ = orc.process_audio(x, 48000)
         _check(y, ref, f"n={n}")
     silent = np.zeros(4096, dtype=np.float32)
-    y, _ = qd.process_audio(silent, 48000)
+    y, _ = qd.process_audio(silent, 48000, **SB)
     assert np.array_equal(y, silent)
     stereo = np.stack([synth.bass_clip(1, 3000), synth.noise_clip(2, 3000)], axis=1)
-    y, _ = qd.process_audio(stereo, 48000)
+    y, _ = qd.process_audio(stereo, 48000, **SB)
     ref, _ = orc.process_audio(stereo, 48000)
     _check(y, ref, "stereo->mono")
 
@@ -198,17 +199,17 @@ def test_float64_kernels_vs_reference_fixtures(qd, pipe, name):
     kind, seed, n, sr, n_fft, rng_seed, kw = qd_cases.CASES[name]
     if rng_seed is not None:
         np.random.seed(rng_seed)
-    y, taps = qd.process_audio(pipe[f"{name}/x"], sr, n_fft=n_fft, precision="float64", **kw)
+    y, taps = qd.process_audio(pipe[f"{name}/x"], sr, n_fft=n_fft, precision="float64", **SB, **kw)
     _check(y, pipe[f"{name}/y"], f"{name}/y f64", 2e-6)
     _check(taps["pre_quant"], pipe[f"{name}/pre_quant"], f"{name}/pre_quant f64", 2e-6)
 
 
 def test_auto_precision_rule():
     from quantumdistortion_b200.pipeline import _resolve_kwargs
-    assert _resolve_kwargs(1000, 48000, 2048, {})[0].params.precision == 0
-    assert _resolve_kwargs(1000, 48000, 8192, {})[0].params.precision == 1
-    assert _resolve_kwargs(1000, 48000, 2048, {"sub_cut_hz": 0.0, "air_cut_hz": 0.0})[0].params.precision == 1
-    assert _resolve_kwargs(1000, 48000, 2048, {"precision": "float64"})[0].params.precision == 1
+    assert _resolve_kwargs(1000, 48000, 2048, dict(SB))[0].params.precision == 0
+    assert _resolve_kwargs(1000, 48000, 8192, dict(SB))[0].params.precision == 1
+    assert _resolve_kwargs(1000, 48000, 2048, dict(SB, sub_cut_hz=0.0, air_cut_hz=0.0))[0].params.precision == 1
+    assert _resolve_kwargs(1000, 48000, 2048, dict(SB, precision="float64"))[0].params.precision == 1
 
 
 @pytest.mark.gpu
@@ -218,7 +219,7 @@ def test_ui_config_dict_vs_reference_fixtures(qd, name):
     g = np.load(os.path.join(G, "frontend.npz"))
     kind, seed, n, sr, rng_seed, cfg, kw = qd_cases.UI_CASES[name]
     np.random.seed(rng_seed)
-    y, _ = qd.process_audio(g[f"{name}/x"], sr, config=cfg, **kw)
+    y, _ = qd.process_audio(g[f"{name}/x"], sr, config=cfg, **SB, **kw)
     _check(y, g[f"{name}/y"], name)
 
 
@@ -233,8 +234,8 @@ def test_file_harness_single_and_batched(qd, tmp_path):
         save_audio(p, synth.bass_clip(80 + i, 22050 if i < 2 else 11025, sr), sr)
         ins.append(p)
         outs.append(tmp_path / "out" / f"o{i}.wav")
-    qd.process_file_to_file(ins[0], outs[0], preset="Perc To Tonal Clang", extra_params={"dry_wet": 0.8})
-    assert qd.process_files(list(zip(ins, outs))[1:], preset="Perc To Tonal Clang", extra_params={"dry_wet": 0.8}) == 2
+    qd.process_file_to_file(ins[0], outs[0], preset="Perc To Tonal Clang", extra_params=dict(SB, dry_wet=0.8))
+    assert qd.process_files(list(zip(ins, outs))[1:], preset="Perc To Tonal Clang", extra_params=dict(SB, dry_wet=0.8)) == 2
     from quantumdistortion_b200 import PipelineConfig
     for i in range(3):
         x, _ = load_audio(ins[i])
@@ -297,7 +298,7 @@ def test_cents_metric_batch_of_renders(qd):
     from quantumdistortion_b200 import analyses
     n, sr = 24000, 48000
     x = np.stack([synth.bass_clip(70 + i, n, sr) for i in range(4)])
-    y, _ = qd.process_batch(x, sr, limiter_on=False)
+    y, _ = qd.process_batch(x, sr, limiter_on=False, **SB)
     for sig in (x, y):
         avgs, per = analyses.avg_cents_offset_batch(sig, sr, "D", "minor")
         for i in range(len(sig)):
@@ -318,7 +319,7 @@ def test_formant_shift_float64_kernels(qd, pipe, name):
     x = pipe[f"{name}/x"]
     if rng_seed is not None:
         np.random.seed(rng_seed)
-    y, _ = qd.process_audio(x, sr, n_fft=n_fft, precision="float64", **kw)
+    y, _ = qd.process_audio(x, sr, n_fft=n_fft, precision="float64", **SB, **kw)
     _check(y, pipe[f"{name}/y"], f"{name}/y float64", 5e-6)
 
 
@@ -342,7 +343,7 @@ def test_random_configs_vs_oracle(qd):
                   use_multiband=bool(rng.integers(2)), crossover_hz=float(rng.choice([200.0, 300.0, 500.0])),
                   lowband_drive=float(rng.uniform(0.5, 2.0)), harmonic_lock_hz=float(rng.choice([0.0, 0.0, 55.0])))
         x = qd_cases.make_signal(["bass", "loud", "noise"][i % 3], 300 + i, n, sr)
-        y, taps = qd.process_audio(x, sr, **kw)
+        y, taps = qd.process_audio(x, sr, **SB, **kw)
         ref, rt = orc.process_audio(x, sr, **kw)
         worst = max(worst, _check(y, ref, f"case {i} {kw}"))
         _check(taps["pre_quant"], rt["pre_quant"], f"case {i} pre_quant")

@@ -74,13 +74,20 @@ def test_reference_error_behaviour_before_launch():
 
 
 def test_resolved_flags_follow_reference_gates():
-    r, _ = _resolve_kwargs(1000, 48000, 2048, {"snap_strength": 0.0})
-    assert r.params.pre_quant == 0 and r.params.post_quant == 0 and r.tables is None
-    r, _ = _resolve_kwargs(1000, 48000, 2048, {"dry_wet": 1.7, "output_trim_db": -6.0, "snap_strength": 2.0})
+    SB = {"quantize_mode": "spectral_bins"}
+    r, _ = _resolve_kwargs(1000, 48000, 2048, dict(SB, snap_strength=0.0))
+    assert r.params.pre_quant == 0 and r.params.post_quant == 0 and r.tables is None and r.params.no_spectral == 0
+    r, _ = _resolve_kwargs(1000, 48000, 2048, dict(SB, dry_wet=1.7, output_trim_db=-6.0, snap_strength=2.0))
     assert r.params.wet == 1.0 and r.params.dry == 0.0 and r.params.apply_trim == 1
     assert r.tables.snap == 1.0 and r.params.pre_quant == 1
     assert abs(r.params.trim_gain - np.float32(10 ** (-6 / 20))) == 0.0
-    r, _ = _resolve_kwargs(1000, 44100, 2048, {"pipeline_config": PipelineConfig.from_preset("Subtle Tube Glue")})
+    pc = PipelineConfig.from_preset("Subtle Tube Glue")
+    assert pc.quantize_mode == "autotune_v1" and PipelineConfig().quantize_mode == "autotune_v1"   # config.py:77, :140
+    from quantumdistortion_b200 import autotune as host_at
+    assert isinstance(_resolve_kwargs(1000, 44100, 2048, {"pipeline_config": pc})[0], host_at.QdAutotuneParams)
+    assert isinstance(_resolve_kwargs(1000, 44100, 2048, {})[0], host_at.QdAutotuneParams)          # bare call: config.py:44
+    pc.quantize_mode = "spectral_bins"
+    r, _ = _resolve_kwargs(1000, 44100, 2048, {"pipeline_config": pc})
     assert r.params.post_quant == 0 and r.params.distortion_mode == 1 and abs(r.params.wet - np.float32(0.7)) == 0
     assert r.params.lookahead == 220
     with pytest.raises(NotImplementedError):
@@ -92,7 +99,7 @@ def test_resolved_flags_follow_reference_gates():
     # formant shift (dsp/pipeline.py:306-310): ratio 2^(st/12), float32 kernels, flips autotune_v1 to the STFT path
     r, _ = _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1", "formant_shift": 12.0})
     assert r.params.formant_ratio == 2.0 and r.params.formant_order == 30 and r.params.precision == 0
-    r, _ = _resolve_kwargs(1000, 48000, 2048, {"formant_shift": 3.0, "snap_strength": 0.0})
+    r, _ = _resolve_kwargs(1000, 48000, 2048, {"formant_shift": 3.0, "snap_strength": 0.0})   # formant flips the mode
     assert r.params.formant_ratio == 0.0   # the spectral stage does not run at all (:635, :728)
     with pytest.raises(NotImplementedError):
         _resolve_kwargs(1000, 48000, 8192, {"formant_shift": 3.0})
@@ -118,8 +125,9 @@ def test_autotune_params_follow_reference_rules():
     assert p44.filt_on[0] == 0 and p44.filt_on[1] == 1 and p44.max_tau == int(44100 / 71.5) and p44.lookahead == 220
     with pytest.raises(ValueError):     # scipy's sosfiltfilt: input shorter than the padding
         _resolve_kwargs(12, 48000, 2048, {"quantize_mode": "autotune_v1"})
-    with pytest.raises(NotImplementedError):
-        _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1", "snap_strength": 0.0, "use_multiband": True})
+    # the one combination that keeps autotune_v1 inside a multiband render (:1326-1327): pitch stage gated off, no STFT
+    r, _ = _resolve_kwargs(1000, 48000, 2048, {"snap_strength": 0.0, "use_multiband": True})
+    assert r.params.no_spectral == 1 and r.params.multiband == 1 and r.params.pre_quant == 0 and r.tables is None
     r, _ = _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1", "passthrough_test": True})
     assert r.params.passthrough == 1     # the passthrough branch comes first (:477)
     src = ('#include <stdio.h>\n#include <stddef.h>\n#include "qd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", '
