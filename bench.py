@@ -160,6 +160,84 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples_under_load": len(sm), "reasons": sorted(reasons)}
 
 
+def copy_ceiling(xh, yh, chunk: int, dev, world: int, reps: int = 2):
+    """Kernel-free copy benchmark with the e2e leg's traffic pattern: the pinned `xh` [clips, n] H2D and a same-sized
+    result D2H into the pinned `yh`, in chunks of `chunk` clips on two streams at once.  Seconds per pass, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    clips, n, dt = int(xh.shape[0]), int(xh.shape[1]), xh.dtype
+    dx = [torch.empty((chunk, n), dtype=dt, device=dev) for _ in range(2)]
+    dy = [torch.zeros((chunk, n), dtype=dt, device=dev) for _ in range(2)]
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def one_pass():
+        for i, b0 in enumerate(range(0, clips, chunk)):
+            nb = min(chunk, clips - b0)
+            with torch.cuda.stream(s_in):
+                dx[i & 1][:nb].copy_(xh[b0:b0 + nb], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                yh[b0:b0 + nb].copy_(dy[i & 1][:nb], non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    one_pass()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_pass()
+    t = (time.perf_counter() - t0) / reps
+    if world > 1:
+        tt = torch.tensor([t], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+    return t
+
+
+GROWL = dict(key="F", scale="minor", snap_strength=0.9, smear=0.3, distortion_mode="wavefold",
+             distortion_params={"fold_amount": 5.0, "bias": 0.1, "drive": 1.0, "warmth": 0.5}, limiter_ceiling_db=-1.0)
+# BASELINE configs[2..4], device-resident, for the record inside the driver's own run (not the headline)
+OTHER_CONFIGS = [
+    ("configs[2] multiband LR4 @300 Hz", dict(use_multiband=True, crossover_hz=300.0), 2048, None),
+    ("configs[3] growl + multiband + bitcrush 0.5", dict(GROWL, use_multiband=True, spectral_fx_mode="bitcrush", spectral_fx_strength=0.5), 2048, 1234),
+    ("configs[3] growl + multiband + phase_dispersal 0.6", dict(GROWL, use_multiband=True, spectral_fx_mode="phase_dispersal", spectral_fx_strength=0.6), 2048, 1234),
+    ("configs[3] growl + multiband + bin_scramble 0.55", dict(GROWL, use_multiband=True, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.55), 2048, 1234),
+    ("configs[3] growl + multiband + bin_scramble 0.3 (swap)", dict(GROWL, use_multiband=True, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.3), 2048, 1234),
+    ("configs[4] n_fft 512", {}, 512, None),
+    ("configs[4] n_fft 1024", {}, 1024, None),
+    ("configs[4] n_fft 4096", {}, 4096, None),
+    ("configs[4] n_fft 8192 (precision=auto -> float64 kernels)", {}, 8192, None),
+]
+
+
+def other_configs(qd, x, clips: int):
+    """One device-resident number per BASELINE config outside the headline: `clips` clips x 10 s, 1 warm-up + 2 timed."""
+    import torch
+    out = []
+    xs = x[:clips]
+    for name, kw, n_fft, seed in OTHER_CONFIGS:
+        try:
+            r = qd.make_renderer(N_SAMPLES, SR, n_fft, seeds=seed, quantize_mode="spectral_bins", **kw)
+            r.set_fx_seeds(clips, seed)
+            nclips = clips if n_fft < 8192 else max(1, clips // 4)    # float64 parity path: a quarter of the clips
+            xi = xs[:nclips]
+            y, _ = r.render_device(xi)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                y, _ = r.render_device(xi)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            out.append({"config": name, "clips": nclips, "ms_per_render": round(ms, 3),
+                        "audio_s_per_s": round(nclips * CLIP_SECONDS / (ms / 1e3)), "peak": round(float(y.abs().max()), 4)})
+            del r, y
+        except Exception as exc:  # noqa: BLE001 -- the record says what failed instead of hiding the headline
+            out.append({"config": name, "error": f"{type(exc).__name__}: {exc}"})
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -256,6 +334,79 @@ def run_ours(args):
         raise SystemExit("host pipeline output differs from the device-resident render")
     e2e_value = audio_s / (ms_e2e / 1e3)
 
+    # ---- what the machine's host<->device links deliver with the same traffic and no kernels: `e2e.copy_ceiling`
+    t_copy = copy_ceiling(x_host, y_host, args.chunk_clips, dev, world)
+    copy_ceil = {"audio_s_per_s": audio_s / t_copy, "gbs_each_way": 4.0 * B * N_SAMPLES * world / t_copy / 1e9,
+                 "ms_per_step": t_copy * 1e3,
+                 "how": "same pinned buffers, chunking and two copy streams as the e2e leg, H2D and D2H at once, no kernels; max over ranks"}
+
+    # ---- the same render with 16-bit PCM on the PCIe link (what a WAV-to-WAV batch moves): `e2e_pcm16`, not the headline
+    # (int16 views of the float buffers' pinned storage: no further pinned allocation)
+    x16 = x_host.view(torch.int16).view(-1)[:B * N_SAMPLES].view(B, N_SAMPLES)
+    y16 = y_host.view(torch.int16).view(-1)[:B * N_SAMPLES].view(B, N_SAMPLES)
+    x16.copy_((x * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+    torch.cuda.synchronize()
+    for _ in range(2):
+        qd.process_batch(x16, SR, out=y16, chunk_clips=args.chunk_clips, **RENDER_KW)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        qd.process_batch(x16, SR, out=y16, chunk_clips=args.chunk_clips, **RENDER_KW)
+    torch.cuda.synchronize()
+    ms_pcm = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    barrier()
+    t_copy16 = copy_ceiling(x16, y16, args.chunk_clips, dev, world)
+    e2e_pcm16 = {"value": audio_s / (ms_pcm / 1e3), "unit": UNIT, "ms_per_step": ms_pcm,
+                 "h2d_bytes_per_step": 2 * B * N_SAMPLES * world, "d2h_bytes_per_step": 2 * B * N_SAMPLES * world,
+                 "copy_ceiling": {"audio_s_per_s": audio_s / t_copy16, "gbs_each_way": 2.0 * B * N_SAMPLES * world / t_copy16 / 1e9},
+                 "api": "process_batch(pinned int16 tensor, out=pinned int16 tensor): sample/32768 and lrint(y*32767) on the device"}
+    del x16, y16
+
+    # ---- a caller that holds a plain NumPy array (pageable memory): library-side pinned staging ring, one step
+    e2e_pageable = None
+    if world == 1 and not args.no_pageable:
+        Bp = min(B, 1024)
+        xp = x[:Bp].cpu().numpy()
+        qd.process_batch(xp[:256], SR, chunk_clips=args.chunk_clips, **RENDER_KW)
+        t0 = time.perf_counter()
+        yp, _ = qd.process_batch(xp, SR, chunk_clips=args.chunk_clips, **RENDER_KW)
+        tp = time.perf_counter() - t0
+        e2e_pageable = {"value": Bp * CLIP_SECONDS / tp, "unit": UNIT, "clips": Bp, "ms": tp * 1e3,
+                        "api": "process_batch(numpy float32 array) -> numpy array; result allocation and first touch included"}
+        if not np.array_equal(yp[0], y_dev_first.cpu().numpy()):
+            raise SystemExit("pageable host path differs from the device-resident render")
+        del xp, yp
+    del x_host, y_host
+
+    # ---- the limiter-engaged variant of the same batch (the headline workload never reaches the ceiling)
+    variants = {}
+    x_loud = (x * 6.0).clamp_(-1.5, 1.5)
+    for _ in range(2):
+        yl, _ = r.render_device(x_loud)
+    barrier()
+    r.read_timing()
+    ev0.record()
+    for _ in range(args.steps):
+        yl, _ = r.render_device(x_loud)
+    ev1.record()
+    barrier()
+    ms_loud = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    t_loud = r.read_timing()
+    ceiling = 10.0 ** (-1.0 / 20.0)
+    variants["loud"] = {"what": "the same batch as clamp(6 x, -1.5, 1.5): the wavefolded signal exceeds the -1 dB ceiling on every clip, so the limiter scan runs",
+                        "ms_per_step": ms_loud, "value": audio_s / (ms_loud / 1e3), "unit": UNIT,
+                        "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in t_loud.items() if v["launches"]},
+                        "output_peak": float(yl.abs().max()), "ceiling": ceiling,
+                        "clips_limited_frac": float((yl.abs().amax(dim=1) >= ceiling * 0.999).float().mean())}
+    if rank == 0 and args.check_clips > 0:
+        from oracle import qd_oracle as orc
+        ref, _ = orc.process_audio(x_loud[1].cpu().numpy(), SR, **RENDER_KW)
+        err = float(np.max(np.abs(yl[1].cpu().numpy().astype(np.float64) - ref)))
+        variants["loud"]["parity_max_abs_err"] = err
+        if err > 1e-4:
+            raise SystemExit(f"parity check of the loud variant failed: {err}")
+    del x_loud, yl
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -274,6 +425,30 @@ def run_ours(args):
                 "kernel_ms_per_step": step_share,
                 "note": "the pass is bound by instruction issue and shared-memory wavefronts (about 600 flop per sample), "
                         "not by HBM; the limiter launch skips clips that never exceed the ceiling (gain exactly 1); see DESIGN.md"}
+    # the roofs that actually bind the pass (report both): FP32 arithmetic and instruction issue
+    import ctypes as C
+    from quantumdistortion_b200 import _lib
+    tf = C.c_double(0.0)
+    _lib.check(_lib.load().qd_measure_fp32_peak(C.byref(tf), None))
+    frames = B * (1 + N_SAMPLES // 512)
+    FLOP_PER_FRAME = 152e3   # two 2048-point real FFTs (61 kflop each) + 30 kflop of bin math per frame and pass
+    fp32_achieved = FLOP_PER_FRAME * frames / (spec_ms / 1e3) / 1e12
+    roofline.update({"fp32_peak_tflops": tf.value, "fp32_achieved_tflops": fp32_achieved, "fp32_frac": fp32_achieved / tf.value if tf.value else None,
+                     "fp32_peak_source": "qd_measure_fp32_peak: fma.rn.f32x2 (FFMA2) chains, measured on this box in this run",
+                     "algorithmic_flop_per_launch": FLOP_PER_FRAME * frames})
+    ncu_issue = os.path.join(ROOT, "profiles", "spec_issue_per_frame.json")
+    if os.path.exists(ncu_issue):
+        try:
+            ij = json.load(open(ncu_issue))
+            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            cyc = spec_ms / 1e3 * sm_hz * ij.get("sms", 148) / frames
+            roofline.update({"cycles_per_frame_per_sm": cyc, "issue_bound_cycles_per_frame": ij["warp_instructions_per_frame"] / 4.0,
+                             "issue_frac": ij["warp_instructions_per_frame"] / 4.0 / cyc,
+                             "smem_wavefronts_per_frame": ij.get("smem_wavefronts_per_frame"),
+                             "smem_frac": (ij["smem_wavefronts_per_frame"] / cyc) if ij.get("smem_wavefronts_per_frame") else None,
+                             "issue_source": ij.get("source")})
+        except Exception:  # noqa: BLE001
+            pass
     ncu_traffic = os.path.join(ROOT, "profiles", "spec_traffic_bytes_per_launch.json")
     if os.path.exists(ncu_traffic):
         try:
@@ -282,6 +457,8 @@ def run_ours(args):
             roofline["traffic_source"] = tj.get("source")
         except Exception:  # noqa: BLE001
             pass
+
+    others = other_configs(qd, x, args.other_clips) if (world == 1 and args.other_clips > 0) else None
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
@@ -300,8 +477,9 @@ def run_ours(args):
                    "l2": "inputs (7.9 GB per GPU) are far larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 4 * B * N_SAMPLES * world,
                 "d2h_bytes_per_step": 4 * B * N_SAMPLES * world, "chunk_clips": args.chunk_clips,
-                "host_numa_cpus": numa_cpus,
+                "host_numa_cpus": numa_cpus, "copy_ceiling": copy_ceil, "frac_of_copy_ceiling": e2e_value / copy_ceil["audio_s_per_s"],
                 "api": "quantumdistortion_b200.process_batch(pinned host tensor, out=pinned host tensor)"},
+        "e2e_pcm16": e2e_pcm16, "e2e_pageable": e2e_pageable, "variants": variants, "other_configs": others,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
     }))
     if world > 1:
@@ -319,6 +497,8 @@ def main():
     ap.add_argument("--check-clips", type=int, default=2)
     ap.add_argument("--cpu-clips-per-core", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-memory (NumPy) e2e leg")
+    ap.add_argument("--other-clips", type=int, default=1024, help="clips for the device-resident numbers of the other BASELINE configs (0 = skip)")
     ap.add_argument("--workload", default="single_band", choices=["single_band", "multiband"],
                     help="single_band = BASELINE configs[1] (the bench line); multiband = configs[2], for the record")
     args = ap.parse_args()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 4
+#define QD_ABI_VERSION 5
 
 typedef enum qd_status {
     QD_OK = 0,
@@ -69,13 +69,13 @@ typedef struct qd_params {
     int32_t  bin_smoothing;      /* dsp/quantizer.py:523 */
 
     int32_t  distortion_mode;    /* qd_distortion_mode */
-    float    fold_amount;        /* dsp/distortion.py:37 */
-    float    bias;
     float    tube_gain;          /* a * max(drive,0), a = 1 + 4*clip(warmth,0,1)  (:75-83) */
     float    tube_norm;          /* 1 / tanh(a)                                  (:88) */
 
     int32_t  limiter_on;         /* dsp/pipeline.py:882 */
     int32_t  lookahead;          /* samples, dsp/limiter.py:53 (Python round, half-even) */
+    double   fold_amount;        /* dsp/distortion.py:37: the wavefold runs in float64 like the reference's */
+    double   bias;               /*   ((x + bias) * fold_amount, folds, clip) and rounds to float32 once    */
     double   ceiling_lin;        /* 10^(dB/20), dsp/limiter.py:52 */
     double   release_coeff;      /* exp(-1/release_samples), dsp/limiter.py:60 */
 
@@ -98,7 +98,7 @@ typedef struct qd_params {
     int32_t  apply_mono_blend;
 
     int32_t  fx_mode;            /* qd_fx_mode; 0 unless high band of a multiband render */
-    double   fx_a;               /* bitcrush: step_db | step; dispersal: amount */
+    double   fx_a;               /* bitcrush: step_db | step; dispersal: amount; scramble (random_pick): window / 2 */
     double   fx_b;               /* bitcrush: threshold factor (x frame max) or <0 = absolute in fx_c;
                                     dispersal: rand_amt */
     double   fx_c;               /* bitcrush: absolute threshold; dispersal: absolute thresh (<0: 0.01*max) */
@@ -109,8 +109,7 @@ typedef struct qd_params {
                                     QD_PRECISION_F64: the same kernels instantiated in float64 -- the parity path
                                     for ill-conditioned configurations (band mask wide open, n_fft 8192) */
     int32_t  spectral_freeze;    /* dsp/pipeline.py:285-287, 303-304: every frame takes the magnitudes of frame 0 */
-    double   formant_ratio;      /* 2^(formant_shift/12), dsp/spectral_fx.py:173; 0 = off (dsp/pipeline.py:306-310).
-                                    n_fft <= 4096 */
+    double   formant_ratio;      /* 2^(formant_shift/12), dsp/spectral_fx.py:173; 0 = off (dsp/pipeline.py:306-310) */
     int32_t  formant_order;      /* cepstral lifter order, dsp/spectral_fx.py:120 (30) */
     int32_t  no_spectral;        /* 1: no STFT pass at all -- x_pre = band, distortion, limiter, mix.  What
                                     quantize_mode="autotune_v1" does when its pitch stage is gated off (pre_quant off or
@@ -198,6 +197,24 @@ int qd_render_device(qd_plan *plan, const float *x, float *y, int64_t batch,
 int qd_render_host(qd_plan *plan, const float *x_host, float *y_host, int64_t batch,
                    int64_t chunk_clips);
 
+/*
+ * The same with 16-bit PCM on the PCIe link -- what a WAV-to-WAV batch render (dsp/harness.py:24-63 around
+ * io/audio_io.py:10-26) actually moves.  The conversions run on the device with libsndfile's rules, the ones the
+ * reference's file I/O applies on the CPU: sample / 32768 on the way in, lrint(y * 32767) clipped to int16 on the
+ * way out.  Half the bytes of qd_render_host per clip.
+ */
+int qd_render_host_pcm16(qd_plan *plan, const int16_t *x_host, int16_t *y_host, int64_t batch,
+                         int64_t chunk_clips);
+
+/* General form: either side float32 or PCM16.  Host buffers may be pinned (cudaHostAlloc / cudaHostRegister /
+ * qd_host_alloc: copied directly) or pageable (staged through an internal ring of pinned buffers by copy
+ * threads, QD_HOST_COPY_THREADS per direction, default 4).  On any error the call drains its streams before it
+ * returns. */
+#define QD_SAMPLE_F32   0
+#define QD_SAMPLE_PCM16 1
+int qd_render_host_ex(qd_plan *plan, const void *x_host, void *y_host, int64_t batch, int64_t chunk_clips,
+                      int32_t in_format, int32_t out_format);
+
 /* Stage-level entry points (parity ladder). All async on `stream`. */
 /* dsp/limiter.py:14-80 on [batch, n] */
 int qd_limiter_device(const float *x, float *y, int64_t batch, int64_t n, int32_t lookahead,
@@ -206,8 +223,8 @@ int qd_limiter_device(const float *x, float *y, int64_t batch, int64_t n, int32_
 int qd_crossover_device(const float *x, float *low, float *high, int64_t batch, int64_t n,
                         const double sos_low[2][6], const double sos_high[2][6], void *stream);
 /* dsp/distortion.py:93-114 elementwise on `count` samples */
-int qd_distort_device(const float *x, float *y, int64_t count, int32_t mode, float fold_amount,
-                      float bias, float tube_gain, float tube_norm, void *stream);
+int qd_distort_device(const float *x, float *y, int64_t count, int32_t mode, double fold_amount,
+                      double bias, float tube_gain, float tube_norm, void *stream);
 
 /*
  * Device half of the scale-alignment metric avg_cents_offset_from_scale (dsp/analyses.py:53-142):
@@ -257,8 +274,9 @@ typedef struct qd_autotune_params {
     float    phase_k;            /* float32(2 pi f_sub) */
     /* shared tail, same meaning as in qd_params */
     int32_t  distortion_mode;
-    float    fold_amount, bias, tube_gain, tube_norm;
+    float    tube_gain, tube_norm;
     int32_t  limiter_on, lookahead;
+    double   fold_amount, bias;
     double   ceiling_lin, release_coeff;
     float    wet, dry, trim_gain;
     int32_t  apply_trim, delta_listen;
@@ -277,6 +295,12 @@ size_t qd_autotune_workspace_bytes(const qd_autotune_params *params, int64_t bat
 int    qd_autotune_render_device(const qd_autotune_params *params, const float *x, float *y, int64_t batch,
                                  const qd_taps *taps, const qd_autotune_debug *debug, void *workspace,
                                  size_t workspace_bytes, void *stream);
+
+/*
+ * Measurement helper for the roofline report: FP32 throughput of the CUDA cores in TFLOP/s, measured with the packed
+ * fma.rn.f32x2 (FFMA2) instruction the spectral pass is built from (best of a few launches on `stream`; synchronous).
+ */
+int qd_measure_fp32_peak(double *tflops, void *stream);
 
 /* pinned host memory helpers for qd_render_host callers */
 void *qd_host_alloc(size_t bytes);

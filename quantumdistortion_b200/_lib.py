@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libqd_b200.so")
 
-QD_ABI_VERSION = 4
+QD_ABI_VERSION = 5
 QD_FX = {"none": 0, "bitcrush_log": 1, "bitcrush_uniform": 2, "phase_dispersal": 3,
          "scramble_pick": 4, "scramble_swap": 5}
 
@@ -16,9 +16,9 @@ class QdParams(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("n_samples", C.c_int32),
         ("passthrough", C.c_int32), ("pre_quant", C.c_int32), ("post_quant", C.c_int32), ("bin_smoothing", C.c_int32),
-        ("distortion_mode", C.c_int32), ("fold_amount", C.c_float), ("bias", C.c_float), ("tube_gain", C.c_float),
-        ("tube_norm", C.c_float),
-        ("limiter_on", C.c_int32), ("lookahead", C.c_int32), ("ceiling_lin", C.c_double), ("release_coeff", C.c_double),
+        ("distortion_mode", C.c_int32), ("tube_gain", C.c_float), ("tube_norm", C.c_float),
+        ("limiter_on", C.c_int32), ("lookahead", C.c_int32), ("fold_amount", C.c_double), ("bias", C.c_double),
+        ("ceiling_lin", C.c_double), ("release_coeff", C.c_double),
         ("wet", C.c_float), ("dry", C.c_float), ("trim_gain", C.c_float), ("apply_trim", C.c_int32),
         ("delta_listen", C.c_int32),
         ("multiband", C.c_int32), ("low_delay", C.c_int32), ("sos_low", (C.c_double * 6) * 2),
@@ -79,13 +79,16 @@ def load() -> C.CDLL:
     lib.qd_plan_set_fx_table.argtypes = [vp, vp, i64]
     lib.qd_render_device.argtypes = [vp, vp, vp, i64, C.POINTER(QdTaps), vp, C.c_size_t, vp]
     lib.qd_render_host.argtypes = [vp, vp, vp, i64, i64]
+    lib.qd_render_host_pcm16.argtypes = [vp, vp, vp, i64, i64]
+    lib.qd_render_host_ex.argtypes = [vp, vp, vp, i64, i64, i32, i32]
     lib.qd_limiter_device.argtypes = [vp, vp, i64, i64, i32, dbl, dbl, vp]
     lib.qd_crossover_device.argtypes = [vp, vp, vp, i64, i64, C.POINTER((dbl * 6) * 2), C.POINTER((dbl * 6) * 2), vp]
-    lib.qd_distort_device.argtypes = [vp, vp, i64, i32, flt, flt, flt, flt, vp]
+    lib.qd_distort_device.argtypes = [vp, vp, i64, i32, dbl, dbl, flt, flt, vp]
     lib.qd_spectral_peaks_device.argtypes = [vp, i64, i32, i32, i32, dbl, i32, vp, vp]
     lib.qd_autotune_workspace_bytes.argtypes = [vp, i64]
     lib.qd_autotune_workspace_bytes.restype = C.c_size_t
     lib.qd_autotune_render_device.argtypes = [vp, vp, vp, i64, vp, vp, vp, C.c_size_t, vp]
+    lib.qd_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), vp]
     lib.qd_host_alloc.argtypes = [C.c_size_t]
     lib.qd_host_alloc.restype = vp
     lib.qd_host_free.argtypes = [vp]

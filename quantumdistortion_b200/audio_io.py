@@ -27,6 +27,20 @@ def load_audio(path: Union[str, Path]) -> Tuple[np.ndarray, int]:
     return audio, int(sr)
 
 
+def load_pcm16(path: Union[str, Path]):
+    """-> (int16 samples [n] or [n, channels], sample rate) when the file holds 16-bit PCM, else (None, sample rate).
+    The batch harness ships such files to the GPU as they are (int16 on PCIe, ``sample / 32768`` on the device)."""
+    sr, data = wavfile.read(str(path))
+    return (data if data.dtype == np.int16 else None), int(sr)
+
+
+def save_pcm16(path: Union[str, Path], pcm: np.ndarray, sr: int) -> None:
+    """Write int16 samples that are already in the file format (the device applied ``float_to_pcm16``'s rule)."""
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    wavfile.write(str(path), int(sr), np.ascontiguousarray(pcm, dtype=np.int16))
+
+
 def float_to_pcm16(audio: np.ndarray) -> np.ndarray:
     """libsndfile float -> PCM_16: round-half-even of x * 0x7FFF (clipped to the int16 range)."""
     return np.clip(np.rint(np.asarray(audio, dtype=np.float64) * 32767.0), -32768, 32767).astype(np.int16)

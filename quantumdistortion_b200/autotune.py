@@ -40,9 +40,9 @@ class QdAutotuneParams(C.Structure):
         ("sub_enabled", C.c_int32), ("layer_on", C.c_int32),
         ("env_attack", C.c_float), ("env_release", C.c_float),
         ("sub_level", C.c_float), ("sub_preserve", C.c_float), ("air_mix", C.c_float), ("phase_k", C.c_float),
-        ("distortion_mode", C.c_int32), ("fold_amount", C.c_float), ("bias", C.c_float), ("tube_gain", C.c_float),
-        ("tube_norm", C.c_float),
-        ("limiter_on", C.c_int32), ("lookahead", C.c_int32), ("ceiling_lin", C.c_double), ("release_coeff", C.c_double),
+        ("distortion_mode", C.c_int32), ("tube_gain", C.c_float), ("tube_norm", C.c_float),
+        ("limiter_on", C.c_int32), ("lookahead", C.c_int32), ("fold_amount", C.c_double), ("bias", C.c_double),
+        ("ceiling_lin", C.c_double), ("release_coeff", C.c_double),
         ("wet", C.c_float), ("dry", C.c_float), ("trim_gain", C.c_float), ("apply_trim", C.c_int32),
         ("delta_listen", C.c_int32),
     ]

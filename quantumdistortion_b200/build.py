@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libqd_b200.so")
 SOURCES = ["qd_api.cu"]
-DEPS = ["qd_api.cu", "qd_spec.cuh", "qd_peaks.cuh", "qd_autotune.cuh", "qd_autotune_api.inc", "qd_time.cuh", "qd_common.cuh", "qd_host_tables.hpp", "qd_host_time.hpp",
+DEPS = ["qd_api.cu", "qd_spec.cuh", "qd_peaks.cuh", "qd_autotune.cuh", "qd_autotune_api.inc", "qd_host_pipe.inc", "qd_time.cuh", "qd_common.cuh", "qd_host_tables.hpp", "qd_host_time.hpp",
         os.path.join("..", "..", "include", "qd_b200.h")]
 
 NVCC_FLAGS = [

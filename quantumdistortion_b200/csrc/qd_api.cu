@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -62,14 +63,19 @@ cudaError_t upload(const std::vector<T> &h, T **d) {
     return e;
 }
 
-struct HostPipe {   // resources of qd_render_host
+struct HostPipe {   // resources of qd_render_host* (qd_host_pipe.inc)
     int64_t chunk = 0;
     float *dx[2] = {nullptr, nullptr};
     float *dy[2] = {nullptr, nullptr};
+    int16_t *dxr[2] = {nullptr, nullptr};   // PCM16 transport: raw input / output chunks on the device
+    int16_t *dyr[2] = {nullptr, nullptr};
+    void *pin_in[3] = {nullptr, nullptr, nullptr};    // pinned staging rings for pageable callers
+    void *pin_out[3] = {nullptr, nullptr, nullptr};
     void *ws = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ring_in[3] = {nullptr, nullptr, nullptr}, ev_ring_out[3] = {nullptr, nullptr, nullptr};
 };
 
 }  // namespace
@@ -123,10 +129,10 @@ namespace {
 //      shared memory (falls back to 8 warps + L1 tables when they do not fit); float64 (parity path) and the
 //      FX variants read tables through L1.  Must stay in sync with the switch in dispatch_spec().
 template <class T> int pick_nw(int nc, bool fx, bool formant = false) {
-    if (sizeof(T) == 4 && formant) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 0;   // scratch buffer per warp; n_fft 8192: not built
-    if (sizeof(T) == 8 && fx) return nc <= 512 ? 8 : nc == 1024 ? 4 : nc == 2048 ? 2 : 0;  // n_fft 8192: not built
+    if (sizeof(T) == 4 && formant) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 1;   // scratch buffer per warp
+    if (sizeof(T) == 8 && fx) return nc <= 512 ? 8 : nc == 1024 ? 4 : nc == 2048 ? 2 : 1;  // n_fft 8192: one warp (182 KB)
     if (sizeof(T) == 8) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 2;
-    if (fx) return nc == 1024 ? 12 : nc < 1024 ? 8 : 4;   // 12 warps: what fits beside the FX magnitude planes
+    if (fx) return nc == 1024 ? 12 : nc < 1024 ? 8 : nc == 2048 ? 4 : 2;   // what fits beside the FX magnitude planes
     return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4;  // 16 = two independent groups of 8 warps per CTA
 }
 
@@ -148,18 +154,23 @@ size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int form
                  : nw == 4 ? smem_of<T, 1024, 4>(n_slots, false, 0, fm, fx) : 0;
         case 2048: return nw == 4 ? smem_of<T, 2048, 4>(n_slots, false, 0, fm, fx)
                         : nw == 2 ? smem_of<T, 2048, 2>(n_slots, false, 0, fm, fx) : 0;
-        case 4096: return nw == 4 ? smem_of<T, 4096, 4>(n_slots, false, 0, fm, fx)
-                        : nw == 2 ? smem_of<T, 4096, 2>(n_slots, false, 0, fm, fx) : 0;
+        case 4096:
+            if (nw == 1 && sizeof(T) == 8 && fm)   // float64 formant shift at n_fft 8192: samples staged in the scratch buffer
+                return qd::SpecSmem<T, 4096, 1, 1, true>::bytes(n_slots, false, 0, 0, fx, true);
+            return nw == 4 ? smem_of<T, 4096, 4>(n_slots, false, 0, fm, fx)
+                 : nw == 2 ? smem_of<T, 4096, 2>(n_slots, false, 0, fm, fx)
+                 : nw == 1 ? smem_of<T, 4096, 1>(n_slots, false, 0, fm, fx) : 0;
     }
     return 0;
 }
 
-template <class T, int NC, int NW, bool TS, bool FX, int NG = 1>
+template <class T, int NC, int NW, bool TS, bool FX, int NG = 1, bool SA = false>
 int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st) {
     static std::atomic<uint64_t> attr_mask{0};  // devices this instantiation was opted in on
-    auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX, NG>;
+    auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX, NG, SA>;
     if (int rc_ = ensure_dyn_smem(kern, attr_mask, 227 * 1024)) return rc_;
-    const size_t smem = qd::SpecSmem<T, NC, NW, NG>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX, FX && a.formant_idx != nullptr);
+    const size_t smem = qd::SpecSmem<T, NC, NW, NG, SA>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX, FX && a.formant_idx != nullptr);
+    if (smem > 227 * 1024) return fail(QD_ERR_UNSUPPORTED, "shared memory need of this kernel variant exceeds 227 KB");
     for (int64_t b0 = 0; b0 < batch; b0 += 65535 * NG) {  // gridDim.y limit
         const int64_t nb = std::min<int64_t>(65535 * NG, batch - b0);
         qd::SpecArgsT<T> c = a;
@@ -168,6 +179,7 @@ int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStrea
         c.y = a.y + (size_t)b0 * a.n;
         if (a.tap) c.tap = a.tap + (size_t)b0 * a.n;
         if (a.clip_peak) c.clip_peak = a.clip_peak + b0;
+        if (a.frozen) c.frozen = a.frozen + (size_t)b0 * qd::buf_slots<NC>();
         c.fx.clip_offset = a.fx.clip_offset + (int)b0;
         kern<<<dim3((unsigned)tiles, (unsigned)((nb + NG - 1) / NG), 1), 32 * NW * NG, smem, st>>>(c);
     }
@@ -192,9 +204,13 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
             if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 2048, 2, false, true>(a, tiles, batch, st);
             else return launch_spec_t<T, 2048, 4, false, FX>(a, tiles, batch, st);
         case 4096:
-            if constexpr (sizeof(T) == 8 && FX) return fail(QD_ERR_UNSUPPORTED, "float64 spectral FX are not built for n_fft 8192");
-            else if constexpr (sizeof(T) == 8) return launch_spec_t<T, 4096, 2, false, false>(a, tiles, batch, st);
-            else return launch_spec_t<T, 4096, 4, false, FX>(a, tiles, batch, st);
+            if constexpr (sizeof(T) == 8 && FX) {   // one warp per CTA; with the formant scratch the samples are staged in it
+                if (a.formant_idx) return launch_spec_t<T, 4096, 1, false, true, 1, true>(a, tiles, batch, st);
+                return launch_spec_t<T, 4096, 1, false, true>(a, tiles, batch, st);
+            } else if constexpr (sizeof(T) == 8) return launch_spec_t<T, 4096, 2, false, false>(a, tiles, batch, st);
+            else if constexpr (FX) return nw == 1 ? launch_spec_t<T, 4096, 1, false, true>(a, tiles, batch, st)
+                                                  : launch_spec_t<T, 4096, 2, false, true>(a, tiles, batch, st);
+            else return launch_spec_t<T, 4096, 4, false, false>(a, tiles, batch, st);
     }
     return fail(QD_ERR_UNSUPPORTED, "n_fft not supported");
 }
@@ -296,6 +312,24 @@ int launch_limiter(const qd::LimiterArgs &a, int64_t batch, cudaStream_t st) {
     }
     QD_CUDA(cudaGetLastError());
     return QD_OK;
+}
+
+// the wavefold's (x + bias) * fold is exact in float32 when there is no bias and the gain is a power of two
+int fold_exact_in_f32(double fold, double bias) {
+    int e = 0;
+    return bias == 0.0 && fold > 0.0 && std::frexp(fold, &e) == 0.5 && e > -100 && e < 100;
+}
+
+void launch_crossover(const qd::CrossoverArgs &c, int64_t batch, cudaStream_t st) {
+    const long long n_tiles = (c.n + c.tile - 1) / c.tile;
+    const unsigned gx = (unsigned)((n_tiles + 32 * qd::QD_XO_WARPS - 1) / (32 * qd::QD_XO_WARPS));
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {   // gridDim.y limit
+        const int64_t nb = std::min<int64_t>(65535, batch - b0);
+        qd::CrossoverArgs k = c;
+        const size_t off = (size_t)b0 * (size_t)c.n;
+        k.x = c.x + off; k.low = c.low + off; k.high = c.high + off;
+        qd::crossover_kernel<<<dim3(gx, (unsigned)nb, 1), 32 * qd::QD_XO_WARPS, 0, st>>>(k);
+    }
 }
 
 int ew_grid(int64_t count, int sm_count) {
@@ -422,8 +456,8 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
     if (need_quant && !tables) return fail(QD_ERR_INVALID_ARG, "quantizer tables required");
     if (p.fx_mode < QD_FX_NONE || p.fx_mode > QD_FX_SCRAMBLE_SWAP) return fail(QD_ERR_INVALID_ARG, "bad fx_mode");
     if (p.fx_mode != QD_FX_NONE && !p.multiband) return fail(QD_ERR_INVALID_ARG, "spectral FX act on the high band of a multiband render only");
-    if ((p.fx_mode == QD_FX_SCRAMBLE_PICK || p.fx_mode == QD_FX_SCRAMBLE_SWAP) && p.n_fft > 4096)
-        return fail(QD_ERR_UNSUPPORTED, "bin scramble is built for n_fft <= 4096");
+    if (p.fx_mode == QD_FX_SCRAMBLE_PICK && p.n_fft > 2048 && p.fx_a > 512.0)
+        return fail(QD_ERR_UNSUPPORTED, "bin scramble at n_fft > 2048 gathers in tiles: window / 2 must be <= 512 bins");
     if (p.precision != QD_PRECISION_F32 && p.precision != QD_PRECISION_F64) return fail(QD_ERR_INVALID_ARG, "bad precision");
 
     qd_plan *pl = new qd_plan();
@@ -471,7 +505,6 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         n_slots = qt.n_slots;
     }
     const bool formant = need_quant && p.formant_ratio > 0.0;
-    if (formant && p.n_fft > 4096) return bail(QD_ERR_UNSUPPORTED, "formant shift is built for n_fft <= 4096");
     if (formant && p.formant_order < 2) return bail(QD_ERR_INVALID_ARG, "formant_order must be >= 2");
     const bool fx = need_quant && (p.fx_mode != QD_FX_NONE || p.spectral_freeze || formant);
     qd::FxDev fxd{};
@@ -510,6 +543,7 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         a.n = p.n_samples;
         a.n_frames = pl->n_frames;
         a.fold = p.fold_amount; a.bias = p.bias; a.tube_gain = p.tube_gain; a.tube_norm = p.tube_norm;
+        a.fold_exact_f32 = fold_exact_in_f32(p.fold_amount, p.bias);
         a.wtab = reinterpret_cast<const double2 *>(d_wtab);
         a.tw1 = reinterpret_cast<const double2 *>(d_tw1);
         a.tw2 = reinterpret_cast<const double2 *>(d_tw2);
@@ -533,6 +567,7 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         a.n = p.n_samples;
         a.n_frames = pl->n_frames;
         a.fold = p.fold_amount; a.bias = p.bias; a.tube_gain = p.tube_gain; a.tube_norm = p.tube_norm;
+        a.fold_exact_f32 = fold_exact_in_f32(p.fold_amount, p.bias);
         a.wtab = reinterpret_cast<const float2 *>(d_wtab);
         a.tw1 = reinterpret_cast<const float2 *>(d_tw1);
         a.tw2 = reinterpret_cast<const float2 *>(d_tw2);
@@ -566,9 +601,17 @@ void qd_plan_destroy(qd_plan *pl) {
     for (int i = 0; i < 2; ++i) {
         if (hp.dx[i]) cudaFree(hp.dx[i]);
         if (hp.dy[i]) cudaFree(hp.dy[i]);
+        if (hp.dxr[i]) cudaFree(hp.dxr[i]);
+        if (hp.dyr[i]) cudaFree(hp.dyr[i]);
         if (hp.ev_in[i]) cudaEventDestroy(hp.ev_in[i]);
         if (hp.ev_run[i]) cudaEventDestroy(hp.ev_run[i]);
         if (hp.ev_out[i]) cudaEventDestroy(hp.ev_out[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (hp.pin_in[i]) cudaFreeHost(hp.pin_in[i]);
+        if (hp.pin_out[i]) cudaFreeHost(hp.pin_out[i]);
+        if (hp.ev_ring_in[i]) cudaEventDestroy(hp.ev_ring_in[i]);
+        if (hp.ev_ring_out[i]) cudaEventDestroy(hp.ev_ring_out[i]);
     }
     if (hp.ws) cudaFree(hp.ws);
     if (hp.s_in) cudaStreamDestroy(hp.s_in);
@@ -674,7 +717,7 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
         c.low_trim = p.low_trim_gain; c.apply_low_trim = p.apply_low_trim;
         {
             TimeScope ts(pl, st, QD_KERNEL_CROSSOVER);
-            qd::crossover_kernel<<<(unsigned)batch, qd::QD_TT, 0, st>>>(c);
+            launch_crossover(c, batch, st);
         }
         QD_CUDA(cudaGetLastError());
         src = w_high;
@@ -752,62 +795,6 @@ int qd_render_device(qd_plan *pl, const float *x, float *y, int64_t batch, const
     return launch_limiter(l, batch, st);
 }
 
-int qd_render_host(qd_plan *pl, const float *x_host, float *y_host, int64_t batch, int64_t chunk_clips) {
-    if (!pl || !x_host || !y_host || batch < 0) return fail(QD_ERR_INVALID_ARG, "null argument");
-    if (batch == 0 || pl->p.n_samples == 0) return QD_OK;
-    if (chunk_clips <= 0) chunk_clips = 128;
-    if (chunk_clips > batch) chunk_clips = batch;
-    HostPipe &hp = pl->pipe;
-    const size_t clip = (size_t)pl->p.n_samples * sizeof(float);
-    if (hp.chunk < chunk_clips) {  // (re)allocate the double buffers once per plan / chunk size
-        for (int i = 0; i < 2; ++i) {
-            if (hp.dx[i]) cudaFree(hp.dx[i]);
-            if (hp.dy[i]) cudaFree(hp.dy[i]);
-            hp.dx[i] = hp.dy[i] = nullptr;
-        }
-        if (hp.ws) cudaFree(hp.ws);
-        hp.ws = nullptr;
-        for (int i = 0; i < 2; ++i) {
-            QD_CUDA(cudaMalloc((void **)&hp.dx[i], clip * chunk_clips));
-            QD_CUDA(cudaMalloc((void **)&hp.dy[i], clip * chunk_clips));
-        }
-        hp.ws_bytes = qd_plan_workspace_bytes(pl, chunk_clips);
-        QD_CUDA(cudaMalloc(&hp.ws, hp.ws_bytes));
-        hp.chunk = chunk_clips;
-    }
-    if (!hp.s_in) {
-        QD_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
-        QD_CUDA(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
-        QD_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            QD_CUDA(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
-            QD_CUDA(cudaEventCreateWithFlags(&hp.ev_run[i], cudaEventDisableTiming));
-            QD_CUDA(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
-        }
-    }
-    int64_t idx = 0;
-    for (int64_t b0 = 0; b0 < batch; b0 += chunk_clips, ++idx) {
-        const int buf = (int)(idx & 1);
-        const int64_t nb = std::min<int64_t>(chunk_clips, batch - b0);
-        if (idx >= 2) QD_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_run[buf], 0));   // dx[buf] consumed
-        QD_CUDA(cudaMemcpyAsync(hp.dx[buf], x_host + (size_t)b0 * pl->p.n_samples, clip * nb, cudaMemcpyHostToDevice, hp.s_in));
-        QD_CUDA(cudaEventRecord(hp.ev_in[buf], hp.s_in));
-        QD_CUDA(cudaStreamWaitEvent(hp.s_run, hp.ev_in[buf], 0));
-        if (idx >= 2) QD_CUDA(cudaStreamWaitEvent(hp.s_run, hp.ev_out[buf], 0));  // dy[buf] drained
-        pl->clip_offset = (int)b0;
-        int rc = qd_render_device(pl, hp.dx[buf], hp.dy[buf], nb, nullptr, hp.ws, hp.ws_bytes, hp.s_run);
-        pl->clip_offset = 0;
-        if (rc != QD_OK) return rc;
-        QD_CUDA(cudaEventRecord(hp.ev_run[buf], hp.s_run));
-        QD_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_run[buf], 0));
-        QD_CUDA(cudaMemcpyAsync(y_host + (size_t)b0 * pl->p.n_samples, hp.dy[buf], clip * nb, cudaMemcpyDeviceToHost, hp.s_out));
-        QD_CUDA(cudaEventRecord(hp.ev_out[buf], hp.s_out));
-    }
-    QD_CUDA(cudaStreamSynchronize(hp.s_out));
-    QD_CUDA(cudaStreamSynchronize(hp.s_run));
-    return QD_OK;
-}
-
 int qd_limiter_device(const float *x, float *y, int64_t batch, int64_t n, int32_t lookahead, double ceiling_lin,
                       double release_coeff, void *stream) {
     if (!x || !y || batch < 0 || n < 0 || lookahead < 1) return fail(QD_ERR_INVALID_ARG, "bad limiter argument");
@@ -825,12 +812,12 @@ int qd_crossover_device(const float *x, float *low, float *high, int64_t batch, 
     qd::CrossoverArgs c{};
     c.x = x; c.low = low; c.high = high; c.n = (long long)n;
     qd_host::fill_crossover(c, &sos_low[0][0], &sos_high[0][0]);
-    qd::crossover_kernel<<<(unsigned)batch, qd::QD_TT, 0, (cudaStream_t)stream>>>(c);
+    launch_crossover(c, batch, (cudaStream_t)stream);
     QD_CUDA(cudaGetLastError());
     return QD_OK;
 }
 
-int qd_distort_device(const float *x, float *y, int64_t count, int32_t mode, float fold_amount, float bias,
+int qd_distort_device(const float *x, float *y, int64_t count, int32_t mode, double fold_amount, double bias,
                       float tube_gain, float tube_norm, void *stream) {
     if (!x || !y || count < 0) return fail(QD_ERR_INVALID_ARG, "bad distortion argument");
     if (mode != QD_DIST_WAVEFOLD && mode != QD_DIST_TUBE) return fail(QD_ERR_INVALID_ARG, "unsupported distortion mode");
@@ -855,3 +842,4 @@ void qd_host_free(void *p) {
 }  // extern "C"
 
 #include "qd_autotune_api.inc"
+#include "qd_host_pipe.inc"

@@ -1,5 +1,6 @@
 // qd_host_time.hpp -- host helpers for qd_time.cuh (plain C++; shared with the emulation tests).
 #pragma once
+#include <cmath>
 #include <cstddef>
 
 namespace qd_host {
@@ -12,25 +13,28 @@ inline size_t limiter_smem_bytes(int lookahead) {
     return 2 * (abs_stride + gmax_stride) * sizeof(float) + 16 + 2 * (8 + 2) * sizeof(double);
 }
 
-// A = [[-a1, 1], [-a2, 0]] is the DF2T state matrix of a section; apow[s][l] = A_s^(8 * 2^l)
-// sos_low / sos_high: [2][6] rows (b0 b1 b2 a0 a1 a2), a0 == 1 (scipy layout)
+// sos_low / sos_high: [2][6] rows (b0 b1 b2 a0 a1 a2), a0 == 1 (scipy layout).  Besides the coefficients this picks the
+// tiling of crossover_kernel: `halo` = warm-up samples after which a zero-started state equals the true one to below
+// 1e-15 (the zero-input response of a double pole pair decays like n r^n, r = largest pole radius: 44 / (1 - r)
+// samples), `tile` = output samples per thread (>= 4096 and >= 2 halo, so the warm-up costs at most half the work).
 template <class Args>
 inline void fill_crossover(Args &a, const double *sos_low, const double *sos_high) {
+    double r = 0.0;
     for (int s = 0; s < 4; ++s) {
         const double *src = (s < 2 ? sos_low : sos_high) + 6 * (s & 1);
         for (int i = 0; i < 6; ++i) a.co[s][i] = src[i];
-        auto mul = [](const double *p, const double *q, double *o) {
-            double r[4] = {p[0] * q[0] + p[1] * q[2], p[0] * q[1] + p[1] * q[3],
-                           p[2] * q[0] + p[3] * q[2], p[2] * q[1] + p[3] * q[3]};
-            for (int i = 0; i < 4; ++i) o[i] = r[i];
-        };
-        double p[4] = {-src[4], 1.0, -src[5], 0.0};
-        for (int k = 0; k < 3; ++k) mul(p, p, p);  // A^8
-        for (int l = 0; l < 6; ++l) {
-            a.apow[s][l].a = p[0]; a.apow[s][l].b = p[1]; a.apow[s][l].c = p[2]; a.apow[s][l].d = p[3];
-            mul(p, p, p);
-        }
+        const double a1 = src[4], a2 = src[5], disc = a1 * a1 - 4.0 * a2;
+        const double rad = disc < 0.0 ? std::sqrt(a2 > 0.0 ? a2 : 0.0)
+                                      : std::fmax(std::fabs((-a1 + std::sqrt(disc)) * 0.5), std::fabs((-a1 - std::sqrt(disc)) * 0.5));
+        r = std::fmax(r, rad);
     }
+    double h = r < 1.0 ? 44.0 / (1.0 - r) : 1e9;
+    if (h > (double)(1 << 22)) h = (double)(1 << 22);     // a (nearly) unstable design: bounded work, bounded accuracy
+    const int halo = (((int)std::ceil(h)) + 31) & ~31;
+    int tile = 4096;
+    while (tile < 2 * halo) tile *= 2;
+    a.halo = halo;
+    a.tile = tile;
 }
 
 }  // namespace qd_host

@@ -118,7 +118,9 @@ struct SpecArgsT {
     int tile_blocks;       // output hops per CTA tile
     int quant;             // run the quantizer (else pure STFT -> iSTFT)
     int epilogue;          // 0 none, 1 wavefold, 2 tube
-    float fold, bias, tube_gain, tube_norm;
+    double fold, bias;     // wavefold in float64 like dsp/distortion.py:37-58 ...
+    int fold_exact_f32;    // ... unless bias == 0 and fold is a power of two: float32 arithmetic is exact then
+    float tube_gain, tube_norm;
     const V2<T> *wtab;     // [2 NC/R1] Hann window factors (-0.5 cos A, 0.5 sin A) per first-pass butterfly (host builder)
     const V2<T> *tw1;      // access-ordered twiddles of pass 1 / pass 2 (see host builder)
     const V2<T> *tw2;
@@ -626,10 +628,9 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
         }
     } else if (fx.mode == 4 || fx.mode == 5) {
         // bin scramble (dsp/spectral_fx.py:326-390): gather through the host-replayed index table
-        static_assert(ROWS <= 72 || NC > 2048, "row registers");
-        if constexpr (NC <= 2048) {
-            sm = warp_sum(sm);
-            const int16_t *idx = reinterpret_cast<const int16_t *>(fx.table);
+        sm = warp_sum(sm);
+        const int16_t *idx = reinterpret_cast<const int16_t *>(fx.table);
+        if constexpr (ROWS <= 33) {   // n_fft <= 2048: the whole frame fits the row registers
             T val[ROWS];
             T s2 = 0.0f;
 #pragma unroll
@@ -647,6 +648,44 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
 #pragma unroll
             for (int row = 0; row < ROWS; ++row)
                 if (row < ROWS - 1 || lane == 0) mags[rpos<T, NC>(lane, row)] = val[row] * scale;
+        } else {
+            // longer frames: tiles of CH rows.  A tile's sources lie within `half` bins of it (half <= 32 CH, checked
+            // by the host), so tile c-1 may be overwritten once tile c has been gathered; the energy rescale needs the
+            // sum over the whole frame and runs as a second sweep (same product m[idx] * scale as the reference).
+            constexpr int CH = sizeof(T) == 4 ? 32 : 16;
+            constexpr int NCH = (ROWS + CH - 1) / CH;
+            T prev[CH], cur[CH];
+            T s2 = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c <= NCH; ++c) {
+                if (c < NCH) {
+#pragma unroll
+                    for (int r = 0; r < CH; ++r) {
+                        const int row = c * CH + r;
+                        cur[r] = 0.0f;
+                        if (row < ROWS - 1 || (row == ROWS - 1 && lane == 0)) {
+                            const int src = idx ? (int)__ldg(idx + tab_base + 32 * row + lane) : 32 * row + lane;
+                            cur[r] = mags[spos<T, NC>(src)];
+                            s2 += cur[r];
+                        }
+                    }
+                }
+                __syncwarp();   // every lane has gathered tile c before tile c-1 is overwritten
+                if (c > 0) {
+#pragma unroll
+                    for (int r = 0; r < CH; ++r) {
+                        const int row = (c - 1) * CH + r;
+                        if (row < ROWS - 1 || (row == ROWS - 1 && lane == 0)) mags[rpos<T, NC>(lane, row)] = prev[r];
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < CH; ++r) prev[r] = cur[r];
+            }
+            s2 = warp_sum(s2);
+            const T scale = sm / (s2 + 1e-12f);
+            __syncwarp();
+            for (int row = 0; row < ROWS; ++row)
+                if (row < ROWS - 1 || lane == 0) mags[rpos<T, NC>(lane, row)] *= scale;
         }
     }
     __syncwarp();
@@ -973,15 +1012,19 @@ QD_DEV void quantize_frame_fused(V2<T> *buf, T *slotG, V2<T> *slotP, const Quant
 // ---------------------------------------------------------------- the kernel
 // NG independent groups of NW warps share one CTA (and its tables); each group streams its own clip and
 // synchronises only with itself (named barrier), so one group's overlap-add step overlaps the other's FFTs.
-template <class T, int NC, int NW, int NG = 1>
+// SA ("stage aliased"): the one-warp float64 formant variant of n_fft 8192 does not fit 227 KB with a staging buffer
+// of its own, so the samples are staged in the warp's formant scratch buffer (dead until the frame's FFT is done;
+// no prefetch of the next batch).
+template <class T, int NC, int NW, int NG = 1, bool SA = false>
 struct SpecSmem {
     static constexpr int HOP = NC / 2;                       // n_fft / 4 samples
     static constexpr int BUF = buf_slots<NC>();               // V2<T> per warp buffer
     static constexpr int STAGE = (NW + 3) * HOP;              // floats
     static constexpr int TAIL = 3 * HOP;                      // floats
+    static_assert(!SA || (NW == 1 && NG == 1 && (size_t)STAGE * sizeof(float) <= (size_t)BUF * sizeof(V2<T>)), "stage alias");
     static constexpr size_t off_buf = 0;
     static constexpr size_t off_stage = off_buf + (size_t)NW * BUF * sizeof(V2<T>);
-    static constexpr size_t off_tail = off_stage + (size_t)STAGE * sizeof(float);
+    static constexpr size_t off_tail = off_stage + (SA ? 0 : (size_t)STAGE * sizeof(float));
     static constexpr size_t off_flags = off_tail + (size_t)TAIL * sizeof(T);
     static constexpr size_t off_slot = off_flags + 64 * sizeof(int);
     // per-warp gather scratch: G[cap] floats then P[cap] V2<T>, cap even so P stays 8-byte aligned
@@ -1011,10 +1054,19 @@ struct SpecSmem {
 };
 
 // wavefold / tube on the float32 iSTFT sample (dsp/distortion.py:18-90)
-QD_DEV float epilogue_apply(float v, int mode, float fold, float bias, float tg, float tn) {
+QD_DEV float epilogue_apply(float v, int mode, double fold, double bias, int exact_f32, float tg, float tn) {
     if (mode == 1) {
-        // dsp/distortion.py:44-56: the negative fold is tested on the already folded value
-        float y = (v + bias) * fold;
+        // dsp/distortion.py:37-58 computes in float64 and rounds to float32 once; the negative fold is tested on the
+        // already folded value (:44-56).  (x + bias) * fold reaches several units before it is folded back, so float32
+        // arithmetic would carry the rounding error of the large intermediate (~2e-7) into the small result -- and the
+        // second spectral pass amplifies its input error.  With bias == 0 and fold a power of two float32 is exact.
+        if (!exact_f32) {
+            double y = ((double)v + bias) * fold;
+            if (y > 1.0) y = 2.0 - y;
+            if (y < -1.0) y = -2.0 - y;
+            return (float)fmin(fmax(y, -1.0), 1.0);
+        }
+        float y = v * (float)fold;
         if (y > 1.0f) y = 2.0f - y;
         if (y < -1.0f) y = -2.0f - y;
         return fminf(fmaxf(y, -1.0f), 1.0f);
@@ -1037,10 +1089,10 @@ QD_DEV void group_sync(int g) {
     }
 }
 
-template <class T, int NC, int NW, bool TS = false, bool FX = false, int NG = 1>
+template <class T, int NC, int NW, bool TS = false, bool FX = false, int NG = 1, bool SA = false>
 __global__ void __launch_bounds__(32 * NW * NG)
 spec_pass_kernel(const SpecArgsT<T> a) {
-    using L = SpecSmem<T, NC, NW, NG>;
+    using L = SpecSmem<T, NC, NW, NG, SA>;
     constexpr int HOP = L::HOP;
     constexpr int HP = HOP / 2;              // V2<T> pairs per hop
     constexpr int HPP = HP + HP / 32;        // the same span inside a padded warp buffer
@@ -1053,6 +1105,8 @@ spec_pass_kernel(const SpecArgsT<T> a) {
     unsigned char *tables_base = smem + (size_t)NG * L::group_bytes(a.q.n_slots);
     V2<T> *bufs = reinterpret_cast<V2<T> *>(gs + L::off_buf);
     float *stage = reinterpret_cast<float *>(gs + L::off_stage);
+    if constexpr (SA)   // the formant scratch buffer of the (only) warp, see SpecSmem
+        stage = reinterpret_cast<float *>(tables_base + 16 + (size_t)NG * NW * L::BUF * sizeof(T));
     V2<T> *tail = reinterpret_cast<V2<T> *>(gs + L::off_tail);
     V2<T> *buf = bufs + (size_t)warp * L::BUF;
     const int slot_cap = (a.q.n_slots + 2) & ~1;
@@ -1131,7 +1185,7 @@ spec_pass_kernel(const SpecArgsT<T> a) {
         // ---- stage the samples of frames tb .. tb+NW-1 (zero outside the clip)
         const long long s0 = (long long)tb * HOP - NC;  // clip index of staging[0]
         const long long s0n = s0 + (long long)NW * HOP;  // the same for the next batch
-        const bool next_by_tma = vec4 && (tb + NW < j1) && s0n >= 0 && s0n + L::STAGE <= a.n;
+        const bool next_by_tma = !SA && vec4 && (tb + NW < j1) && s0n >= 0 && s0n + L::STAGE <= a.n;
         if (tma_pending) {
             mbar_wait(full, full_parity);  // bulk copy issued during the previous batch
             full_parity ^= 1u;
@@ -1195,21 +1249,21 @@ spec_pass_kernel(const SpecArgsT<T> a) {
         group_sync<NG, 32 * NW>(grp);
         // ---- overlap-add in frame order; blocks tb .. tb+NW-1 are now complete.  A thread owns one
         //      column of sample pairs: slice sl of warp w's frame sits at bufs[w][sl*HPP + pidx(c)].
+        //      The hop loop is deliberately NOT unrolled: the kernel's code already fills the instruction cache, and
+        //      this part (a few per cent of the instructions) used to be replicated NW + 3 times.
         for (int c = tid; c < HP; c += nthreads) {
             const int pc = pidx(c);
-            V2<T> carry[3];
-#pragma unroll
-            for (int g = 0; g < 3; ++g) carry[g] = tail[g * HP + c];
-#pragma unroll
+#pragma unroll 1
             for (int h = 0; h < NW + 3; ++h) {
-                V2<T> v = (h < 3) ? carry[h] : mk2<T>(0.0f, 0.0f);
+                V2<T> v = (h < 3) ? tail[h * HP + c] : mk2<T>(0.0f, 0.0f);   // partial sums carried from the last batch
+                const int w0 = h - 3 > 0 ? h - 3 : 0, w1 = h < NW - 1 ? h : NW - 1;
 #pragma unroll
-                for (int w = (h - 3 > 0 ? h - 3 : 0); w <= (h < NW - 1 ? h : NW - 1); ++w) {
-                    const V2<T> f = bufs[(size_t)w * L::BUF + (h - w) * HPP + pc];
-                    v = padd(v, f);
+                for (int k = 0; k < 4; ++k) {
+                    const int w = w0 + k;
+                    if (w <= w1) v = padd(v, bufs[(size_t)w * L::BUF + (h - w) * HPP + pc]);
                 }
                 if (h >= NW) {
-                    tail[(h - NW) * HP + c] = v;  // partial sums of the next three blocks
+                    tail[(h - NW) * HP + c] = v;  // partial sums of the next three blocks (slot h - NW < h: already read)
                     continue;
                 }
                 const int j = tb + h;
@@ -1223,8 +1277,8 @@ spec_pass_kernel(const SpecArgsT<T> a) {
                 if (sl_a <= sl_b) inv = __ldg(reinterpret_cast<const V2<T> *>(a.invw + (sl_a * 4 + sl_b) * HOP) + c);
                 const V2<T> vi = pmul(v, inv);
                 const float2 o = make_float2((float)vi.x, (float)vi.y);  // float32 like istft_mono
-                const float2 r = make_float2(epilogue_apply(o.x, a.epilogue, a.fold, a.bias, a.tube_gain, a.tube_norm),
-                                             epilogue_apply(o.y, a.epilogue, a.fold, a.bias, a.tube_gain, a.tube_norm));
+                const float2 r = make_float2(epilogue_apply(o.x, a.epilogue, a.fold, a.bias, a.fold_exact_f32, a.tube_gain, a.tube_norm),
+                                             epilogue_apply(o.y, a.epilogue, a.fold, a.bias, a.fold_exact_f32, a.tube_gain, a.tube_norm));
                 if (vec2) {  // nidx is even and n is even, so nidx + 1 < n
                     if (tap) *reinterpret_cast<float2 *>(tap + nidx) = o;
                     *reinterpret_cast<float2 *>(y + nidx) = r;

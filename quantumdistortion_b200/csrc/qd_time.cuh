@@ -278,7 +278,8 @@ struct CrossoverArgs {
     float *high;          // [batch, n]
     long long n;
     double co[4][6];      // sections lp1, lp2, hp1, hp2 as (b0 b1 b2 1 a1 a2)
-    Mat2 apow[4][6];      // per section A^(KS * 2^l), l = 0..5, A = [[-a1, 1], [-a2, 0]]
+    int tile;             // output samples per thread (multiple of 32), see crossover_kernel
+    int halo;             // warm-up samples before a tile (multiple of 32), from the pole radius
     int low_delay;        // samples the low band is delayed by (dsp/pipeline.py:389-396)
     int process_low;      // 1: saturate / blend / trim the low band (dsp/pipeline.py:1063-1073)
     float low_gain;
@@ -357,61 +358,101 @@ QD_DEV float low_process(float v, const CrossoverArgs &a) {
     return r;
 }
 
-__global__ void __launch_bounds__(QD_TT) crossover_kernel(const CrossoverArgs a) {
-    __shared__ double s_w[2 * (QD_TT / 32) + 2];
-    const int tid = threadIdx.x;
-    const size_t base = (size_t)blockIdx.x * (size_t)a.n;
+// Linkwitz-Riley split (dsp/crossover.py:71-118): four DF2T sections (LP, LP | HP, HP) run SEQUENTIALLY by one thread
+// over its own tile of one clip, in float64, in scipy's operation order.  What makes the tiles independent is the
+// filters' memory: the poles of a crossover at f_c have radius r = exp(-pi sqrt(2) f_c / sr) (0.9726 at 300 Hz / 48 kHz),
+// so a state started from zero `halo` samples before the tile differs from the true state by the decayed zero-input
+// response, below 1e-15 of the signal for halo = 44 / (1 - r) (host: qd_host::fill_crossover) -- under the rounding of
+// the float64 recurrence itself, and nine orders below the float32 the band is stored in.  Samples before the clip are
+// zeros, which IS the true initial state, so the first tile needs no special case.  No scan, no block barrier: a warp
+// stages 32 samples of its 32 tiles through shared memory (coalesced 128-byte rows both ways), each lane filters its
+// own row.  Algorithmic HBM bytes: 4 read + 8 written per sample (the halo re-reads hit L2).
+constexpr int QD_XO_WARPS = 4;
+QD_DEV void xo_section(const double *co, double xin, double &z0, double &z1, double &o) {
+    o = co[0] * xin + z0;
+    z0 = co[1] * xin - co[4] * o + z1;
+    z1 = co[2] * xin - co[5] * o;
+}
+
+__global__ void __launch_bounds__(32 * QD_XO_WARPS) crossover_kernel(const CrossoverArgs a) {
+    __shared__ float s_lo[QD_XO_WARPS][32][33];   // input row, overwritten by the low band
+    __shared__ float s_hi[QD_XO_WARPS][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t base = (size_t)blockIdx.y * (size_t)a.n;
     const float *x = a.x + base;
-    double st[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // chunk states: lp1, lp2, hp1, hp2
-    if (a.low_delay > 0)
-        for (long long i = tid; i < a.low_delay && i < a.n; i += QD_TT) a.low[base + i] = a.process_low ? low_process(0.0f, a) : 0.0f;
-    for (long long n0 = 0; n0 < a.n; n0 += QD_CHUNK) {
-        const long long s0 = n0 + (long long)tid * QD_KS;
-        double xin[QD_KS];
+    float *low = a.low + base, *high = a.high + base;
+    const long long n_tiles = (a.n + a.tile - 1) / a.tile;
+    const long long tile0 = ((long long)blockIdx.x * QD_XO_WARPS + warp) * 32;   // the warp's first tile; lane l owns tile0 + l
+    if (blockIdx.x == 0 && a.low_delay > 0) {   // head of the delayed low band: the processed zero input
+        const float z = a.process_low ? low_process(0.0f, a) : 0.0f;
+        for (long long i = threadIdx.x; i < a.low_delay && i < a.n; i += 32 * QD_XO_WARPS) low[i] = z;
+    }
+    if (tile0 >= n_tiles) return;
+    float (*rl)[33] = s_lo[warp];
+    float (*rh)[33] = s_hi[warp];
+    const int rows = (int)(n_tiles - tile0 < 32 ? n_tiles - tile0 : 32);
+    double st[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    const int steps = (a.halo + a.tile) / 32;
+    const long long s_first = tile0 * a.tile - a.halo;     // sample index of row 0, step 0, column 0
+    // row r of a step = 32 consecutive samples of tile tile0 + r: one 128-byte row per warp load.  The rows of step
+    // j + 1 are fetched into registers while step j is filtered, so no global latency sits between the steps.
+    float nxt[32];
+    auto fetch = [&](int j) {
 #pragma unroll
-        for (int k = 0; k < QD_KS; ++k) xin[k] = (s0 + k < a.n) ? (double)x[s0 + k] : 0.0;
+        for (int r = 0; r < 32; ++r) {
+            const long long sidx = s_first + (long long)r * a.tile + 32LL * j + lane;
+            nxt[r] = (r < rows && sidx >= 0 && sidx < a.n) ? x[sidx] : 0.0f;
+        }
+    };
+    fetch(0);
+    for (int j = 0; j < steps; ++j) {
 #pragma unroll
-        for (int f = 0; f < 2; ++f) {
-            double v[QD_KS];
-#pragma unroll
-            for (int k = 0; k < QD_KS; ++k) v[k] = xin[k];
-#pragma unroll
-            for (int sec = 0; sec < 2; ++sec) {
-                double z0, z1, e0, e1;
-                const double *co = a.co[2 * f + sec];
-                biquad_scan(co, a.apow[2 * f + sec], v, st[2 * f + sec][0], st[2 * f + sec][1], s_w, tid, z0, z1, e0, e1);
-                biquad_run(co, v, z0, z1);
-                st[2 * f + sec][0] = e0;
-                st[2 * f + sec][1] = e1;
+        for (int r = 0; r < 32; ++r) rl[r][lane] = nxt[r];
+        __syncwarp();
+        if (j + 1 < steps) fetch(j + 1);
+        // ---- filter the own row
+        if (lane < rows) {
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const double xin = (double)rl[lane][k];
+                double l1, l2, h1, h2;
+                xo_section(a.co[0], xin, st[0][0], st[0][1], l1);
+                xo_section(a.co[1], l1, st[1][0], st[1][1], l2);
+                xo_section(a.co[2], xin, st[2][0], st[2][1], h1);
+                xo_section(a.co[3], h1, st[3][0], st[3][1], h2);
+                const float lf = (float)l2;
+                rl[lane][k] = a.process_low ? low_process(lf, a) : lf;
+                rh[lane][k] = (float)h2;
             }
-#pragma unroll
-            for (int k = 0; k < QD_KS; ++k) {
-                const long long s = s0 + k;
-                if (s >= a.n) break;
-                const float o = (float)v[k];
-                if (f == 0) {
-                    const long long dsts = s + a.low_delay;
-                    if (dsts < a.n) a.low[base + dsts] = a.process_low ? low_process(o, a) : o;
-                } else {
-                    a.high[base + s] = o;
+        }
+        __syncwarp();
+        // ---- store (the warm-up steps produce nothing)
+        if (32 * j >= a.halo) {
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) {
+                const long long sidx = s_first + (long long)r * a.tile + 32LL * j + lane;
+                if (sidx < a.n) {
+                    high[sidx] = rh[r][lane];
+                    if (sidx + a.low_delay < a.n) low[sidx + a.low_delay] = rl[r][lane];
                 }
             }
         }
+        __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------- elementwise
 __global__ void distort_kernel(const float *__restrict__ x, float *__restrict__ y, long long count, int mode,
-                               float fold, float bias, float tg, float tn) {
+                               double fold, double bias, float tg, float tn) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         const float v = x[i];
         float r;
-        if (mode == 0) {
-            float t = (v + bias) * fold;
-            if (t > 1.0f) t = 2.0f - t;
-            if (t < -1.0f) t = -2.0f - t;  // sequential masks, dsp/distortion.py:44-53
-            r = fminf(fmaxf(t, -1.0f), 1.0f);
+        if (mode == 0) {   // float64 like the reference, one rounding to float32 (see epilogue_apply)
+            double t = ((double)v + bias) * fold;
+            if (t > 1.0) t = 2.0 - t;
+            if (t < -1.0) t = -2.0 - t;  // sequential masks, dsp/distortion.py:44-53
+            r = (float)fmin(fmax(t, -1.0), 1.0);
         } else {
             r = tanhf(tg * v) * tn;
         }

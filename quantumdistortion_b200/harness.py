@@ -8,7 +8,7 @@ from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .audio_io import load_audio, save_audio
+from .audio_io import load_audio, load_pcm16, save_audio, save_pcm16
 from .config import PipelineConfig, ensure_mono_float32
 
 
@@ -48,24 +48,33 @@ def process_files(pairs: Iterable[Tuple[Path, Path]], preset: Optional[str] = No
     per_file = seeds is not None and not isinstance(seeds, (int, np.integer))
     if per_file and len(seeds) != len(pairs):
         raise ValueError("need one seed per file")
-    groups: Dict[Tuple[int, int], List[Tuple[Path, np.ndarray, Any]]] = {}
+    # (length, sample rate, is 16-bit PCM mono) -> [(outfile, samples, seed)]
+    groups: Dict[Tuple[int, int, bool], List[Tuple[Path, np.ndarray, Any]]] = {}
     for i, (infile, outfile) in enumerate(pairs):
         infile = Path(infile)
         if not infile.exists():
             raise FileNotFoundError(f"Input file not found: {infile}")
-        audio, sr = load_audio(infile)
-        x = ensure_mono_float32(preview_truncate(audio, sr, None, cfg))   # process_audio truncates before the mono mix
-        groups.setdefault((x.shape[0], sr), []).append((Path(outfile), x, seeds[i] if per_file else None))
+        pcm, sr = load_pcm16(infile)
+        if pcm is not None and pcm.ndim == 1:
+            # mono 16-bit PCM stays int16 until it is on the device: same samples as load_audio's int16 / 32768
+            x = preview_truncate(pcm, sr, None, cfg)
+        else:
+            audio, sr = load_audio(infile)
+            x = ensure_mono_float32(preview_truncate(audio, sr, None, cfg))   # process_audio truncates before the mono mix
+        groups.setdefault((x.shape[0], sr, x.dtype == np.int16), []).append((Path(outfile), x, seeds[i] if per_file else None))
     written = 0
-    for (n, sr), items in groups.items():
+    for (n, sr, is_pcm), items in groups.items():
         if n == 0:
             for out, x, _ in items:
-                save_audio(out, x, sr)
+                save_audio(out, x.astype(np.float32), sr)
                 written += 1
             continue
         batch = np.stack([x for _, x, _ in items])
         y, _ = process_batch(batch, sr, pipeline_config=cfg, seeds=[s for _, _, s in items] if per_file else seeds)
         for (out, _, _), row in zip(items, y):
-            save_audio(out, row, sr)
+            if is_pcm:
+                save_pcm16(out, row, sr)    # the device already applied save_audio's float -> PCM16 rule
+            else:
+                save_audio(out, row, sr)
             written += 1
     return written

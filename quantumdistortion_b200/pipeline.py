@@ -34,9 +34,20 @@ _PC_FIELDS = ("key", "scale", "quantize_mode", "snap_strength", "smear", "bin_sm
 
 @dataclass
 class RenderTiming:
-    """Device-side timing of the last render (cf. RenderTiming, dsp/pipeline.py:153-161)."""
+    """Device-side timing of a render, per kernel class (cf. RenderTiming, dsp/pipeline.py:153-161, whose stft / proc /
+    istft stages are one fused kernel here).  Filled by ``Renderer.timing()`` from CUDA events recorded on the launch
+    stream (qd_plan_enable_timing); milliseconds since the previous call."""
+    spectral_ms: float = 0.0     # STFT -> FX -> quantizer -> iSTFT -> overlap-add -> distortion (both passes)
+    limiter_ms: float = 0.0      # lookahead limiter + dry/wet + trim + recombine + delta
+    crossover_ms: float = 0.0    # LR4 split + low-band delay / saturation
+    other_ms: float = 0.0
     total_ms: float = 0.0
     launches: int = 0
+
+    def line(self, mode: str = "spectral_bins") -> str:
+        """The reference's one-line report (dsp/pipeline.py:1382-1390), with this implementation's stages."""
+        return (f"[RENDER_TIMING] mode={mode} spectral={self.spectral_ms:.3f}ms limiter={self.limiter_ms:.3f}ms "
+                f"crossover={self.crossover_ms:.3f}ms total={self.total_ms:.3f}ms launches={self.launches}")
 
 
 def _torch():
@@ -119,6 +130,14 @@ class Renderer:
         names = ("spectral", "limiter", "crossover", "other")
         return {n: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, n in enumerate(names)}
 
+    def timing(self) -> RenderTiming:
+        """RenderTiming of the renders since the last call (needs enable_timing(True); waits for the events)."""
+        t = self.read_timing()
+        ms = {k: v["ms"] for k, v in t.items()}
+        return RenderTiming(spectral_ms=ms["spectral"], limiter_ms=ms["limiter"], crossover_ms=ms["crossover"],
+                            other_ms=ms["other"], total_ms=sum(ms.values()),
+                            launches=sum(v["launches"] for v in t.values()))
+
     def _workspace(self, batch: int):
         torch = _torch()
         need = int(self._lib.qd_plan_workspace_bytes(self._plan, batch))
@@ -162,10 +181,19 @@ class Renderer:
         return y, taps
 
     def render_host(self, x_host, y_host, chunk_clips: int = 128) -> None:
-        """x_host / y_host: CPU float32 [B, n] (pinned for full speed).  Synchronous; H2D, kernels and
-        D2H of consecutive chunks overlap inside the library."""
+        """x_host / y_host: contiguous CPU tensors [B, n], float32 or int16 (16-bit PCM, converted on the device with
+        the WAV layer's rules: half the PCIe bytes).  Pinned memory is copied directly; pageable memory is staged
+        through the library's pinned ring by copy threads.  Synchronous; H2D, kernels and D2H of consecutive chunks
+        overlap inside the library (qd_render_host_ex)."""
+        torch = _torch()
+        fmt = {torch.float32: 0, torch.int16: 1}
+        if x_host.dtype not in fmt or y_host.dtype not in fmt:
+            raise ValueError("host buffers must be float32 or int16 (PCM16)")
+        if x_host.shape != y_host.shape or not x_host.is_contiguous() or not y_host.is_contiguous():
+            raise ValueError("x_host and y_host must be contiguous and of the same [B, n] shape")
         batch = int(x_host.shape[0])
-        _lib.check(self._lib.qd_render_host(self._plan, x_host.data_ptr(), y_host.data_ptr(), batch, int(chunk_clips)))
+        _lib.check(self._lib.qd_render_host_ex(self._plan, x_host.data_ptr(), y_host.data_ptr(), batch, int(chunk_clips),
+                                               fmt[x_host.dtype], fmt[y_host.dtype]))
 
 
 class AutotuneRenderer:
@@ -192,11 +220,31 @@ class AutotuneRenderer:
         return (y, taps, dbg) if debug else (y, taps)
 
     def render_host(self, x_host, y_host, chunk_clips: int = 128) -> None:
-        """Chunked H2D -> render -> D2H (no copy/compute overlap in this first version of the mode)."""
+        """Chunked H2D -> render -> D2H with the copies on their own streams, so that the transfers of chunk i+1 / i-1
+        run under the kernels of chunk i (pinned host tensors).  float32 or int16 (PCM16, converted on the device:
+        sample / 32768 in, rint(y * 32767) clipped out -- the rules of audio_io)."""
+        torch = _torch()
+        run = torch.cuda.current_stream()
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        s_in, s_out = self._s_in, self._s_out
+        s_in.wait_stream(run)
         for b0 in range(0, int(x_host.shape[0]), int(chunk_clips)):
-            xs = x_host[b0:b0 + chunk_clips].cuda(non_blocking=True)
-            y, _ = self.render_device(xs, chunk_clips=chunk_clips)
-            y_host[b0:b0 + chunk_clips].copy_(y)
+            with torch.cuda.stream(s_in):
+                xs = x_host[b0:b0 + chunk_clips].to("cuda", non_blocking=True)
+            run.wait_stream(s_in)
+            xs.record_stream(run)
+            if xs.dtype == torch.int16:
+                xs = xs.to(torch.float32) * (1.0 / 32768.0)
+            y, _ = self.render_device(xs.float(), chunk_clips=chunk_clips)
+            if y_host.dtype == torch.int16:
+                y = torch.clamp(torch.round(y.double() * 32767.0), -32768.0, 32767.0).to(torch.int16)
+            s_out.wait_stream(run)
+            with torch.cuda.stream(s_out):
+                y_host[b0:b0 + chunk_clips].copy_(y, non_blocking=True)
+            y.record_stream(s_out)
+        s_out.synchronize()
+        run.synchronize()
 
 
 _RENDERERS: Dict[Any, Renderer] = {}
@@ -353,15 +401,23 @@ def process_batch(x, sr: int = DEFAULT_SAMPLE_RATE, *, n_fft: int = N_FFT_DEFAUL
     clip like a loop of reference calls; int: reseed before every clip; list: one seed per clip); ``shard=(lo, hi,
     total)`` marks ``x`` as clips lo..hi of a larger batch rendered across several processes (see fx_tables).
     ``x`` may be a CUDA tensor (returns CUDA tensors, asynchronous), a CPU tensor or a NumPy array
-    (returns the same kind; the copy/compute pipeline of ``qd_render_host`` is used when no taps are
-    requested).  ``out`` (CPU tensor, ideally pinned like ``x``) receives the result of the host path
-    without a fresh allocation.  Keyword arguments are the reference's ``process_audio`` arguments.
+    (returns the same kind; the copy/compute pipeline of ``qd_render_host_ex`` is used when no taps are
+    requested: pinned tensors are copied directly, pageable ones -- every NumPy array -- go through the
+    library's pinned staging ring).  An int16 array / tensor is 16-bit PCM: it crosses PCIe as int16 and the
+    result comes back as int16, converted on the device with the WAV layer's rules (audio_io).  ``out`` (CPU
+    tensor, ideally pinned like ``x``) receives the result of the host path without a fresh allocation.  Keyword arguments are the reference's ``process_audio`` arguments.
     """
     torch = _torch()
     is_np = isinstance(x, np.ndarray)
-    xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) if is_np else x
+    if is_np:
+        pcm = x.dtype == np.int16
+        xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int16 if pcm else np.float32))
+    else:
+        xt, pcm = x, x.dtype == torch.int16
     if xt.dim() != 2:
         raise ValueError("process_batch expects [batch, samples]")
+    if pcm and (xt.is_cuda or return_taps):
+        raise ValueError("int16 (PCM16) input is the host transport format: CPU arrays only, no taps")
     r = make_renderer(xt.shape[1], sr, n_fft, seeds=seeds, **kwargs)
     r.set_fx_seeds(int(xt.shape[0]), seeds, shard)  # no-op unless a random spectral FX is active
     if xt.is_cuda:
@@ -370,10 +426,10 @@ def process_batch(x, sr: int = DEFAULT_SAMPLE_RATE, *, n_fft: int = N_FFT_DEFAUL
         y, taps = r.render_device(xt.float().cuda(), want_taps=True)
         y, taps = y.cpu(), {k: v.cpu() for k, v in taps.items()}
     else:
-        xin = xt.float().contiguous()
+        xin = (xt if pcm else xt.float()).contiguous()
         if out is not None:
-            if out.shape != xin.shape or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
-                raise ValueError("out must be a contiguous CPU float32 tensor shaped like x")
+            if out.shape != xin.shape or out.dtype not in (torch.float32, torch.int16) or out.is_cuda or not out.is_contiguous():
+                raise ValueError("out must be a contiguous CPU float32 (or int16) tensor shaped like x")
             y = out
         else:
             y = torch.empty_like(xin, pin_memory=xin.is_pinned())

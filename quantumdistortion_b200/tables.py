@@ -204,7 +204,8 @@ def resolve_spectral_fx(mode: Optional[str], strength: float, params: Optional[D
             window += 1
         mode_name = params.get("mode", "swap" if s < 0.4 else "random_pick")
         if mode_name == "random_pick":
-            return {"fx_mode": _lib.QD_FX["scramble_pick"], "a": 0.0, "b": 0.0, "c": 0.0, "rng": ("pick", window // 2)}
+            return {"fx_mode": _lib.QD_FX["scramble_pick"], "a": float(window // 2), "b": 0.0, "c": 0.0,
+                    "rng": ("pick", window // 2)}
         if mode_name == "swap":
             return {"fx_mode": _lib.QD_FX["scramble_swap"], "a": 0.0, "b": 0.0, "c": 0.0, "rng": ("swap",)}
         # unknown scramble mode: copy + energy rescale = identity (dsp/spectral_fx.py:382-388)
@@ -251,7 +252,7 @@ def max_fan_in(target_bins: Optional[np.ndarray], active_mask: Optional[np.ndarr
 
 
 def choose_precision(precision: str, n_fft: int, target_bins, active_mask, fx_active: bool = False,
-                     formant_active: bool = False) -> int:
+                     formant_active: bool = False, fx_mode: int = 0) -> int:
     """0 = float32 kernels, 1 = float64 kernels.  "auto" keeps the fast float32 path for the reference's
     defaults and switches to float64 where float32 cannot hold the 1e-4 parity bound: n_fft 8192
      and quantiser tables whose targets gather more than F64_FAN_IN source bins
@@ -263,10 +264,18 @@ def choose_precision(precision: str, n_fft: int, target_bins, active_mask, fx_ac
         return 1
     if precision != "auto":
         raise ValueError("precision must be 'auto', 'float32' or 'float64'")
-    if formant_active:
-        return 0   # float32 kernels; precision="float64" runs the cepstral FFTs in float64 as well
     if n_fft >= 8192:
-        return 0 if fx_active else 1   # the float64 FX kernels are not built for n_fft 8192
+        return 1   # every variant of the pass: the float32 FFT alone is 1e-4 ... 3e-4 off there
+    if fx_mode == _lib.QD_FX["bitcrush_uniform"]:
+        # round(m / step) on a LINEAR grid flips wherever float32 rounding moves a magnitude across a boundary, and a
+        # flip moves the bin by a whole step whatever its size (measured: 1.3e-4 at step 0.004, 4e-6 in float64); the
+        # default log-domain method is not affected (a flip there is proportional to the bin)
+        return 1
+    if formant_active:
+        # the cepstral envelope takes log(max(m, 1e-12)) of EVERY bin: bins under the float32 FFT's noise floor (1e-7 of
+        # the frame's strongest bin -- the far skirts of any DC-heavy or tonal frame) come out as noise, the envelope
+        # follows, and the render moves by 2e-3 (measured on the fade-in of a wavefolded clip); float64 has 1e-16
+        return 1
     return 1 if max_fan_in(target_bins, active_mask) > F64_FAN_IN else 0
 
 
@@ -393,11 +402,9 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
         pass
     p.spectral_freeze = int(bool(spectral_freeze) and quant_on)   # dsp/pipeline.py:285-287 (any band)
     formant_on = bool(quant_on and float(formant_shift) != 0.0)  # dsp/pipeline.py:306-310 (any band)
-    if formant_on and n_fft > 4096:
-        raise NotImplementedError("formant_shift is built for n_fft <= 4096")
     p.formant_ratio = float(2.0 ** (float(formant_shift) / 12.0)) if formant_on else 0.0  # dsp/spectral_fx.py:173
     p.formant_order = 30                                                                  # dsp/spectral_fx.py:120
     p.precision = choose_precision(precision, n_fft, tb, mask, fx_active=bool(p.fx_mode) or bool(p.spectral_freeze),
-                                   formant_active=formant_on)
+                                   formant_active=formant_on, fx_mode=int(p.fx_mode))
     return Resolved(params=p, tables=tables, keepalive=tuple(keep), target_bins=tb, active_mask=mask,
                     fx_rng=fx_rng, fx_passes=fx_passes, n_frames=n_frames, n_bins=n_fft // 2 + 1)

@@ -44,7 +44,7 @@ int main(int argc, char **argv) {
         write_all(argv[7], y);
         return 0;
     }
-    if (mode == "crossover" && argc == 9) {
+    if (mode == "crossover" && (argc == 9 || argc == 11)) {
         const long long n = std::atoll(argv[2]);
         auto lp = read_all<double>(argv[4]);
         auto hp = read_all<double>(argv[5]);
@@ -54,7 +54,10 @@ int main(int argc, char **argv) {
         a.x = x.data(); a.low = lo.data(); a.high = hi.data(); a.n = n;
         a.low_delay = std::atoi(argv[3]);
         qd_host::fill_crossover(a, lp.data(), hp.data());
-        qd_emu::launch(dim3(1), dim3(qd::QD_TT), 0, [&] { qd::crossover_kernel(a); });
+        if (argc > 9) { a.tile = std::atoi(argv[9]); a.halo = std::atoi(argv[10]); }   // small tiles: many tiles per clip
+        const long long n_tiles = (n + a.tile - 1) / a.tile;
+        const unsigned gx = (unsigned)((n_tiles + 32 * qd::QD_XO_WARPS - 1) / (32 * qd::QD_XO_WARPS));
+        qd_emu::launch(dim3(gx, 1, 1), dim3(32 * qd::QD_XO_WARPS), 0, [&] { qd::crossover_kernel(a); });
         write_all(argv[7], lo);
         write_all(argv[8], hi);
         return 0;

@@ -128,8 +128,11 @@ def test_emu_limiter(emu_time, n, sr, kind):
     assert np.max(np.abs(y.astype(np.float64) - ref)) <= 6e-8, float(np.max(np.abs(y - ref)))
 
 
-@pytest.mark.parametrize("n,delay", [(6000, 0), (5003, 1024), (100, 0), (2048, 300)])
-def test_emu_crossover(emu_time, n, delay):
+@pytest.mark.parametrize("n,delay,tiling", [(6000, 0, None), (5003, 1024, None), (100, 0, None), (2048, 300, None),
+                                            (6000, 1024, (256, 1632)), (5003, 0, (512, 2048)), (9000, 64, (32, 1632))])
+def test_emu_crossover(emu_time, n, delay, tiling):
+    """`tiling` = (tile, halo) forces many tiles per clip: every tile but the first starts from a zero state `halo`
+    samples early and must land on the sequential filter's output."""
     x = synth.loud_clip(3, n)
     sl, sh = orc.linkwitz_riley_sos(48000, 300.0)
     with tempfile.TemporaryDirectory() as d:
@@ -137,7 +140,8 @@ def test_emu_crossover(emu_time, n, delay):
         x.tofile(p("x"))
         sl.astype(np.float64).tofile(p("lp"))
         sh.astype(np.float64).tofile(p("hp"))
-        subprocess.check_call([emu_time, "crossover", str(n), str(delay), p("lp"), p("hp"), p("x"), p("lo"), p("hi")])
+        subprocess.check_call([emu_time, "crossover", str(n), str(delay), p("lp"), p("hp"), p("x"), p("lo"), p("hi")] +
+                              ([str(tiling[0]), str(tiling[1])] if tiling else []))
         lo = np.fromfile(p("lo"), dtype=np.float32)
         hi = np.fromfile(p("hi"), dtype=np.float32)
     rlo, rhi = orc.linkwitz_riley_split(x, 48000, 300.0)

@@ -83,7 +83,6 @@ def test_float64_fx_kernels_vs_reference_fixtures(qd, r2, pipe, name):
     _check(taps["pre_quant"], fix[f"{name}/pre_quant"], f"{name}/pre_quant f64", 5e-6)
 
 
-@pytest.mark.gpu
 def test_auto_precision_never_picks_a_path_outside_tolerance():
     """precision="auto": float64 kernels for every n_fft 8192 configuration."""
     from quantumdistortion_b200.pipeline import _resolve_kwargs
@@ -210,3 +209,70 @@ def test_process_files_preview_and_per_file_seeds(qd, tmp_path, monkeypatch):
     out = tmp_path / "c" / "0.wav"
     assert qd.process_files([(ins[0], out)], extra_params=extra, seeds=5) == 1
     assert load_audio(out)[0].shape == (80000,)
+
+
+# ---------------------------------------------------------------------------------------------- host transport
+@pytest.mark.gpu
+def test_pcm16_transport_and_pageable_staging(qd):
+    """qd_render_host_ex: 16-bit PCM on the PCIe link (converted on the device with the WAV layer's rules) and pageable
+    host memory staged through the pinned ring -- every variant bit-identical to the device-resident render."""
+    import torch
+    from quantumdistortion_b200 import synth
+    from quantumdistortion_b200.audio_io import float_to_pcm16
+    n, sr, b = 30000, 48000, 5
+    x16 = float_to_pcm16(np.stack([synth.loud_clip(300 + i, n, sr) * 0.6 for i in range(b)]))
+    xf = x16.astype(np.float32) / 32768.0                      # what load_audio hands to process_audio
+    kw = dict(SB, use_multiband=True, dry_wet=0.8)
+    y_dev, _ = qd.process_batch(torch.from_numpy(xf).cuda(), sr, **kw)
+    y_dev = y_dev.cpu().numpy()
+    want16 = float_to_pcm16(y_dev)
+    # NumPy arrays are pageable: 5 one-clip chunks wrap the 3-slot ring in both directions
+    y_np, _ = qd.process_batch(xf, sr, chunk_clips=1, **kw)
+    assert y_np.dtype == np.float32 and np.array_equal(y_np, y_dev)
+    y16, _ = qd.process_batch(x16, sr, chunk_clips=1, **kw)
+    assert y16.dtype == np.int16 and np.array_equal(y16, want16)
+    # pinned int16 tensors (direct copies), then int16 in / float32 out
+    xp = torch.from_numpy(x16).pin_memory()
+    out16 = torch.empty_like(xp).pin_memory()
+    qd.process_batch(xp, sr, out=out16, chunk_clips=2, **kw)
+    assert np.array_equal(out16.numpy(), want16)
+    outf = torch.empty((b, n), dtype=torch.float32).pin_memory()
+    qd.process_batch(xp, sr, out=outf, chunk_clips=2, **kw)
+    assert np.array_equal(outf.numpy(), y_dev)
+    # the other mode (autotune_v1 host path: torch streams) with PCM16
+    xt = float_to_pcm16(np.stack([synth.tone_clip(i, 12000, sr) for i in range(3)]))
+    ya, _ = qd.process_batch(torch.from_numpy(xt.astype(np.float32) / 32768.0).cuda(), sr)
+    ya16, _ = qd.process_batch(xt, sr, chunk_clips=2)
+    assert np.array_equal(ya16, float_to_pcm16(ya.cpu().numpy()))
+    with pytest.raises(ValueError):
+        qd.process_batch(x16, sr, return_taps=True, **kw)
+
+
+@pytest.mark.gpu
+def test_pageable_staging_large_chunks(qd):
+    """Chunks large enough for the multi-threaded staging copies (> 8 MB), more chunks than ring slots."""
+    import torch
+    from quantumdistortion_b200 import synth
+    n, sr, b = 480000, 48000, 40
+    x = synth.bass_batch_torch(b, n, sr, "cuda", seed=9)
+    y_dev, _ = qd.process_batch(x, sr, **SB)
+    x_np = x.cpu().numpy()
+    y_np, _ = qd.process_batch(x_np, sr, chunk_clips=8, **SB)
+    assert np.array_equal(y_np, y_dev.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_render_timing_struct(qd):
+    """RenderTiming (dsp/pipeline.py:153-161) is filled from the CUDA events of the launch stream."""
+    import torch
+    from quantumdistortion_b200 import synth
+    x = synth.bass_batch_torch(4, 48000, 48000, "cuda", seed=1)
+    r = qd.make_renderer(48000, 48000, use_multiband=True, **SB)
+    r.enable_timing(True)
+    r.render_device(x)
+    torch.cuda.synchronize()
+    t = r.timing()
+    assert t.launches == r.launches_per_render == 4 and t.spectral_ms > 0 and t.crossover_ms > 0 and t.limiter_ms > 0
+    assert abs(t.total_ms - (t.spectral_ms + t.limiter_ms + t.crossover_ms + t.other_ms)) < 1e-9
+    assert t.line().startswith("[RENDER_TIMING] mode=spectral_bins")
+    r.enable_timing(False)

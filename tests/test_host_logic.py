@@ -101,8 +101,8 @@ def test_resolved_flags_follow_reference_gates():
     assert r.params.formant_ratio == 2.0 and r.params.formant_order == 30 and r.params.precision == 0
     r, _ = _resolve_kwargs(1000, 48000, 2048, {"formant_shift": 3.0, "snap_strength": 0.0})   # formant flips the mode
     assert r.params.formant_ratio == 0.0   # the spectral stage does not run at all (:635, :728)
-    with pytest.raises(NotImplementedError):
-        _resolve_kwargs(1000, 48000, 8192, {"formant_shift": 3.0})
+    r, _ = _resolve_kwargs(1000, 48000, 8192, {"formant_shift": 3.0})
+    assert r.params.formant_ratio > 1.0 and r.params.precision == 1   # n_fft 8192: always the float64 kernels
 
 
 def test_autotune_params_follow_reference_rules():
