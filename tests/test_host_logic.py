@@ -96,9 +96,12 @@ def test_resolved_flags_follow_reference_gates():
     assert r.params.pre_quant == 1          # an FX / freeze / formant / lock option flips the mode (:1315-1324)
     with pytest.raises(TypeError):
         _resolve_kwargs(1000, 48000, 2048, {"bogus": 1})
-    # formant shift (dsp/pipeline.py:306-310): ratio 2^(st/12), float32 kernels, flips autotune_v1 to the STFT path
+    # formant shift (dsp/pipeline.py:306-310): ratio 2^(st/12), flips autotune_v1 to the STFT path; precision="auto" takes
+    # the float64 kernels (bins under the float32 FFT's noise floor would reach the cepstral envelope as noise)
     r, _ = _resolve_kwargs(1000, 48000, 2048, {"quantize_mode": "autotune_v1", "formant_shift": 12.0})
-    assert r.params.formant_ratio == 2.0 and r.params.formant_order == 30 and r.params.precision == 0
+    assert r.params.formant_ratio == 2.0 and r.params.formant_order == 30 and r.params.precision == 1
+    r, _ = _resolve_kwargs(1000, 48000, 2048, {"formant_shift": 12.0, "precision": "float32"})
+    assert r.params.precision == 0
     r, _ = _resolve_kwargs(1000, 48000, 2048, {"formant_shift": 3.0, "snap_strength": 0.0})   # formant flips the mode
     assert r.params.formant_ratio == 0.0   # the spectral stage does not run at all (:635, :728)
     r, _ = _resolve_kwargs(1000, 48000, 8192, {"formant_shift": 3.0})
