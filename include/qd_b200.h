@@ -208,7 +208,7 @@ int qd_render_host_pcm16(qd_plan *plan, const int16_t *x_host, int16_t *y_host, 
 
 /* General form: either side float32 or PCM16.  Host buffers may be pinned (cudaHostAlloc / cudaHostRegister /
  * qd_host_alloc: copied directly) or pageable (staged through an internal ring of pinned buffers by copy
- * threads, QD_HOST_COPY_THREADS per direction, default 4).  On any error the call drains its streams before it
+ * threads, QD_HOST_COPY_THREADS per direction, default 8 on hosts with 16 or more cores).  On any error the call drains its streams before it
  * returns. */
 #define QD_SAMPLE_F32   0
 #define QD_SAMPLE_PCM16 1

@@ -56,14 +56,19 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     from . import build as _build
-    if _build.needs_build():
+    override = os.environ.get("QD_B200_LIB")   # A/B runs of two builds on one box (profiles/): no rebuild, no fallback
+    if override:
+        path = override
+    elif _build.needs_build():
         try:
             _build.build()
         except Exception as exc:  # noqa: BLE001
             if not os.path.exists(LIB_PATH):
                 raise QdError(f"libqd_b200.so is missing and could not be built ({exc}); "
                               "quantumdistortion_b200 has no CPU fallback") from exc
-    lib = C.CDLL(LIB_PATH)
+    if not override:
+        path = LIB_PATH
+    lib = C.CDLL(path)
     vp, i64, i32, dbl, flt = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_float
     lib.qd_abi_version.restype = C.c_int
     lib.qd_last_error.restype = C.c_char_p

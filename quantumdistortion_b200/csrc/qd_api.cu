@@ -12,9 +12,10 @@
 #include <vector>
 
 #include "../../include/qd_b200.h"
+#include "qd_err.hpp"
 #include "qd_host_tables.hpp"
 #include "qd_host_time.hpp"
-#include "qd_spec.cuh"
+#include "qd_spec_launch.hpp"
 #include "qd_peaks.cuh"
 #include "qd_autotune.cuh"
 #include "qd_time.cuh"
@@ -25,33 +26,9 @@
 
 namespace {
 
-thread_local std::string g_err;
-
-int fail(int code, const std::string &msg) {
-    g_err = msg;
-    return code;
-}
-
-#define QD_CUDA(call)                                                                              \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess)                                                                     \
-            return fail(QD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
-    } while (0)
-
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember the devices a kernel was opted in on
-// (a process may render on several GPUs one after the other)
-template <class K>
-int ensure_dyn_smem(K kern, std::atomic<uint64_t> &mask, int bytes) {
-    int dev = 0;
-    QD_CUDA(cudaGetDevice(&dev));
-    const uint64_t bit = 1ull << (dev & 63);
-    if (!(mask.load(std::memory_order_acquire) & bit)) {
-        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        mask.fetch_or(bit, std::memory_order_release);
-    }
-    return QD_OK;
-}
+using qd_err::ensure_dyn_smem;
+using qd_err::fail;
+using qd_launch::launch_spec_t;
 
 template <class T>
 cudaError_t upload(const std::vector<T> &h, T **d) {
@@ -89,6 +66,7 @@ struct qd_plan {
     qd::SpecArgsT<double> spec64{};  // the same for the float64 parity path
     bool f64 = false;
     bool ts = false;           // float32 n_fft 2048: tables fit the shared-memory kernel variant
+    bool ts_fx = false;        // the same for the 12-warp FX variant (no formant scratch)
     size_t spec_smem = 0;      // dynamic shared memory of the pass kernel in use
     const void *fx_table = nullptr;
     int64_t fx_tables = 0;
@@ -164,29 +142,6 @@ size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int form
     return 0;
 }
 
-template <class T, int NC, int NW, bool TS, bool FX, int NG = 1, bool SA = false>
-int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st) {
-    static std::atomic<uint64_t> attr_mask{0};  // devices this instantiation was opted in on
-    auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX, NG, SA>;
-    if (int rc_ = ensure_dyn_smem(kern, attr_mask, 227 * 1024)) return rc_;
-    const size_t smem = qd::SpecSmem<T, NC, NW, NG, SA>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX, FX && a.formant_idx != nullptr);
-    if (smem > 227 * 1024) return fail(QD_ERR_UNSUPPORTED, "shared memory need of this kernel variant exceeds 227 KB");
-    for (int64_t b0 = 0; b0 < batch; b0 += 65535 * NG) {  // gridDim.y limit
-        const int64_t nb = std::min<int64_t>(65535 * NG, batch - b0);
-        qd::SpecArgsT<T> c = a;
-        c.batch = (int)nb;
-        c.x = a.x + (size_t)b0 * a.n;
-        c.y = a.y + (size_t)b0 * a.n;
-        if (a.tap) c.tap = a.tap + (size_t)b0 * a.n;
-        if (a.clip_peak) c.clip_peak = a.clip_peak + b0;
-        if (a.frozen) c.frozen = a.frozen + (size_t)b0 * qd::buf_slots<NC>();
-        c.fx.clip_offset = a.fx.clip_offset + (int)b0;
-        kern<<<dim3((unsigned)tiles, (unsigned)((nb + NG - 1) / NG), 1), 32 * NW * NG, smem, st>>>(c);
-    }
-    QD_CUDA(cudaGetLastError());
-    return QD_OK;
-}
-
 template <class T, bool FX>
 int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st) {
     switch (nc) {
@@ -198,6 +153,7 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
             }
             if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 1024, 4, false, true>(a, tiles, batch, st);
             else if constexpr (FX) return nw == 8 ? launch_spec_t<T, 1024, 8, false, true>(a, tiles, batch, st)
+                                             : ts ? launch_spec_t<T, 1024, 12, true, true>(a, tiles, batch, st)
                                                   : launch_spec_t<T, 1024, 12, false, true>(a, tiles, batch, st);
             else return launch_spec_t<T, 1024, 8, false, false>(a, tiles, batch, st);
         case 2048:
@@ -254,7 +210,7 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
     a.fx.table = pl->fx_table;
     // a pass that does not run the FX uses the plain kernel of the same warp count
     int nw = fx ? pl->nw : pick_nw<T>(pl->nc, false) == 16 && !pl->ts ? 8 : pick_nw<T>(pl->nc, false);
-    const bool ts = pl->ts && !fx;
+    const bool ts = fx ? pl->ts_fx : pl->ts;
     const int ng = (nw == 16) ? 2 : 1;   // clips per CTA
     // tiling: whole clips when the batch alone fills the GPU, else cut clips along time
     const int total_blocks = (a.n + pl->hop - 1) / pl->hop;
@@ -281,7 +237,7 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
         if (rc != QD_OK) return rc;
         a.frozen = frozen;
     }
-    if (fx) return dispatch_spec<T, true>(pl->nc, nw, false, a, tiles, batch, st);
+    if (fx) return dispatch_spec<T, true>(pl->nc, nw, ts, a, tiles, batch, st);
     return dispatch_spec<T, false>(pl->nc, nw, ts, a, tiles, batch, st);
     (void)nw;
 }
@@ -415,7 +371,7 @@ extern "C" {
 
 int qd_abi_version(void) { return QD_ABI_VERSION; }
 
-const char *qd_last_error(void) { return g_err.c_str(); }
+const char *qd_last_error(void) { return qd_err::g_err.c_str(); }
 
 int qd_device_count(void) {
     int n = 0;
@@ -578,7 +534,10 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         a.formant_idx = d_fi; a.formant_frac = d_ff; a.formant_order = p.formant_order;
         pl->nw = pick_nw<float>(pl->nc, fx, formant);
         pl->ts = (pl->nc == 1024 && pl->nw == 16);
-        pl->spec_smem = spec_smem_bytes<float>(pl->nc, pl->nw, pl->ts, n_slots, qdev.n_src, formant ? 1 : 0, fx);
+        if (fx && pl->nc == 1024 && pl->nw == 12 && !formant)   // FX variant with its tables in shared memory, when they fit
+            pl->ts_fx = qd::SpecSmem<float, 1024, 12>::bytes(n_slots, true, qdev.n_src, 0, true, false) <= 227 * 1024;
+        pl->spec_smem = pl->ts_fx ? qd::SpecSmem<float, 1024, 12>::bytes(n_slots, true, qdev.n_src, 0, true, false)
+                                  : spec_smem_bytes<float>(pl->nc, pl->nw, pl->ts, n_slots, qdev.n_src, formant ? 1 : 0, fx);
         if (pl->ts && pl->spec_smem > 227 * 1024) {  // tables too large for shared memory: 8 warps, tables through L1
             pl->nw = 8;
             pl->ts = false;

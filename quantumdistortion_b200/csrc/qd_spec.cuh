@@ -551,16 +551,38 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
     constexpr int NBINS = NC + 1;
     constexpr int ROWS = (NBINS + 31) / 32;
     T mx = 0.0f, sm = 0.0f;
-#pragma unroll 4
-    for (int row = 0; row < ROWS; ++row) {
-        if (row < ROWS - 1 || lane == 0) {
-            const int p = rpos<T, NC>(lane, row);
+    // On entry buf holds the packed FFT output Z.  One paired sweep (bin k and its mirror NC - k, like the plain
+    // quantizer) forms X[k] = E/2 + V_k (Z[k] - conj Z[NC-k]) and X[NC-k] in registers and leaves the unit phasors in
+    // buf and the magnitudes in the plane -- no separate real_split sweep.  DC / Nyquist fall out of the same formula
+    // (Z[NC] = Z[0], V_0 = -i/2); the Nyquist phasor goes to the pad slot.
+    {
+        constexpr int HR = NC / 64;
+#pragma unroll 2
+        for (int i = 0; i < HR; ++i) {
+            const int k = 32 * i + lane;
+            const int pa = rpos<T, NC>(lane, i);
+            const int pb = k == 0 ? QD_NYQ_SLOT : mpos<T, NC>(lane, i);
+            const V2<T> za = buf[pa], zb = cconj(buf[k == 0 ? pa : pb]);
+            const V2<T> e = cadd(za, zb);
+            const V2<T> t = cmul(csub(za, zb), wsplit[k]);
+            T ml, mh;
+            V2<T> ul, uh;
+            mag_phasor<T>(pfma(e, splat((T)0.5), t), ml, ul);
+            mag_phasor<T>(cconj(pfma(e, splat((T)0.5), mk2<T>(-t.x, -t.y))), mh, uh);
+            if (frozen) { ml = frozen[pa]; mh = frozen[pb]; }  // dsp/pipeline.py:285-287, 303-304: first-frame magnitudes, own phases
+            buf[pa] = ul; buf[pb] = uh;
+            mags[pa] = ml; mags[pb] = mh;
+            mx = qd_max(mx, qd_max(ml, mh));
+            sm += ml + mh;
+        }
+        if (lane == 0) {   // the walks meet at bin NC/2: X[NC/2] = conj Z[NC/2]
+            const int pm = spos<T, NC>(NC / 2);
             T m;
             V2<T> u;
-            mag_phasor<T>(buf[p], m, u);
-            buf[p] = u;
-            if (frozen) m = frozen[p];  // dsp/pipeline.py:285-287, 303-304: first-frame magnitudes, own phases
-            mags[p] = m;
+            mag_phasor<T>(cconj(buf[pm]), m, u);
+            if (frozen) m = frozen[pm];
+            buf[pm] = u;
+            mags[pm] = m;
             mx = qd_max(mx, m);
             sm += m;
         }
@@ -584,21 +606,25 @@ QD_DEV void fx_frame(V2<T> *buf, T *mags, const FxDev &fx, int lane, long long t
     if (fx.mode == 1 || fx.mode == 2) {
         // bitcrush (dsp/spectral_fx.py:198-260); np.round is half-to-even = rint
         const T thr = fx.c > 0.0f ? fx.c : fx.b * mx;
+        const bool has_step = fx.step > 0.0, log_mode = fx.mode == 1;
+        const T q_scale = (T)(6.020599913279624 / fx.step);          // 20 log10(m) / step_db = log2(m) * q_scale
+        const T e_scale = (T)(fx.step * 0.16609640474436813);        // 10^(q step_db / 20) = 2^(q * e_scale)
+#pragma unroll 2
         for (int row = 0; row < ROWS; ++row) {
             if (row < ROWS - 1 || lane == 0) {
                 const int p = rpos<T, NC>(lane, row);
                 T m = mags[p];
-                if (fx.step > 0.0) {
-                    if (fx.mode == 1) {
+                if (has_step) {
+                    if (log_mode) {
                         const T mm = qd_max(m, 1e-12f);
-                        const T q = log2_fast(mm) * (T)(6.020599913279624 / fx.step);  // 20 log10(m) / step_db
+                        const T q = log2_fast(mm) * q_scale;
                         T rq = qd_rint(q);
                         // close to a rounding boundary: decide in double.  The float32 evaluation of q is good to ~1e-5
                         // (log2f 1 ulp of |log2 m| <= 40, one multiply), so a band of 2e-4 is ample; a wider one sends
                         // most warps down the float64 log10 (a lane in the band is enough)
                         if (qd_abs(qd_abs(q - rq) - 0.5f) < 2e-4f)
                             rq = (T)rint(20.0 * log10((double)mm) / fx.step);
-                        m = exp2_fast(rq * (T)(fx.step * 0.16609640474436813));      // 10^(q step / 20)
+                        m = exp2_fast(rq * e_scale);
                     } else {
                         m = qd_max((T)(rint((double)m / fx.step) * fx.step), 0.0f);
                     }
@@ -698,42 +724,6 @@ QD_DEV T tld(const T *p) {
     else return __ldg(p);
 }
 
-// magnitude / phasor of a bin: from X, or (FX) from the separate magnitude plane
-template <class T, bool FX>
-QD_DEV void load_bin(const V2<T> *buf, const T *mags, int p, T &m, V2<T> &u) {
-    if constexpr (FX) { m = mags[p]; u = buf[p]; }
-    else mag_phasor<T>(buf[p], m, u);
-}
-
-template <class T, int NC, bool TS, bool FX>
-QD_DEV void quant_bin(const V2<T> *buf, const T *mags, const T *slotG, const V2<T> *slotP,
-                      const QuantDev &q, int lane, int row, uint32_t bit, T &nm, V2<T> &u) {
-    T m;
-    load_bin<T, FX>(buf, mags, rpos<T, NC>(lane, row), m, u);
-    nm = (tld<TS>(q.row_active + row) & bit) ? m * (T)q.keep_active : m;
-    // energy arriving from the (at most five) targets within two bins; non-targets read the zero sentinel
-    const uint16_t *sb = q.slot_of_bin + 32 * row + lane;
-    T te = (T)0;
-    V2<T> ps = mk2<T>((T)0, (T)0);
-#pragma unroll
-    for (int e = 0; e < 5; ++e) {
-        const int s = tld<TS>(sb + e);
-        T c = (T)q.tap[e];
-        if (e == 2) c += (T)tld<TS>(q.slot_base + s);
-        const T g = slotG[s];
-        const V2<T> pv = slotP[s];
-        te += c * g;
-        ps = pfma(splat(c), pv, ps);
-    }
-    nm += te;
-    if (te > (T)0) {
-        const T p2 = ps.x * ps.x + ps.y * ps.y;
-        const bool ok = p2 > (T)QD_TINY2;
-        const T r = rsqrt_fast(p2);
-        u = ok ? pmul(ps, splat(r)) : mk2<T>((T)1, (T)0);
-    }
-}
-
 // one step of the segmented warp scan of Q1: add the values shuffled up by d when the lane has at least d
 // same-slot sources below it (one ISETP + three predicated FADD)
 template <class T>
@@ -753,105 +743,9 @@ QD_DEV void seg_scan_step(T &g, V2<T> &p, int off, int d) {
 #endif
 }
 
-template <class T, int NC, bool TS, bool FX>
-QD_DEV void quantize_frame(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, const QuantDev &q, int lane) {
-    // Q1: per-target gathers.  Sources are grouped by target slot; 32 of them are loaded per step and
-    // summed with a segmented warp scan.  The segment structure is static, so the host stores, per
-    // source, how many sources of the same slot precede it inside its step (`off`) and whether it is the
-    // last one of its slot in the step (`tail`): no slot ids have to be shuffled.
-    for (int s = lane; s <= q.n_slots; s += 32) {
-        slotG[s] = 0.0f;
-        slotP[s] = mk2<T>(0.0f, 0.0f);
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int i0 = 0; i0 < q.n_src; i0 += 32) {
-        const int i = i0 + lane;
-        uint32_t e = 0u;  // pos 0, slot 0, off 0, tail 0: a lane past the end adds nothing
-        T g = 0.0f;
-        V2<T> p = mk2<T>(0.0f, 0.0f);
-        if (i < q.n_src) {
-            e = tld<TS>(q.src_tab + i);
-            const int pos = spos<T, NC>((int)(e & 0x1fffu));
-            p = buf[pos];
-            if constexpr (FX) {
-                g = mags[pos];
-                p = pmul(p, splat(g));
-            } else {
-                const T m2 = p.x * p.x + p.y * p.y;
-                g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
-            }
-        }
-        const int off = (int)((e >> 26) & 31u);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) seg_scan_step<T>(g, p, off, d);
-        if (e >> 31) {
-            const int sid = (int)((e >> 13) & 0x1fffu);
-            slotG[sid] += g;
-            const V2<T> t = slotP[sid];
-            slotP[sid] = padd(t, p);
-        }
-        __syncwarp();
-    }
-
-    for (int sl = lane; sl < q.n_slots; sl += 32) {  // H = sum / ksum (ksum = 1 except at the spectrum edges)
-        const T ik = (T)tld<TS>(q.slot_invk + sl);
-        slotG[sl] *= ik;
-        const V2<T> t = slotP[sl];
-        slotP[sl] = pmul(t, splat(ik));
-    }
-    __syncwarp();
-
-    // Q3: rows of 32 bins with a rolling window of three rows for the smoothing.  Rows below
-    // q.row_limit may give energy away or receive it; the rows above only need |X|, the phasor and the
-    // smoothing, and run in a tight loop.
-    constexpr int NBINS = NC + 1;
-    constexpr int ROWS = (NBINS + 31) / 32;   // the last row holds only the Nyquist bin (lane 0)
-    T m_prev = 0.0f, m_cur = 0.0f, m_next = 0.0f;
-    V2<T> u_cur = mk2<T>(1.0f, 0.0f), u_next = mk2<T>(1.0f, 0.0f);
-    const uint32_t bit = 1u << lane;
-    const bool smooth = q.smoothing != 0;
-    const int row_limit = q.row_limit < ROWS - 1 ? q.row_limit : ROWS - 1;
-    // ---- rows [0, row_limit): full logic
-#pragma unroll 1
-    for (int row = 0; row < row_limit; ++row) {
-        quant_bin<T, NC, TS, FX>(buf, mags, slotG, slotP, q, lane, row, bit, m_next, u_next);
-        if (row > 0) {
-            const T out = smooth ? smooth_row<T>(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
-            buf[rpos<T, NC>(lane, row - 1)] = pmul(u_cur, splat(out));
-        }
-        m_prev = m_cur; m_cur = m_next; u_cur = u_next;
-    }
-    // ---- rows [row_limit, ROWS-1): nothing moves, only the smoothing couples neighbours
-#pragma unroll 4
-    for (int row = row_limit; row < ROWS - 1; ++row) {
-        load_bin<T, FX>(buf, mags, rpos<T, NC>(lane, row), m_next, u_next);
-        if (row > 0) {
-            const T out = smooth ? smooth_row<T>(m_prev, m_cur, m_next, lane, row == 1 && lane == 0, false) : m_cur;
-            buf[rpos<T, NC>(lane, row - 1)] = pmul(u_cur, splat(out));
-        }
-        m_prev = m_cur; m_cur = m_next; u_cur = u_next;
-    }
-    // ---- Nyquist row (lane 0 only), then flush the last two rows
-    {
-        m_next = 0.0f;
-        u_next = mk2<T>(1.0f, 0.0f);
-        if (lane == 0) {
-            if (q.row_limit >= ROWS) quant_bin<T, NC, TS, FX>(buf, mags, slotG, slotP, q, 0, ROWS - 1, 1u, m_next, u_next);
-            else load_bin<T, FX>(buf, mags, rpos<T, NC>(0, ROWS - 1), m_next, u_next);
-        }
-        const T out = smooth ? smooth_row<T>(m_prev, m_cur, m_next, lane, ROWS == 2 && lane == 0, false) : m_cur;
-        buf[rpos<T, NC>(lane, ROWS - 2)] = pmul(u_cur, splat(out));
-        m_prev = m_cur; m_cur = m_next; u_cur = u_next;
-        const T outn = smooth ? smooth_row<T>(m_prev, m_cur, 0.0f, lane, false, lane == 0) : m_cur;
-        if (lane == 0) buf[rpos<T, NC>(0, ROWS - 1)] = pmul(u_cur, splat(outn));
-    }
-    __syncwarp();
-}
-
 // ---------------------------------------------------------------- quantizer fused with the real split / merge
-// The spectral pass is bound by shared-memory wavefronts, so the plain (no-FX) quantizer does not run
-// real_split / real_merge as separate sweeps over the warp buffer: it reads the packed-FFT output Z[k], Z[NC-k]
+// The spectral pass is bound by shared-memory wavefronts, so the quantizer does not run real_split / real_merge as
+// separate sweeps over the warp buffer: the plain (no-FX) variant reads the packed-FFT output Z[k], Z[NC-k]
 // as a pair, forms X[k] and X[NC-k] in registers, quantizes both, and writes Z'[k], Z'[NC-k] back -- one read
 // and one write of the buffer instead of three.  A lane walks bin k = 32 i + lane upwards (low side) and its
 // mirror NC - k downwards (high side); both sides keep the rolling three-row window of the smoothing, and
@@ -895,8 +789,10 @@ QD_DEV void quant_apply(T m, V2<T> &u, T &nm, int d, const T *slotG, const V2<T>
     }
 }
 
-template <class T, int NC, bool TS>
-QD_DEV void quantize_frame_fused(V2<T> *buf, T *slotG, V2<T> *slotP, const QuantDev &q, const V2<T> *wsplit, int lane) {
+// FX = true: buf holds the unit phasors of X and `mags` the (processed) magnitudes, both by buffer position with the
+// Nyquist bin in the pad slot (fx_frame): the walk loads them instead of splitting Z, the Hermitian merge is the same.
+template <class T, int NC, bool TS, bool FX = false>
+QD_DEV void quantize_frame_fused(V2<T> *buf, const T *mags, T *slotG, V2<T> *slotP, const QuantDev &q, const V2<T> *wsplit, int lane) {
     // Q1: per-target gathers (see quantize_frame), the source bins split on the fly
     for (int s = lane; s <= q.n_slots; s += 32) {
         slotG[s] = 0.0f;
@@ -911,9 +807,15 @@ QD_DEV void quantize_frame_fused(V2<T> *buf, T *slotG, V2<T> *slotP, const Quant
         V2<T> p = mk2<T>(0.0f, 0.0f);
         if (i < q.n_src) {
             e = tld<TS>(q.src_tab + i);
-            p = split_bin<T, NC>(buf, wsplit, (int)(e & 0x1fffu));
-            const T m2 = p.x * p.x + p.y * p.y;
-            g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
+            if constexpr (FX) {
+                const int pos = spos<T, NC>((int)(e & 0x1fffu));
+                g = mags[pos];
+                p = pmul(buf[pos], splat(g));
+            } else {
+                p = split_bin<T, NC>(buf, wsplit, (int)(e & 0x1fffu));
+                const T m2 = p.x * p.x + p.y * p.y;
+                g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
+            }
         }
         const int off = (int)((e >> 26) & 31u);
 #pragma unroll
@@ -968,14 +870,20 @@ QD_DEV void quantize_frame_fused(V2<T> *buf, T *slotG, V2<T> *slotP, const Quant
         const int pa = rpos<T, NC>(lane, i);
         const int pb = k == 0 ? pa : mpos<T, NC>(lane, i);   // Z[NC] = Z[0]
         vn = wsplit[k];
-        const V2<T> za = buf[pa], zb = cconj(buf[pb]);
-        const V2<T> e = cadd(za, zb);
-        const V2<T> t = cmul(csub(za, zb), vn);
-        const V2<T> xl = pfma(e, splat((T)0.5), t);                            // X[k]
-        const V2<T> xh = cconj(pfma(e, splat((T)0.5), mk2<T>(-t.x, -t.y)));    // X[NC-k]
         T ml, mh;
-        mag_phasor<T>(xl, ml, lun);
-        mag_phasor<T>(xh, mh, hun);
+        if constexpr (FX) {
+            const int pbr = k == 0 ? QD_NYQ_SLOT : pb;        // the Nyquist phasor / magnitude live in the pad slot
+            lun = buf[pa]; ml = mags[pa];
+            hun = buf[pbr]; mh = mags[pbr];
+        } else {
+            const V2<T> za = buf[pa], zb = cconj(buf[pb]);
+            const V2<T> e = cadd(za, zb);
+            const V2<T> t = cmul(csub(za, zb), vn);
+            const V2<T> xl = pfma(e, splat((T)0.5), t);                            // X[k]
+            const V2<T> xh = cconj(pfma(e, splat((T)0.5), mk2<T>(-t.x, -t.y)));    // X[NC-k]
+            mag_phasor<T>(xl, ml, lun);
+            mag_phasor<T>(xh, mh, hun);
+        }
         if (i < q.row_limit) quant_apply<T, TS>(ml, lun, ln, k, slotG, slotP, q);
         else ln = ml;
         if (NC - 32 * i - 31 < 32 * q.row_limit) quant_apply<T, TS>(mh, hun, hn, NC - k, slotG, slotP, q);
@@ -993,7 +901,8 @@ QD_DEV void quantize_frame_fused(V2<T> *buf, T *slotG, V2<T> *slotP, const Quant
         V2<T> um = mk2<T>(1.0f, 0.0f);
         if (lane == 0) {
             T m0;
-            mag_phasor<T>(cconj(buf[pm]), m0, um);
+            if constexpr (FX) { um = buf[pm]; m0 = mags[pm]; }
+            else mag_phasor<T>(cconj(buf[pm]), m0, um);
             if ((NC / 64) < q.row_limit) quant_apply<T, TS>(m0, um, mm, NC / 2, slotG, slotP, q);
             else mm = m0;
         }
@@ -1034,7 +943,7 @@ struct SpecSmem {
     }
     // shared-memory copies of the hot tables (TS kernels): window, pass-1 twiddles, split twiddles,
     // then the quantizer tables (gather list, row masks, affected-bin entries)
-    static size_t table_bytes(int n_src, int n_slots) {
+    __host__ __device__ static size_t table_bytes(int n_src, int n_slots) {
         const int rows = (NC + 1 + 31) / 32;
         size_t b = (size_t)(NC + NC + NC / 2 + 2) * sizeof(V2<T>);
         b += ((size_t)n_src * 4 + 15) & ~(size_t)15;                   // src_tab
@@ -1054,18 +963,30 @@ struct SpecSmem {
 };
 
 // wavefold / tube on the float32 iSTFT sample (dsp/distortion.py:18-90)
+#ifndef QD_EPI64_NOINLINE
+#define QD_EPI64_NOINLINE 0
+#endif
+#ifndef QD_OLA_UNROLL
+#define QD_OLA_UNROLL 0
+#endif
+#if QD_EPI64_NOINLINE && !defined(QD_EMU)
+__device__ __noinline__ float wavefold_f64(float v, double fold, double bias) {
+#else
+QD_DEV float wavefold_f64(float v, double fold, double bias) {
+#endif
+    double y = ((double)v + bias) * fold;
+    if (y > 1.0) y = 2.0 - y;
+    if (y < -1.0) y = -2.0 - y;
+    return (float)fmin(fmax(y, -1.0), 1.0);
+}
+
 QD_DEV float epilogue_apply(float v, int mode, double fold, double bias, int exact_f32, float tg, float tn) {
     if (mode == 1) {
         // dsp/distortion.py:37-58 computes in float64 and rounds to float32 once; the negative fold is tested on the
         // already folded value (:44-56).  (x + bias) * fold reaches several units before it is folded back, so float32
         // arithmetic would carry the rounding error of the large intermediate (~2e-7) into the small result -- and the
         // second spectral pass amplifies its input error.  With bias == 0 and fold a power of two float32 is exact.
-        if (!exact_f32) {
-            double y = ((double)v + bias) * fold;
-            if (y > 1.0) y = 2.0 - y;
-            if (y < -1.0) y = -2.0 - y;
-            return (float)fmin(fmax(y, -1.0), 1.0);
-        }
+        if (!exact_f32) return wavefold_f64(v, fold, bias);
         float y = v * (float)fold;
         if (y > 1.0f) y = 2.0f - y;
         if (y < -1.0f) y = -2.0f - y;
@@ -1224,24 +1145,25 @@ spec_pass_kernel(const SpecArgsT<T> a) {
         }
         if (live) {
             fft_forward<T, NC>(buf, nullptr, a, wtab, tw1, a.tw2, lane);
-            if (FX || !a.quant) real_split<T, NC>(buf, wsplit, lane);
+            if (!a.quant) real_split<T, NC>(buf, wsplit, lane);
             if (a.quant) {
                 if constexpr (FX) {
-                    static_assert(!TS, "FX kernels read their tables through L1");
-                    T *mags = reinterpret_cast<T *>(tables_base + 16) + (size_t)(grp * NW + warp) * L::BUF;
+                    // magnitude planes (and the formant scratch buffers) follow the shared tables
+                    unsigned char *planes = tables_base + (TS ? L::table_bytes(a.q.n_src, a.q.n_slots) : 16);
+                    T *mags = reinterpret_cast<T *>(planes) + (size_t)(grp * NW + warp) * L::BUF;
                     const int tf = t < a.fx.table_frames ? t : a.fx.table_frames - 1;
                     const long long tab_base =
                         (((long long)(a.fx.table_per_clip ? a.fx.clip_offset + clip : 0) * 2 + a.fx.pass) * a.fx.table_frames + tf) * (NC + 1);
-                    V2<T> *scr = reinterpret_cast<V2<T> *>(tables_base + 16 + (size_t)NG * NW * L::BUF * sizeof(T)) +
+                    V2<T> *scr = reinterpret_cast<V2<T> *>(planes + (size_t)NG * NW * L::BUF * sizeof(T)) +
                                  (size_t)(grp * NW + warp) * L::BUF;   // only there when the formant shift is on
                     fx_frame<T, NC>(buf, mags, a.fx, lane, tab_base,
                                     a.frozen ? a.frozen + (size_t)clip * L::BUF : nullptr, scr, a, tw1, wsplit);
-                    quantize_frame<T, NC, TS, true>(buf, mags, slotG, slotP, qq, lane);
+                    quantize_frame_fused<T, NC, TS, true>(buf, mags, slotG, slotP, qq, wsplit, lane);
                 } else {
-                    quantize_frame_fused<T, NC, TS>(buf, slotG, slotP, qq, wsplit, lane);
+                    quantize_frame_fused<T, NC, TS, false>(buf, nullptr, slotG, slotP, qq, wsplit, lane);
                 }
             }
-            if (FX || !a.quant) real_merge<T, NC>(buf, wsplit, lane);
+            if (!a.quant) real_merge<T, NC>(buf, wsplit, lane);
             fft_inverse<T, NC>(buf, wtab, tw1, a.tw2, lane);
         } else {
             for (int i = lane; i < L::BUF; i += 32) buf[i] = mk2<T>(0.0f, 0.0f);
@@ -1253,7 +1175,11 @@ spec_pass_kernel(const SpecArgsT<T> a) {
         //      this part (a few per cent of the instructions) used to be replicated NW + 3 times.
         for (int c = tid; c < HP; c += nthreads) {
             const int pc = pidx(c);
+#if QD_OLA_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int h = 0; h < NW + 3; ++h) {
                 V2<T> v = (h < 3) ? tail[h * HP + c] : mk2<T>(0.0f, 0.0f);   // partial sums carried from the last batch
                 const int w0 = h - 3 > 0 ? h - 3 : 0, w1 = h < NW - 1 ? h : NW - 1;

@@ -369,9 +369,10 @@ QD_DEV float low_process(float v, const CrossoverArgs &a) {
 // own row.  Algorithmic HBM bytes: 4 read + 8 written per sample (the halo re-reads hit L2).
 constexpr int QD_XO_WARPS = 4;
 QD_DEV void xo_section(const double *co, double xin, double &z0, double &z1, double &o) {
-    o = co[0] * xin + z0;
-    z0 = co[1] * xin - co[4] * o + z1;
-    z1 = co[2] * xin - co[5] * o;
+    // DF2T, scipy's recurrence (o = b0 x + z0; z0 = b1 x - a1 o + z1; z1 = b2 x - a2 o) in five fused operations
+    o = fma(co[0], xin, z0);
+    z0 = fma(-co[4], o, fma(co[1], xin, z1));
+    z1 = fma(-co[5], o, co[2] * xin);
 }
 
 __global__ void __launch_bounds__(32 * QD_XO_WARPS) crossover_kernel(const CrossoverArgs a) {
@@ -396,12 +397,20 @@ __global__ void __launch_bounds__(32 * QD_XO_WARPS) crossover_kernel(const Cross
     const long long s_first = tile0 * a.tile - a.halo;     // sample index of row 0, step 0, column 0
     // row r of a step = 32 consecutive samples of tile tile0 + r: one 128-byte row per warp load.  The rows of step
     // j + 1 are fetched into registers while step j is filtered, so no global latency sits between the steps.
+    // A step whose 32 rows all lie inside the clip (nearly all of them) takes the path without per-element bounds tests.
     float nxt[32];
     auto fetch = [&](int j) {
+        const long long s0 = s_first + 32LL * j;                  // row 0, column 0 of this step
+        if (rows == 32 && s0 >= 0 && s0 + 31LL * a.tile + 32 <= a.n) {
+            const float *p = x + s0 + lane;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const long long sidx = s_first + (long long)r * a.tile + 32LL * j + lane;
-            nxt[r] = (r < rows && sidx >= 0 && sidx < a.n) ? x[sidx] : 0.0f;
+            for (int r = 0; r < 32; ++r) nxt[r] = __ldg(p + (size_t)r * a.tile);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const long long sidx = s0 + (long long)r * a.tile + lane;
+                nxt[r] = (r < rows && sidx >= 0 && sidx < a.n) ? x[sidx] : 0.0f;
+            }
         }
     };
     fetch(0);
@@ -410,30 +419,52 @@ __global__ void __launch_bounds__(32 * QD_XO_WARPS) crossover_kernel(const Cross
         for (int r = 0; r < 32; ++r) rl[r][lane] = nxt[r];
         __syncwarp();
         if (j + 1 < steps) fetch(j + 1);
+        const bool emit = 32 * j >= a.halo;   // the warm-up steps only advance the filter states
         // ---- filter the own row
         if (lane < rows) {
+            if (emit) {
 #pragma unroll 4
-            for (int k = 0; k < 32; ++k) {
-                const double xin = (double)rl[lane][k];
-                double l1, l2, h1, h2;
-                xo_section(a.co[0], xin, st[0][0], st[0][1], l1);
-                xo_section(a.co[1], l1, st[1][0], st[1][1], l2);
-                xo_section(a.co[2], xin, st[2][0], st[2][1], h1);
-                xo_section(a.co[3], h1, st[3][0], st[3][1], h2);
-                const float lf = (float)l2;
-                rl[lane][k] = a.process_low ? low_process(lf, a) : lf;
-                rh[lane][k] = (float)h2;
+                for (int k = 0; k < 32; ++k) {
+                    const double xin = (double)rl[lane][k];
+                    double l1, l2, h1, h2;
+                    xo_section(a.co[0], xin, st[0][0], st[0][1], l1);
+                    xo_section(a.co[1], l1, st[1][0], st[1][1], l2);
+                    xo_section(a.co[2], xin, st[2][0], st[2][1], h1);
+                    xo_section(a.co[3], h1, st[3][0], st[3][1], h2);
+                    const float lf = (float)l2;
+                    rl[lane][k] = a.process_low ? low_process(lf, a) : lf;
+                    rh[lane][k] = (float)h2;
+                }
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < 32; ++k) {
+                    const double xin = (double)rl[lane][k];
+                    double l1, l2, h1, h2;
+                    xo_section(a.co[0], xin, st[0][0], st[0][1], l1);
+                    xo_section(a.co[1], l1, st[1][0], st[1][1], l2);
+                    xo_section(a.co[2], xin, st[2][0], st[2][1], h1);
+                    xo_section(a.co[3], h1, st[3][0], st[3][1], h2);
+                }
             }
         }
         __syncwarp();
-        // ---- store (the warm-up steps produce nothing)
-        if (32 * j >= a.halo) {
+        // ---- store
+        if (emit) {
+            const long long s0 = s_first + 32LL * j;
+            if (rows == 32 && s0 + 31LL * a.tile + 32 + a.low_delay <= a.n) {
+                float *ph = high + s0 + lane, *pl = low + s0 + lane + a.low_delay;
 #pragma unroll 8
-            for (int r = 0; r < rows; ++r) {
-                const long long sidx = s_first + (long long)r * a.tile + 32LL * j + lane;
-                if (sidx < a.n) {
-                    high[sidx] = rh[r][lane];
-                    if (sidx + a.low_delay < a.n) low[sidx + a.low_delay] = rl[r][lane];
+                for (int r = 0; r < 32; ++r) {
+                    ph[(size_t)r * a.tile] = rh[r][lane];
+                    pl[(size_t)r * a.tile] = rl[r][lane];
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    const long long sidx = s0 + (long long)r * a.tile + lane;
+                    if (sidx < a.n) {
+                        high[sidx] = rh[r][lane];
+                        if (sidx + a.low_delay < a.n) low[sidx + a.low_delay] = rl[r][lane];
+                    }
                 }
             }
         }

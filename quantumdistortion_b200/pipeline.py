@@ -432,7 +432,10 @@ def process_batch(x, sr: int = DEFAULT_SAMPLE_RATE, *, n_fft: int = N_FFT_DEFAUL
                 raise ValueError("out must be a contiguous CPU float32 (or int16) tensor shaped like x")
             y = out
         else:
-            y = torch.empty_like(xin, pin_memory=xin.is_pinned())
+            # the result lands in page-locked memory straight from the device (torch's host allocator caches the
+            # block, so repeated renders do not pay the page-locking again); a pageable INPUT goes through the
+            # library's staging ring
+            y = torch.empty_like(xin, pin_memory=True)
         r.render_host(xin, y, chunk_clips=chunk_clips)
         taps = None
     if is_np:
