@@ -149,7 +149,12 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
         case 512:  return launch_spec_t<T, 512, 8, false, FX>(a, tiles, batch, st);
         case 1024:
             if constexpr (sizeof(T) == 4 && !FX) {
-                if (nw == 16 && ts) return launch_spec_t<T, 1024, 8, true, false, 2>(a, tiles, batch, st);
+                if (nw == 16 && ts) {
+                    // no epilogue, or a wavefold that is exact in float32 (the reference defaults): the kernel whose
+                    // unrolled overlap-add carries neither the float64 nor the tanh branch
+                    if (a.epilogue == 0 || (a.epilogue == 1 && a.fold_exact_f32)) return launch_spec_t<T, 1024, 8, true, false, 2, false, true>(a, tiles, batch, st);
+                    return launch_spec_t<T, 1024, 8, true, false, 2>(a, tiles, batch, st);
+                }
             }
             if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 1024, 4, false, true>(a, tiles, batch, st);
             else if constexpr (FX) return nw == 8 ? launch_spec_t<T, 1024, 8, false, true>(a, tiles, batch, st)

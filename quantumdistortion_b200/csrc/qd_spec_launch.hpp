@@ -11,8 +11,9 @@
 namespace qd_launch {
 
 // T float | double; NC = n_fft / 2; NW warps per clip group; TS tables in shared memory; FX spectral-FX variant;
-// NG clip groups per CTA; SA samples staged in the formant scratch (qd_spec.cuh, SpecSmem)
-template <class T, int NC, int NW, bool TS, bool FX, int NG = 1, bool SA = false>
+// NG clip groups per CTA; SA samples staged in the formant scratch (qd_spec.cuh, SpecSmem); EF float32-only epilogue
+// (the caller checked that the wavefold is exact in float32, see epilogue_apply)
+template <class T, int NC, int NW, bool TS, bool FX, int NG = 1, bool SA = false, bool EF = false>
 int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st);
 
 }  // namespace qd_launch

@@ -7,10 +7,10 @@
 
 namespace qd_launch {
 
-template <class T, int NC, int NW, bool TS, bool FX, int NG, bool SA>
+template <class T, int NC, int NW, bool TS, bool FX, int NG, bool SA, bool EF>
 int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStream_t st) {
     static std::atomic<uint64_t> attr_mask{0};  // devices this instantiation was opted in on
-    auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX, NG, SA>;
+    auto kern = qd::spec_pass_kernel<T, NC, NW, TS, FX, NG, SA, EF>;
     if (int rc_ = qd_err::ensure_dyn_smem(kern, attr_mask, 227 * 1024)) return rc_;
     const size_t smem = qd::SpecSmem<T, NC, NW, NG, SA>::bytes(a.q.n_slots, TS, a.q.n_src, 0, FX, FX && a.formant_idx != nullptr);
     if (smem > 227 * 1024) return qd_err::fail(QD_ERR_UNSUPPORTED, "shared memory need of this kernel variant exceeds 227 KB");
@@ -32,5 +32,6 @@ int launch_spec_t(const qd::SpecArgsT<T> &a, int tiles, int64_t batch, cudaStrea
 
 }  // namespace qd_launch
 
-#define QD_INSTANTIATE_SPEC(T, NC, NW, TS, FX, NG, SA) \
-    template int qd_launch::launch_spec_t<T, NC, NW, TS, FX, NG, SA>(const qd::SpecArgsT<T> &, int, int64_t, cudaStream_t);
+#define QD_INSTANTIATE_SPEC_EF(T, NC, NW, TS, FX, NG, SA, EF) \
+    template int qd_launch::launch_spec_t<T, NC, NW, TS, FX, NG, SA, EF>(const qd::SpecArgsT<T> &, int, int64_t, cudaStream_t);
+#define QD_INSTANTIATE_SPEC(T, NC, NW, TS, FX, NG, SA) QD_INSTANTIATE_SPEC_EF(T, NC, NW, TS, FX, NG, SA, false)
