@@ -197,12 +197,16 @@ __global__ void __launch_bounds__(256) at_frame_stats_kernel(const AtDetArgs a, 
 }
 
 // ---------------------------------------------------------------- YIN by sliding sums (the fast detector path)
-// The mean of a frame cancels in c[j] - c[j+tau], so the difference function of frame f is a window sum of one
-// per-lag sequence over the (zero-extended) clip:
-//   d_f(tau) = sum_{j = f*hop}^{f*hop + W - tau - 1} e_tau[j],   e_tau[j] = (x[j] - x[j+tau])^2
-// Consecutive frames overlap by 7/8, so one running float64 prefix per lag serves every frame: 8x less arithmetic than
-// frame-by-frame evaluation.  A thread owns one lag and walks the clip hop-block by hop-block; the prefix at each
-// frame start is parked in a 9-deep ring, the frame's value is emitted when the walk reaches f*hop + W - tau.
+// The mean of a frame cancels in c[j] - c[j+tau], so the difference function of frame f is a window sum over the
+// (zero-extended) clip, and with the square expanded it needs ONE float64 operation per (sample, lag) pair instead of two:
+//   d_f(tau) = sum_{j=s}^{p-1} (x[j] - x[j+tau])^2 = E(s, p) + E(s+tau, p+tau) - 2 R_tau(s, p),   s = f*hop, p = s + W - tau
+//   E(a, b) = sum_{a <= j < b} x[j]^2  (shared by all lags),   R_tau(a, b) = sum_{a <= j < b} x[j] x[j+tau]
+// (the inputs are float32, so every product is exact in float64).  Consecutive frames overlap by 7/8, so the sums are kept
+// per hop block: a thread owns AT_YL lags and walks the clip block by block accumulating R_tau of the block; for a
+// finished block it parks V = E(block + tau) - 2 R_tau(block) in a ring per lag, block energies go to a small shared
+// ring, and a frame's value is assembled from the parked blocks f .. b-1, the partial block, and prefix sums of squares
+// over the current tile.  Every term is a sum over at most one frame, so nothing cancels against a clip-long running
+// total (the largest term is 2 E_frame against d: relative error ~4e-16 E_frame / d).
 struct AtYinArgs {
     const float *det;        // [batch, n]
     double *diff;            // [batch, frames, stride] difference function, entry tau
@@ -217,19 +221,31 @@ struct AtYinArgs {
 // Register tiling: a thread owns AT_YL = 4 consecutive lags and walks the samples four at a time, so 16 (sample, lag)
 // pairs come from 4 broadcast loads of x[j..j+3] and 7 loads of x[j+tau..j+tau+6]; the tile is stored de-interleaved by four
 // (element i at (i & 3) * Q + (i >> 2)) so that the lanes' stride-4 addresses fall on consecutive words: 1.1 shared-memory
-// wavefronts per pair instead of 3, which brings the walk down to the float64 pipe's rate.
+// wavefronts per pair instead of 3.  B200's vector float64 pipe is 32 lanes per SM: 3.3e11 pairs per 1024 clips x 10 s are
+// 36 ms of DFMA at its peak.
 constexpr int AT_YL = 4;     // lags per thread
 constexpr int AT_YT = 96;    // threads per CTA -> 384 lags per CTA (671 lags at 48 kHz = 2 CTAs per clip)
+constexpr int AT_YR = 9;     // ring depth: frame_size / hop + 1 blocks
+
+// shared memory of at_yin_diff_kernel in doubles, for a tile of `span` samples
+__host__ __device__ inline size_t at_yin_smem_doubles(size_t span) {
+    const size_t q = (span + 3) / 4;
+    return 4 * q + (span + 8) + (size_t)AT_YR * AT_YT * AT_YL + AT_YT + 16;
+}
 
 __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
     QD_DYN_SMEM(smem);
-    const int tid = threadIdx.x;
-    const int tau0 = 1 + blockIdx.x * AT_YT * AT_YL;    // lags of this CTA: tau0 .. tau0 + 4 * AT_YT - 1
-    const int taub = tau0 + AT_YL * tid;                 // this thread: taub .. taub + 3
-    const int span = a.hop + tau0 + AT_YL * AT_YT + 8;   // samples a hop-block needs (+ the look-ahead of the last sub-block)
+    constexpr int NL = AT_YT * AT_YL;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tau0 = 1 + blockIdx.x * NL;               // lags of this CTA: tau0 .. tau0 + NL - 1
+    const int taub = tau0 + AT_YL * tid;                // this thread: taub .. taub + 3
+    const int span = a.hop + tau0 + NL + 8;             // samples a hop-block needs (+ the look-ahead of the last sub-block)
     const int Q = (span + 3) >> 2;
-    double *tile = reinterpret_cast<double *>(smem);     // [4][Q] de-interleaved
-    double *ring = tile + 4 * Q;                         // [9][AT_YT * AT_YL]
+    double *tile = reinterpret_cast<double *>(smem);    // [4][Q] de-interleaved samples of the block and its look-ahead
+    double *qt = tile + 4 * Q;                          // [span + 1] prefix sums of squares over the tile: qt[i] = E(j0, j0 + i)
+    double *ringV = qt + span + 8;                      // [AT_YR][NL] E(block + tau) - 2 R_tau(block) of finished blocks
+    double *part = ringV + AT_YR * NL;                  // [AT_YT] scan scratch
+    double *be = part + AT_YT;                          // [16] energies of the last blocks
     const float *x = a.det + (size_t)blockIdx.y * a.n;
     double *out = a.diff + (size_t)blockIdx.y * a.frames * a.stride;
     int q[AT_YL], off[AT_YL];
@@ -241,12 +257,28 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
         q[u] = wlen / a.hop;                              // frame f ends inside hop-block f + q at offset off
         off[u] = wlen % a.hop;
     }
-    double S[AT_YL] = {0.0, 0.0, 0.0, 0.0};
+    double S[AT_YL];
     const int blocks = a.frames + a.frame_size / a.hop;
     const int sh = (tau0 & 3);                            // (taub & 3) is the same for every thread
-    auto emit = [&](int u, int b) {
+    const int chunk = (span + AT_YT - 1) / AT_YT;         // samples per thread in the prefix sum of squares
+    auto sample = [&](int i) { return tile[(i & 3) * Q + (i >> 2)]; };
+    // Every lag closes exactly one frame per block (frame b - q at offset off).  The lanes of a warp reach their offsets
+    // in different iterations, so inside the walk a lane only CAPTURES its partial sum (two predicated moves); the frame's
+    // value is assembled after the walk by all lanes together.
+    double P[AT_YL];
+    auto finish = [&](int u, int b) {
         const int f = b - q[u];
-        if (live[u] && f >= 0 && f < a.frames) out[(size_t)f * a.stride + taub + u] = S[u] - ring[(f % 9) * (AT_YT * AT_YL) + AT_YL * tid + u];
+        if (live[u] && f >= 0 && f < a.frames) {
+            const int col = AT_YL * tid + u, tau = taub + u;
+            double v = 0.0, eb = 0.0;
+            for (int bb = f; bb < b; ++bb) {
+                v += ringV[(bb % AT_YR) * NL + col];
+                eb += be[bb & 15];
+            }
+            const double e1 = eb + qt[off[u]];                                   // E(s, p)
+            const double cur = (qt[off[u] + tau] - qt[tau]) - 2.0 * P[u];        // the partial block: E(. + tau) - 2 R
+            out[(size_t)f * a.stride + tau] = fmax(e1 + (v + cur), 0.0);
+        }
     };
     for (int b = 0; b < blocks; ++b) {
         const long long j0 = (long long)b * a.hop;
@@ -256,10 +288,34 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
             tile[(i & 3) * Q + (i >> 2)] = sidx < a.n ? (double)x[sidx] : 0.0;
         }
         __syncthreads();
-        if (b < a.frames) {
+        // ---- prefix sums of squares over the tile (three warps: local sums, scan of the 96 partials, local prefixes)
+        {
+            const int i0 = tid * chunk, i1 = min(i0 + chunk, span);
+            double loc = 0.0;
+            for (int i = i0; i < i1; ++i) { const double v = sample(i); loc = fma(v, v, loc); }
+            part[tid] = loc;
+            __syncthreads();
+            if (tid < 32) {
+                const double a0 = part[3 * lane], a1 = part[3 * lane + 1], a2 = part[3 * lane + 2];
+                const double tot = a0 + a1 + a2;
+                double inc = tot;
 #pragma unroll
-            for (int u = 0; u < AT_YL; ++u) ring[(b % 9) * (AT_YT * AT_YL) + AT_YL * tid + u] = S[u];
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double o = __shfl_up_sync(QD_FULL, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                const double exc = inc - tot;
+                part[3 * lane] = exc; part[3 * lane + 1] = exc + a0; part[3 * lane + 2] = exc + a0 + a1;
+            }
+            __syncthreads();
+            double run = part[tid];
+            for (int i = i0; i < i1; ++i) { qt[i] = run; const double v = sample(i); run = fma(v, v, run); }
+            if (i1 == span && i0 < span) qt[span] = run;
         }
+        __syncthreads();
+        if (tid == 0) be[b & 15] = qt[a.hop];              // read by the emits of later blocks (after the next barrier)
+#pragma unroll
+        for (int u = 0; u < AT_YL; ++u) { S[u] = 0.0; P[u] = 0.0; }
         for (int jj = 0; jj < a.hop; jj += 4) {
             // x[j0 + jj + s], s = 0..3 (broadcast) and x[j0 + jj + taub + v], v = 0..6
             double av[4], bv[7];
@@ -274,21 +330,22 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
 #pragma unroll
                 for (int s4 = 0; s4 < 4; ++s4)
 #pragma unroll
-                    for (int u = 0; u < AT_YL; ++u) {
-                        const double d = av[s4] - bv[s4 + u];
-                        S[u] = fma(d, d, S[u]);
-                    }
-            } else {   // a window of one of the four lags ends inside this sub-block: emit before the sample at `off`
+                    for (int u = 0; u < AT_YL; ++u) S[u] = fma(av[s4], bv[s4 + u], S[u]);
+            } else {   // a window of one of the four lags ends inside this sub-block: capture before the sample at `off`
 #pragma unroll
                 for (int s4 = 0; s4 < 4; ++s4)
 #pragma unroll
                     for (int u = 0; u < AT_YL; ++u) {
-                        if (jj + s4 == off[u]) emit(u, b);
-                        const double d = av[s4] - bv[s4 + u];
-                        S[u] = fma(d, d, S[u]);
+                        if (jj + s4 == off[u]) P[u] = S[u];
+                        S[u] = fma(av[s4], bv[s4 + u], S[u]);
                     }
             }
         }
+#pragma unroll
+        for (int u = 0; u < AT_YL; ++u) finish(u, b);
+#pragma unroll
+        for (int u = 0; u < AT_YL; ++u)
+            ringV[(b % AT_YR) * NL + AT_YL * tid + u] = (qt[a.hop + taub + u] - qt[taub + u]) - 2.0 * S[u];
     }
 }
 
