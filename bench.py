@@ -211,7 +211,8 @@ OTHER_CONFIGS = [
 
 
 def other_configs(qd, x, clips: int):
-    """One device-resident number per BASELINE config outside the headline: `clips` clips x 10 s, 1 warm-up + 2 timed."""
+    """One device-resident number per BASELINE config outside the headline: `clips` clips x 10 s, 2 warm-ups, then the
+    median of 3 individually timed renders (CUDA events)."""
     import torch
     out = []
     xs = x[:clips]
@@ -221,16 +222,20 @@ def other_configs(qd, x, clips: int):
             r.set_fx_seeds(clips, seed)
             nclips = clips if n_fft < 8192 else max(1, clips // 4)    # float64 parity path: a quarter of the clips
             xi = xs[:nclips]
-            y, _ = r.render_device(xi)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(2):
+            for _ in range(2):   # two warm-ups: the second one makes torch's allocator create the second output block
                 y, _ = r.render_device(xi)
-            e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 2
-            out.append({"config": name, "clips": nclips, "ms_per_render": round(ms, 3),
+            times = []
+            for _ in range(3):   # each render timed on its own: the record keeps the median and says how far the others were
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                y, _ = r.render_device(xi)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            times.sort()
+            ms = times[1]
+            out.append({"config": name, "clips": nclips, "ms_per_render": round(ms, 3), "ms_min_max": [round(times[0], 3), round(times[2], 3)],
                         "audio_s_per_s": round(nclips * CLIP_SECONDS / (ms / 1e3)), "peak": round(float(y.abs().max()), 4)})
             del r, y
         except Exception as exc:  # noqa: BLE001 -- the record says what failed instead of hiding the headline
@@ -491,7 +496,13 @@ def run_ours(args):
         except Exception:  # noqa: BLE001
             pass
 
-    others = other_configs(qd, x, args.other_clips) if (world == 1 and args.other_clips > 0 and not args.no_extras) else None
+    others = None
+    if world == 1 and args.other_clips > 0 and not args.no_extras:
+        sampler2 = ClockSampler(local)
+        sampler2.start()
+        time.sleep(1.0)          # nvidia-smi needs about a second to deliver its first sample
+        others = other_configs(qd, x, args.other_clips)
+        others.append({"clocks_during_other_configs": sampler2.stop()})
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
