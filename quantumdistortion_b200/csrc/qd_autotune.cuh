@@ -229,7 +229,7 @@ constexpr int AT_YR = 9;     // ring depth: frame_size / hop + 1 blocks
 
 // shared memory of at_yin_diff_kernel in doubles, for a tile of `span` samples
 __host__ __device__ inline size_t at_yin_smem_doubles(size_t span) {
-    const size_t q = (span + 3) / 4;
+    const size_t q = (((span + 3) / 4) + 1) & ~(size_t)1;
     return 4 * q + (span + 8) + (size_t)AT_YR * AT_YT * AT_YL + AT_YT + 16;
 }
 
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
     const int tau0 = 1 + blockIdx.x * NL;               // lags of this CTA: tau0 .. tau0 + NL - 1
     const int taub = tau0 + AT_YL * tid;                // this thread: taub .. taub + 3
     const int span = a.hop + tau0 + NL + 8;             // samples a hop-block needs (+ the look-ahead of the last sub-block)
-    const int Q = (span + 3) >> 2;
+    const int Q = (((span + 3) >> 2) + 1) & ~1;         // even: the 16-byte loads of the walk stay aligned
     double *tile = reinterpret_cast<double *>(smem);    // [4][Q] de-interleaved samples of the block and its look-ahead
     double *qt = tile + 4 * Q;                          // [span + 1] prefix sums of squares over the tile: qt[i] = E(j0, j0 + i)
     double *ringV = qt + span + 8;                      // [AT_YR][NL] E(block + tau) - 2 R_tau(block) of finished blocks
@@ -262,21 +262,29 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
     const int sh = (tau0 & 3);                            // (taub & 3) is the same for every thread
     const int chunk = (span + AT_YT - 1) / AT_YT;         // samples per thread in the prefix sum of squares
     auto sample = [&](int i) { return tile[(i & 3) * Q + (i >> 2)]; };
-    // Every lag closes exactly one frame per block (frame b - q at offset off).  The lanes of a warp reach their offsets
-    // in different iterations, so inside the walk a lane only CAPTURES its partial sum (two predicated moves); the frame's
-    // value is assembled after the walk by all lanes together.
+    // Every lag closes exactly one frame per block (frame b - q at offset off); the frame's value is assembled after the
+    // walk by all lanes together from the sum captured inside the walk.
     double P[AT_YL];
+    int osb[AT_YL];            // the 8-sample iteration in which the lag's window ends
+    const double *pb[4];       // lagged samples: x[jj + taub + v] = pb[v & 3][jj / 4 + (v >> 2)]
+#pragma unroll
+    for (int u = 0; u < AT_YL; ++u) osb[u] = off[u] >> 3;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) pb[v] = tile + ((sh + v) & 3) * Q + ((taub + v) >> 2);
     auto finish = [&](int u, int b) {
         const int f = b - q[u];
         if (live[u] && f >= 0 && f < a.frames) {
             const int col = AT_YL * tid + u, tau = taub + u;
+            double pu = P[u];                                    // R_tau of the block up to the window's end: the sum at
+            for (int k = 8 * osb[u]; k < off[u]; ++k)            // the start of its 8-sample iteration + the rest of it
+                pu = fma(sample(k), sample(k + tau), pu);
             double v = 0.0, eb = 0.0;
             for (int bb = f; bb < b; ++bb) {
                 v += ringV[(bb % AT_YR) * NL + col];
                 eb += be[bb & 15];
             }
             const double e1 = eb + qt[off[u]];                                   // E(s, p)
-            const double cur = (qt[off[u] + tau] - qt[tau]) - 2.0 * P[u];        // the partial block: E(. + tau) - 2 R
+            const double cur = (qt[off[u] + tau] - qt[tau]) - 2.0 * pu;          // the partial block: E(. + tau) - 2 R
             out[(size_t)f * a.stride + tau] = fmax(e1 + (v + cur), 0.0);
         }
     };
@@ -316,30 +324,30 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
         if (tid == 0) be[b & 15] = qt[a.hop];              // read by the emits of later blocks (after the next barrier)
 #pragma unroll
         for (int u = 0; u < AT_YL; ++u) { S[u] = 0.0; P[u] = 0.0; }
-        for (int jj = 0; jj < a.hop; jj += 4) {
-            // x[j0 + jj + s], s = 0..3 (broadcast) and x[j0 + jj + taub + v], v = 0..6
-            double av[4], bv[7];
+        // ---- the walk: 8 samples x 4 lags per iteration.  Sample jj + k sits in plane k & 3 at index i + (k >> 2), i = jj / 4,
+        //      so the eight own samples are four broadcast 16-byte loads and the eleven lagged ones eleven 8-byte loads from
+        //      four per-thread base pointers with constant offsets: no address arithmetic inside the loop.  A lag's window
+        //      ends somewhere in every block, and the lanes of a warp reach their ends in different iterations, so the loop
+        //      only records the sum at the START of that iteration (one predicated move per lag: no divergence); the up to
+        //      seven products of the partial iteration are added when the frame is assembled.
+        for (int i = 0; i < (a.hop >> 2); i += 2) {
+            double av[8], bv[11];
 #pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) av[s4] = tile[s4 * Q + (jj >> 2)];
-            const int base = jj + taub;                    // (base & 3) == sh for every thread (jj % 4 == 0)
-#pragma unroll
-            for (int v = 0; v < 7; ++v) bv[v] = tile[((sh + v) & 3) * Q + ((base + v) >> 2)];
-            const int sb = jj >> 2;
-            const bool special = (off[0] >> 2) == sb || (off[1] >> 2) == sb || (off[2] >> 2) == sb || (off[3] >> 2) == sb;
-            if (!special) {
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4)
-#pragma unroll
-                    for (int u = 0; u < AT_YL; ++u) S[u] = fma(av[s4], bv[s4 + u], S[u]);
-            } else {   // a window of one of the four lags ends inside this sub-block: capture before the sample at `off`
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4)
-#pragma unroll
-                    for (int u = 0; u < AT_YL; ++u) {
-                        if (jj + s4 == off[u]) P[u] = S[u];
-                        S[u] = fma(av[s4], bv[s4 + u], S[u]);
-                    }
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const double2 t = *reinterpret_cast<const double2 *>(tile + s4 * Q + i);
+                av[s4] = t.x;
+                av[s4 + 4] = t.y;
             }
+#pragma unroll
+            for (int v = 0; v < 11; ++v) bv[v] = pb[v & 3][i + (v >> 2)];
+            const int sb8 = i >> 1;
+#pragma unroll
+            for (int u = 0; u < AT_YL; ++u)
+                if (osb[u] == sb8) P[u] = S[u];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int u = 0; u < AT_YL; ++u) S[u] = fma(av[k], bv[k + u], S[u]);
         }
 #pragma unroll
         for (int u = 0; u < AT_YL; ++u) finish(u, b);
