@@ -1,15 +1,15 @@
 // qd_time.cuh -- time-domain kernels of the STFT path: lookahead limiter + mix, Linkwitz-Riley
 // crossover + low-band processing, elementwise distortion.
 //
-// Both recurrences are run as parallel scans in float64:
+// Both recurrences run in float64, each parallelised the way its memory allows:
 //   limiter   u_n = c * max(u_{n-1}, e_n)              dsp/limiter.py:62-77
-//             associative on pairs (a, b): u -> max(a*u, b)
+//             30 ms release = a memory of ~57 000 samples: a parallel scan, associative on pairs (a, b): u -> max(a*u, b).
+//             One CTA streams one clip in chunks; every thread owns KS consecutive samples, runs the recurrence over
+//             them from a zero state, the per-thread aggregates are combined with warp shuffles (+ one shared-memory
+//             hop across warps), and the thread re-runs its samples from its true incoming state.
 //   biquad    z_{n+1} = A z_n + B x_n (DF2T state)     scipy sosfilt, dsp/crossover.py:96-97
-//             associative on pairs (A^k, v): z -> A^k z + v
-// One CTA streams one clip in chunks; every thread owns KS consecutive samples, runs the
-// recurrence over them from a zero state, the per-thread aggregates are combined with warp
-// shuffles (+ one shared-memory hop across warps), and the thread re-runs its samples from
-// its true incoming state.  The chunk-to-chunk state enters through thread 0.
+//             pole radius 0.97: a memory of ~1 600 samples: independent tiles with a warm-up halo, one thread per tile
+//             (crossover_kernel below).
 #pragma once
 #include "qd_common.cuh"
 
@@ -271,7 +271,6 @@ __global__ void __launch_bounds__(QD_TT, 3) limiter_mix_kernel(const LimiterArgs
 }
 
 // ---------------------------------------------------------------- crossover
-struct Mat2 { double a, b, c, d; };   // [[a b],[c d]]
 struct CrossoverArgs {
     const float *x;       // [batch, n]
     float *low;           // [batch, n]
@@ -289,65 +288,6 @@ struct CrossoverArgs {
     float low_trim;
     int apply_low_trim;
 };
-
-QD_DEV void mat_apply(const Mat2 &m, double &z0, double &z1) {
-    const double t0 = m.a * z0 + m.b * z1;
-    const double t1 = m.c * z0 + m.d * z1;
-    z0 = t0; z1 = t1;
-}
-
-// one DF2T section over the thread's KS samples, in place on v[], state (z0,z1) in/out
-QD_DEV void biquad_run(const double *co, double (&v)[QD_KS], double &z0, double &z1) {
-#pragma unroll
-    for (int k = 0; k < QD_KS; ++k) {
-        const double xin = v[k];
-        const double o = co[0] * xin + z0;
-        z0 = co[1] * xin - co[4] * o + z1;
-        z1 = co[2] * xin - co[5] * o;
-        v[k] = o;
-    }
-}
-
-// state entering each thread for one section whose input is in[]; chunk state enters at thread 0
-QD_DEV void biquad_scan(const double *co, const Mat2 *apow, const double (&in)[QD_KS], double cz0, double cz1,
-                        double *s_w, int tid, double &zin0, double &zin1, double &zend0, double &zend1) {
-    const int lane = tid & 31, warp = tid >> 5;
-    double tmp[QD_KS];
-#pragma unroll
-    for (int k = 0; k < QD_KS; ++k) tmp[k] = in[k];
-    double v0 = (tid == 0) ? cz0 : 0.0, v1 = (tid == 0) ? cz1 : 0.0;
-    biquad_run(co, tmp, v0, v1);
-    // inclusive scan: v_t = A^(KS*d) v_{t-d} + v_t
-#pragma unroll
-    for (int l = 0; l < 5; ++l) {
-        const int d = 1 << l;
-        double o0 = __shfl_up_sync(QD_FULL, v0, d);
-        double o1 = __shfl_up_sync(QD_FULL, v1, d);
-        if (lane >= d) { mat_apply(apow[l], o0, o1); v0 += o0; v1 += o1; }
-    }
-    if (lane == 31) { s_w[2 * warp] = v0; s_w[2 * warp + 1] = v1; }
-    __syncthreads();
-    double p0 = 0.0, p1 = 0.0;  // aggregate of the warps before this one
-    for (int w = 0; w < warp; ++w) { mat_apply(apow[5], p0, p1); p0 += s_w[2 * w]; p1 += s_w[2 * w + 1]; }
-    // exclusive within the warp
-    double e0 = __shfl_up_sync(QD_FULL, v0, 1), e1 = __shfl_up_sync(QD_FULL, v1, 1);
-    if (lane == 0) { e0 = 0.0; e1 = 0.0; }
-    // A^(KS*lane) applied to the warp-prefix
-    double q0 = p0, q1 = p1;
-#pragma unroll
-    for (int l = 0; l < 5; ++l) if (lane & (1 << l)) mat_apply(apow[l], q0, q1);
-    zin0 = q0 + e0; zin1 = q1 + e1;
-    if (tid == 0) { zin0 = cz0; zin1 = cz1; }
-    // end-of-chunk state = inclusive value of the last thread
-    double t0 = p0, t1 = p1;
-    mat_apply(apow[5], t0, t1);
-    t0 += s_w[2 * warp]; t1 += s_w[2 * warp + 1];
-    __syncthreads();
-    if (tid == QD_TT - 1) { s_w[0] = t0; s_w[1] = t1; }
-    __syncthreads();
-    zend0 = s_w[0]; zend1 = s_w[1];
-    __syncthreads();
-}
 
 QD_DEV float low_process(float v, const CrossoverArgs &a) {
     // dsp/saturation.py:44-54: float32 gain, float32 tanh(3x), float64 division by tanh(3)
