@@ -228,10 +228,12 @@ __global__ void __launch_bounds__(256) at_frame_stats_kernel(const AtDetArgs a, 
     double lg = 0.0, ar = 0.0;
     for (int row = 0; row < ROWS; ++row) {
         if (row < ROWS - 1 || lane == 0) {
+            // |X| + 1e-8 and its logarithm in float32 (1e-7 relative, like the float32 FFT that produced X; the flatness
+            // is only compared with a threshold), the two sums over 2049 bins in float64
             const float2 v = buf[rpos<float, NC>(lane, row)];
-            const double m = sqrt((double)v.x * (double)v.x + (double)v.y * (double)v.y) + 1e-8;
-            lg += log(m);
-            ar += m;
+            const float m = sqrtf(fmaf(v.x, v.x, v.y * v.y)) + 1e-8f;
+            lg += (double)logf(m);
+            ar += (double)m;
         }
     }
     lg = warp_sum(lg);
