@@ -270,19 +270,23 @@ struct AtYinArgs {
     double sr, min_freq, max_freq, threshold;
 };
 
-// Register tiling: a thread owns AT_YL = 4 consecutive lags and walks the samples four at a time, so 16 (sample, lag)
-// pairs come from 4 broadcast loads of x[j..j+3] and 7 loads of x[j+tau..j+tau+6]; the tile is stored de-interleaved by four
-// (element i at (i & 3) * Q + (i >> 2)) so that the lanes' stride-4 addresses fall on consecutive words: 1.1 shared-memory
-// wavefronts per pair instead of 3.  B200's vector float64 pipe is 32 lanes per SM: 3.3e11 pairs per 1024 clips x 10 s are
+// Register tiling: a thread owns AT_YL consecutive lags and walks the samples AT_YS = 8 at a time, so AT_YL * 8 (sample,
+// lag) pairs come from the broadcast loads of x[j..j+7] and AT_YL + 7 loads of x[j+tau..]; the tile is stored de-interleaved
+// by AT_YL (element i at (i % AT_YL) * Q + i / AT_YL) so that the lanes' stride-AT_YL addresses fall on consecutive words.  B200's vector float64 pipe is 32 lanes per SM: 3.3e11 pairs per 1024 clips x 10 s are
 // 36 ms of DFMA at its peak.
-constexpr int AT_YL = 4;     // lags per thread
+#ifndef QD_AT_YL
+#define QD_AT_YL 4
+#endif
+constexpr int AT_YL = QD_AT_YL;   // lags per thread = de-interleave factor of the tile (4 or 8)
+constexpr int AT_YS = 8;          // samples per iteration of the walk
+static_assert(AT_YL == 4 || AT_YL == 8, "the walk is written for 4 or 8 lags per thread");
 constexpr int AT_YT = 96;    // threads per CTA -> 384 lags per CTA (671 lags at 48 kHz = 2 CTAs per clip)
 constexpr int AT_YR = 9;     // ring depth: frame_size / hop + 1 blocks
 
 // shared memory of at_yin_diff_kernel in doubles, for a tile of `span` samples
 __host__ __device__ inline size_t at_yin_smem_doubles(size_t span) {
-    const size_t q = (((span + 3) / 4) + 1) & ~(size_t)1;
-    return 4 * q + (span + 8) + (size_t)AT_YR * AT_YT * AT_YL + AT_YT + 16;
+    const size_t q = (((span + AT_YL - 1) / AT_YL) + 1) & ~(size_t)1;
+    return AT_YL * q + (span + 8) + (size_t)AT_YR * AT_YT * AT_YL + AT_YT + 16;
 }
 
 __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
@@ -290,11 +294,11 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
     constexpr int NL = AT_YT * AT_YL;
     const int tid = threadIdx.x, lane = tid & 31;
     const int tau0 = 1 + blockIdx.x * NL;               // lags of this CTA: tau0 .. tau0 + NL - 1
-    const int taub = tau0 + AT_YL * tid;                // this thread: taub .. taub + 3
+    const int taub = tau0 + AT_YL * tid;                // this thread: taub .. taub + AT_YL - 1
     const int span = a.hop + tau0 + NL + 8;             // samples a hop-block needs (+ the look-ahead of the last sub-block)
-    const int Q = (((span + 3) >> 2) + 1) & ~1;         // even: the 16-byte loads of the walk stay aligned
+    const int Q = (((span + AT_YL - 1) / AT_YL) + 1) & ~1;   // even: the 16-byte loads of the walk stay aligned
     double *tile = reinterpret_cast<double *>(smem);    // [4][Q] de-interleaved samples of the block and its look-ahead
-    double *qt = tile + 4 * Q;                          // [span + 1] prefix sums of squares over the tile: qt[i] = E(j0, j0 + i)
+    double *qt = tile + AT_YL * Q;                          // [span + 1] prefix sums of squares over the tile: qt[i] = E(j0, j0 + i)
     double *ringV = qt + span + 8;                      // [AT_YR][NL] E(block + tau) - 2 R_tau(block) of finished blocks
     double *part = ringV + AT_YR * NL;                  // [AT_YT] scan scratch
     double *be = part + AT_YT;                          // [16] energies of the last blocks
@@ -311,18 +315,18 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
     }
     double S[AT_YL];
     const int blocks = a.frames + a.frame_size / a.hop;
-    const int sh = (tau0 & 3);                            // (taub & 3) is the same for every thread
+    const int sh = tau0 % AT_YL;                          // taub % AT_YL is the same for every thread
     const int chunk = (span + AT_YT - 1) / AT_YT;         // samples per thread in the prefix sum of squares
-    auto sample = [&](int i) { return tile[(i & 3) * Q + (i >> 2)]; };
+    auto sample = [&](int i) { return tile[(i % AT_YL) * Q + (i / AT_YL)]; };
     // Every lag closes exactly one frame per block (frame b - q at offset off); the frame's value is assembled after the
     // walk by all lanes together from the sum captured inside the walk.
-    double P[AT_YL];
+    double P[AT_YL] = {};
     int osb[AT_YL];            // the 8-sample iteration in which the lag's window ends
-    const double *pb[4];       // lagged samples: x[jj + taub + v] = pb[v & 3][jj / 4 + (v >> 2)]
+    const double *pb[AT_YL];   // lagged samples: x[jj + taub + v] = pb[v % AT_YL][jj / AT_YL + v / AT_YL]
 #pragma unroll
     for (int u = 0; u < AT_YL; ++u) osb[u] = off[u] >> 3;
 #pragma unroll
-    for (int v = 0; v < 4; ++v) pb[v] = tile + ((sh + v) & 3) * Q + ((taub + v) >> 2);
+    for (int v = 0; v < AT_YL; ++v) pb[v] = tile + ((sh + v) % AT_YL) * Q + ((taub + v) / AT_YL);
     auto finish = [&](int u, int b) {
         const int f = b - q[u];
         if (live[u] && f >= 0 && f < a.frames) {
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
         __syncthreads();
         for (int i = tid; i < span; i += AT_YT) {
             const long long sidx = j0 + i;
-            tile[(i & 3) * Q + (i >> 2)] = sidx < a.n ? (double)x[sidx] : 0.0;
+            tile[(i % AT_YL) * Q + (i / AT_YL)] = sidx < a.n ? (double)x[sidx] : 0.0;
         }
         __syncthreads();
         // ---- prefix sums of squares over the tile (three warps: local sums, scan of the 96 partials, local prefixes)
@@ -382,22 +386,28 @@ __global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
         //      ends somewhere in every block, and the lanes of a warp reach their ends in different iterations, so the loop
         //      only records the sum at the START of that iteration (one predicated move per lag: no divergence); the up to
         //      seven products of the partial iteration are added when the frame is assembled.
-        for (int i = 0; i < (a.hop >> 2); i += 2) {
-            double av[8], bv[11];
+        constexpr int IPI = AT_YS / AT_YL;                 // tile indices per iteration and plane (2 for 4 lags, 1 for 8)
+        for (int it = 0; it < a.hop / AT_YS; ++it) {
+            const int i = it * IPI;
+            double av[AT_YS], bv[AT_YS + AT_YL - 1];
+            if constexpr (AT_YL == 4) {
 #pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
-                const double2 t = *reinterpret_cast<const double2 *>(tile + s4 * Q + i);
-                av[s4] = t.x;
-                av[s4 + 4] = t.y;
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const double2 t = *reinterpret_cast<const double2 *>(tile + s4 * Q + i);
+                    av[s4] = t.x;
+                    av[s4 + 4] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < AT_YS; ++k) av[k] = tile[k * Q + i];
             }
 #pragma unroll
-            for (int v = 0; v < 11; ++v) bv[v] = pb[v & 3][i + (v >> 2)];
-            const int sb8 = i >> 1;
+            for (int v = 0; v < AT_YS + AT_YL - 1; ++v) bv[v] = pb[v % AT_YL][i + v / AT_YL];
 #pragma unroll
             for (int u = 0; u < AT_YL; ++u)
-                if (osb[u] == sb8) P[u] = S[u];
+                if (osb[u] == it) P[u] = S[u];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < AT_YS; ++k)
 #pragma unroll
                 for (int u = 0; u < AT_YL; ++u) S[u] = fma(av[k], bv[k + u], S[u]);
         }
