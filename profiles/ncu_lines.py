@@ -58,5 +58,6 @@ ts = sum(v[1] for v in agg.values()) or 1
 tw = sum(v[2] for v in agg.values()) or 1
 print(f"total: {ti:.3e} warp-instructions, {ts:.0f} samples, {tw:.3e} shared wavefronts")
 print(" inst%  smpl%   wf%  excessM  file:line  source")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+by = 1 if len(sys.argv) > 4 and sys.argv[4] == "samples" else 0
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][by])[:top]:
     print(f"{v[0] / ti * 100:5.1f}  {v[1] / ts * 100:5.1f}  {v[2] / tw * 100:5.1f}  {v[3] / 1e6:6.1f}  {k[0]}:{k[1]:<4d} {v[4]}")

@@ -15,6 +15,7 @@
 
 #include "qd_spec.cuh"
 #include "qd_time.cuh"
+#include "qd_yin.cuh"
 
 namespace qd {
 
@@ -195,13 +196,14 @@ struct AtDetArgs {
 // rms, spectral flatness and the silence flag with one WARP per frame:
 // the lanes load the frame once, accumulate the sums and write the Hann-windowed samples straight into the warp's FFT
 // buffer.  feat = (rms, flatness, 1 or 0 for "not silent", 0).
+constexpr int AT_SW_STATS = 12;   // frames (warps) per CTA: 12 x 16.9 KB of FFT buffers = 203 KB, one CTA per SM
 template <int NC>
-__global__ void __launch_bounds__(256) at_frame_stats_kernel(const AtDetArgs a, long long total_frames) {
+__global__ void __launch_bounds__(32 * AT_SW_STATS) at_frame_stats_kernel(const AtDetArgs a, long long total_frames) {
     constexpr int FS = 2 * NC;
     constexpr int BUF = buf_slots<NC>();
     QD_DYN_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long fr = (long long)blockIdx.x * 8 + warp;
+    const long long fr = (long long)blockIdx.x * AT_SW_STATS + warp;
     if (fr >= total_frames) return;
     float2 *buf = reinterpret_cast<float2 *>(smem) + (size_t)warp * BUF;
     const long long clip = fr / a.frames;
@@ -248,176 +250,7 @@ __global__ void __launch_bounds__(256) at_frame_stats_kernel(const AtDetArgs a, 
     }
 }
 
-// ---------------------------------------------------------------- YIN by sliding sums (the fast detector path)
-// The mean of a frame cancels in c[j] - c[j+tau], so the difference function of frame f is a window sum over the
-// (zero-extended) clip, and with the square expanded it needs ONE float64 operation per (sample, lag) pair instead of two:
-//   d_f(tau) = sum_{j=s}^{p-1} (x[j] - x[j+tau])^2 = E(s, p) + E(s+tau, p+tau) - 2 R_tau(s, p),   s = f*hop, p = s + W - tau
-//   E(a, b) = sum_{a <= j < b} x[j]^2  (shared by all lags),   R_tau(a, b) = sum_{a <= j < b} x[j] x[j+tau]
-// (the inputs are float32, so every product is exact in float64).  Consecutive frames overlap by 7/8, so the sums are kept
-// per hop block: a thread owns AT_YL lags and walks the clip block by block accumulating R_tau of the block; for a
-// finished block it parks V = E(block + tau) - 2 R_tau(block) in a ring per lag, block energies go to a small shared
-// ring, and a frame's value is assembled from the parked blocks f .. b-1, the partial block, and prefix sums of squares
-// over the current tile.  Every term is a sum over at most one frame, so nothing cancels against a clip-long running
-// total (the largest term is 2 E_frame against d: relative error ~4e-16 E_frame / d).
-struct AtYinArgs {
-    const float *det;        // [batch, n]
-    double *diff;            // [batch, frames, stride] difference function, entry tau
-    double *feat;            // [batch, frames, 4]; feat[2] holds 1 / 0 (frame not silent) on entry of the pick kernel
-    long long n;
-    long long total_frames;  // batch * frames
-    int frames, frame_size, hop, stride;
-    int min_tau, max_tau;
-    double sr, min_freq, max_freq, threshold;
-};
-
-// Register tiling: a thread owns AT_YL consecutive lags and walks the samples AT_YS = 8 at a time, so AT_YL * 8 (sample,
-// lag) pairs come from the broadcast loads of x[j..j+7] and AT_YL + 7 loads of x[j+tau..]; the tile is stored de-interleaved
-// by AT_YL (element i at (i % AT_YL) * Q + i / AT_YL) so that the lanes' stride-AT_YL addresses fall on consecutive words.  B200's vector float64 pipe is 32 lanes per SM: 3.3e11 pairs per 1024 clips x 10 s are
-// 36 ms of DFMA at its peak.
-#ifndef QD_AT_YL
-#define QD_AT_YL 4
-#endif
-constexpr int AT_YL = QD_AT_YL;   // lags per thread = de-interleave factor of the tile (4 or 8)
-constexpr int AT_YS = 8;          // samples per iteration of the walk
-static_assert(AT_YL == 4 || AT_YL == 8, "the walk is written for 4 or 8 lags per thread");
-constexpr int AT_YT = 96;    // threads per CTA -> 384 lags per CTA (671 lags at 48 kHz = 2 CTAs per clip)
-constexpr int AT_YR = 9;     // ring depth: frame_size / hop + 1 blocks
-
-// shared memory of at_yin_diff_kernel in doubles, for a tile of `span` samples
-__host__ __device__ inline size_t at_yin_smem_doubles(size_t span) {
-    const size_t q = (((span + AT_YL - 1) / AT_YL) + 1) & ~(size_t)1;
-    return AT_YL * q + (span + 8) + (size_t)AT_YR * AT_YT * AT_YL + AT_YT + 16;
-}
-
-__global__ void __launch_bounds__(AT_YT) at_yin_diff_kernel(const AtYinArgs a) {
-    QD_DYN_SMEM(smem);
-    constexpr int NL = AT_YT * AT_YL;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int tau0 = 1 + blockIdx.x * NL;               // lags of this CTA: tau0 .. tau0 + NL - 1
-    const int taub = tau0 + AT_YL * tid;                // this thread: taub .. taub + AT_YL - 1
-    const int span = a.hop + tau0 + NL + 8;             // samples a hop-block needs (+ the look-ahead of the last sub-block)
-    const int Q = (((span + AT_YL - 1) / AT_YL) + 1) & ~1;   // even: the 16-byte loads of the walk stay aligned
-    double *tile = reinterpret_cast<double *>(smem);    // [4][Q] de-interleaved samples of the block and its look-ahead
-    double *qt = tile + AT_YL * Q;                          // [span + 1] prefix sums of squares over the tile: qt[i] = E(j0, j0 + i)
-    double *ringV = qt + span + 8;                      // [AT_YR][NL] E(block + tau) - 2 R_tau(block) of finished blocks
-    double *part = ringV + AT_YR * NL;                  // [AT_YT] scan scratch
-    double *be = part + AT_YT;                          // [16] energies of the last blocks
-    const float *x = a.det + (size_t)blockIdx.y * a.n;
-    double *out = a.diff + (size_t)blockIdx.y * a.frames * a.stride;
-    int q[AT_YL], off[AT_YL];
-    bool live[AT_YL];
-#pragma unroll
-    for (int u = 0; u < AT_YL; ++u) {
-        const int wlen = a.frame_size - (taub + u);       // window length of the lag
-        live[u] = taub + u <= a.max_tau;
-        q[u] = wlen / a.hop;                              // frame f ends inside hop-block f + q at offset off
-        off[u] = wlen % a.hop;
-    }
-    double S[AT_YL];
-    const int blocks = a.frames + a.frame_size / a.hop;
-    const int sh = tau0 % AT_YL;                          // taub % AT_YL is the same for every thread
-    const int chunk = (span + AT_YT - 1) / AT_YT;         // samples per thread in the prefix sum of squares
-    auto sample = [&](int i) { return tile[(i % AT_YL) * Q + (i / AT_YL)]; };
-    // Every lag closes exactly one frame per block (frame b - q at offset off); the frame's value is assembled after the
-    // walk by all lanes together from the sum captured inside the walk.
-    double P[AT_YL] = {};
-    int osb[AT_YL];            // the 8-sample iteration in which the lag's window ends
-    const double *pb[AT_YL];   // lagged samples: x[jj + taub + v] = pb[v % AT_YL][jj / AT_YL + v / AT_YL]
-#pragma unroll
-    for (int u = 0; u < AT_YL; ++u) osb[u] = off[u] >> 3;
-#pragma unroll
-    for (int v = 0; v < AT_YL; ++v) pb[v] = tile + ((sh + v) % AT_YL) * Q + ((taub + v) / AT_YL);
-    auto finish = [&](int u, int b) {
-        const int f = b - q[u];
-        if (live[u] && f >= 0 && f < a.frames) {
-            const int col = AT_YL * tid + u, tau = taub + u;
-            double pu = P[u];                                    // R_tau of the block up to the window's end: the sum at
-            for (int k = 8 * osb[u]; k < off[u]; ++k)            // the start of its 8-sample iteration + the rest of it
-                pu = fma(sample(k), sample(k + tau), pu);
-            double v = 0.0, eb = 0.0;
-            for (int bb = f; bb < b; ++bb) {
-                v += ringV[(bb % AT_YR) * NL + col];
-                eb += be[bb & 15];
-            }
-            const double e1 = eb + qt[off[u]];                                   // E(s, p)
-            const double cur = (qt[off[u] + tau] - qt[tau]) - 2.0 * pu;          // the partial block: E(. + tau) - 2 R
-            out[(size_t)f * a.stride + tau] = fmax(e1 + (v + cur), 0.0);
-        }
-    };
-    for (int b = 0; b < blocks; ++b) {
-        const long long j0 = (long long)b * a.hop;
-        __syncthreads();
-        for (int i = tid; i < span; i += AT_YT) {
-            const long long sidx = j0 + i;
-            tile[(i % AT_YL) * Q + (i / AT_YL)] = sidx < a.n ? (double)x[sidx] : 0.0;
-        }
-        __syncthreads();
-        // ---- prefix sums of squares over the tile (three warps: local sums, scan of the 96 partials, local prefixes)
-        {
-            const int i0 = tid * chunk, i1 = min(i0 + chunk, span);
-            double loc = 0.0;
-            for (int i = i0; i < i1; ++i) { const double v = sample(i); loc = fma(v, v, loc); }
-            part[tid] = loc;
-            __syncthreads();
-            if (tid < 32) {
-                const double a0 = part[3 * lane], a1 = part[3 * lane + 1], a2 = part[3 * lane + 2];
-                const double tot = a0 + a1 + a2;
-                double inc = tot;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const double o = __shfl_up_sync(QD_FULL, inc, d);
-                    if (lane >= d) inc += o;
-                }
-                const double exc = inc - tot;
-                part[3 * lane] = exc; part[3 * lane + 1] = exc + a0; part[3 * lane + 2] = exc + a0 + a1;
-            }
-            __syncthreads();
-            double run = part[tid];
-            for (int i = i0; i < i1; ++i) { qt[i] = run; const double v = sample(i); run = fma(v, v, run); }
-            if (i1 == span && i0 < span) qt[span] = run;
-        }
-        __syncthreads();
-        if (tid == 0) be[b & 15] = qt[a.hop];              // read by the emits of later blocks (after the next barrier)
-#pragma unroll
-        for (int u = 0; u < AT_YL; ++u) { S[u] = 0.0; P[u] = 0.0; }
-        // ---- the walk: 8 samples x 4 lags per iteration.  Sample jj + k sits in plane k & 3 at index i + (k >> 2), i = jj / 4,
-        //      so the eight own samples are four broadcast 16-byte loads and the eleven lagged ones eleven 8-byte loads from
-        //      four per-thread base pointers with constant offsets: no address arithmetic inside the loop.  A lag's window
-        //      ends somewhere in every block, and the lanes of a warp reach their ends in different iterations, so the loop
-        //      only records the sum at the START of that iteration (one predicated move per lag: no divergence); the up to
-        //      seven products of the partial iteration are added when the frame is assembled.
-        constexpr int IPI = AT_YS / AT_YL;                 // tile indices per iteration and plane (2 for 4 lags, 1 for 8)
-        for (int it = 0; it < a.hop / AT_YS; ++it) {
-            const int i = it * IPI;
-            double av[AT_YS], bv[AT_YS + AT_YL - 1];
-            if constexpr (AT_YL == 4) {
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) {
-                    const double2 t = *reinterpret_cast<const double2 *>(tile + s4 * Q + i);
-                    av[s4] = t.x;
-                    av[s4 + 4] = t.y;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < AT_YS; ++k) av[k] = tile[k * Q + i];
-            }
-#pragma unroll
-            for (int v = 0; v < AT_YS + AT_YL - 1; ++v) bv[v] = pb[v % AT_YL][i + v / AT_YL];
-#pragma unroll
-            for (int u = 0; u < AT_YL; ++u)
-                if (osb[u] == it) P[u] = S[u];
-#pragma unroll
-            for (int k = 0; k < AT_YS; ++k)
-#pragma unroll
-                for (int u = 0; u < AT_YL; ++u) S[u] = fma(av[k], bv[k + u], S[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < AT_YL; ++u) finish(u, b);
-#pragma unroll
-        for (int u = 0; u < AT_YL; ++u)
-            ringV[(b % AT_YR) * NL + AT_YL * tid + u] = (qt[a.hop + taub + u] - qt[taub + u]) - 2.0 * S[u];
-    }
-}
+// ---------------------------------------------------------------- YIN: the difference function lives in qd_yin.cuh
 
 // cumulative-mean normalisation and pick (dsp/autotune.py:162-197), one warp per frame
 __global__ void __launch_bounds__(256) at_yin_pick_kernel(const AtYinArgs a) {
@@ -444,16 +277,24 @@ __global__ void __launch_bounds__(256) at_yin_pick_kernel(const AtYinArgs a) {
         run += __shfl_sync(QD_FULL, inc, 31);
     }
     __syncwarp();
+    // the first lag below the threshold: 32 lags per step, the lowest set bit of the ballot
+    int first = -1;
+    const bool wanted = ft[2] != 0.0 && a.max_tau > a.min_tau;
+    if (wanted) {
+        for (int t0 = a.min_tau; t0 <= a.max_tau && first < 0; t0 += 32) {
+            const int t = t0 + lane;
+            const unsigned hit = __ballot_sync(QD_FULL, t <= a.max_tau && cm[t] < a.threshold);
+            if (hit) first = t0 + __ffs(hit) - 1;
+        }
+    }
     if (lane == 0) {
         double pitch = 0.0, conf = 0.0;
-        if (ft[2] != 0.0 && a.max_tau > a.min_tau) {
+        if (wanted) {
             int est = -1;
-            for (int t = a.min_tau; t <= a.max_tau; ++t) {
-                if (cm[t] < a.threshold) {
-                    while (t + 1 <= a.max_tau && cm[t + 1] < cm[t]) ++t;
-                    est = t;
-                    break;
-                }
+            if (first >= 0) {
+                int t = first;
+                while (t + 1 <= a.max_tau && cm[t + 1] < cm[t]) ++t;
+                est = t;
             }
             if (est >= 0) {
                 double better = (double)est;
@@ -603,13 +444,16 @@ QD_DEV AtSeg at_segment_at(const double *ratio, int frames, long long n, int hop
 // [0.5, 2]) is a multiple of 2^-24 with |slope| <= 1, the taps start at multiples of 2^-24 and stay below max_delay, so
 // every float64 addition and every wrap of the reference's loop (dsp/autotune.py:327-337) is exact.  In units of 2^-24 the
 // taps are T_n = (T_0 + sum_{k<=n} S_k) mod M -- an int64 prefix sum, associative and bit-exact, so it runs as a scan:
-// one warp per clip, 16 consecutive samples per lane and tile, a warp scan of the lane totals, a carry from tile to tile.
+// one CTA per clip, each of its AT_TW warps takes one tile of a round (16 consecutive samples per lane, a warp scan of the
+// lane totals), the tile totals of a round are chained through shared memory, the carry goes from round to round.
 constexpr int AT_SPL = AT_TS / 32;   // samples per lane and tile
+constexpr int AT_TW = 8;             // warps per clip = tiles per round
 
-__global__ void __launch_bounds__(32 * AT_FW) at_taps_kernel(const AtShiftArgs a) {
+__global__ void __launch_bounds__(32 * AT_TW) at_taps_kernel(const AtShiftArgs a) {
+    __shared__ long long s_tot[2][AT_TW];
+    __shared__ int s_flat[AT_TW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int clip = blockIdx.x * AT_FW + warp;
-    if (clip >= a.batch) return;
+    const int clip = blockIdx.x;
     const double *__restrict__ ratio = a.ratio + (size_t)clip * a.frames;
     double2 *__restrict__ taps = reinterpret_cast<double2 *>(a.taps + (size_t)clip * a.n * 2);
     float *__restrict__ rt = a.ratio_track ? a.ratio_track + (size_t)clip * a.n : nullptr;
@@ -618,12 +462,19 @@ __global__ void __launch_bounds__(32 * AT_FW) at_taps_kernel(const AtShiftArgs a
     const long long half_m = M / 2;                      // the second tap runs half a grain behind: 0.75 md = 0.25 md + md / 2
     long long carry = M / 4;                             // tap 0 starts at 0.25 * max_delay
     bool flat = true;
+    auto wrap = [&](long long t) {                       // a round moves a tap by at most 8 * 2^33 units: a few wraps
+        while (t < 0) t += M;
+        while (t >= M) t -= M;
+        return t;
+    };
     // a tile holds no frame centre strictly inside when hop and frame_size / 2 are multiples of the tile (512 | 512, 2048)
     const bool aligned = (a.hop % AT_TS) == 0 && (a.half % AT_TS) == 0 && (a.max_delay % 4) == 0;
     const double r_last = ratio[a.frames - 1];
-    for (long long i0 = 0; i0 < a.n; i0 += AT_TS) {
+    int par = 0;
+    for (long long r0 = 0; r0 < a.n; r0 += (long long)AT_TS * AT_TW, par ^= 1) {
+        const long long i0 = r0 + (long long)warp * AT_TS;   // this warp's tile (possibly past the end: it then adds nothing)
         AtSeg sg{0.0, 1.0, 0.0};
-        if (aligned) sg = at_segment_at(ratio, a.frames, a.n, a.hop, a.half, i0);
+        if (aligned && i0 < a.n) sg = at_segment_at(ratio, a.frames, a.n, a.hop, a.half, i0);
         long long loc[AT_SPL];
         long long run = 0;
 #pragma unroll
@@ -647,27 +498,36 @@ __global__ void __launch_bounds__(32 * AT_FW) at_taps_kernel(const AtShiftArgs a
             const long long o = __shfl_up_sync(QD_FULL, incl, d);
             if (lane >= d) incl += o;
         }
-        const long long before = carry + (incl - run);
+        if (lane == 31) s_tot[par][warp] = incl;
+        __syncthreads();                                 // (the other parity's totals are rewritten a whole round later)
+        long long before = carry, total = 0;
+#pragma unroll
+        for (int w = 0; w < AT_TW; ++w) {
+            const long long tw = s_tot[par][w];
+            if (w < warp) before += tw;
+            total += tw;
+        }
+        before = wrap(before) + (incl - run);
 #pragma unroll
         for (int k = 0; k < AT_SPL; ++k) {
             const long long i = i0 + (long long)lane * AT_SPL + k;
             if (i < a.n) {
-                // |tile sum| <= 2^33 < M / 2 steps from a value in [0, M): at most a few wraps, done like the reference's loops
-                long long t0 = before + loc[k];
-                while (t0 < 0) t0 += M;
-                while (t0 >= M) t0 -= M;
+                const long long t0 = wrap(before + loc[k]);
                 long long t1 = t0 + half_m;
                 if (t1 >= M) t1 -= M;
                 taps[i] = make_double2((double)t0 * (1.0 / (double)unit), (double)t1 * (1.0 / (double)unit));
             }
         }
-        long long c2 = carry + __shfl_sync(QD_FULL, incl, 31);
-        while (c2 < 0) c2 += M;
-        while (c2 >= M) c2 -= M;
-        carry = c2;
+        carry = wrap(carry + total);
     }
     flat = __all_sync(QD_FULL, flat);
-    if (lane == 0) a.flat_flag[clip] = flat ? 1 : 0;
+    if (lane == 0) s_flat[warp] = flat ? 1 : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int f = 1;
+        for (int w = 0; w < AT_TW; ++w) f &= s_flat[w];
+        a.flat_flag[clip] = f;
+    }
 }
 
 __global__ void at_shift_kernel(const AtShiftArgs a) {

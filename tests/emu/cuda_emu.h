@@ -51,9 +51,10 @@ struct Block {
     pthread_barrier_t bar;
     std::vector<pthread_barrier_t> warp_bar;
     std::vector<uint64_t> xchg;  // [warps][32]
-    pthread_barrier_t named[16];
     int named_count[16] = {0};
+    unsigned named_gen[16] = {0};
     pthread_mutex_t named_mu = PTHREAD_MUTEX_INITIALIZER;
+    pthread_cond_t named_cv = PTHREAD_COND_INITIALIZER;
     std::vector<unsigned char> smem;
 };
 extern thread_local Block *g_blk;
@@ -77,17 +78,23 @@ inline T shfl_idx(T v, int src) {
     return out;
 }
 
-// bar.sync id, count: the first caller fixes the participant count of that barrier id for the block
-inline void named_barrier(int id, int count) {
+// bar.sync id, count / bar.arrive id, count: `count` threads take part in one generation of barrier `id`; a syncing thread
+// waits for the generation to complete, an arriving thread only counts (producer / consumer hand-offs)
+inline void named_barrier_op(int id, int count, bool wait) {
     Block *b = g_blk;
     pthread_mutex_lock(&b->named_mu);
-    if (b->named_count[id] == 0) {
-        pthread_barrier_init(&b->named[id], nullptr, (unsigned)count);
-        b->named_count[id] = count;
+    const unsigned gen = b->named_gen[id];
+    if (++b->named_count[id] == count) {
+        b->named_count[id] = 0;
+        ++b->named_gen[id];
+        pthread_cond_broadcast(&b->named_cv);
+    } else if (wait) {
+        while (b->named_gen[id] == gen) pthread_cond_wait(&b->named_cv, &b->named_mu);
     }
     pthread_mutex_unlock(&b->named_mu);
-    pthread_barrier_wait(&b->named[id]);
 }
+inline void named_barrier(int id, int count) { named_barrier_op(id, count, true); }
+inline void named_arrive(int id, int count) { named_barrier_op(id, count, false); }
 
 // Run `body` once per CUDA thread of every block of the grid (blocks sequentially).
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body) {

@@ -221,3 +221,36 @@ def test_emu_formant_shift_pass(emu_spec, n_fft, nw, n, semitones):
     ref = orc.istft(Sq, sr, n_fft, length=n)
     err = float(np.max(np.abs(y - ref)))
     assert err < 2e-5, err
+
+
+@pytest.fixture(scope="module")
+def emu_yin():
+    exe = os.path.join(tempfile.gettempdir(), "qd_emu_yin")
+    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_yin.cpp", "cuda_emu.h")] + [os.path.join(CSRC, f) for f in ("qd_yin.cuh", "qd_common.cuh")]
+    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-DQD_EMU", "-I", EMU_DIR, "-o", exe,
+                               os.path.join(EMU_DIR, "emu_yin.cpp"), "-lpthread"])
+    return exe
+
+
+@pytest.mark.parametrize("n,frame,hop,max_tau,cols", [(1500, 512, 64, 100, 88), (1500, 512, 64, 100, 3), (1000, 1024, 128, 61, 88),
+                                                      (2100, 512, 128, 201, 7), (700, 512, 64, 255, 20), (3000, 512, 64, 255, 2),
+                                                      (900, 4096, 512, 2047, 42)])   # the last: a tile that needs two prefix rounds
+def test_emu_yin_difference_function(emu_yin, n, frame, hop, max_tau, cols):
+    """The sliding-sum walk (walker and helper warps, three sample groups x columns of 16 lags, captures inside the iteration,
+    `cols` columns per CTA)
+    against the definition d_f(tau) = sum_j (x[s+j] - x[s+j+tau])^2 over the zero-extended clip (dsp/autotune.py:141-151)."""
+    t = np.arange(n)
+    x = (0.5 * np.sin(2 * np.pi * t / 37.3) + 0.1 * np.random.default_rng(n).standard_normal(n)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        x.tofile(os.path.join(d, "x"))
+        subprocess.check_call([emu_yin, str(n), str(frame), str(hop), str(max_tau), str(cols), os.path.join(d, "x"), os.path.join(d, "d")])
+        got = np.fromfile(os.path.join(d, "d")).reshape(-1, (max_tau + 2) & ~1)[:, 1:max_tau + 1]
+    xz = np.concatenate([x.astype(np.float64), np.zeros(frame + max_tau + hop)])
+    ref = np.zeros_like(got)
+    for f in range(got.shape[0]):
+        for tau in range(1, max_tau + 1):
+            dd = xz[f * hop:f * hop + frame - tau] - xz[f * hop + tau:f * hop + frame]
+            ref[f, tau - 1] = np.dot(dd, dd)
+    assert (got >= 0).all(), "every (frame, lag) entry is written"
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
