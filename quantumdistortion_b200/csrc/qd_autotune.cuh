@@ -631,6 +631,70 @@ __global__ void __launch_bounds__(32 * AT_FW) at_env_kernel(const AtMixArgs a) {
     if (lane == 0) a.env_max[clip] = top;
 }
 
+// The same follower, segment-parallel: both branches of the recurrence pull `cur` towards |x| by a factor of at least
+// 1 - max(att, rel), so two runs over the same input that start from different states approach each other by that factor
+// per sample whichever branches they take.  One thread follows one tile of `tile` samples after a warm-up of `halo`
+// samples from zero (host: max(att, rel)^halo < 1e-10, far below a float32 ulp); a warp stages 32 samples of its 32 tiles
+// through shared memory like the zero-phase filters.  The clip maximum is an atomicMax on the float bits (env >= 0);
+// env_max must be zeroed before the launch.
+__global__ void __launch_bounds__(32 * AT_SW) at_env_seg_kernel(const AtMixArgs a, int tile, int halo) {
+    __shared__ float s_row[AT_SW][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int clip = blockIdx.y;
+    const long long n = a.n;
+    const float *__restrict__ x = a.x + (size_t)clip * n;
+    float *__restrict__ env = a.env + (size_t)clip * n;
+    const long long n_tiles = (n + tile - 1) / tile;
+    const long long tile0 = ((long long)blockIdx.x * AT_SW + warp) * 32;
+    if (tile0 >= n_tiles) return;
+    const int rows = (int)(n_tiles - tile0 < 32 ? n_tiles - tile0 : 32);
+    float (*row)[33] = s_row[warp];
+    const long long p_first = tile0 * tile - halo;          // row 0, step 0, column 0
+    const long long p_own = p_first + (long long)lane * tile;
+    const int steps = (halo + tile) / 32;
+    float nxt[32];
+    auto fetch = [&](int j) {                               // loads only: the values are consumed one step later
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const long long p = p_first + (long long)r * tile + 32LL * j + lane;
+            nxt[r] = x[(r < rows && p >= 0 && p < n) ? p : 0];
+        }
+    };
+    float cur = 0.0f, top = 0.0f;
+    fetch(0);
+    for (int j = 0; j < steps; ++j) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) row[r][lane] = nxt[r];
+        __syncwarp();
+        if (j + 1 < steps) fetch(j + 1);
+        const long long p_step = p_own + 32LL * j;          // steps are 32-aligned: a step lies wholly before or after p = 0
+        const bool own = 32 * j >= halo;                    // past the warm-up: these samples are the tile's output
+        if (lane < rows && p_step >= 0 && p_step < n) {
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const float s = fabsf(row[lane][k]);
+                const float c = s > cur ? a.att : a.rel;
+                cur = __fadd_rn(s, __fmul_rn(c, __fsub_rn(cur, s)));
+                if (own) {
+                    row[lane][k] = cur;
+                    if (p_step + k < n) top = fmaxf(top, cur);
+                }
+            }
+        }
+        __syncwarp();
+        if (own) {
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) {
+                const long long p = p_first + (long long)r * tile + 32LL * j + lane;
+                if (p < n) env[p] = row[r][lane];
+            }
+        }
+        __syncwarp();
+    }
+    top = warp_max(top);
+    if (lane == 0) atomicMax(reinterpret_cast<int *>(a.env_max + clip), __float_as_int(top));
+}
+
 __global__ void at_mix_kernel(const AtMixArgs a) {
     const int clip = blockIdx.y;
     const size_t base = (size_t)clip * a.n;
