@@ -347,6 +347,18 @@ QD_DEV double at_nearest_scale_freq(double freq, const AtHoldArgs &a) {   // dsp
     return 440.0 * exp2((best - 69.0) / 12.0);
 }
 
+// The target note of a voiced frame depends on that frame alone: one thread per frame leaves it in ratio[] (0 = unvoiced),
+// so the sequential kernel below only runs the state machine.
+__global__ void at_target_kernel(const AtHoldArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)a.batch * a.frames) return;
+    const double *f = a.feat + (size_t)i * 4;
+    const double rms = f[0], flat = f[1], p = f[2], conf = f[3];
+    const bool voiced = p > 0.0 && rms >= a.rms_thr && flat <= a.flat_thr && conf >= a.conf_thr;
+    a.ratio[i] = voiced ? at_nearest_scale_freq(p, a) : 0.0;
+}
+
+// note-hold state machine (dsp/autotune.py:236-285), one thread per clip; ratio[] holds the targets on entry
 __global__ void at_hold_kernel(const AtHoldArgs a) {
     const int clip = blockIdx.x * blockDim.x + threadIdx.x;
     if (clip >= a.batch) return;
@@ -354,12 +366,13 @@ __global__ void at_hold_kernel(const AtHoldArgs a) {
     double *out = a.ratio + (size_t)clip * a.frames;
     double held = 0.0, cand = 0.0, last = 1.0;
     int cand_n = 0, rel = a.release_frames + 1;
+    double tgt_n = out[0], p_n = f[2];                   // the next frame's inputs are loaded one step ahead
     for (int i = 0; i < a.frames; ++i) {
-        const double rms = f[4 * i], flat = f[4 * i + 1], p = f[4 * i + 2], conf = f[4 * i + 3];
-        const bool voiced = p > 0.0 && rms >= a.rms_thr && flat <= a.flat_thr && conf >= a.conf_thr;
+        const double tgt = tgt_n, p = p_n;
+        if (i + 1 < a.frames) { tgt_n = out[i + 1]; p_n = f[4 * (i + 1) + 2]; }
+        const bool voiced = tgt > 0.0;                   // the target of a voiced frame is a positive frequency
         double r;
         if (voiced) {
-            const double tgt = at_nearest_scale_freq(p, a);
             if (held <= 0.0) {
                 held = tgt; cand = 0.0; cand_n = 0;
             } else {
