@@ -430,7 +430,6 @@ struct AtShiftArgs {
     double *taps;            // [batch, n, 2]
     float *ratio_track;      // optional [batch, n]
     int *flat_flag;          // [batch] 1: ratio track allclose to 1 -> output = body
-    float *raw;              // [batch, n] shifter output before the latency trim
     float *out;              // [batch, n] corrected body
     long long n;
     int batch, frames, hop, half;
@@ -543,16 +542,21 @@ __global__ void __launch_bounds__(32 * AT_TW) at_taps_kernel(const AtShiftArgs a
     }
 }
 
+// read-out with the latency trim folded in: out = raw[lat:] ++ zeros(lat) unless the early-out copied the body
+// (dsp/autotune.py:339-358); sample i of the shifter lands at out[i - lat]
 __global__ void at_shift_kernel(const AtShiftArgs a) {
     const int clip = blockIdx.y;
     const float *x = a.body + (size_t)clip * a.n;
     const double *taps = a.taps + (size_t)clip * a.n * 2;
-    float *raw = a.raw + (size_t)clip * a.n;
+    float *out = a.out + (size_t)clip * a.n;
     const bool flat = a.flat_flag[clip] != 0;
+    const long long lat = (!flat && a.n > a.max_delay / 2) ? a.max_delay / 2 : 0;
     const double md = (double)a.max_delay, size = (double)a.buf_size;
     const int mask = a.buf_size - 1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
-        if (flat) { raw[i] = x[i]; continue; }
+        if (flat) { out[i] = x[i]; continue; }
+        if (i >= a.n - lat) out[i] = 0.0f;               // the tail that no shifted sample reaches
+        if (i < lat) continue;
         const int w = (int)(i & mask);
         double mixed = 0.0, wsum = 0.0;
 #pragma unroll
@@ -570,19 +574,8 @@ __global__ void at_shift_kernel(const AtShiftArgs a) {
             mixed += (double)smp * weight;
             wsum += weight;
         }
-        raw[i] = wsum > 1e-6 ? (float)(mixed / wsum) : 0.0f;
+        out[i - lat] = wsum > 1e-6 ? (float)(mixed / wsum) : 0.0f;
     }
-}
-
-// latency trim: out = raw[lat:] ++ zeros(lat) unless the early-out copied the body (dsp/autotune.py:355-358)
-__global__ void at_trim_kernel(const AtShiftArgs a) {
-    const int clip = blockIdx.y;
-    const float *raw = a.raw + (size_t)clip * a.n;
-    float *out = a.out + (size_t)clip * a.n;
-    const bool flat = a.flat_flag[clip] != 0;
-    const long long lat = (!flat && a.n > a.max_delay / 2) ? a.max_delay / 2 : 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x)
-        out[i] = (i + lat < a.n) ? raw[i + lat] : 0.0f;
 }
 
 // ---------------------------------------------------------------- sub layer and final mix
