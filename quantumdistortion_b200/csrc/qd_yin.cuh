@@ -15,9 +15,11 @@
 // the walk has to reuse its operands from registers, and everything that is not the walk has to stay off its critical path.
 //
 //  * One CTA per SM works on one clip (and up to 42 * 16 lags); its twelve warps have two roles.
-//  * EIGHT WALKER WARPS (two per SM sub-partition, i.e. per FP64 pipe: a single warp cannot keep the pipe busy through its
-//    own loads and block changes).  A walker thread owns L = 16 consecutive lags (a "column") and one SIXTH of the block's
-//    samples (the six partial sums of a lag meet in shared memory once per block), and walks it 16 samples at a time: the 16 own samples are eight broadcast 16-byte loads from a
+//  * EIGHT WALKER WARPS in two teams of four (one warp of each team per SM sub-partition, i.e. per FP64 pipe: a single
+//    warp cannot keep the pipe busy through its own loads and block changes).  Team 0 walks the even hop blocks, team 1
+//    the odd ones, so the two warps that share a pipe are in different phases of their blocks.  A walker thread owns
+//    L = 16 consecutive lags (a "column") and one THIRD of a block's samples (the three partial sums of a lag meet in
+//    shared memory once per block), and walks it 16 samples at a time: the 16 own samples are eight broadcast 16-byte loads from a
 //    natural-order copy of the block, and of the 31 lagged samples x[j + tau0 .. j + tau0 + 30] fifteen are the previous
 //    iteration's registers -- 16 new 8-byte loads, one per plane of the tile, which is stored de-interleaved by 16 so that
 //    the lanes' stride-16 addresses are consecutive words.  24 loads and 256 DFMA per iteration.
@@ -26,7 +28,8 @@
 //    that iteration (predicated stores, no divergence, no remainder products afterwards).
 //  * FOUR HELPER WARPS run one block ahead and one block behind the walkers: they load the next block's samples (through
 //    registers, fetched before the assembly starts), build its prefix sums of squares, and assemble the frames that the
-//    previous block closed.  Tile, prefix sums and partial sums are double-buffered; the roles meet at four mbarriers
+//    previous block closed.  Tile, prefix sums and partial sums exist three times (two blocks being walked, one being
+//    assembled and refilled); the roles meet at six mbarriers
 //    (full / done per buffer): the producer side arrives, the consumer side only waits for the phase, so a walker warp
 //    never waits for another walker warp.
 #pragma once
@@ -47,10 +50,12 @@ struct AtYinArgs {
 };
 
 constexpr int AT_YL = 16;         // lags per walker thread = samples per iteration = planes of the tile
-constexpr int AT_YG = 6;          // sample groups per block: a walker owns a sixth of every block
-constexpr int AT_YC = 42;         // columns per CTA: AT_YG * AT_YC = 252 walker threads
-constexpr int AT_YW = 256;        // walker threads (warps 0-7: two per SM sub-partition)
+constexpr int AT_YG = 3;          // sample groups per block: a walker owns a third of a block
+constexpr int AT_YC = 42;         // columns per CTA: AT_YG * AT_YC = 126 walker threads per team
+constexpr int AT_YTEAM = 128;     // threads of a walker team: four warps, one per SM sub-partition
+constexpr int AT_YW = 2 * AT_YTEAM;   // two teams (warps 0-3 take the even blocks, warps 4-7 the odd ones)
 constexpr int AT_YH = 128;        // helper threads (warps 8-11)
+constexpr int AT_YNS = 3;         // buffers: two blocks being walked, one being assembled / refilled
 constexpr int AT_YT = AT_YW + AT_YH;
 constexpr int AT_YR = 9;          // ring depth: frame_size / hop + 1 blocks
 enum { AT_BAR_HELP = 1 };         // named barrier of the helper warps (0 is __syncthreads)
@@ -60,11 +65,11 @@ __host__ __device__ inline int at_yin_odd(int v) { return v | 1; }
 // fastest by the helpers; with an odd stride the 32 doubles of a warp then fall on the 16 eight-byte bank slots twice each,
 // the two wavefronts 256 bytes need anyway.
 
-// shared memory in doubles: 2 x (tile, natural-order block, prefix sums, partial sums, captures), ring, scratch, lag table
+// shared memory in doubles: 3 x (tile, natural-order block, prefix sums, partial sums, captures), ring, scratch, lag table
 __host__ __device__ inline size_t at_yin_smem_doubles(int hop, int first_col, int cols) {
     const int span = hop + AT_YL * (first_col + cols);
     const size_t plane = (size_t)AT_YL * at_yin_odd(span / AT_YL + 1), rs = (size_t)AT_YL * at_yin_odd(cols);
-    return 2 * (2 * plane + hop + (AT_YG + 1) * rs) + AT_YR * rs + 48 + 4 + (AT_YL * cols + 1) / 2 + 16;
+    return AT_YNS * (2 * plane + hop + (AT_YG + 1) * rs) + AT_YR * rs + 48 + 2 * AT_YNS + (AT_YL * cols + 1) / 2 + 16;
 }
 
 QD_DEV void at_bar_sync(int id, int count) {
@@ -113,43 +118,42 @@ __global__ void __launch_bounds__(AT_YT, 1) at_yin_diff_kernel(const AtYinArgs a
     const int PL = L * Q;
     const int sp = at_yin_odd(cols);                    // row stride of the per-lag arrays
     const int RS = L * sp;                              // one [L][sp] array
-    double *tile = reinterpret_cast<double *>(smem);    // [2][L][Q]: sample i of the block at (i % L) * Q + i / L
-    double *own = tile + 2 * PL;                        // [2][hop] the block's own samples in natural order
-    double *qt = own + 2 * hop;                         // [2][L][Q] prefix sums of squares, same layout: qt(i) = E(j0, j0 + i)
-    double *xs = qt + 2 * PL;                           // [2][G][L][sp] R_tau of each third of the block
-    double *xp = xs + 2 * G * RS;                       // [2][cols][L] R_tau of the block up to the lag's window end
-    double *ringV = xp + 2 * RS;                        // [AT_YR][L][sp] E(block + tau) - 2 R_tau(block) of finished blocks
+    double *tile = reinterpret_cast<double *>(smem);    // [3][L][Q]: sample i of the block at (i % L) * Q + i / L
+    double *own = tile + AT_YNS * PL;                   // [3][hop] the block's own samples in natural order
+    double *qt = own + AT_YNS * hop;                    // [3][L][Q] prefix sums of squares, same layout: qt(i) = E(j0, j0 + i)
+    double *xs = qt + AT_YNS * PL;                      // [3][G][L][sp] R_tau of each third of the block
+    double *xp = xs + AT_YNS * G * RS;                  // [3][cols][L] R_tau of the block up to the lag's window end
+    double *ringV = xp + AT_YNS * RS;                   // [AT_YR][L][sp] E(block + tau) - 2 R_tau(block) of finished blocks
     double *wtot = ringV + (size_t)AT_YR * RS;          // [16] warp totals of the prefix sum
     double *be = wtot + 16;                             // [16] energies of the last blocks
     double *ebq = be + 16;                              // [16] ebq[q] = energy of the q blocks before the one being assembled
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(ebq + 16);   // full[2] (helpers -> walkers), done[2] (walkers -> helpers)
-    int *lagc = reinterpret_cast<int *>(mbar + 4);      // [L * cols] per lag: off | q << 12 | group << 16 | live << 20
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(ebq + 16);   // full[3] (helpers -> walkers), done[3] (walkers -> helpers)
+    int *lagc = reinterpret_cast<int *>(mbar + 2 * AT_YNS);      // [L * cols] per lag: off | q << 12 | group << 16 | live << 20
     const float *x = a.det + (size_t)blockIdx.y * a.n;
     double *out = a.diff + (size_t)blockIdx.y * a.frames * a.stride;
     const int blocks = a.frames + W / hop;
     const int n_all = hop / L;                          // iterations per block, split over the G groups as evenly as possible
     auto group_begin = [&](int g) { return g * (n_all / G) + min(g, n_all % G); };
-    uint64_t *full = mbar, *done = mbar + 2;
-    if (tid == 0) {
-        at_mbar_init(full, 1);                          // one helper thread arrives after the helpers' own barrier
-        at_mbar_init(full + 1, 1);
-        at_mbar_init(done, AT_YW / 32);                 // one lane per walker warp
-        at_mbar_init(done + 1, AT_YW / 32);
+    uint64_t *full = mbar, *done = mbar + AT_YNS;
+    if (tid < AT_YNS) {
+        at_mbar_init(full + tid, 1);                    // one helper thread arrives after the helpers' own barrier
+        at_mbar_init(done + tid, AT_YTEAM / 32);        // one lane per warp of the team that walked the block
     }
     __syncthreads();
 
     if (tid < AT_YW) {
-        // ================================================================ walkers: group g (a third of the samples), column t
-        const bool walker = tid < G * cols;
-        const int g = walker ? tid / cols : 0, t = walker ? tid % cols : 0;
-                const int it0 = group_begin(g), n_it = group_begin(g + 1) - it0;
+        // ================================================================ walkers: team, group g (a third of the samples), column t
+        const int team = tid / AT_YTEAM, wt = tid % AT_YTEAM;
+        const bool walker = wt < G * cols;
+        const int g = walker ? wt / cols : 0, t = walker ? wt % cols : 0;
+        const int it0 = group_begin(g), n_it = group_begin(g + 1) - it0;
         // window length of the thread's first lag: W - tau0 - L t = L - 1 (mod L); lag u ends L - 1 - u samples into
         // iteration off0 / L of the block
         const int off0 = (W - tau0 - L * t) % hop;
         const int cap = off0 / L - it0;                 // the thread's own iteration index of the capture (or out of range)
-        for (int b = 0; b < blocks; ++b) {
-            const int s = b & 1;
-            at_mbar_wait(full + s, (b >> 1) & 1);       // tile / own of block b are in buffer s (the warp waits for nobody else)
+        for (int b = team; b < blocks; b += 2) {
+            const int s = b % AT_YNS;
+            at_mbar_wait(full + s, (b / AT_YNS) & 1);   // tile / own of block b are in buffer s (the warp waits for nobody else)
             if (walker) {
                 const double *ownp = own + s * hop + L * it0;
                 const double *lagp = tile + s * PL + (it0 + t + c0);    // plane p of iteration it: lagp[p * Q + it (+ 1)]
@@ -326,17 +330,16 @@ __global__ void __launch_bounds__(AT_YT, 1) at_yin_diff_kernel(const AtYinArgs a
             helper_sync();                                                       // ebq, qt[s], xs[s], xp[s] have been read
         };
         helper_sync();
-        fetch(0);
-        produce(0, 0);
-        fetch(1);
-        if (blocks > 1) produce(1, 1);
-        for (int b = 0; b < blocks; ++b) {
-            const int s = b & 1;
-            const bool more = b + 2 < blocks;
-            if (more) fetch(b + 2);                      // lands while the walkers finish block b and its frames are assembled
-            at_mbar_wait(done + s, (b >> 1) & 1);        // the walkers have left block b
+        for (int b = 0; b < AT_YNS && b < blocks; ++b) {
+            fetch(b);
+            produce(b, b);
+        }
+        for (int b = 0, s = 0; b < blocks; ++b, s = s + 1 == AT_YNS ? 0 : s + 1) {
+            const bool more = b + AT_YNS < blocks;
+            if (more) fetch(b + AT_YNS);                 // lands while the walkers finish block b and its frames are assembled
+            at_mbar_wait(done + s, (b / AT_YNS) & 1);    // the walkers have left block b
             assemble(b, s);
-            if (more) produce(b + 2, s);
+            if (more) produce(b + AT_YNS, s);
         }
     }
 }
