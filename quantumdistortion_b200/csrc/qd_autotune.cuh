@@ -227,19 +227,21 @@ __global__ void __launch_bounds__(32 * AT_SW_STATS) at_frame_stats_kernel(const 
     fft_forward<float, NC>(buf, nullptr, sa, nullptr, a.tw1, a.tw2, lane);
     real_split<float, NC>(buf, a.wsplit, lane);
     constexpr int ROWS = (NC + 1 + 31) / 32;
-    double lg = 0.0, ar = 0.0;
+    // |X| + 1e-8 and its logarithm with the fast float32 units (rsqrt, lg2: ~1e-6 relative, like the float32 FFT that
+    // produced X; the flatness is only compared with a threshold); a lane adds its 64 (65) bins in float32, the lanes'
+    // partial sums are added in float64
+    float lgf = 0.0f, arf = 0.0f;
+#pragma unroll 4
     for (int row = 0; row < ROWS; ++row) {
         if (row < ROWS - 1 || lane == 0) {
-            // |X| + 1e-8 and its logarithm in float32 (1e-7 relative, like the float32 FFT that produced X; the flatness
-            // is only compared with a threshold), the two sums over 2049 bins in float64
             const float2 v = buf[rpos<float, NC>(lane, row)];
-            const float m = sqrtf(fmaf(v.x, v.x, v.y * v.y)) + 1e-8f;
-            lg += (double)logf(m);
-            ar += (double)m;
+            const float p2 = fmaf(v.x, v.x, v.y * v.y);
+            const float m = (p2 > 0.0f ? p2 * rsqrtf(p2) : 0.0f) + 1e-8f;
+            lgf += __log2f(m);
+            arf += m;
         }
     }
-    lg = warp_sum(lg);
-    ar = warp_sum(ar);
+    const double lg = warp_sum((double)lgf) * 0.693147180559945309417, ar = warp_sum((double)arf);
     if (lane == 0) {
         const double geo = exp(lg / (double)(NC + 1)), ari = ar / (double)(NC + 1);
         double *o = a.feat + (size_t)fr * 4;
