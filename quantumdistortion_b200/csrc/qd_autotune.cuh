@@ -97,7 +97,31 @@ __global__ void __launch_bounds__(32 * AT_SW) at_filt_seg_kernel(const AtFiltSeg
     // shared memory.  Consuming them inside the fetch made every step wait for DRAM (forward sweep: 26 -> 6 ms).
     Raw nxt[32];
     unsigned m_ok = 0u, m_left = 0u, m_right = 0u;         // bit r: row r holds a sample / a left- / right-edge sample
+    bool nxt_plain = false;                                // the fetched step lies wholly inside the clip: no masks needed
+    // A step is "plain" when all 32 rows of the warp exist and every position of the step lies in [lo, hi): then a row is
+    // one pointer plus r * tile, and the bookkeeping below (64-bit positions, edge masks, selects: three quarters of the
+    // kernel's instructions before this path existed) is skipped.  Forward loads and backward stores need the interior of
+    // the odd extension, backward loads and forward stores only the extended range itself.
+    const bool full = rows == 32;
+    auto plain = [&](int j, long long lo, long long hi) {
+        const long long p0 = p_first + 32LL * j;
+        return full && p0 >= lo && p0 + 31LL * tile + 31 < hi;
+    };
     auto fetch = [&](int j) {
+        nxt_plain = BWD ? plain(j, 0, m) : plain(j, AT_EDGE, n + AT_EDGE);
+        if (nxt_plain) {
+            const long long p = p_first + 32LL * j + lane;
+            if (BWD) {
+                const double *src = s + (m - 1 - p);
+#pragma unroll
+                for (int r = 0; r < 32; ++r) nxt[r] = (Raw)src[-(long long)r * tile];
+            } else {
+                const float *src = x + (p - AT_EDGE);
+#pragma unroll
+                for (int r = 0; r < 32; ++r) nxt[r] = (Raw)src[(long long)r * tile];
+            }
+            return;
+        }
         m_ok = 0u; m_left = 0u; m_right = 0u;
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
@@ -124,15 +148,20 @@ __global__ void __launch_bounds__(32 * AT_SW) at_filt_seg_kernel(const AtFiltSeg
     }
     fetch(0);
     for (int j = 0; j < steps; ++j) {
+        if (nxt_plain) {
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const bool ok = (m_ok >> r) & 1u;
-            if (BWD) {
-                row[r][lane] = ok ? (double)nxt[r] : 0.0;
-            } else {   // odd extension in float32: 2 x[0] - x[AT_EDGE - p] on the left, 2 x[n-1] - x[mirror] on the right
-                const float v = (float)nxt[r];
-                const bool l = (m_left >> r) & 1u, rt = (m_right >> r) & 1u;
-                row[r][lane] = !ok ? 0.0 : (double)((l || rt) ? __fsub_rn(__fmul_rn(2.0f, l ? x_first : x_last), v) : v);
+            for (int r = 0; r < 32; ++r) row[r][lane] = (double)nxt[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const bool ok = (m_ok >> r) & 1u;
+                if (BWD) {
+                    row[r][lane] = ok ? (double)nxt[r] : 0.0;
+                } else {   // odd extension in float32: 2 x[0] - x[AT_EDGE - p] on the left, 2 x[n-1] - x[mirror] on the right
+                    const float v = (float)nxt[r];
+                    const bool l = (m_left >> r) & 1u, rt = (m_right >> r) & 1u;
+                    row[r][lane] = !ok ? 0.0 : (double)((l || rt) ? __fsub_rn(__fmul_rn(2.0f, l ? x_first : x_last), v) : v);
+                }
             }
         }
         __syncwarp();
@@ -155,15 +184,28 @@ __global__ void __launch_bounds__(32 * AT_SW) at_filt_seg_kernel(const AtFiltSeg
         }
         __syncwarp();
         if (32 * j >= halo) {
+            if (BWD ? plain(j, AT_EDGE, n + AT_EDGE) : plain(j, 0, m)) {
+                const long long p = p_first + 32LL * j + lane;
+                if (!BWD) {
+                    double *dst = s + p;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) dst[(long long)r * tile] = row[r][lane];
+                } else {
+                    float *dst = y + (m - 1 - p - AT_EDGE);
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) dst[-(long long)r * tile] = (float)row[r][lane];
+                }
+            } else {
 #pragma unroll 8
-            for (int r = 0; r < rows; ++r) {
-                const long long p = p_first + (long long)r * tile + 32LL * j + lane;
-                if (p < m) {
-                    if (!BWD) {
-                        s[p] = row[r][lane];
-                    } else {
-                        const long long i = m - 1 - p;
-                        if (i >= AT_EDGE && i < n + AT_EDGE) y[i - AT_EDGE] = (float)row[r][lane];
+                for (int r = 0; r < rows; ++r) {
+                    const long long p = p_first + (long long)r * tile + 32LL * j + lane;
+                    if (p < m) {
+                        if (!BWD) {
+                            s[p] = row[r][lane];
+                        } else {
+                            const long long i = m - 1 - p;
+                            if (i >= AT_EDGE && i < n + AT_EDGE) y[i - AT_EDGE] = (float)row[r][lane];
+                        }
                     }
                 }
             }
@@ -661,7 +703,17 @@ __global__ void __launch_bounds__(32 * AT_SW) at_env_seg_kernel(const AtMixArgs 
     const long long p_own = p_first + (long long)lane * tile;
     const int steps = (halo + tile) / 32;
     float nxt[32];
+    auto plain = [&](int j) {                               // all 32 rows exist and the whole step lies inside the clip
+        const long long p0 = p_first + 32LL * j;
+        return rows == 32 && p0 >= 0 && p0 + 31LL * tile + 31 < n;
+    };
     auto fetch = [&](int j) {                               // loads only: the values are consumed one step later
+        if (plain(j)) {
+            const float *src = x + (p_first + 32LL * j + lane);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) nxt[r] = src[(long long)r * tile];
+            return;
+        }
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
             const long long p = p_first + (long long)r * tile + 32LL * j + lane;
@@ -691,10 +743,16 @@ __global__ void __launch_bounds__(32 * AT_SW) at_env_seg_kernel(const AtMixArgs 
         }
         __syncwarp();
         if (own) {
+            if (plain(j)) {
+                float *dst = env + (p_first + 32LL * j + lane);
+#pragma unroll
+                for (int r = 0; r < 32; ++r) dst[(long long)r * tile] = row[r][lane];
+            } else {
 #pragma unroll 8
-            for (int r = 0; r < rows; ++r) {
-                const long long p = p_first + (long long)r * tile + 32LL * j + lane;
-                if (p < n) env[p] = row[r][lane];
+                for (int r = 0; r < rows; ++r) {
+                    const long long p = p_first + (long long)r * tile + 32LL * j + lane;
+                    if (p < n) env[p] = row[r][lane];
+                }
             }
         }
         __syncwarp();
