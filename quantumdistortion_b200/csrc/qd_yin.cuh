@@ -67,9 +67,9 @@ __host__ __device__ inline int at_yin_odd(int v) { return v | 1; }
 
 // shared memory in doubles: 3 x (tile, natural-order block, prefix sums, partial sums, captures), ring, scratch, lag table
 __host__ __device__ inline size_t at_yin_smem_doubles(int hop, int first_col, int cols) {
-    const int span = hop + AT_YL * (first_col + cols);
-    const size_t plane = (size_t)AT_YL * at_yin_odd(span / AT_YL + 1), rs = (size_t)AT_YL * at_yin_odd(cols);
-    return AT_YNS * (2 * plane + hop + (AT_YG + 1) * rs) + AT_YR * rs + 48 + 2 * AT_YNS + (AT_YL * cols + 1) / 2 + 16;
+    (void)first_col;    // the tile starts at the CTA's first lag: its size does not depend on where the lag range begins
+    const size_t plane = (size_t)AT_YL * at_yin_odd(hop / AT_YL + cols + 1), rs = (size_t)AT_YL * at_yin_odd(cols);
+    return AT_YNS * (2 * plane + 2 * hop + 8 + (AT_YG + 1) * rs) + AT_YR * rs + 48 + 2 * AT_YNS + (AT_YL * cols + 1) / 2 + 16;
 }
 
 QD_DEV void at_bar_sync(int id, int count) {
@@ -113,15 +113,21 @@ __global__ void __launch_bounds__(AT_YT, 1) at_yin_diff_kernel(const AtYinArgs a
     const int c0 = blockIdx.x * cols;                   // first column: lags tau0 .. tau0 + L cols - 1, tau0 = 1 + L c0
     const int tau0 = 1 + L * c0;
     const int W = a.frame_size, hop = a.hop;
-    const int span = hop + L * (c0 + cols);             // samples a block needs: its own and the lagged ones
+    // A block needs its own samples [0, hop) and the lagged ones [B0, B0 + span), B0 = L c0 (relative to the block start):
+    // one range when the CTA holds the first lags (c0 = 0), two when a wide lag range is split over several CTAs.  The
+    // tile and its prefix sums cover the lagged range; prefix sums only ever meet as differences within one range, except
+    // E(s, p) = energies of whole blocks + qa(off), which wants the own range (`qa`, natural order, used when c0 > 0).
+    const int B0 = L * c0;
+    const int span = hop + L * cols;
     const int Q = at_yin_odd(span / L + 1);             // plane stride of tile and prefix sums
     const int PL = L * Q;
     const int sp = at_yin_odd(cols);                    // row stride of the per-lag arrays
     const int RS = L * sp;                              // one [L][sp] array
-    double *tile = reinterpret_cast<double *>(smem);    // [3][L][Q]: sample i of the block at (i % L) * Q + i / L
+    double *tile = reinterpret_cast<double *>(smem);    // [3][L][Q]: sample B0 + i of the block at (i % L) * Q + i / L
     double *own = tile + AT_YNS * PL;                   // [3][hop] the block's own samples in natural order
     double *qt = own + AT_YNS * hop;                    // [3][L][Q] prefix sums of squares, same layout: qt(i) = E(j0, j0 + i)
-    double *xs = qt + AT_YNS * PL;                      // [3][G][L][sp] R_tau of each third of the block
+    double *qa = qt + AT_YNS * PL;                      // [3][hop + 1] prefix sums of squares of the own range (c0 > 0 only)
+    double *xs = qa + AT_YNS * (hop + 8);               // [3][G][L][sp] R_tau of each third of the block
     double *xp = xs + AT_YNS * G * RS;                  // [3][cols][L] R_tau of the block up to the lag's window end
     double *ringV = xp + AT_YNS * RS;                   // [AT_YR][L][sp] E(block + tau) - 2 R_tau(block) of finished blocks
     double *wtot = ringV + (size_t)AT_YR * RS;          // [16] warp totals of the prefix sum
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(AT_YT, 1) at_yin_diff_kernel(const AtYinArgs a
             at_mbar_wait(full + s, (b / AT_YNS) & 1);   // tile / own of block b are in buffer s (the warp waits for nobody else)
             if (walker) {
                 const double *ownp = own + s * hop + L * it0;
-                const double *lagp = tile + s * PL + (it0 + t + c0);    // plane p of iteration it: lagp[p * Q + it (+ 1)]
+                const double *lagp = tile + s * PL + (it0 + t);         // plane p of iteration it: lagp[p * Q + it (+ 1)]
                 double *xpp = xp + s * RS + L * t;          // captures: xp[column][lag]
                 double S[L], wo[L];
 #pragma unroll
@@ -217,45 +223,37 @@ __global__ void __launch_bounds__(AT_YT, 1) at_yin_diff_kernel(const AtYinArgs a
         if (h < 16) be[h] = 0.0;
         // the samples of a block travel through registers: fetched before the assembly of an earlier block starts, stored
         // after it (the global-memory latency is off the helpers' critical path)
-        constexpr int PF = 10;                           // 10 x 128 samples; a wider tile loads the rest directly
-        float pf[PF];
+        constexpr int PF = 10, PFO = 4;                  // 10 x 128 lagged-range samples, 4 x 128 own samples; any rest directly
+        float pf[PF], pfo[PFO];
         auto fetch = [&](int b) {
             const long long j0 = (long long)b * hop;
 #pragma unroll
             for (int r = 0; r < PF; ++r) {
                 const int i = h + r * AT_YH;
-                const long long sidx = j0 + i;
+                const long long sidx = j0 + B0 + i;
                 pf[r] = (i < span && sidx < a.n) ? x[sidx] : 0.0f;
             }
-        };
-        // samples (from the registers) and prefix sums of squares of block b into buffer s
-        auto produce = [&](int b, int s) {
-            double *tl = tile + s * PL, *q = qt + s * PL;
+            if (c0 > 0) {
 #pragma unroll
-            for (int r = 0; r < PF; ++r) {
-                const int i = h + r * AT_YH;
-                if (i < span) {
-                    const double v = (double)pf[r];
-                    tl[(i % L) * Q + i / L] = v;
-                    if (i < hop) own[s * hop + i] = v;
+                for (int r = 0; r < PFO; ++r) {
+                    const int i = h + r * AT_YH;
+                    const long long sidx = j0 + i;
+                    pfo[r] = (i < hop && sidx < a.n) ? x[sidx] : 0.0f;
                 }
             }
-            for (int i = h + PF * AT_YH; i < span; i += AT_YH) {
-                const long long sidx = (long long)b * hop + i;
-                tl[(i % L) * Q + i / L] = sidx < a.n ? (double)x[sidx] : 0.0;
-            }
-            helper_sync();
-            // thread hh scans samples 16 hh .. 16 hh + 15 (plane p, index hh: conflict-free), the totals are scanned over the
-            // threads, and every entry is written once: qt(16 hh + p) = total before the thread + its own first p squares.
-            // One round of 128 threads covers a tile of 2032 samples; wider lag ranges take a second round.
-            const int nth = span / L;
+        };
+        // Prefix sums of squares of nth chunks of L samples: thread hh scans chunk hh (sample p of it at src[p * sp_ + hh * sh_]:
+        // plane p, index hh of a tile, conflict-free; or own[L hh + p]), the chunk totals are scanned over the threads, and
+        // every entry is written once: dst(L hh + p) = total before the chunk + its first p squares, entry L nth = the total.
+        // 128 threads cover 2032 samples per round.  `be_hh`: the chunk boundary that is the end of the block (or -1).
+        auto prefix = [&](const double *src, double *dst, int sp_, int sh_, int nth, int be_hh, int b) {
             double carry = 0.0;
             for (int r0 = 0, par = 0; r0 <= nth; r0 += AT_YH, par ^= 4) {
                 const int hh = r0 + h;
                 double sq[L], loc[L];
 #pragma unroll
                 for (int p = 0; p < L; ++p) {
-                    const double v = hh < nth ? tl[p * Q + hh] : 0.0;
+                    const double v = hh < nth ? src[p * sp_ + hh * sh_] : 0.0;
                     sq[p] = v * v;
                 }
                 loc[0] = sq[0];
@@ -274,13 +272,47 @@ __global__ void __launch_bounds__(AT_YT, 1) at_yin_diff_kernel(const AtYinArgs a
                 for (int w = 0; w < hw; ++w) base += wtot[par + w];
                 for (int w = 0; w < AT_YH / 32; ++w) carry += wtot[par + w];
                 if (hh <= nth) {
-                    q[hh] = base;
+                    dst[hh * sh_] = base;
                     if (hh < nth) {
 #pragma unroll
-                        for (int p = 1; p < L; ++p) q[p * Q + hh] = base + loc[p - 1];
+                        for (int p = 1; p < L; ++p) dst[p * sp_ + hh * sh_] = base + loc[p - 1];
                     }
-                    if (hh == hop / L) be[b & 15] = base;                         // E(j0, j0 + hop)
+                    if (hh == be_hh) be[b & 15] = base;                           // E(j0, j0 + hop)
                 }
+            }
+        };
+        // samples (from the registers) and prefix sums of squares of block b into buffer s
+        auto produce = [&](int b, int s) {
+            double *tl = tile + s * PL, *ow = own + s * hop;
+#pragma unroll
+            for (int r = 0; r < PF; ++r) {
+                const int i = h + r * AT_YH;
+                if (i < span) {
+                    const double v = (double)pf[r];
+                    tl[(i % L) * Q + i / L] = v;
+                    if (c0 == 0 && i < hop) ow[i] = v;
+                }
+            }
+            for (int i = h + PF * AT_YH; i < span; i += AT_YH) {
+                const long long sidx = (long long)b * hop + B0 + i;
+                tl[(i % L) * Q + i / L] = sidx < a.n ? (double)x[sidx] : 0.0;
+            }
+            if (c0 > 0) {
+#pragma unroll
+                for (int r = 0; r < PFO; ++r) {
+                    const int i = h + r * AT_YH;
+                    if (i < hop) ow[i] = (double)pfo[r];
+                }
+                for (int i = h + PFO * AT_YH; i < hop; i += AT_YH) {
+                    const long long sidx = (long long)b * hop + i;
+                    ow[i] = sidx < a.n ? (double)x[sidx] : 0.0;
+                }
+            }
+            helper_sync();
+            prefix(tl, qt + s * PL, Q, 1, span / L, c0 == 0 ? hop / L : -1, b);
+            if (c0 > 0) {
+                helper_sync();                                                   // the scan scratch is free again
+                prefix(ow, qa + s * (hop + 8), 1, L, hop / L, hop / L, b);
             }
             helper_sync();                                                       // everything of block b is in buffer s
             if (h == 0) at_mbar_arrive(full + s);
@@ -294,8 +326,8 @@ __global__ void __launch_bounds__(AT_YT, 1) at_yin_diff_kernel(const AtYinArgs a
                 ebq[h] = e;
             }
             helper_sync();
-            const double *q = qt + s * PL, *xsb = xs + (size_t)s * G * RS, *xpb = xp + s * RS;
-            auto qv = [&](int i) { return q[(i % L) * Q + i / L]; };
+            const double *q = qt + s * PL, *qown = qa + s * (hop + 8), *xsb = xs + (size_t)s * G * RS, *xpb = xp + s * RS;
+            auto qv = [&](int i) { return q[(i % L) * Q + i / L]; };           // lagged range: entry i is sample B0 + i
             for (int col = h; col < L * cols; col += AT_YH) {
                 const int lc = lagc[col];
                 const int off = lc & 4095, qq = (lc >> 12) & 15, gc = (lc >> 16) & 15, tau = tau0 + col;
@@ -318,13 +350,14 @@ __global__ void __launch_bounds__(AT_YT, 1) at_yin_diff_kernel(const AtYinArgs a
                     slot = slot + 1 == AT_YR ? 0 : slot + 1;
                 }
                 const double v = ((rv[0] + rv[1]) + (rv[2] + rv[3])) + ((rv[4] + rv[5]) + (rv[6] + rv[7]));
-                const double qa = qv(tau);
+                const int tr = 1 + col;                                                  // tau relative to the lagged range
+                const double qtau = qv(tr);
                 if ((lc >> 20) && f >= 0 && f < a.frames) {
-                    const double e1 = ebq[qq] + qv(off);                                 // E(s, p)
-                    const double cur = (qv(off + tau) - qa) - 2.0 * pu;                  // the partial block: E(. + tau) - 2 R
+                    const double e1 = ebq[qq] + (c0 == 0 ? qv(off) : qown[off]);         // E(s, p)
+                    const double cur = (qv(off + tr) - qtau) - 2.0 * pu;                 // the partial block: E(. + tau) - 2 R
                     out[(size_t)f * a.stride + tau] = fmax(e1 + (v + cur), 0.0);
                 }
-                ringV[slot_b * RS + at] = (qv(hop + tau) - qa) - 2.0 * r;
+                ringV[slot_b * RS + at] = (qv(hop + tr) - qtau) - 2.0 * r;
             }
             slot_b = slot_b + 1 == AT_YR ? 0 : slot_b + 1;
             helper_sync();                                                       // ebq, qt[s], xs[s], xp[s] have been read

@@ -127,6 +127,19 @@ def test_autotune_full_length_clip_vs_oracle(qd):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sr,n", [(96000, 96000), (22050, 40000), (44100, 80000), (192000, 70000)])
+def test_autotune_other_sample_rates_vs_oracle(qd, sr, n):
+    """The detector's lag range follows the sample rate (max_tau = sr / 71.5 Hz, at most 2047): 308 lags at 22.05 kHz,
+    1342 at 96 kHz and 2047 at 192 kHz, where a clip's lags are split over two, three or four CTAs of the difference-function
+    kernel.  Clips longer than four envelope tiles (65 536 samples) also take the segment-parallel follower."""
+    x = qd_cases.make_signal("tone", 5 + sr % 97, n, sr)
+    y, taps = qd.process_audio(x, sr, quantize_mode="autotune_v1")
+    ref, rt = at.process_audio_autotune(x, sr)
+    _check(taps["pre_quant"], rt["pre_quant"], f"sr={sr} pre_quant")
+    _check(y, ref, f"sr={sr} output")
+
+
+@pytest.mark.gpu
 def test_autotune_through_the_file_harness(qd, tmp_path):
     """process_file_to_file / process_files with quantize_mode="autotune_v1" -- what the reference's harness and
     render_preset.py run by default (dsp/harness.py:24-63)."""
