@@ -471,11 +471,11 @@ QD_DEV float at_ratio_at(const double *ratio, int frames, long long n, int hop, 
 struct AtShiftArgs {
     const float *body;       // [batch, n]
     const double *ratio;     // [batch, frames]
-    double *taps;            // [batch, n, 2]
+    long long *tile_sum;     // [batch, tiles] slope sums per 512-sample tile, then the tap at every tile start
     float *ratio_track;      // optional [batch, n]
     int *flat_flag;          // [batch] 1: ratio track allclose to 1 -> output = body
     float *out;              // [batch, n] corrected body
-    long long n;
+    long long n, tiles;      // tiles = ceil(n / 512)
     int batch, frames, hop, half;
     int max_delay, buf_size;
 };
@@ -499,126 +499,174 @@ QD_DEV AtSeg at_segment_at(const double *ratio, int frames, long long n, int hop
 // The tap accumulation is exact integer arithmetic in disguise: the per-sample slope 1 - ratio (ratio a float32 in
 // [0.5, 2]) is a multiple of 2^-24 with |slope| <= 1, the taps start at multiples of 2^-24 and stay below max_delay, so
 // every float64 addition and every wrap of the reference's loop (dsp/autotune.py:327-337) is exact.  In units of 2^-24 the
-// taps are T_n = (T_0 + sum_{k<=n} S_k) mod M -- an int64 prefix sum, associative and bit-exact, so it runs as a scan:
-// one CTA per clip, each of its AT_TW warps takes one tile of a round (16 consecutive samples per lane, a warp scan of the
-// lane totals), the tile totals of a round are chained through shared memory, the carry goes from round to round.
+// taps are T_n = (T_0 + sum_{k<=n} S_k) mod M -- an int64 prefix sum, associative and bit-exact, so it runs as a scan in
+// three launches, and the taps themselves never go to memory:
+//   at_tap_sums_kernel  one warp per 512-sample tile: the tile's sum of slopes (and whether its ratio track is flat)
+//   at_tap_scan_kernel  one warp per clip: exclusive scan of the tile sums (mod M) = the tap at every tile start
+//   at_shift_kernel     one warp per tile: slopes again, warp scan + tile start = the taps of its samples, then the read-out
 constexpr int AT_SPL = AT_TS / 32;   // samples per lane and tile
-constexpr int AT_TW = 8;             // warps per clip = tiles per round
+constexpr int AT_TW = 8;             // tiles (warps) per CTA
 
-__global__ void __launch_bounds__(32 * AT_TW) at_taps_kernel(const AtShiftArgs a) {
-    __shared__ long long s_tot[2][AT_TW];
-    __shared__ int s_flat[AT_TW];
+// the ratio track at sample i (np.interp of the per-frame ratios, float32) and its slope 1 - ratio in units of 2^-24
+struct AtTileCtx {
+    AtSeg sg;                // the np.interp segment of the whole tile (aligned tiles only)
+    bool aligned;
+    double r_last;
+};
+QD_DEV long long at_slope(const AtShiftArgs &a, const double *__restrict__ ratio, const AtTileCtx &c, long long i, float *r_out) {
+    float r;
+    if (!c.aligned) r = at_ratio_at(ratio, a.frames, a.n, a.hop, a.half, i);
+    else if (i == a.n - 1) r = (float)c.r_last;                 // the last sample sits on the (repeated) last centre
+    else if ((double)i == c.sg.x0) r = (float)c.sg.y0;
+    else r = (float)__dadd_rn(__dmul_rn(c.sg.slope, (double)i - c.sg.x0), c.sg.y0);
+    *r_out = r;
+    return (long long)((1.0 - (double)fminf(fmaxf(r, 0.5f), 2.0f)) * (double)(1ll << 24));   // exact: a multiple of 2^-24
+}
+QD_DEV AtTileCtx at_tile_ctx(const AtShiftArgs &a, const double *__restrict__ ratio, long long i0) {
+    AtTileCtx c{AtSeg{0.0, 1.0, 0.0}, false, ratio[a.frames - 1]};
+    c.aligned = (a.hop % AT_TS) == 0 && (a.half % AT_TS) == 0 && (a.max_delay % 4) == 0;
+    if (c.aligned) c.sg = at_segment_at(ratio, a.frames, a.n, a.hop, a.half, i0);
+    return c;
+}
+
+// (a tile holds no frame centre strictly inside when hop and frame_size / 2 are multiples of the tile: 512 | 512, 2048)
+__global__ void __launch_bounds__(32 * AT_TW) at_tap_sums_kernel(const AtShiftArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int clip = blockIdx.x;
+    const int clip = blockIdx.y;
+    const long long tile = (long long)blockIdx.x * AT_TW + warp;
+    if (tile >= a.tiles) return;
     const double *__restrict__ ratio = a.ratio + (size_t)clip * a.frames;
-    double2 *__restrict__ taps = reinterpret_cast<double2 *>(a.taps + (size_t)clip * a.n * 2);
     float *__restrict__ rt = a.ratio_track ? a.ratio_track + (size_t)clip * a.n : nullptr;
-    const long long unit = 1ll << 24;
-    const long long M = (long long)a.max_delay * unit;
-    const long long half_m = M / 2;                      // the second tap runs half a grain behind: 0.75 md = 0.25 md + md / 2
-    long long carry = M / 4;                             // tap 0 starts at 0.25 * max_delay
+    const AtTileCtx cx = at_tile_ctx(a, ratio, tile * AT_TS);
     bool flat = true;
-    auto wrap = [&](long long t) {                       // a round moves a tap by at most 8 * 2^33 units: a few wraps
-        while (t < 0) t += M;
-        while (t >= M) t -= M;
-        return t;
-    };
-    // a tile holds no frame centre strictly inside when hop and frame_size / 2 are multiples of the tile (512 | 512, 2048)
-    const bool aligned = (a.hop % AT_TS) == 0 && (a.half % AT_TS) == 0 && (a.max_delay % 4) == 0;
-    const double r_last = ratio[a.frames - 1];
-    int par = 0;
-    for (long long r0 = 0; r0 < a.n; r0 += (long long)AT_TS * AT_TW, par ^= 1) {
-        const long long i0 = r0 + (long long)warp * AT_TS;   // this warp's tile (possibly past the end: it then adds nothing)
-        AtSeg sg{0.0, 1.0, 0.0};
-        if (aligned && i0 < a.n) sg = at_segment_at(ratio, a.frames, a.n, a.hop, a.half, i0);
-        long long loc[AT_SPL];
-        long long run = 0;
-#pragma unroll
-        for (int k = 0; k < AT_SPL; ++k) {
-            const long long i = i0 + (long long)lane * AT_SPL + k;
-            float r = 1.0f;
-            if (i < a.n) {
-                if (!aligned) r = at_ratio_at(ratio, a.frames, a.n, a.hop, a.half, i);
-                else if (i == a.n - 1) r = (float)r_last;               // the last sample sits on the (repeated) last centre
-                else if ((double)i == sg.x0) r = (float)sg.y0;
-                else r = (float)__dadd_rn(__dmul_rn(sg.slope, (double)i - sg.x0), sg.y0);
-                if (rt) rt[i] = r;
-                if (!(fabs((double)r - 1.0) <= 1e-3 + 1e-5)) flat = false;   // np.allclose(r, 1.0, atol=1e-3)
-                run += (long long)((1.0 - (double)fminf(fmaxf(r, 0.5f), 2.0f)) * (double)unit);   // exact: a multiple of 2^-24
-            }
-            loc[k] = run;
+    long long run = 0;
+#pragma unroll 4
+    for (int k = 0; k < AT_SPL; ++k) {
+        const long long i = tile * AT_TS + (long long)lane * AT_SPL + k;
+        if (i < a.n) {
+            float r;
+            run += at_slope(a, ratio, cx, i, &r);
+            if (rt) rt[i] = r;
+            if (!(fabs((double)r - 1.0) <= 1e-3 + 1e-5)) flat = false;   // np.allclose(r, 1.0, atol=1e-3)
         }
-        long long incl = run;   // inclusive scan of the lane totals
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const long long o = __shfl_up_sync(QD_FULL, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_tot[par][warp] = incl;
-        __syncthreads();                                 // (the other parity's totals are rewritten a whole round later)
-        long long before = carry, total = 0;
-#pragma unroll
-        for (int w = 0; w < AT_TW; ++w) {
-            const long long tw = s_tot[par][w];
-            if (w < warp) before += tw;
-            total += tw;
-        }
-        before = wrap(before) + (incl - run);
-#pragma unroll
-        for (int k = 0; k < AT_SPL; ++k) {
-            const long long i = i0 + (long long)lane * AT_SPL + k;
-            if (i < a.n) {
-                const long long t0 = wrap(before + loc[k]);
-                long long t1 = t0 + half_m;
-                if (t1 >= M) t1 -= M;
-                taps[i] = make_double2((double)t0 * (1.0 / (double)unit), (double)t1 * (1.0 / (double)unit));
-            }
-        }
-        carry = wrap(carry + total);
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) run += __shfl_xor_sync(QD_FULL, run, d);
     flat = __all_sync(QD_FULL, flat);
-    if (lane == 0) s_flat[warp] = flat ? 1 : 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int f = 1;
-        for (int w = 0; w < AT_TW; ++w) f &= s_flat[w];
-        a.flat_flag[clip] = f;
+    if (lane == 0) {
+        a.tile_sum[(size_t)clip * a.tiles + tile] = run;
+        if (!flat) a.flat_flag[clip] = 1;                // zeroed before the launch: "some tile is not flat" until the scan
     }
 }
 
+// tile_sum -> tap 0 at the start of every tile (in [0, M)); flat_flag -> 1 when no tile of the clip raised it
+__global__ void __launch_bounds__(32) at_tap_scan_kernel(const AtShiftArgs a) {
+    const int lane = threadIdx.x;
+    const int clip = blockIdx.x;
+    long long *ts = a.tile_sum + (size_t)clip * a.tiles;
+    const long long M = (long long)a.max_delay << 24;
+    long long carry = M / 4;                             // tap 0 starts at 0.25 * max_delay
+    for (long long t0 = 0; t0 < a.tiles; t0 += 32) {
+        const long long t = t0 + lane;
+        const long long v = t < a.tiles ? ts[t] : 0;
+        long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(QD_FULL, inc, d);
+            if (lane >= d) inc += o;
+        }
+        long long start = carry + (inc - v);             // 32 tiles move a tap by at most 2^38 units: a few wraps
+        while (start < 0) start += M;
+        while (start >= M) start -= M;
+        if (t < a.tiles) ts[t] = start;
+        carry += __shfl_sync(QD_FULL, inc, 31);
+        while (carry < 0) carry += M;
+        while (carry >= M) carry -= M;
+    }
+    if (lane == 0) a.flat_flag[clip] = a.flat_flag[clip] ? 0 : 1;   // from "some tile is not flat" to "the clip is flat"
+}
+
 // read-out with the latency trim folded in: out = raw[lat:] ++ zeros(lat) unless the early-out copied the body
-// (dsp/autotune.py:339-358); sample i of the shifter lands at out[i - lat]
-__global__ void at_shift_kernel(const AtShiftArgs a) {
+// (dsp/autotune.py:339-358); sample i of the shifter lands at out[i - lat].  A lane computes its 16 consecutive samples and
+// the warp writes the tile through shared memory (stride 17: no bank conflicts either way) in coalesced rows.
+__global__ void __launch_bounds__(32 * AT_TW) at_shift_kernel(const AtShiftArgs a) {
+    __shared__ float s_out[AT_TW][AT_TS + AT_TS / 16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int clip = blockIdx.y;
-    const float *x = a.body + (size_t)clip * a.n;
-    const double *taps = a.taps + (size_t)clip * a.n * 2;
-    float *out = a.out + (size_t)clip * a.n;
-    const bool flat = a.flat_flag[clip] != 0;
-    const long long lat = (!flat && a.n > a.max_delay / 2) ? a.max_delay / 2 : 0;
+    const long long tile = (long long)blockIdx.x * AT_TW + warp;
+    if (tile >= a.tiles) return;
+    const long long i0 = tile * AT_TS;
+    const float *__restrict__ x = a.body + (size_t)clip * a.n;
+    float *__restrict__ out = a.out + (size_t)clip * a.n;
+    if (a.flat_flag[clip] != 0) {
+        for (long long i = i0 + lane; i < i0 + AT_TS && i < a.n; i += 32) out[i] = x[i];
+        return;
+    }
+    const long long lat = a.n > a.max_delay / 2 ? a.max_delay / 2 : 0;
+    const double *__restrict__ ratio = a.ratio + (size_t)clip * a.frames;
+    const long long unit = 1ll << 24;
+    const long long M = (long long)a.max_delay * unit, half_m = M / 2;   // the second tap runs half a grain behind
+    const AtTileCtx cx = at_tile_ctx(a, ratio, i0);
+    long long run = 0;                                   // the lane's 16 slopes: summed here, walked again below
+#pragma unroll 4
+    for (int k = 0; k < AT_SPL; ++k) {
+        const long long i = i0 + (long long)lane * AT_SPL + k;
+        float r;
+        if (i < a.n) run += at_slope(a, ratio, cx, i, &r);
+    }
+    long long incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long o = __shfl_up_sync(QD_FULL, incl, d);
+        if (lane >= d) incl += o;
+    }
+    long long tap = a.tile_sum[(size_t)clip * a.tiles + tile] + (incl - run);   // tap 0 before the lane's first sample, unwrapped
     const double md = (double)a.max_delay, size = (double)a.buf_size;
     const int mask = a.buf_size - 1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
-        if (flat) { out[i] = x[i]; continue; }
-        if (i >= a.n - lat) out[i] = 0.0f;               // the tail that no shifted sample reaches
-        if (i < lat) continue;
-        const int w = (int)(i & mask);
-        double mixed = 0.0, wsum = 0.0;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const double d = taps[2 * i + t];
-            const double phase = d / md;
-            const double weight = 0.5 * (1.0 - cos(2.0 * 3.141592653589793 * phase));
-            const double rp = fmod(((double)w - d) + size, size);
-            const int b = ((int)rp) & mask;
-            const int nx = (b + 1) & mask;
-            const double fr = rp - (double)(int)rp;
-            const long long j0 = i - ((w - b) & mask), j1 = i - ((w - nx) & mask);
-            const float s0 = j0 >= 0 ? x[j0] : 0.0f, s1 = j1 >= 0 ? x[j1] : 0.0f;
-            const float smp = __fadd_rn(__fmul_rn(s0, (float)(1.0 - fr)), __fmul_rn(s1, (float)fr));   // float32 (NEP 50)
-            mixed += (double)smp * weight;
-            wsum += weight;
+    float *so = s_out[warp];
+#pragma unroll 1
+    for (int k = 0; k < AT_SPL; ++k) {
+        const long long i = i0 + (long long)lane * AT_SPL + k;
+        float val = 0.0f;
+        if (i < a.n) {
+            float r;
+            tap += at_slope(a, ratio, cx, i, &r);        // |tap| stays below M + 2^34: a few wraps at most
         }
-        out[i - lat] = wsum > 1e-6 ? (float)(mixed / wsum) : 0.0f;
+        if (i < a.n && i >= lat) {
+            long long t0 = tap;
+            while (t0 < 0) t0 += M;
+            while (t0 >= M) t0 -= M;
+            long long t1 = t0 + half_m;
+            if (t1 >= M) t1 -= M;
+            const int w = (int)(i & mask);
+            double mixed = 0.0, wsum = 0.0;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const double d = (double)(t == 0 ? t0 : t1) * (1.0 / (double)unit);
+                const double phase = d / md;
+                const double weight = 0.5 * (1.0 - cos(2.0 * 3.141592653589793 * phase));
+                // (w - d) + size lies in (size / 2, 2 size): Python's float % is one exact conditional subtraction here
+                const double wd = ((double)w - d) + size;
+                const double rp = wd >= size ? wd - size : wd;
+                const int b = ((int)rp) & mask;
+                const int nx = (b + 1) & mask;
+                const double fr = rp - (double)(int)rp;
+                const long long j0 = i - ((w - b) & mask), j1 = i - ((w - nx) & mask);
+                const float s0 = j0 >= 0 ? x[j0] : 0.0f, s1 = j1 >= 0 ? x[j1] : 0.0f;
+                const float smp = __fadd_rn(__fmul_rn(s0, (float)(1.0 - fr)), __fmul_rn(s1, (float)fr));   // float32 (NEP 50)
+                mixed += (double)smp * weight;
+                wsum += weight;
+            }
+            val = wsum > 1e-6 ? (float)(mixed / wsum) : 0.0f;
+        }
+        so[lane * (AT_SPL + 1) + k] = val;
+    }
+    __syncwarp();
+    for (int j = lane; j < AT_TS; j += 32) {
+        const long long i = i0 + j;
+        if (i >= a.n) break;
+        if (i >= a.n - lat) out[i] = 0.0f;               // the tail that no shifted sample reaches
+        if (i >= lat) out[i - lat] = so[j + j / AT_SPL];
     }
 }
 
