@@ -17,15 +17,22 @@ EMU_DIR = os.path.join(HERE, "emu")
 CSRC = os.path.join(os.path.dirname(HERE), "quantumdistortion_b200", "csrc")
 
 
+def _build_emu(exe, srcs, main):
+    """Compile an emulator once per source change; link under a private name and rename, so that pytest-xdist workers
+    (or two suites on one box) never execute a half-written binary."""
+    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
+        tmp = f"{exe}.{os.getpid()}"
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-DQD_EMU", "-I", EMU_DIR, "-o", tmp, main, "-lpthread"])
+        os.replace(tmp, exe)
+    return exe
+
+
 @pytest.fixture(scope="module")
 def emu_spec():
     exe = os.path.join(tempfile.gettempdir(), "qd_emu_spec")
     srcs = [os.path.join(EMU_DIR, f) for f in ("emu_spec.cpp", "cuda_emu.h")]
     srcs += [os.path.join(CSRC, f) for f in ("qd_spec.cuh", "qd_common.cuh", "qd_host_tables.hpp")]
-    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-DQD_EMU", "-I", EMU_DIR, "-o", exe,
-                               os.path.join(EMU_DIR, "emu_spec.cpp"), "-lpthread"])
-    return exe
+    return _build_emu(exe, srcs, os.path.join(EMU_DIR, "emu_spec.cpp"))
 
 
 def run_emu(exe, x, sr, n_fft, nw, tile_blocks, quant, smoothing, snap, smear, epilogue=0, fold=1.0,
@@ -107,10 +114,7 @@ def emu_time():
     exe = os.path.join(tempfile.gettempdir(), "qd_emu_time")
     srcs = [os.path.join(EMU_DIR, f) for f in ("emu_time.cpp", "cuda_emu.h")]
     srcs += [os.path.join(CSRC, f) for f in ("qd_time.cuh", "qd_common.cuh", "qd_host_time.hpp")]
-    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-DQD_EMU", "-I", EMU_DIR, "-o", exe,
-                               os.path.join(EMU_DIR, "emu_time.cpp"), "-lpthread"])
-    return exe
+    return _build_emu(exe, srcs, os.path.join(EMU_DIR, "emu_time.cpp"))
 
 
 @pytest.mark.parametrize("n,sr,kind", [(6000, 48000, "loud"), (2048, 44100, "noise"), (5000, 48000, "noise"),
@@ -227,10 +231,7 @@ def test_emu_formant_shift_pass(emu_spec, n_fft, nw, n, semitones):
 def emu_yin():
     exe = os.path.join(tempfile.gettempdir(), "qd_emu_yin")
     srcs = [os.path.join(EMU_DIR, f) for f in ("emu_yin.cpp", "cuda_emu.h")] + [os.path.join(CSRC, f) for f in ("qd_yin.cuh", "qd_common.cuh")]
-    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-DQD_EMU", "-I", EMU_DIR, "-o", exe,
-                               os.path.join(EMU_DIR, "emu_yin.cpp"), "-lpthread"])
-    return exe
+    return _build_emu(exe, srcs, os.path.join(EMU_DIR, "emu_yin.cpp"))
 
 
 @pytest.mark.parametrize("n,frame,hop,max_tau,cols", [(1500, 512, 64, 100, 88), (1500, 512, 64, 100, 3), (1000, 1024, 128, 61, 88),
