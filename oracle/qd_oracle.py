@@ -684,10 +684,13 @@ def process_audio(audio, sr=48000, key="D", scale="minor", quantize_mode="spectr
     if quantize_mode == "autotune_v1" and (spectral_fx_mode is not None or spectral_freeze
                                             or formant_shift != 0.0 or harmonic_lock_hz > 0.0):
         quantize_mode = "spectral_bins"
+    if quantize_mode == "autotune_v1" and snap_strength > 0.0:
+        use_multiband = False  # :1326-1327, ahead of every branch (a passthrough_test render is single band then too)
     # autotune_v1 survives inside a multiband render only with snap_strength <= 0 (:1326-1327), where its pitch stage
     # is gated off (:538): the high band is distorted, limited and mixed without any STFT
     no_spectral = quantize_mode == "autotune_v1" and use_multiband and not snap_strength > 0.0 and not passthrough_test
-    if quantize_mode != "spectral_bins" and not no_spectral:
+    # passthrough_test (:477) returns the STFT -> iSTFT round trip before the mode is looked at
+    if quantize_mode != "spectral_bins" and not no_spectral and not passthrough_test:
         raise NotImplementedError("this oracle covers quantize_mode='spectral_bins'; autotune_v1 is oracle/qd_autotune.py")
     x = np.asarray(audio, dtype=np.float32)  # config.py:19-24
     if x.ndim == 2:

@@ -347,6 +347,8 @@ def _resolve_kwargs(n_samples: int, sr: int, n_fft: int, kw: Dict[str, Any]) -> 
         raise TypeError(f"process_audio() got unexpected keyword arguments: {sorted(kw)}")
     if quantize_mode == "autotune_v1" and (fx_mode is not None or freeze or formant != 0.0 or lock_hz > 0.0):
         quantize_mode = "spectral_bins"  # :1315-1324
+    if quantize_mode == "autotune_v1" and snap > 0.0:
+        use_multiband = False  # :1326-1327, ahead of every branch: also a passthrough_test render is single band then
     no_spectral = False
     if quantize_mode == "autotune_v1" and not passthrough and use_multiband and not snap > 0.0:
         # :1326-1327 only forces single band when snap > 0; with snap <= 0 the high band of the multiband render goes

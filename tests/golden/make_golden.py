@@ -304,7 +304,29 @@ def gen_refwav():
     print("refwav:", len(out), os.path.getsize(os.path.join(HERE, "refwav.npz")) // 1024, "KiB")
 
 
+def gen_scenarios():
+    """The reference's own pipeline-level test scenarios (qd_cases.REF_SCENARIOS): its signals and its arguments through
+    the LIVE process_audio, output and taps kept, so that the CUDA path is checked on exactly what the reference's test
+    suite exercises."""
+    out = {}
+    for name, (spec, sr, rng_seed, kw, prop, cite) in qd_cases.REF_SCENARIOS.items():
+        x = qd_cases.scenario_signal(spec, sr)
+        if rng_seed is not None:
+            np.random.seed(rng_seed)
+        y, taps = quiet(ref_pipeline.process_audio, x, sr=sr, **kw)
+        assert y.dtype == np.float32 and set(taps) == {"input", "pre_quant", "post_dist", "output"}
+        out[f"{name}/x"], out[f"{name}/y"] = x, y
+        out[f"{name}/pre_quant"] = np.asarray(taps["pre_quant"], dtype=np.float32)
+        out[f"{name}/post_dist"] = np.asarray(taps["post_dist"], dtype=np.float32)
+        print(f"scenario {name} ({cite}): n={len(x)} peak={np.max(np.abs(y)):.4f} moved={np.max(np.abs(y - x[:len(y)])):.4f}")
+    np.savez_compressed(os.path.join(HERE, "scenarios.npz"), **out)
+    print("scenarios:", len(out), os.path.getsize(os.path.join(HERE, "scenarios.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["scenarios"]:
+        gen_scenarios()
+        sys.exit(0)
     if sys.argv[1:] == ["round2"]:
         gen_round2()
         sys.exit(0)
@@ -325,5 +347,6 @@ if __name__ == "__main__":
     gen_pipeline()
     gen_round2()
     gen_refwav()
+    gen_scenarios()
     for f in ("tables.npz", "stages.npz", "pipeline.npz", "frontend.npz", "analysis.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

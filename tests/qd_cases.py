@@ -5,6 +5,10 @@ process_audio).  quantize_mode="spectral_bins" is always passed (SURVEY.md secti
 """
 from __future__ import annotations
 
+import os
+
+import numpy as np
+
 GROWL = dict(key="F", scale="minor", snap_strength=0.9, smear=0.3, bin_smoothing=True,
              pre_quant=True, post_quant=True, distortion_mode="wavefold",
              distortion_params={"fold_amount": 5.0, "bias": 0.1, "drive": 1.0, "warmth": 0.5},
@@ -222,3 +226,172 @@ UI_AT_CASES = {
                          {"quantization": {"sub_source": "manual", "sub_note": "A", "sub_level": 0.8},
                           "low_band": {"saturation_amount": 0.2}}, {"snap_strength": 0.7}),
 }
+
+
+# ---------------------------------------------------------------- the reference's own pipeline-level test scenarios
+# Every process_audio call the reference's test suite makes at pipeline level (tests/test_pipeline.py,
+# test_passthrough_null.py, test_multiband_alignment.py, test_pipeline_multiband_identity.py, test_m12_quantum_fx.py,
+# test_quantization_integration.py), with the reference's own signals and arguments -- quantize_mode is left at the
+# reference default wherever the reference test leaves it there.  name -> (signal, sr, rng_seed, kwargs, property, cite).
+# `property` names the assertion of the reference test, repeated on OUR output by tests/test_gpu_ref_scenarios.py.
+def scenario_signal(spec, sr):
+    kind = spec[0]
+    if kind == "sine":        # (kind, freq, seconds, amp): amp * sin(2 pi f t), t = linspace(0, s, int(sr s), endpoint=False)
+        _, f, sec, amp = spec
+        t = np.linspace(0.0, sec, int(sr * sec), endpoint=False)
+        return (amp * np.sin(2.0 * np.pi * f * t)).astype(np.float32)
+    if kind == "sweep_t":     # instantaneous "frequency" f0 + (f1 - f0) t / s inside sin(2 pi f t)  (test_pipeline.py:65-71)
+        _, f0, f1, sec, amp = spec
+        t = np.linspace(0.0, sec, int(sr * sec), endpoint=False)
+        return (amp * np.sin(2.0 * np.pi * (f0 + (f1 - f0) * t / sec) * t)).astype(np.float32)
+    if kind == "sweep_phase":  # phase = 2 pi cumsum(f) / sr  (test_passthrough_null.py:33-45)
+        _, f0, f1, sec, amp = spec
+        t = np.linspace(0.0, sec, int(sr * sec), endpoint=False)
+        return (amp * np.sin(2.0 * np.pi * np.cumsum(f0 + (f1 - f0) * t / sec) / sr)).astype(np.float32)
+    if kind == "click":       # single-sample spike in the middle (test_multiband_alignment.py:14-20)
+        n = int(sr * spec[1])
+        x = np.zeros(n, dtype=np.float32)
+        x[n // 2] = 1.0
+        return x
+    if kind == "harmonic":    # sum_h (0.1 / h) sin(2 pi f0 h t), h = 1..5  (test_m12_quantum_fx.py:34-40)
+        _, f0, sec = spec
+        t = np.linspace(0, sec, int(sr * sec), endpoint=False)
+        s = np.zeros_like(t)
+        for h in range(1, 6):
+            s += (0.1 / h) * np.sin(2 * np.pi * f0 * h * t)
+        return s.astype(np.float32)
+    if kind == "two_tone":    # 0.2 sin(80 Hz) + 0.2 sin(2 kHz)  (test_pipeline_multiband_identity.py:72-76)
+        t = np.linspace(0.0, spec[1], int(sr * spec[1]), endpoint=False)
+        return (0.2 * np.sin(2.0 * np.pi * 80.0 * t) + 0.2 * np.sin(2.0 * np.pi * 2000.0 * t)).astype(np.float32)
+    if kind == "refwav":      # first `seconds` of one of the reference's WAV files (tests/golden/refwav.npz)
+        d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refwav.npz"))
+        x = d[f"{spec[1]}/x16"].astype(np.float32) / 32768.0
+        return x[: int(int(d[f"{spec[1]}/sr"]) * spec[2])]
+    raise KeyError(kind)
+
+
+_NEUTRAL = dict(snap_strength=0.0, pre_quant=False, post_quant=False, distortion_mode="wavefold", limiter_on=False, dry_wet=1.0)
+_FXI = dict(use_multiband=True, crossover_hz=300.0, snap_strength=0.5, pre_quant=True, post_quant=False, limiter_on=False)
+A4_35_CENTS_SHARP = 440.0 * 2.0 ** (0.35 / 12.0)
+REF_SCENARIOS = {
+    "taps_shapes": (("sine", 220.0, 0.2, 0.1), 44100, None,
+                    dict(snap_strength=0.0, pre_quant=False, post_quant=False, limiter_on=False),
+                    "taps", "test_pipeline.py:16-35"),
+    "neutral_passthrough": (("sine", 220.0, 0.2, 0.1), 44100, None,
+                            dict(key="C", scale="major", snap_strength=0.0, smear=0.0, bin_smoothing=False, pre_quant=False,
+                                 post_quant=False, distortion_mode="wavefold",
+                                 distortion_params={"fold_amount": 1.0, "bias": 0.0}, limiter_on=False, dry_wet=1.0),
+                            "allclose_input_1e-3", "test_pipeline.py:38-62"),
+    "fx_baseline": (("sweep_t", 440.0, 880.0, 0.1, 0.1), 44100, None,
+                    dict(_FXI, spectral_fx_mode=None, spectral_fx_strength=0.0), "shape", "test_pipeline.py:79-90"),
+    "fx_bitcrush": (("sweep_t", 440.0, 880.0, 0.1, 0.1), 44100, None,
+                    dict(_FXI, spectral_fx_mode="bitcrush", spectral_fx_strength=0.3), "differs:fx_baseline",
+                    "test_pipeline.py:94-113"),
+    "fx_phase_dispersal": (("sweep_t", 440.0, 880.0, 0.1, 0.1), 44100, 11,
+                           dict(_FXI, spectral_fx_mode="phase_dispersal", spectral_fx_strength=0.3), "differs:fx_baseline",
+                           "test_pipeline.py:94-113"),
+    "fx_bin_scramble": (("sweep_t", 440.0, 880.0, 0.1, 0.1), 44100, 12,
+                        dict(_FXI, spectral_fx_mode="bin_scramble", spectral_fx_strength=0.3), "differs:fx_baseline",
+                        "test_pipeline.py:94-113"),
+    "passthrough_sweep": (("sweep_phase", 100.0, 2000.0, 0.5, 0.1), 44100, None, dict(passthrough_test=True),
+                          "delta_rms_below_-80dB", "test_passthrough_null.py:56-109"),
+    "passthrough_sine": (("sine", 440.0, 0.2, 0.1), 44100, None, dict(passthrough_test=True),
+                         "delta_rms_below_-80dB", "test_passthrough_null.py:112-150"),
+    "click_single": (("click", 0.1), 44100, None,
+                     dict(_NEUTRAL, distortion_params={"fold_amount": 1.0, "bias": 0.0}, use_multiband=False),
+                     "peak_above_0.1", "test_multiband_alignment.py:22-33"),
+    "click_multi": (("click", 0.1), 44100, None,
+                    dict(_NEUTRAL, distortion_params={"fold_amount": 1.0, "bias": 0.0}, use_multiband=True, crossover_hz=300.0,
+                         lowband_drive=0.0),
+                    "argmax_within_50_of:click_single", "test_multiband_alignment.py:35-63"),
+    **{f"click_xover_{int(c)}": (("click", 0.1), 44100, None,
+                                 dict(_NEUTRAL, distortion_params={"fold_amount": 1.0}, use_multiband=True, crossover_hz=c,
+                                      lowband_drive=0.0),
+                                 "argmax_within_1200_of_click", "test_multiband_alignment.py:80-119")
+       for c in (200.0, 500.0, 1000.0)},
+    "wobble_multiband": (("refwav", "wobble_bass", 0.5), 48000, None,   # the file's own rate (load_audio)
+                         dict(snap_strength=0.5, pre_quant=True, post_quant=True, distortion_mode="wavefold",
+                              distortion_params={"fold_amount": 1.0, "bias": 0.0}, limiter_on=False, dry_wet=1.0,
+                              use_multiband=True, crossover_hz=300.0, lowband_drive=1.0),
+                         "taps", "test_pipeline_multiband_identity.py:9-64"),
+    **{f"two_tone_xover_{int(c)}": (("two_tone", 0.3), 44100, None,
+                                    dict(snap_strength=0.3, pre_quant=True, post_quant=False, distortion_mode="wavefold",
+                                         distortion_params={"fold_amount": 1.0}, limiter_on=False, dry_wet=1.0,
+                                         use_multiband=True, crossover_hz=c),
+                                    "taps", "test_pipeline_multiband_identity.py:67-103")
+       for c in (200.0, 500.0, 1000.0)},
+    "mb_passthrough_null": (("sine", 200.0, 0.5, 0.1), 44100, None,
+                            dict(passthrough_test=True, use_multiband=True, crossover_hz=300.0, lowband_drive=1.0),
+                            "delta_rms_below_-10dB_and_audible", "test_m12_quantum_fx.py:57-88"),
+    "freeze_on": (("harmonic", 110.0, 0.5), 44100, None,
+                  dict(spectral_freeze=True, snap_strength=0.0, pre_quant=True, post_quant=False), "shape",
+                  "test_m12_quantum_fx.py:96-103"),
+    "freeze_off": (("harmonic", 110.0, 0.5), 44100, None,
+                   dict(spectral_freeze=False, snap_strength=0.0, pre_quant=True, post_quant=False), "shape",
+                   "test_m12_quantum_fx.py:104-115"),
+    "freeze_multiband": (("sine", 440.0, 0.3, 0.1), 44100, None, dict(use_multiband=True, spectral_freeze=True), "shape",
+                         "test_m12_quantum_fx.py:119-127"),
+    "formant_multiband": (("sine", 440.0, 0.3, 0.1), 44100, None, dict(formant_shift=3.0, use_multiband=True), "shape",
+                          "test_m12_quantum_fx.py:151-159"),
+    "formant_zero": (("harmonic", 110.0, 0.3), 44100, None, dict(formant_shift=0.0), "shape", "test_m12_quantum_fx.py:163-164"),
+    "formant_six": (("harmonic", 110.0, 0.3), 44100, None, dict(formant_shift=6.0), "differs_1e-6:formant_zero",
+                    "test_m12_quantum_fx.py:165-167"),
+    "harmonic_lock": (("harmonic", 110.0, 0.3), 44100, None, dict(harmonic_lock_hz=110.0), "shape",
+                      "test_m12_quantum_fx.py:198-205"),
+    "delta_off": (("sine", 440.0, 0.3, 0.1), 44100, None, dict(delta_listen=False), "shape", "test_m12_quantum_fx.py:237"),
+    "delta_on": (("sine", 440.0, 0.3, 0.1), 44100, None, dict(delta_listen=True), "is_input_minus:delta_off",
+                 "test_m12_quantum_fx.py:240-250"),
+    "autotune_detuned_a4": (("sine", A4_35_CENTS_SHARP, 1.0, 0.2), 48000, None,
+                            dict(key="A", scale="minor", quantize_mode="autotune_v1", snap_strength=1.0, smear=0.0,
+                                 bin_smoothing=False, pre_quant=True, post_quant=False, distortion_mode="wavefold",
+                                 distortion_params={"fold_amount": 1.0, "bias": 0.0, "drive": 1.0, "warmth": 0.5},
+                                 limiter_on=False, dry_wet=1.0, sub_enabled=False),
+                            "dominant_freq_moves_to_440", "test_quantization_integration.py:46-74"),
+}
+
+
+def _rms_db(v):
+    r = float(np.sqrt(np.mean(np.asarray(v, dtype=np.float64) ** 2)))
+    return -np.inf if r == 0.0 else 20.0 * np.log10(r)
+
+
+def _dominant_freq(a, sr, lo=80.0, hi=1200.0, t0=0.25, t1=0.85):
+    seg = np.asarray(a[int(t0 * sr): min(len(a), int(t1 * sr))], dtype=np.float64)
+    spec = np.abs(np.fft.rfft(seg * np.hanning(len(seg))))
+    fr = np.fft.rfftfreq(len(seg), d=1.0 / sr)
+    m = (fr >= lo) & (fr <= hi)
+    return float(fr[m][int(np.argmax(spec[m]))])
+
+
+def check_scenario_property(name, x, y, other_output):
+    """The assertion the reference's own test makes on this scenario, on the output `y` of any implementation;
+    `other_output(name)` returns the same implementation's output of another scenario."""
+    spec, sr, _seed, _kw, prop, cite = REF_SCENARIOS[name]
+    what = f"{name} ({cite}): {prop}"
+    assert y.shape == x.shape and y.dtype == np.float32, what
+    assert np.all(np.isfinite(y)), what
+    arg = prop.split(":", 1)[1] if ":" in prop else None
+    if prop == "allclose_input_1e-3":
+        assert np.allclose(y, x, atol=1e-3), what
+    elif prop == "delta_rms_below_-80dB":
+        assert _rms_db(y - x) < -80.0, what
+    elif prop == "delta_rms_below_-10dB_and_audible":
+        assert _rms_db(x - y) < -10.0 and _rms_db(y) > -60.0, what
+    elif prop == "peak_above_0.1":
+        assert np.max(np.abs(y)) > 0.1, what
+    elif prop.startswith("argmax_within_50_of"):
+        o = other_output(arg)
+        assert abs(int(np.argmax(np.abs(y))) - int(np.argmax(np.abs(o)))) < 50 and np.max(np.abs(y)) > 0.1, what
+    elif prop == "argmax_within_1200_of_click":
+        assert abs(int(np.argmax(np.abs(y))) - len(x) // 2) < 1200, what
+    elif prop.startswith("differs_1e-6"):
+        assert not np.allclose(other_output(arg), y, atol=1e-6), what
+    elif prop.startswith("differs"):
+        assert float(np.sqrt(np.mean((y - other_output(arg)) ** 2))) > 0.0, what
+    elif prop.startswith("is_input_minus"):
+        np.testing.assert_allclose(y, x - other_output(arg), atol=1e-6, err_msg=what)
+    elif prop == "dominant_freq_moves_to_440":
+        fi, fo = _dominant_freq(x, sr), _dominant_freq(y, sr)
+        assert abs(fo - 440.0) < abs(fi - 440.0) and abs(fo - 440.0) < 6.0, what
+    else:
+        assert prop in ("taps", "shape"), prop
