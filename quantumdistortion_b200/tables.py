@@ -252,12 +252,12 @@ def max_fan_in(target_bins: Optional[np.ndarray], active_mask: Optional[np.ndarr
 
 
 def choose_precision(precision: str, n_fft: int, target_bins, active_mask, fx_active: bool = False,
-                     formant_active: bool = False, fx_mode: int = 0) -> int:
+                     formant_active: bool = False, fx_mode: int = 0, freeze_active: bool = False) -> int:
     """0 = float32 kernels, 1 = float64 kernels.  "auto" keeps the fast float32 path for the reference's
     defaults and switches to float64 where float32 cannot hold the 1e-4 parity bound: n_fft 8192
      and quantiser tables whose targets gather more than F64_FAN_IN source bins
     (e.g. sub_cut_hz = air_cut_hz = 0), where the phase of a near-cancelling phasor sum is decided below
-    float32 resolution."""
+    float32 resolution; bitcrush on a linear grid, the formant shift and the spectral freeze (reasons below)."""
     if precision in ("float32", "f32", "fp32"):
         return 0
     if precision in ("float64", "f64", "fp64"):
@@ -275,6 +275,12 @@ def choose_precision(precision: str, n_fft: int, target_bins, active_mask, fx_ac
         # the cepstral envelope takes log(max(m, 1e-12)) of EVERY bin: bins under the float32 FFT's noise floor (1e-7 of
         # the frame's strongest bin -- the far skirts of any DC-heavy or tonal frame) come out as noise, the envelope
         # follows, and the render moves by 2e-3 (measured on the fade-in of a wavefolded clip); float64 has 1e-16
+        return 1
+    if freeze_active:
+        # every frame gets the magnitudes of frame 0 (half of it centre padding: a broadband spectrum) on its OWN phases;
+        # on a tonal clip most bins of the later frames sit under the float32 FFT's noise floor, their float32 phases are
+        # noise, and the frozen magnitudes make that noise audible: 4e-4 after one pass for 1e-7 of spectral noise on the
+        # reference's own test signal (tests/test_oracle_ref_scenarios.py), 2e-3 measured on the GPU; float64: 2e-9
         return 1
     return 1 if max_fan_in(target_bins, active_mask) > F64_FAN_IN else 0
 
@@ -405,6 +411,7 @@ def resolve(*, sr: int, n_samples: int, n_fft: int = N_FFT_DEFAULT, key: str, sc
     p.formant_ratio = float(2.0 ** (float(formant_shift) / 12.0)) if formant_on else 0.0  # dsp/spectral_fx.py:173
     p.formant_order = 30                                                                  # dsp/spectral_fx.py:120
     p.precision = choose_precision(precision, n_fft, tb, mask, fx_active=bool(p.fx_mode) or bool(p.spectral_freeze),
-                                   formant_active=formant_on, fx_mode=int(p.fx_mode))
+                                   formant_active=formant_on, fx_mode=int(p.fx_mode),
+                                   freeze_active=bool(p.spectral_freeze))
     return Resolved(params=p, tables=tables, keepalive=tuple(keep), target_bins=tb, active_mask=mask,
                     fx_rng=fx_rng, fx_passes=fx_passes, n_frames=n_frames, n_bins=n_fft // 2 + 1)

@@ -109,7 +109,7 @@ static int go(Cli &c) {
     bool formant = false;
     if (const char *fr = std::getenv("QD_EMU_FORMANT_RATIO")) {
         const double ratio = std::atof(fr);
-        if (ratio > 0.0 && !is_double) {
+        if (ratio > 0.0) {
             const int nb = c.n_fft / 2 + 1;
             fidx.resize(nb); ffrac.resize(nb);
             for (int k = 0; k < nb; ++k) {

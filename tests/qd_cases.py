@@ -349,6 +349,14 @@ REF_SCENARIOS = {
                             "dominant_freq_moves_to_440", "test_quantization_integration.py:46-74"),
 }
 
+# Tolerance of the final output where the REFERENCE ITSELF is ill-conditioned (taps before the ill-conditioned stage keep
+# 1e-4).  formant_six: the second quantised pass takes log(max(|X|, 1e-12)) of every bin of the wavefolded first-pass
+# output, whose inter-harmonic bins hold nothing but that signal's float32 rounding noise -- moving the reference's own
+# pass-2 input by 1e-9 (a seventh of its float32 ulp) moves the reference's output by 2e-4
+# (tests/test_oracle_ref_scenarios.py::test_reference_formant_second_pass_is_ill_conditioned), so a single differently
+# rounded sample of the first pass is enough.  The float64 kernels reproduce each pass to 7.5e-9 (same test file, emulator).
+REF_SCENARIO_Y_TOL = {"formant_six": 1e-3}
+
 
 def _rms_db(v):
     r = float(np.sqrt(np.mean(np.asarray(v, dtype=np.float64) ** 2)))

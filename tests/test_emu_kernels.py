@@ -227,6 +227,21 @@ def test_emu_formant_shift_pass(emu_spec, n_fft, nw, n, semitones):
     assert err < 2e-5, err
 
 
+def test_emu_formant_float64_on_reference_scenario(emu_spec):
+    """Both quantised passes of the reference's own formant test (qd_cases.REF_SCENARIOS["formant_six"], fixture from the
+    live reference) through the float64 kernel source: each pass on the REFERENCE's input of that pass reproduces the
+    reference's output to one float32 rounding, while the float32 kernels are 1e-3 off -- the case is ill-conditioned
+    (tests/test_oracle_ref_scenarios.py), which is why precision="auto" renders the formant shift in float64."""
+    sc = np.load(os.path.join(HERE, "golden", "scenarios.npz"))
+    ratio = 2.0 ** (6.0 / 12.0)
+    for src, dst in (("x", "pre_quant"), ("post_dist", "y")):
+        x, ref = sc[f"formant_six/{src}"], sc[f"formant_six/{dst}"]
+        _, tap = run_emu(emu_spec, x, 44100, 2048, 8, 64, True, True, 1.0, 0.1, prec="f64", formant_ratio=ratio)
+        assert float(np.max(np.abs(tap - ref))) <= 1.5e-8, (src, dst)
+    _, tap32 = run_emu(emu_spec, sc["formant_six/x"], 44100, 2048, 8, 64, True, True, 1.0, 0.1, formant_ratio=ratio)
+    assert float(np.max(np.abs(tap32 - sc["formant_six/pre_quant"]))) > 1e-4
+
+
 @pytest.fixture(scope="module")
 def emu_yin():
     exe = os.path.join(tempfile.gettempdir(), "qd_emu_yin")

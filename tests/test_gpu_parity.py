@@ -210,6 +210,8 @@ def test_auto_precision_rule():
     assert _resolve_kwargs(1000, 48000, 8192, dict(SB))[0].params.precision == 1
     assert _resolve_kwargs(1000, 48000, 2048, dict(SB, sub_cut_hz=0.0, air_cut_hz=0.0))[0].params.precision == 1
     assert _resolve_kwargs(1000, 48000, 2048, dict(SB, precision="float64"))[0].params.precision == 1
+    assert _resolve_kwargs(1000, 48000, 2048, dict(SB, spectral_freeze=True))[0].params.precision == 1
+    assert _resolve_kwargs(1000, 48000, 2048, dict(SB, spectral_freeze=True, precision="float32"))[0].params.precision == 0
 
 
 @pytest.mark.gpu

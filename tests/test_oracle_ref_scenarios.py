@@ -59,3 +59,43 @@ def test_reference_assertions_hold_on_the_fixtures(sc):
     """The fixtures themselves satisfy what the reference's tests assert (a guard for the generator)."""
     for name in qd_cases.REF_SCENARIOS:
         qd_cases.check_scenario_property(name, sc[f"{name}/x"], sc[f"{name}/y"], lambda other: sc[f"{other}/y"])
+
+
+def test_reference_formant_second_pass_is_ill_conditioned(sc):
+    """Why formant_six carries a wider tolerance on its final output (qd_cases.REF_SCENARIO_Y_TOL): the reference's
+    second quantised pass amplifies a 1e-9 change of its input -- far below the float32 resolution of that input -- by
+    five orders of magnitude.  The oracle reproduces the reference bit for bit on this case (test above), so its
+    sensitivity is the reference's."""
+    name, sr = "formant_six", 44100
+    x = sc[f"{name}/post_dist"]
+
+    def second_pass(sig):
+        S, freqs = orc.stft(sig, sr, 2048)
+        Sq = orc.spectral_quantize_stft(S, freqs, "D", "minor", 1.0, 0.1, True, formant_shift=6.0)
+        return orc.istft(Sq, sr, 2048, length=len(sig)).astype(np.float32)
+
+    y0 = second_pass(x)
+    assert np.array_equal(y0, sc[f"{name}/y"])   # limiter idle (peak 0.07): the pass output is the render
+    rng = np.random.default_rng(0)
+    y1 = second_pass(x.astype(np.float64) + 1e-9 * rng.standard_normal(len(x)))
+    assert float(np.max(np.abs(y1 - y0))) > 1e-4
+
+
+def test_reference_freeze_needs_a_float64_fft(sc):
+    """Why precision="auto" renders spectral_freeze in float64 (tables.choose_precision): spectral noise at the float32
+    FFT's level (1e-7 of the frame's strongest bin) moves the reference's frozen pass by more than the 1e-4 bound on the
+    reference's own test signal, noise at the float64 level does not."""
+    name, sr = "freeze_multiband", 44100
+    _, high = orc.linkwitz_riley_split(sc[f"{name}/x"], sr, 300.0)
+    S, freqs = orc.stft(high.astype(np.float32), sr, 2048)
+
+    def frozen_pass(Sx):
+        Sq = orc.spectral_quantize_stft(Sx, freqs, "D", "minor", 1.0, 0.1, True, is_high_band=True, spectral_freeze=True)
+        return orc.istft(Sq, sr, 2048, length=high.shape[0]).astype(np.float32)
+
+    y0 = frozen_pass(S)
+    rng = np.random.default_rng(1)
+    peak = np.abs(S).max(axis=0, keepdims=True)
+    unit = rng.standard_normal(S.shape) + 1j * rng.standard_normal(S.shape)
+    assert float(np.max(np.abs(frozen_pass(S + 1e-7 * peak * unit) - y0))) > 1e-4
+    assert float(np.max(np.abs(frozen_pass(S + 1e-15 * peak * unit) - y0))) < 1e-6
