@@ -6,7 +6,7 @@ TGALLOWAY1/QuantumDistortion behind the reference's ``process_audio`` / ``Pipeli
 The heavy lifting is in ``csrc/`` (hand-written CUDA, C ABI in ``include/qd_b200.h``).
 """
 from .config import PipelineConfig, ensure_mono_float32  # noqa: F401
-from .presets import get_preset, list_presets  # noqa: F401
+from .presets import SPECTRAL_FX_PRESETS, get_preset, list_presets, spectral_fx_preset_kwargs  # noqa: F401
 
 
 def __getattr__(name):  # lazy: importing the package must not need torch or a GPU

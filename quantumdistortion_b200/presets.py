@@ -34,3 +34,30 @@ def get_preset(name: str) -> Dict[str, Any]:
     out = dict(_PRESETS[name])
     out["distortion_params"] = dict(out["distortion_params"])
     return out
+
+
+# Spectral-FX presets of the high band (dsp/spectral_fx.py:34-113): name -> FX mode, strength (0..1) and the
+# spectral_fx_params overrides, as scripts/quick_regression_suite.py:65-84 hands them to the renderer.
+def _fx(fx_mode: str, strength: float, description: str, **params) -> Dict[str, Any]:
+    return {"mode": fx_mode, "distortion_strength": strength, "params": params, "description": description}
+
+
+SPECTRAL_FX_PRESETS: Dict[str, Dict[str, Any]] = {
+    "sub_safe_glue": _fx("bitcrush", 0.35, "Sub-safe subtle log-domain bitcrush for main bass growls.",
+                         method="log", step_db=2.0, threshold=0.0),
+    "digital_growl": _fx("bitcrush", 0.55, "More obvious digital grit for aggressive growls.", method="log", step_db=3.0),
+    "hard_crush_fx": _fx("bitcrush", 0.8, "Heavy bitcrush for stabs and FX, not main bass.", method="uniform", step=0.07),
+    "gentle_movement": _fx("phase_dispersal", 0.25, "Small phase rotation for subtle shimmer.", randomized=False),
+    "laser_zap": _fx("phase_dispersal", 0.6, "Laser/zap phase dispersal for neuro-style tops.", randomized=True),
+    "phase_chaos_fx": _fx("phase_dispersal", 0.9, "Extreme phase chaos for risers and FX beds.", randomized=True),
+    "stereo_smear": _fx("bin_scramble", 0.3, "Subtle local swaps for smeared high-end texture.", mode="swap"),
+    "grainy_top": _fx("bin_scramble", 0.55, "Noticeable granular smear on the high band.", mode="random_pick"),
+    "granular_shred": _fx("bin_scramble", 0.85, "Heavily shredded high band for FX-only usage.", mode="random_pick"),
+}
+
+
+def spectral_fx_preset_kwargs(name: str) -> Dict[str, Any]:
+    """process_audio keyword arguments of one spectral-FX preset (KeyError for an unknown name)."""
+    p = SPECTRAL_FX_PRESETS[name]
+    return {"spectral_fx_mode": p["mode"], "spectral_fx_strength": float(p["distortion_strength"]),
+            "spectral_fx_params": dict(p["params"])}

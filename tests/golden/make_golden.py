@@ -323,7 +323,70 @@ def gen_scenarios():
     print("scenarios:", len(out), os.path.getsize(os.path.join(HERE, "scenarios.npz")) // 1024, "KiB")
 
 
+def _ref_wav_slice(name, seconds):
+    d = np.load(os.path.join(HERE, "refwav.npz"))
+    sr = int(d[f"{name}/sr"])
+    return d[f"{name}/x16"][: int(sr * seconds)], sr
+
+
+def gen_scripts():
+    """The process_audio / process_file_to_file calls of the reference's scripts/ (qd_cases.SCRIPT_SCENARIOS,
+    HARNESS_SCENARIOS) on the first second of its own WAV files, through the LIVE reference; the file-to-file renders go
+    through the reference's own harness and WAV layer and are kept as the PCM16 samples it wrote."""
+    import tempfile
+    import types
+    from pathlib import Path
+    from scipy.io import wavfile
+    if "soundfile" not in sys.modules:
+        # python-soundfile / libsndfile are not in this image.  The reference's io/audio_io.py only calls sf.read and
+        # sf.write on 16-bit PCM WAV files; this stand-in gives them libsndfile's PCM_16 conventions (read: sample /
+        # 32768 as float64; write: round-half-even of x * 0x7FFF, clipped), so that the reference's harness and WAV layer
+        # run unmodified on top of it.
+        sf = types.ModuleType("soundfile")
+
+        def _read(path, always_2d=False):
+            sr, d = wavfile.read(str(path))
+            assert d.dtype == np.int16
+            return d.astype(np.float64) / 32768.0, sr
+
+        def _write(path, audio, sr):
+            pcm = np.clip(np.rint(np.asarray(audio, dtype=np.float64) * 32767.0), -32768, 32767).astype(np.int16)
+            wavfile.write(str(path), int(sr), pcm)
+
+        sf.read, sf.write = _read, _write
+        sys.modules["soundfile"] = sf
+    from quantum_distortion.dsp.harness import process_file_to_file
+    out = {}
+    for name, (wav, seconds, rng_seed, _kw, cite) in qd_cases.SCRIPT_SCENARIOS.items():
+        x16, sr = _ref_wav_slice(wav, seconds)
+        x = x16.astype(np.float32) / 32768.0
+        if rng_seed is not None:
+            np.random.seed(rng_seed)
+        y, taps = quiet(ref_pipeline.process_audio, audio=x, sr=sr, **qd_cases.script_scenario_kwargs(name))
+        out[f"{name}/y"] = y
+        out[f"{name}/pre_quant"] = np.asarray(taps["pre_quant"], dtype=np.float32)
+        out[f"{name}/post_dist"] = np.asarray(taps["post_dist"], dtype=np.float32)
+        print(f"script {name} ({cite}): n={len(x)} peak={np.max(np.abs(y)):.4f}")
+    with tempfile.TemporaryDirectory() as td:
+        for name, (wav, seconds, rng_seed, preset, _ep, cite) in qd_cases.HARNESS_SCENARIOS.items():
+            x16, sr = _ref_wav_slice(wav, seconds)
+            src, dst = Path(td) / f"{name}_in.wav", Path(td) / f"{name}_out.wav"
+            wavfile.write(str(src), sr, x16)
+            if rng_seed is not None:
+                np.random.seed(rng_seed)
+            quiet(process_file_to_file, src, dst, preset=preset, extra_params=qd_cases.harness_extra_params(name))
+            sr2, y16 = wavfile.read(str(dst))
+            assert sr2 == sr and y16.dtype == np.int16 and y16.shape == x16.shape
+            out[f"{name}/y16"] = y16
+            print(f"harness {name} ({cite}): n={len(x16)} peak={np.max(np.abs(y16.astype(np.int32)))}")
+    np.savez_compressed(os.path.join(HERE, "scripts.npz"), **out)
+    print("scripts:", len(out), os.path.getsize(os.path.join(HERE, "scripts.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["scripts"]:
+        gen_scripts()
+        sys.exit(0)
     if sys.argv[1:] == ["scenarios"]:
         gen_scenarios()
         sys.exit(0)
@@ -348,5 +411,6 @@ if __name__ == "__main__":
     gen_round2()
     gen_refwav()
     gen_scenarios()
+    gen_scripts()
     for f in ("tables.npz", "stages.npz", "pipeline.npz", "frontend.npz", "analysis.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -403,3 +403,69 @@ def check_scenario_property(name, x, y, other_output):
         assert abs(fo - 440.0) < abs(fi - 440.0) and abs(fo - 440.0) < 6.0, what
     else:
         assert prop in ("taps", "shape"), prop
+
+
+# ---------------------------------------------------------------- the reference's scripts as scenarios
+# The process_audio / process_file_to_file calls of the reference's scripts/ on the first second of its own WAV files.
+# SCRIPT_SCENARIOS: direct process_audio calls, name -> (wav, seconds, rng_seed, kwargs, cite).
+# HARNESS_SCENARIOS: file-to-file renders, name -> (wav, seconds, rng_seed, preset, extra_params, cite); compared as PCM16.
+_DP3 = {"fold_amount": 3.0, "bias": 0.0, "drive": 1.0, "warmth": 0.5}
+_PRESET_ARGS = ("key", "scale", "snap_strength", "smear", "bin_smoothing", "pre_quant", "post_quant", "distortion_mode",
+                "distortion_params", "limiter_on", "limiter_ceiling_db", "dry_wet")   # scripts/render_preset.py:50-81
+
+
+def _preset_kwargs(name):
+    from quantumdistortion_b200.presets import get_preset
+    p = get_preset(name)
+    return {k: p[k] for k in _PRESET_ARGS}
+
+
+SCRIPT_SCENARIOS = {
+    "validate_metrics_main": ("midrange_growl_like", 1.0, None,
+                              dict(key="D", scale="minor", snap_strength=0.8, smear=0.4, bin_smoothing=True, pre_quant=True,
+                                   post_quant=True, distortion_mode="wavefold", distortion_params=_DP3, limiter_on=True,
+                                   limiter_ceiling_db=-1.0, dry_wet=1.0), "scripts/validate_dsp_metrics.py:59-74"),
+    "validate_metrics_quantizer_only": ("midrange_growl_like", 1.0, None,
+                                        dict(key="D", scale="minor", snap_strength=1.0, smear=0.0, bin_smoothing=False,
+                                             pre_quant=True, post_quant=True, distortion_mode="wavefold",
+                                             distortion_params={"fold_amount": 1.0, "bias": 0.0, "drive": 1.0, "warmth": 0.5},
+                                             limiter_on=False, limiter_ceiling_db=-1.0, dry_wet=1.0),
+                                        "scripts/validate_dsp_metrics.py:92-107"),
+    "profile_pipeline": ("kick_sub_combo", 1.0, None,
+                         dict(key="C", scale="minor", snap_strength=0.8, smear=0.3, bin_smoothing=True, pre_quant=True,
+                              post_quant=True, distortion_mode="wavefold", distortion_params=_DP3, limiter_on=True,
+                              limiter_ceiling_db=-1.0, dry_wet=1.0), "scripts/profile_pipeline.py:35-50"),
+    **{f"render_preset_{n.split()[0].lower()}": ("wobble_bass", 1.0, None, n, "scripts/render_preset.py:67-82")
+       for n in ("Chordal Noise Wash", "Controlled Dubstep Growl", "Perc To Tonal Clang", "Subtle Tube Glue")},
+}
+
+
+def script_scenario_kwargs(name):
+    kw = SCRIPT_SCENARIOS[name][3]
+    return _preset_kwargs(kw) if isinstance(kw, str) else dict(kw)
+
+
+_MB = {"use_multiband": True, "crossover_hz": 300.0}
+HARNESS_SCENARIOS = {
+    "qrs_single": ("sub_sweep", 1.0, None, None, {"use_multiband": False}, "scripts/quick_regression_suite.py:148-153"),
+    "qrs_multiband_baseline": ("sub_sweep", 1.0, None, None, dict(_MB, spectral_fx_mode=None, spectral_fx_strength=0.0),
+                               "scripts/quick_regression_suite.py:158-168"),
+    "qrs_single_growl_preset": ("wobble_bass", 1.0, None, "Controlled Dubstep Growl", {"use_multiband": False},
+                                "scripts/quick_regression_suite.py:148-153 --preset"),
+    **{f"qrs_fxpreset_{p}": ("wobble_bass", 1.0, 300 + i, None, ("fx_preset", p), "scripts/quick_regression_suite.py:198-209")
+       for i, p in enumerate(("sub_safe_glue", "digital_growl", "laser_zap", "grainy_top"))},
+    **{f"qrs_fx_{m}": ("kick_sub_combo", 1.0, 400 + i, None, dict(_MB, spectral_fx_mode=m, spectral_fx_strength=0.5),
+                       "scripts/quick_regression_suite.py:237-247")
+       for i, m in enumerate(("bitcrush", "phase_dispersal", "bin_scramble"))},
+    "harness_extra_params": ("sub_sweep", 1.0, None, None,
+                             {"snap_strength": 0.0, "pre_quant": False, "post_quant": False, "limiter_on": False, "dry_wet": 1.0},
+                             "tests/test_harness_smoke.py:50-70"),
+}
+
+
+def harness_extra_params(name):
+    ep = HARNESS_SCENARIOS[name][4]
+    if isinstance(ep, tuple):   # a spectral-FX preset applied like scripts/quick_regression_suite.py:65-84, 198-209
+        from quantumdistortion_b200.presets import spectral_fx_preset_kwargs
+        return dict(_MB, **spectral_fx_preset_kwargs(ep[1]))
+    return dict(ep)

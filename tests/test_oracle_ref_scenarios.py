@@ -99,3 +99,50 @@ def test_reference_freeze_needs_a_float64_fft(sc):
     unit = rng.standard_normal(S.shape) + 1j * rng.standard_normal(S.shape)
     assert float(np.max(np.abs(frozen_pass(S + 1e-7 * peak * unit) - y0))) > 1e-4
     assert float(np.max(np.abs(frozen_pass(S + 1e-15 * peak * unit) - y0))) < 1e-6
+
+
+# ---------------------------------------------------------------- the reference's scripts (tests/golden/scripts.npz)
+@pytest.fixture(scope="module")
+def scr():
+    return np.load(os.path.join(G, "scripts.npz"))
+
+
+def _wav_slice(name, seconds):
+    d = np.load(os.path.join(G, "refwav.npz"))
+    sr = int(d[f"{name}/sr"])
+    return d[f"{name}/x16"][: int(sr * seconds)], sr
+
+
+@pytest.mark.parametrize("name", list(qd_cases.SCRIPT_SCENARIOS))
+def test_oracle_on_reference_script_calls(scr, name):
+    wav, seconds, rng_seed, _kw, cite = qd_cases.SCRIPT_SCENARIOS[name]
+    x16, sr = _wav_slice(wav, seconds)
+    x = x16.astype(np.float32) / 32768.0
+    if rng_seed is not None:
+        np.random.seed(rng_seed)
+    y, taps = oracle_render(x, sr, qd_cases.script_scenario_kwargs(name))
+    for got, key in ((y, "y"), (taps["pre_quant"], "pre_quant"), (taps["post_dist"], "post_dist")):
+        ref = scr[f"{name}/{key}"]
+        err = float(np.max(np.abs(np.asarray(got, dtype=np.float64) - ref)))
+        assert err <= 2e-7, f"{name}/{key} ({cite}): max abs err {err:.3e}"
+
+
+@pytest.mark.parametrize("name", list(qd_cases.HARNESS_SCENARIOS))
+def test_oracle_on_reference_harness_renders(scr, name):
+    """process_file_to_file (dsp/harness.py:23-67): PipelineConfig() or from_preset(), extra_params override the fields
+    they name, the render goes out as 16-bit PCM."""
+    from quantumdistortion_b200.presets import get_preset
+    wav, seconds, rng_seed, preset, _ep, cite = qd_cases.HARNESS_SCENARIOS[name]
+    x16, sr = _wav_slice(wav, seconds)
+    x = x16.astype(np.float32) / 32768.0
+    kw = {}
+    if preset is not None:
+        p = get_preset(preset)
+        kw = {k: p[k] for k in qd_cases._PRESET_ARGS}
+    kw.update(qd_cases.harness_extra_params(name))
+    if rng_seed is not None:
+        np.random.seed(rng_seed)
+    y, _ = oracle_render(x, sr, kw)
+    pcm = np.clip(np.rint(y.astype(np.float64) * 32767.0), -32768, 32767).astype(np.int32)
+    d = int(np.max(np.abs(pcm - scr[f"{name}/y16"].astype(np.int32))))
+    assert d <= 1, f"{name} ({cite}): {d} PCM16 steps"
