@@ -219,3 +219,22 @@ def test_wav_io_roundtrip_and_pcm_rules(tmp_path):
     assert cfg.dry_wet == 0.25 and cfg.distortion_mode == "tube" and not hasattr(cfg, "not_a_field")
     with pytest.raises(KeyError):
         harness._config("nope", None)
+
+
+def test_streamlit_default_dict_raises_like_the_reference():
+    """ui/app_streamlit.py:74-163 with harmonic lock "Off" hands over quantum_fx.fundamental_hz = None, and the
+    reference's parser calls float() on it (dsp/pipeline.py:1003): the reference raises TypeError on its own UI's
+    default dict (checked against the live reference).  Same exception here, before any launch; a numeric
+    fundamental (lock mode "G1" = 49.0 Hz) resolves to the STFT path."""
+    from quantumdistortion_b200.pipeline import _resolve_kwargs
+    cfg = {"quantization": {"key": "D", "scale": "minor", "mode": "autotune_v1"}, "crossover_freq": 300,
+           "low_band": {"saturation_amount": 0.3, "saturation_type": "Tube", "mono_strength": 1.0, "output_trim_db": 0},
+           "high_band": {"fft_size": 2048, "window_type": "hann", "precision_mode": "Quantized", "mag_decimation": 0.5,
+                         "phase_dispersal": 0.3, "bin_scrambling": 0.2, "output_trim_db": 0},
+           "quantum_fx": {"spectral_freeze": False, "formant_shift": 0, "harmonic_lock_mode": "Off", "fundamental_hz": None},
+           "delta_listen": False}
+    with pytest.raises(TypeError):
+        _resolve_kwargs(4800, 48000, 2048, dict(config=cfg))
+    cfg["quantum_fx"].update(harmonic_lock_mode="G1", fundamental_hz=49.0)
+    r, _ = _resolve_kwargs(4800, 48000, 2048, dict(config=cfg))
+    assert r.params.multiband == 1 and r.params.fx_mode != 0   # bin_scrambling 0.2 wins (:986-994), mode flipped (:1315)
