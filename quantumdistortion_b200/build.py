@@ -22,7 +22,7 @@ HEADER = os.path.join("..", "..", "include", "qd_b200.h")
 _KERNEL_DEPS = ["qd_spec.cuh", "qd_common.cuh", "qd_spec_launch.hpp", "qd_spec_launch.inl", "qd_err.hpp", HEADER]
 # translation unit -> what it includes
 UNITS = {
-    "qd_api.cu": ["qd_spec.cuh", "qd_spec_launch.hpp", "qd_peaks.cuh", "qd_autotune.cuh", "qd_yin.cuh", "qd_autotune_api.inc",
+    "qd_api.cu": ["qd_spec.cuh", "qd_spec_launch.hpp", "qd_spec_team.cuh", "qd_spec_team_launch.hpp", "qd_peaks.cuh", "qd_autotune.cuh", "qd_yin.cuh", "qd_autotune_api.inc",
                   "qd_host_pipe.inc", "qd_time.cuh", "qd_common.cuh", "qd_host_tables.hpp", "qd_host_time.hpp",
                   "qd_err.hpp", HEADER],
     "qd_k_spec_f32.cu": _KERNEL_DEPS,
@@ -30,6 +30,7 @@ UNITS = {
     "qd_k_spec_fx32b.cu": _KERNEL_DEPS,
     "qd_k_spec_f64.cu": _KERNEL_DEPS,
     "qd_k_spec_fx64.cu": _KERNEL_DEPS,
+    "qd_k_spec_team.cu": ["qd_spec_team.cuh", "qd_spec_team_launch.hpp", "qd_spec.cuh", "qd_common.cuh", "qd_err.hpp", HEADER],
 }
 
 # no --split-compile: it changes the generated code from build to build (the headline kernel came out 21 % slower

@@ -16,6 +16,7 @@
 #include "qd_host_tables.hpp"
 #include "qd_host_time.hpp"
 #include "qd_spec_launch.hpp"
+#include "qd_spec_team_launch.hpp"
 #include "qd_peaks.cuh"
 #include "qd_autotune.cuh"
 #include "qd_time.cuh"
@@ -74,6 +75,9 @@ struct qd_plan {
     int sm_count = 148;
     int clip_offset = 0;       // first clip of the current render inside a per-clip FX table
     void *frozen_ws = nullptr; // slice of the render workspace: frame-0 magnitudes (spectral freeze)
+    qd::TeamGather team_tg{};  // gather lists of the team kernel (long frames, plain passes); team_nf = 0: not used
+    int team_nf = 0, team_cw = 0;
+    size_t team_smem = 0;
     // optional per-kernel device timing (qd_plan_enable_timing)
     bool timing = false;
     struct Stamp { cudaEvent_t a, b; int cls; };
@@ -217,11 +221,13 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
     int nw = fx ? pl->nw : pick_nw<T>(pl->nc, false) == 16 && !pl->ts ? 8 : pick_nw<T>(pl->nc, false);
     const bool ts = fx ? pl->ts_fx : pl->ts;
     const int ng = (nw == 16) ? 2 : 1;   // clips per CTA
+    // long frames without FX: teams of warps per frame (qd_spec_team.cuh), one CTA per SM
+    const bool team = !fx && pl->team_nf > 0;
     // tiling: whole clips when the batch alone fills the GPU, else cut clips along time
     const int total_blocks = (a.n + pl->hop - 1) / pl->hop;
-    const int ctas_per_sm = std::max<int>(1, (int)((227 * 1024) / (pl->spec_smem + 1024)));
+    const int ctas_per_sm = team ? 1 : std::max<int>(1, (int)((227 * 1024) / (pl->spec_smem + 1024)));
     const int64_t want = (int64_t)pl->sm_count * ctas_per_sm * 2 * ng;
-    const int wpg = nw / ng;  // warps (= frames per batch) of one clip group
+    const int wpg = team ? pl->team_nf : nw / ng;  // frames per batch of one clip group
     int tile = total_blocks;
     if (batch < want) {
         const int64_t per_clip = (want + batch - 1) / batch;
@@ -242,6 +248,7 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
         if (rc != QD_OK) return rc;
         a.frozen = frozen;
     }
+    if (team) return qd_launch::launch_spec_team<T>(pl->nc, a, pl->team_tg, tiles, batch, st);
     if (fx) return dispatch_spec<T, true>(pl->nc, nw, ts, a, tiles, batch, st);
     return dispatch_spec<T, false>(pl->nc, nw, ts, a, tiles, batch, st);
     (void)nw;
@@ -448,6 +455,16 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         uint32_t *d_ra, *d_st;
         float *d_ik, *d_bs;
         QD_UP(qt.src_tab, d_st);
+        {   // long frames: the plain passes run the team kernel, which reads one gather list per warp of a team
+            const qd_launch::TeamShape ts_ = pl->f64 ? qd_launch::team_shape<double>(st.nc) : qd_launch::team_shape<float>(st.nc);
+            if (ts_.nf > 0) {
+                std::vector<uint32_t> ttab;
+                qd_host::build_team_gather(qt, ts_.cw, &ttab, pl->team_tg.begin);
+                uint32_t *d_tt;
+                QD_UP(ttab, d_tt);
+                pl->team_tg.src_tab = d_tt;
+            }
+        }
         QD_UP(qt.row_active, d_ra);
         QD_UP(qt.slot_of_bin, d_sb);
         QD_UP(qt.slot_invk, d_ik);
@@ -550,6 +567,11 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         }
     }
 #undef QD_UP
+    {   // long frames: plain passes on the team kernel when its CTA fits (else the one-warp-per-frame kernel above)
+        const qd_launch::TeamShape ts_ = pl->f64 ? qd_launch::team_shape<double>(pl->nc) : qd_launch::team_shape<float>(pl->nc);
+        const size_t tsm = pl->f64 ? qd_launch::team_smem_bytes<double>(pl->nc, n_slots) : qd_launch::team_smem_bytes<float>(pl->nc, n_slots);
+        if (ts_.nf > 0 && tsm > 0 && tsm <= 227 * 1024) { pl->team_nf = ts_.nf; pl->team_cw = ts_.cw; pl->team_smem = tsm; }
+    }
     if (pl->spec_smem == 0 || pl->spec_smem > 227 * 1024)
         return bail(QD_ERR_UNSUPPORTED, "shared memory need of this (n_fft, target table, precision) exceeds 227 KB");
     *out = pl;

@@ -212,4 +212,38 @@ inline bool build_quant_tables(const qd_tables &in, QuantTablesH *q, std::string
     return true;
 }
 
+// Gather lists of the team kernel (qd_spec_team.cuh): the target slots, in ascending order, are cut into `cw` contiguous
+// ranges of about equal source counts; warp w's list holds the sources of its slots in the order of src_tab, `off` and
+// `tail` counted in groups of 32 from the start of ITS list, padded with null entries (0: no tail, nothing stored) to a
+// multiple of 32.  begin[w] .. begin[w + 1] delimits warp w's list inside `tab`.
+inline void build_team_gather(const QuantTablesH &q, int cw, std::vector<uint32_t> *tab, int *begin /* [cw + 1] */) {
+    tab->clear();
+    const int ns_total = q.n_slots > 0 ? (int)q.slot_begin[q.n_slots] : 0;
+    int slot = 0;
+    for (int w = 0; w < cw; ++w) {
+        begin[w] = (int)tab->size();
+        // slots whose first source lies below the w+1-th share of the sources
+        const long long limit = ((long long)ns_total * (w + 1) + cw - 1) / cw;
+        std::vector<int> slot_of_src;
+        std::vector<uint16_t> bins;
+        while (slot < q.n_slots && (w == cw - 1 || (long long)q.slot_begin[slot] < limit)) {
+            for (int i = q.slot_begin[slot]; i < q.slot_begin[slot + 1]; ++i) {
+                slot_of_src.push_back(slot);
+                bins.push_back(q.src_bin[i]);
+            }
+            ++slot;
+        }
+        const int ns = (int)slot_of_src.size();
+        for (int i = 0; i < ns; ++i) {
+            int off = 0;
+            for (int j = i - 1; j >= (i / 32) * 32 && slot_of_src[j] == slot_of_src[i]; --j) ++off;
+            const bool tail = (i % 32 == 31) || (i == ns - 1) || (slot_of_src[i + 1] != slot_of_src[i]);
+            tab->push_back(((uint32_t)tail << 31) | ((uint32_t)off << 26) | ((uint32_t)slot_of_src[i] << 13) | (uint32_t)bins[i]);
+        }
+        while (tab->size() % 32) tab->push_back(0u);
+    }
+    begin[cw] = (int)tab->size();
+    if (tab->empty()) tab->push_back(0u);
+}
+
 }  // namespace qd_host

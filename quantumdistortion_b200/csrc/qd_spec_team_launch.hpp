@@ -1,0 +1,30 @@
+// qd_spec_team_launch.hpp -- launcher of the team kernel (qd_spec_team.cuh: CW warps per frame, n_fft >= 4096, plain
+// variant).  qd_api.cu sees only this declaration; qd_k_spec_team.cu holds the definition and the instantiations.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "qd_spec_team.cuh"
+
+namespace qd_launch {
+
+// frames per batch (NF) and warps per frame (CW) of the team kernel for this precision and n_fft / 2, or {0, 0} when the
+// configuration keeps the one-warp-per-frame kernel.  Sized so that the CTA fills one SM: float32 n_fft 4096 has 7
+// frame buffers of 17 KB (28 warps at 72 registers), float64 n_fft 4096 four of 34 KB, float64 n_fft 8192 two of 68 KB.
+struct TeamShape { int nf, cw; };
+template <class T> inline TeamShape team_shape(int nc) {
+    if (sizeof(T) == 4) return nc == 2048 ? TeamShape{7, 4} : TeamShape{0, 0};
+    return nc == 2048 ? TeamShape{4, 4} : nc == 4096 ? TeamShape{2, 8} : TeamShape{0, 0};
+}
+
+// dynamic shared memory of that kernel (0: none)
+template <class T> inline size_t team_smem_bytes(int nc, int n_slots) {
+    if (sizeof(T) == 4) return nc == 2048 ? qd::SpecSmem<float, 2048, 7>::bytes(n_slots) : 0;
+    return nc == 2048 ? qd::SpecSmem<double, 2048, 4>::bytes(n_slots) : nc == 4096 ? qd::SpecSmem<double, 4096, 2>::bytes(n_slots) : 0;
+}
+
+template <class T>
+int launch_spec_team(int nc, const qd::SpecArgsT<T> &a, const qd::TeamGather &tg, int tiles, int64_t batch, cudaStream_t st);
+
+}  // namespace qd_launch

@@ -14,6 +14,7 @@ thread_local dim3 g_tid, g_bid;
 
 #include "../../quantumdistortion_b200/csrc/qd_host_tables.hpp"
 #include "../../quantumdistortion_b200/csrc/qd_spec.cuh"
+#include "../../quantumdistortion_b200/csrc/qd_spec_team.cuh"
 
 #include <cstdlib>
 #include <fstream>
@@ -127,6 +128,23 @@ static int go(Cli &c) {
     const int n_tiles = (blocks_total + c.tile_blocks - 1) / c.tile_blocks;
     const int nc = c.n_fft / 2, nw = c.nw;
     const int fx_mode = c.fx_mode;
+    // team kernel (qd_spec_team.cuh): <nw> = 100 * frames per batch + warps per frame
+    if (c.nw >= 100) {
+        const int nf = c.nw / 100, cw = c.nw % 100;
+        std::vector<uint32_t> ttab;
+        qd::TeamGather tg{};
+        qd_host::build_team_gather(qt, cw, &ttab, tg.begin);
+        tg.src_tab = ttab.data();
+#define QD_TEAMCASE(NC_, NF_, CW_)                                                                                  \
+        if (nc == NC_ && nf == NF_ && cw == CW_) {                                                                  \
+            qd_emu::launch(dim3(n_tiles, a.batch, 1), dim3(32 * NF_ * CW_, 1, 1), qd::SpecSmem<T, NC_, NF_>::bytes(qt.n_slots), \
+                           [&] { qd::spec_pass_team_kernel<T, NC_, NF_, CW_>(a, tg); });                               \
+            return 0;                                                                                                \
+        }
+        QD_TEAMCASE(2048, 7, 4) QD_TEAMCASE(2048, 4, 4) QD_TEAMCASE(2048, 2, 2) QD_TEAMCASE(4096, 2, 8) QD_TEAMCASE(4096, 2, 4)
+        std::cerr << "no team instantiation for nc=" << nc << " nf=" << nf << " cw=" << cw << "\n";
+        return 2;
+    }
 #define QD_FXCASE(NC_, NW_)                                                                                       \
     if ((fx_mode || formant) && nc == NC_ && nw == NW_) {                                                         \
         run<T, NC_, NW_, false, true>(a, n_tiles, qd::SpecSmem<T, NC_, NW_>::bytes(qt.n_slots, false, 0, 0, true, formant)); \

@@ -31,7 +31,7 @@ def _build_emu(exe, srcs, main):
 def emu_spec():
     exe = os.path.join(tempfile.gettempdir(), "qd_emu_spec")
     srcs = [os.path.join(EMU_DIR, f) for f in ("emu_spec.cpp", "cuda_emu.h")]
-    srcs += [os.path.join(CSRC, f) for f in ("qd_spec.cuh", "qd_common.cuh", "qd_host_tables.hpp")]
+    srcs += [os.path.join(CSRC, f) for f in ("qd_spec.cuh", "qd_spec_team.cuh", "qd_common.cuh", "qd_host_tables.hpp")]
     return _build_emu(exe, srcs, os.path.join(EMU_DIR, "emu_spec.cpp"))
 
 
@@ -225,6 +225,36 @@ def test_emu_formant_shift_pass(emu_spec, n_fft, nw, n, semitones):
     ref = orc.istft(Sq, sr, n_fft, length=n)
     err = float(np.max(np.abs(y - ref)))
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("n_fft,shape,n,tile,prec", [(4096, 704, 9000, 64, "f32"), (4096, 704, 9000, 3, "f32"),
+                                                     (4096, 704, 60000, 17, "f32"),   # interior batches: bulk-copy staging
+                                                     (4096, 404, 5003, 64, "f64"), (8192, 208, 17000, 64, "f64"),
+                                                     (8192, 208, 17001, 5, "f64")])
+def test_emu_team_kernel(emu_spec, n_fft, shape, n, tile, prec):
+    """qd_spec_team.cuh (a team of warps per frame, n_fft >= 4096; `shape` = 100 x frames per batch + warps per frame):
+    pure STFT -> iSTFT and the quantised pass, source single-stepped on the CPU against the oracle -- butterfly groups
+    dealt to the warps, per-warp gather lists, the row ranges of the paired walk with their border rows."""
+    x = synth.noise_clip(5, n)
+    y, tap = run_emu(emu_spec, x, 48000, n_fft, shape, tile, False, False, 1.0, 0.1, prec=prec)
+    assert np.max(np.abs(y - oracle_pass(x, 48000, n_fft, False, False, 1.0, 0.1))) < 2e-6
+    assert np.array_equal(y, tap)
+    y, _ = run_emu(emu_spec, x, 48000, n_fft, shape, tile, True, True, 1.0, 0.1, prec=prec)
+    assert np.max(np.abs(y - oracle_pass(x, 48000, n_fft, True, True, 1.0, 0.1))) < (1e-5 if prec == "f32" else 5e-7)
+
+
+@pytest.mark.parametrize("n_fft,shape,prec", [(4096, 704, "f32"), (4096, 404, "f64"), (8192, 208, "f64")])
+def test_emu_team_kernel_wide_mask_and_epilogue(emu_spec, n_fft, shape, prec):
+    """Targets that gather more than 32 sources (a slot's sources span several groups of its warp's list), no smoothing,
+    and the wavefold epilogue."""
+    x = synth.loud_clip(6, 9000)
+    kw = dict(key="A", scale="pentatonic", lo=0.0, hi=0.0)
+    y, tap = run_emu(emu_spec, x, 48000, n_fft, shape, 64, True, True, 0.9, 0.3, epilogue=1, fold=5.0, bias=0.1, prec=prec, **kw)
+    ref_tap = oracle_pass(x, 48000, n_fft, True, True, 0.9, 0.3, **kw)
+    assert np.max(np.abs(tap - ref_tap)) < (2e-5 if prec == "f32" else 5e-7)
+    assert np.max(np.abs(y - orc.apply_distortion(tap, "wavefold", fold_amount=5.0, bias=0.1))) < 1e-5
+    y, _ = run_emu(emu_spec, x, 48000, n_fft, shape, 64, True, False, 0.75, 0.0, prec=prec)
+    assert np.max(np.abs(y - oracle_pass(x, 48000, n_fft, True, False, 0.75, 0.0))) < (1e-5 if prec == "f32" else 5e-7)
 
 
 def test_emu_formant_float64_on_reference_scenario(emu_spec):
