@@ -41,6 +41,38 @@ QD_DEV void team_sync(int team) {
     }
 }
 
+// ---------------------------------------------------------------- buffer layout: XOR swizzle instead of the 33/32 padding
+// The padding of qd_spec.cuh is conflict-free for the 32 x 32 plan only.  The three-pass plans touch the buffer in four
+// patterns -- per half-warp (8-byte elements) or quarter-warp (16-byte elements) the lanes differ in
+//   first / last pass, overlap-add : the lowest index bits,
+//   middle pass (stride S2)        : the lowest bits below S2 and the bits from M2 upwards,
+//   third pass (stride 1 per lane) : the bits from R3 upwards,
+//   rows of the walk (bin k)       : the bits from NC / R1 upwards (k mod R1 is the slowest digit of the position)
+// and element a sits at  a ^ ((a >> S1) & M1) ^ ((a >> S2) & M2),  which folds exactly those higher bits onto the bank
+// bits, so that each pattern is a bijection onto the 16 (8) banks.  Bits above the bank bits are untouched: the map is a
+// permutation of [0, NC), and it is linear over XOR, so pos(a0 + q S) = pos(a0) ^ pos(q S) with a compile-time second term
+// whenever a0 and q S occupy different bits (they do in every pass).
+template <class T, int NC> struct TeamSwz;
+template <> struct TeamSwz<float, 2048>  { static constexpr int S1 = 4, M1 = 15, S2 = 8, M2 = 7; };
+template <> struct TeamSwz<float, 4096>  { static constexpr int S1 = 4, M1 = 15, S2 = 8, M2 = 15; };
+template <> struct TeamSwz<double, 2048> { static constexpr int S1 = 3, M1 = 7,  S2 = 7, M2 = 7; };
+template <> struct TeamSwz<double, 4096> { static constexpr int S1 = 4, M1 = 7,  S2 = 8, M2 = 7; };
+template <class T, int NC>
+QD_DEV constexpr int tpos(int a) {
+    using Z = TeamSwz<T, NC>;
+    return a ^ ((a >> Z::S1) & Z::M1) ^ ((a >> Z::S2) & Z::M2);
+}
+// position of spectrum bin k (0 <= k < NC) after the in-place DIF passes (digit order of qd::spos)
+template <class T, int NC>
+QD_DEV int tspos(int k) {
+    using C = FftCfg<T, NC>;
+    const unsigned uk = (unsigned)k;
+    const unsigned k1 = uk & (unsigned)(C::R1 - 1);
+    const unsigned k2 = (uk / (unsigned)C::R1) & (unsigned)(C::R2 - 1);
+    const unsigned k3 = uk / (unsigned)(C::R1 * C::R2);
+    return tpos<T, NC>((int)(k1 * (unsigned)(NC / C::R1) + k2 * (unsigned)(NC / (C::R1 * C::R2)) + k3));
+}
+
 // ---------------------------------------------------------------- FFT passes, butterfly groups dealt to the team's warps
 template <class T, int NC, int R, int CW>
 QD_DEV void t_fwd_first(V2<T> *buf, const float2 *frame, const V2<T> *wtab, const V2<T> *tw, int lane, int wsub, int team) {
@@ -58,11 +90,12 @@ QD_DEV void t_fwd_first(V2<T> *buf, const float2 *frame, const V2<T> *wtab, cons
             v[q] = pmul(mk2<T>((T)s.x, (T)s.y), hann_pair<T, R>(wc, ws, q));
         }
         dft_reg<R, -1, T>(v);
-        buf[pidx(a0)] = v[0];
+        const int p0 = tpos<T, NC>(a0);
+        buf[p0] = v[0];
         twiddle_walk<T, R>(tw + (i * R) * 32 + lane,
                            [&](auto kc, V2<T> w) {
                                constexpr int k = decltype(kc)::value;
-                               buf[pidx(a0 + k * S)] = cmul(v[qd_bitrev(k, LG)], w);
+                               buf[p0 ^ tpos<T, NC>(k * S)] = cmul(v[qd_bitrev(k, LG)], w);
                            });
     }
 }
@@ -75,17 +108,17 @@ QD_DEV void t_fwd_pass(V2<T> *buf, const V2<T> *tw, int lane, int wsub) {
 #pragma unroll 1
     for (int i = wsub; i < NB; i += CW) {
         const int u = lane + 32 * i;
-        const int a0 = (u / S) * M + (u % S);
+        const int p0 = tpos<T, NC>((u / S) * M + (u % S));
         V2<T> v[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = buf[pidx(a0 + q * S)];
+        for (int q = 0; q < R; ++q) v[q] = buf[p0 ^ tpos<T, NC>(q * S)];
         dft_reg<R, -1, T>(v);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int k = qd_bitrev(r, LG);
             V2<T> t = v[r];
             if (TW && k > 0) t = cmul(t, __ldg(tw + (i * R + k) * 32 + lane));
-            buf[pidx(a0 + k * S)] = t;
+            buf[p0 ^ tpos<T, NC>(k * S)] = t;
         }
     }
 }
@@ -98,17 +131,17 @@ QD_DEV void t_inv_pass(V2<T> *buf, const V2<T> *tw, int lane, int wsub) {
 #pragma unroll 1
     for (int i = wsub; i < NB; i += CW) {
         const int u = lane + 32 * i;
-        const int a0 = (u / S) * M + (u % S);
+        const int p0 = tpos<T, NC>((u / S) * M + (u % S));
         V2<T> v[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            V2<T> t = buf[pidx(a0 + k * S)];
+            V2<T> t = buf[p0 ^ tpos<T, NC>(k * S)];
             if (TW && k > 0) t = cmulc(t, __ldg(tw + (i * R + k) * 32 + lane));
             v[k] = t;
         }
         dft_reg<R, +1, T>(v);
 #pragma unroll
-        for (int r = 0; r < R; ++r) buf[pidx(a0 + qd_bitrev(r, LG) * S)] = v[r];
+        for (int r = 0; r < R; ++r) buf[p0 ^ tpos<T, NC>(qd_bitrev(r, LG) * S)] = v[r];
     }
 }
 
@@ -121,17 +154,18 @@ QD_DEV void t_inv_last(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw, int lane,
     for (int i = wsub; i < NB; i += CW) {
         const int a0 = lane + 32 * i;
         V2<T> v[R];
-        v[0] = buf[pidx(a0)];
+        const int p0 = tpos<T, NC>(a0);
+        v[0] = buf[p0];
         twiddle_walk<T, R>(tw + (i * R) * 32 + lane, [&](auto kc, V2<T> w) {
             constexpr int k = decltype(kc)::value;
-            v[k] = cmulc(buf[pidx(a0 + k * S)], w);
+            v[k] = cmulc(buf[p0 ^ tpos<T, NC>(k * S)], w);
         });
         dft_reg<R, +1, T>(v);
         const V2<T> wc = __ldg(wtab + 2 * a0), ws = __ldg(wtab + 2 * a0 + 1);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int q = qd_bitrev(r, LG);
-            buf[pidx(a0 + q * S)] = pmul(v[r], hann_pair<T, R>(wc, ws, q));
+            buf[p0 ^ tpos<T, NC>(q * S)] = pmul(v[r], hann_pair<T, R>(wc, ws, q));
         }
     }
 }
@@ -166,14 +200,14 @@ QD_DEV void t_split_merge(V2<T> *buf, const V2<T> *wsplit, int lane, int wsub) {
     for (int row = wsub; row < NC / 64; row += CW) {
         const int k = lane + 32 * row;
         if (k == 0) {
-            const V2<T> z0 = buf[0];
+            const V2<T> z0 = buf[0];                          // tspos(0) = 0
             const T a = z0.x + z0.y, b = z0.x - z0.y;       // X[0], X[NC] (real)
             buf[0] = mk2<T>(a + b, a - b);
-            const int pm = spos<T, NC>(NC / 2);
+            const int pm = tspos<T, NC>(NC / 2);
             const V2<T> xm = cconj(buf[pm]);
             buf[pm] = mk2<T>(2.0f * xm.x, -2.0f * xm.y);
         } else {
-            const int pa = rpos<T, NC>(lane, row), pb = mpos<T, NC>(lane, row);
+            const int pa = tspos<T, NC>(k), pb = tspos<T, NC>(NC - k);
             const V2<T> w = __ldg(wsplit + k);
             const V2<T> za = buf[pa], zb = cconj(buf[pb]);
             const V2<T> e = cadd(za, zb);
@@ -202,7 +236,17 @@ QD_DEV void quantize_frame_team(V2<T> *buf, T *slotG, V2<T> *slotP, const QuantD
 #pragma unroll 1
     for (int i0 = tg.begin[wsub]; i0 < tg.begin[wsub + 1]; i0 += 32) {
         const uint32_t e = __ldg(tg.src_tab + i0 + lane);
-        V2<T> p = split_bin<T, NC>(buf, wsplit, (int)(e & 0x1fffu));
+        V2<T> p;
+        {   // X[k] straight from the packed spectrum (qd::split_bin with this kernel's positions)
+            const int k = (int)(e & 0x1fffu);
+            const bool hi = 2 * k > NC;
+            const int kk = hi ? NC - k : k;
+            const V2<T> za = buf[tspos<T, NC>(kk)];
+            const V2<T> zb = cconj(buf[tspos<T, NC>((NC - kk) & (NC - 1))]);
+            const V2<T> t = cmul(csub(za, zb), __ldg(wsplit + kk));
+            const V2<T> ee = cadd(za, zb);
+            p = hi ? cconj(pfma(ee, splat((T)0.5), mk2<T>(-t.x, -t.y))) : pfma(ee, splat((T)0.5), t);
+        }
         const T m2 = p.x * p.x + p.y * p.y;
         T g = m2 > QD_TINY2 ? m2 * rsqrt_fast(m2) : 0.0f;
         const int off = (int)((e >> 26) & 31u);
@@ -234,8 +278,8 @@ QD_DEV void quantize_frame_team(V2<T> *buf, T *slotG, V2<T> *slotP, const QuantD
     // X[k], X[NC-k] of row i from the packed spectrum, magnitudes after the quantizer (ml, mh) and phasors
     auto row = [&](int i, T &nl, T &nh, V2<T> &ul, V2<T> &uh, V2<T> &v, int &pa, int &pb) {
         const int k = 32 * i + lane;
-        pa = rpos<T, NC>(lane, i);
-        pb = k == 0 ? pa : mpos<T, NC>(lane, i);   // Z[NC] = Z[0]
+        pa = tspos<T, NC>(k);
+        pb = k == 0 ? pa : tspos<T, NC>(NC - k);   // Z[NC] = Z[0]
         v = __ldg(wsplit + k);
         const V2<T> za = buf[pa], zb = cconj(buf[pb]);
         const V2<T> e = cadd(za, zb);
@@ -257,7 +301,7 @@ QD_DEV void quantize_frame_team(V2<T> *buf, T *slotG, V2<T> *slotP, const QuantD
         if (rb < HR) row(rb, post_l, post_h, u0, u1, v, p0, p1);
     }
     // the two walks meet at bin NC/2 (lane 0 of the last warp)
-    const int pm = spos<T, NC>(NC / 2);
+    const int pm = tspos<T, NC>(NC / 2);
     T mm = 0.0f;
     V2<T> um = mk2<T>(1.0f, 0.0f);
     if (rb == HR && lane == 0) {
@@ -323,7 +367,6 @@ spec_pass_team_kernel(const SpecArgsT<T> a, const TeamGather tg) {
     using C = FftCfg<T, NC>;
     constexpr int HOP = L::HOP;
     constexpr int HP = HOP / 2;
-    constexpr int HPP = HP + HP / 32;
     constexpr int nthreads = 32 * NF * CW;
     static_assert(NF <= 15, "one named barrier per team");
     QD_DYN_SMEM(smem);
@@ -422,7 +465,6 @@ spec_pass_team_kernel(const SpecArgsT<T> a, const TeamGather tg) {
         __syncthreads();
         // ---- overlap-add in frame order (spec_pass_kernel's general hop, rolled)
         for (int c = tid; c < HP; c += nthreads) {
-            const int pc = pidx(c);
 #pragma unroll 1
             for (int h = 0; h < NF + 3; ++h) {
                 V2<T> v = (h < 3) ? tail[h * HP + c] : mk2<T>(0.0f, 0.0f);
@@ -430,7 +472,7 @@ spec_pass_team_kernel(const SpecArgsT<T> a, const TeamGather tg) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int w = w0 + k;
-                    if (w <= w1) v = padd(v, bufs[(size_t)w * L::BUF + (h - w) * HPP + pc]);
+                    if (w <= w1) v = padd(v, bufs[(size_t)w * L::BUF + tpos<T, NC>((h - w) * HP + c)]);
                 }
                 if (h >= NF) {
                     tail[(h - NF) * HP + c] = v;
