@@ -221,11 +221,11 @@ int launch_spec_prec(qd_plan *pl, qd::SpecArgsT<T> a, const float *src, float *d
     int nw = fx ? pl->nw : pick_nw<T>(pl->nc, false) == 16 && !pl->ts ? 8 : pick_nw<T>(pl->nc, false);
     const bool ts = fx ? pl->ts_fx : pl->ts;
     const int ng = (nw == 16) ? 2 : 1;   // clips per CTA
-    // long frames without FX: teams of warps per frame (qd_spec_team.cuh), one CTA per SM
+    // three-pass plans without FX: the team kernel (qd_spec_team.cuh; several warps per frame at n_fft >= 4096)
     const bool team = !fx && pl->team_nf > 0;
     // tiling: whole clips when the batch alone fills the GPU, else cut clips along time
     const int total_blocks = (a.n + pl->hop - 1) / pl->hop;
-    const int ctas_per_sm = team ? 1 : std::max<int>(1, (int)((227 * 1024) / (pl->spec_smem + 1024)));
+    const int ctas_per_sm = std::max<int>(1, (int)((227 * 1024) / ((team ? pl->team_smem : pl->spec_smem) + 1024)));
     const int64_t want = (int64_t)pl->sm_count * ctas_per_sm * 2 * ng;
     const int wpg = team ? pl->team_nf : nw / ng;  // frames per batch of one clip group
     int tile = total_blocks;

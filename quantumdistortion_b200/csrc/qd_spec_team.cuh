@@ -48,20 +48,30 @@ QD_DEV void team_sync(int team) {
 //   middle pass (stride S2)        : the lowest bits below S2 and the bits from M2 upwards,
 //   third pass (stride 1 per lane) : the bits from R3 upwards,
 //   rows of the walk (bin k)       : the bits from NC / R1 upwards (k mod R1 is the slowest digit of the position)
-// and element a sits at  a ^ ((a >> S1) & M1) ^ ((a >> S2) & M2),  which folds exactly those higher bits onto the bank
-// bits, so that each pattern is a bijection onto the 16 (8) banks.  Bits above the bank bits are untouched: the map is a
+// and element a sits at  a ^ low(a),  low = a GF(2)-linear image of the higher index bits (for the long frames
+// ((a >> S1) & M1) ^ ((a >> S2) & M2)) that folds exactly those bits onto the bank bits, so that each pattern is a
+// bijection onto the 16 (8) banks.  Bits above the bank bits are untouched: the map is a
 // permutation of [0, NC), and it is linear over XOR, so pos(a0 + q S) = pos(a0) ^ pos(q S) with a compile-time second term
 // whenever a0 and q S occupy different bits (they do in every pass).
+// low(a): what is XORed onto the bank bits; a function of index bits above the bank bits only.
 template <class T, int NC> struct TeamSwz;
-template <> struct TeamSwz<float, 2048>  { static constexpr int S1 = 4, M1 = 15, S2 = 8, M2 = 7; };
-template <> struct TeamSwz<float, 4096>  { static constexpr int S1 = 4, M1 = 15, S2 = 8, M2 = 15; };
-template <> struct TeamSwz<double, 2048> { static constexpr int S1 = 3, M1 = 7,  S2 = 7, M2 = 7; };
-template <> struct TeamSwz<double, 4096> { static constexpr int S1 = 4, M1 = 7,  S2 = 8, M2 = 7; };
+template <> struct TeamSwz<float, 2048>  { static __host__ __device__ constexpr int low(int a) { return ((a >> 4) & 15) ^ ((a >> 8) & 7); } };
+template <> struct TeamSwz<float, 4096>  { static __host__ __device__ constexpr int low(int a) { return ((a >> 4) & 15) ^ ((a >> 8) & 15); } };
+template <> struct TeamSwz<double, 2048> { static __host__ __device__ constexpr int low(int a) { return ((a >> 3) & 7) ^ ((a >> 7) & 7); } };
+template <> struct TeamSwz<double, 4096> { static __host__ __device__ constexpr int low(int a) { return ((a >> 4) & 7) ^ ((a >> 8) & 7); } };
+// the short frames (one warp per frame, CW = 1) have three-pass plans too: 8 x 8 x 8 (n_fft 1024) and 8 x 8 x 4 (n_fft 512).
+// Half-warp patterns of 8 x 8 x 8: {a0..a3}, {a0,a1,a2,a6}, {a3..a6}, rows {a6,a7,a8,a3};
+// of 8 x 8 x 4: {a0..a3}, {a0,a1,a5,a6}, {a2..a5}, rows {a5,a6,a7,a2}.  Bank images of the higher bits (b3 b2 b1 b0):
+template <> struct TeamSwz<float, 512> {   // a4 -> 0001, a5 -> 0010, a6 -> 1100, a7 -> 0001, a8 -> 0010
+    static __host__ __device__ constexpr int low(int a) { return ((a >> 4) & 3) ^ (((a >> 6) & 1) * 12) ^ ((a >> 7) & 3); }
+};
+template <> struct TeamSwz<float, 256> {   // a4 -> 0010, a5 -> 0101, a6 -> 1000, a7 -> 0010
+    static __host__ __device__ constexpr int low(int a) { return (((a >> 4) & 1) << 1) ^ (((a >> 5) & 1) * 5) ^ (((a >> 6) & 1) << 3) ^ (((a >> 7) & 1) << 1); }
+};
+template <> struct TeamSwz<double, 512> { static __host__ __device__ constexpr int low(int a) { return ((a >> 3) & 7) ^ ((a >> 6) & 7); } };
+template <> struct TeamSwz<double, 256> { static __host__ __device__ constexpr int low(int a) { return ((a >> 3) & 7) ^ ((a >> 6) & 3); } };
 template <class T, int NC>
-QD_DEV constexpr int tpos(int a) {
-    using Z = TeamSwz<T, NC>;
-    return a ^ ((a >> Z::S1) & Z::M1) ^ ((a >> Z::S2) & Z::M2);
-}
+QD_DEV constexpr int tpos(int a) { return a ^ TeamSwz<T, NC>::low(a); }
 // position of spectrum bin k (0 <= k < NC) after the in-place DIF passes (digit order of qd::spos)
 template <class T, int NC>
 QD_DEV int tspos(int k) {
@@ -174,7 +184,7 @@ QD_DEV void t_inv_last(V2<T> *buf, const V2<T> *wtab, const V2<T> *tw, int lane,
 template <class T, int NC, int CW>
 QD_DEV void t_fft_forward_rest(V2<T> *buf, const V2<T> *tw2, int lane, int wsub, int team) {
     using C = FftCfg<T, NC>;
-    static_assert(C::R3 > 1, "the team kernel is built for the three-pass plans (n_fft >= 4096)");
+    static_assert(C::R3 > 1, "the team kernel is built for the three-pass plans");
     t_fwd_pass<T, NC, NC / C::R1, C::R2, true, CW>(buf, tw2, lane, wsub);
     team_sync<CW>(team);
     t_fwd_pass<T, NC, C::R3, C::R3, false, CW>(buf, nullptr, lane, wsub);

@@ -13,14 +13,19 @@ namespace qd_launch {
 // configuration keeps the one-warp-per-frame kernel.  Sized so that the CTA fills one SM: float32 n_fft 4096 has 7
 // frame buffers of 17 KB (28 warps at 72 registers), float64 n_fft 4096 four of 34 KB, float64 n_fft 8192 two of 68 KB.
 struct TeamShape { int nf, cw; };
+// The short three-pass plans (n_fft 512 / 1024, float32) run the same kernel with one warp per frame (CW = 1) for its
+// swizzled buffer layout: the padded layout of spec_pass_kernel spends 45 % / 33 % of its shared-memory wavefronts on
+// bank-conflict replays there and is bound by them (LSU data pipe 84 %).
 template <class T> inline TeamShape team_shape(int nc) {
-    if (sizeof(T) == 4) return nc == 2048 ? TeamShape{7, 4} : TeamShape{0, 0};
+    if (sizeof(T) == 4) return nc == 2048 ? TeamShape{7, 4} : (nc == 256 || nc == 512) ? TeamShape{8, 1} : TeamShape{0, 0};
     return nc == 2048 ? TeamShape{4, 4} : nc == 4096 ? TeamShape{2, 8} : TeamShape{0, 0};
 }
 
 // dynamic shared memory of that kernel (0: none)
 template <class T> inline size_t team_smem_bytes(int nc, int n_slots) {
-    if (sizeof(T) == 4) return nc == 2048 ? qd::SpecSmem<float, 2048, 7>::bytes(n_slots) : 0;
+    if (sizeof(T) == 4)
+        return nc == 2048 ? qd::SpecSmem<float, 2048, 7>::bytes(n_slots) : nc == 512 ? qd::SpecSmem<float, 512, 8>::bytes(n_slots)
+             : nc == 256 ? qd::SpecSmem<float, 256, 8>::bytes(n_slots) : 0;
     return nc == 2048 ? qd::SpecSmem<double, 2048, 4>::bytes(n_slots) : nc == 4096 ? qd::SpecSmem<double, 4096, 2>::bytes(n_slots) : 0;
 }
 
