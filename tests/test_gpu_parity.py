@@ -104,6 +104,29 @@ def test_tiling_and_batch_size_do_not_change_bits(qd):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n_fft,prec,copies", [(512, "float32", 1200), (1024, "float32", 1200), (4096, "float32", 400),
+                                               (4096, "float64", 400), (8192, "auto", 350)])
+def test_team_kernel_is_deterministic_across_tilings_and_runs(qd, n_fft, prec, copies):
+    """The team kernel (qd_spec_team.cuh: several warps per frame, named barriers, per-warp gather lists): the same clip
+    alone (cut into time tiles), inside a batch that fills the GPU with whole-clip CTAs, and rendered three times over --
+    bit for bit the same, and within the north-star tolerance of the oracle.  A missing barrier shows up here as a
+    run-to-run difference (compute-sanitizer is not available on this pool)."""
+    import torch
+    n, sr = 60000, 48000
+    clip = synth.bass_clip(78, n, sr)
+    kw = dict(SB, n_fft=n_fft, precision=prec)
+    y1, _ = qd.process_batch(torch.from_numpy(clip[None, :]).cuda(), sr, **kw)
+    big = torch.from_numpy(np.repeat(clip[None, :], copies, axis=0)).cuda()
+    runs = [qd.process_batch(big, sr, **kw)[0] for _ in range(3)]
+    for y in runs:
+        assert torch.equal(y[0], y1[0]) and torch.equal(y[copies - 1], y1[0]) and torch.equal(y[copies // 2], y1[0])
+        assert torch.equal(y, runs[0])
+    ref, _ = orc.process_audio(clip, sr, n_fft=n_fft)
+    got = y1[0].cpu().numpy()
+    assert float(np.max(np.abs(got.astype(np.float64) - ref))) <= 1e-4 and orc.null_test_db(got, ref) <= -80.0
+
+
+@pytest.mark.gpu
 def test_full_size_properties(qd):
     """BASELINE config #2 clip length (480 000 samples): passthrough null, limiter ceiling, determinism."""
     import torch
