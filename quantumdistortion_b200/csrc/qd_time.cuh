@@ -55,7 +55,22 @@ QD_DEV void load8(const float *x, long long s, long long n, bool vec, float (&v)
 
 QD_DEV double limiter_e(float peak, double ceiling) {  // dsp/limiter.py:68-72
     const double p = (double)peak;
+#ifdef QD_EMU
     return (p > ceiling && p > 1e-12) ? 1.0 - ceiling / p : 0.0;
+#else
+    // 1 - ceiling / p without the IEEE division subroutine, which was 29 % of the kernel's instructions (it runs twice
+    // per sample, ncu): the peak is a float32 value, so MUFU.RCP gives 1/p to 2^-23 and two Newton steps in float64
+    // square that error twice (2^-46, 2^-92: below the rounding of the steps themselves); e = fma(-ceiling, r, 1) then
+    // differs from the correctly rounded 1 - ceiling / p by about 2^-52 absolute -- the same size as the rounding of the
+    // reference's own two operations, and 2^-29 of the float32 step of y = float32(x (1 - u)).
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(peak));
+    double r = (double)r0;
+    r = fma(fma(-p, r, 1.0), r, r);
+    r = fma(fma(-p, r, 1.0), r, r);
+    const double e = fma(-ceiling, r, 1.0);
+    return (p > ceiling && p > 1e-12) ? e : 0.0;   // a select: the lanes with a tiny or zero peak never use r
+#endif
 }
 
 // dsp/limiter.py:14-80 then dsp/pipeline.py:894-910, 1096, 1371-1375.
