@@ -14,6 +14,7 @@
 #include <type_traits>
 
 #include "qd_spec.cuh"
+#include "qd_spec_team.cuh"
 #include "qd_time.cuh"
 #include "qd_yin.cuh"
 
@@ -258,29 +259,42 @@ __global__ void __launch_bounds__(32 * AT_SW_STATS) at_frame_stats_kernel(const 
         const float v0 = s0 < a.n ? x[s0] : 0.0f, v1 = s0 + 1 < a.n ? x[s0 + 1] : 0.0f;
         sq += v0 * v0 + v1 * v1;
         mx = fmaxf(mx, fmaxf(fabsf(v0), fabsf(v1)));
-        buf[pidx(j)] = make_float2(v0 * a.hann[2 * j], v1 * a.hann[2 * j + 1]);
+        buf[tpos<float, NC>(j)] = make_float2(v0 * a.hann[2 * j], v1 * a.hann[2 * j + 1]);
     }
     sq = warp_sum(sq);
     mx = warp_max(mx);
     __syncwarp();
-    SpecArgsT<float> sa{};
-    sa.tw2 = a.tw2;
-    fwd_first_buf<float, NC, FftCfg<float, NC>::R1>(buf, a.tw1, lane);
-    fft_forward<float, NC>(buf, nullptr, sa, nullptr, a.tw1, a.tw2, lane);
-    real_split<float, NC>(buf, a.wsplit, lane);
-    constexpr int ROWS = (NC + 1 + 31) / 32;
+    // the three-pass FFT on the swizzled buffer layout of qd_spec_team.cuh (one warp per frame: CW = 1); on the padded
+    // layout this kernel was bound by shared-memory bank conflicts (LSU data pipe 82 %)
+    t_fwd_first_buf<float, NC, FftCfg<float, NC>::R1, 1>(buf, a.tw1, lane, 0);
+    __syncwarp();
+    t_fft_forward_rest<float, NC, 1>(buf, a.tw2, lane, 0, 0);
     // |X| + 1e-8 and its logarithm with the fast float32 units (rsqrt, lg2: ~1e-6 relative, like the float32 FFT that
-    // produced X; the flatness is only compared with a threshold); a lane adds its 64 (65) bins in float32, the lanes'
-    // partial sums are added in float64
+    // produced X; the flatness is only compared with a threshold); a lane adds its bins in float32, the lanes'
+    // partial sums are added in float64.  X[k] and X[NC-k] come out of the packed spectrum pair by pair (real split).
     float lgf = 0.0f, arf = 0.0f;
-#pragma unroll 4
-    for (int row = 0; row < ROWS; ++row) {
-        if (row < ROWS - 1 || lane == 0) {
-            const float2 v = buf[rpos<float, NC>(lane, row)];
-            const float p2 = fmaf(v.x, v.x, v.y * v.y);
-            const float m = (p2 > 0.0f ? p2 * rsqrtf(p2) : 0.0f) + 1e-8f;
-            lgf += __log2f(m);
-            arf += m;
+    auto add_bin = [&](float re, float im) {
+        const float p2 = fmaf(re, re, im * im);
+        const float m = (p2 > 0.0f ? p2 * rsqrtf(p2) : 0.0f) + 1e-8f;
+        lgf += __log2f(m);
+        arf += m;
+    };
+#pragma unroll 2
+    for (int row = 0; row < NC / 64; ++row) {
+        const int k = 32 * row + lane;
+        if (k == 0) {
+            const float2 z0 = buf[0];
+            add_bin(z0.x + z0.y, 0.0f);                                   // DC
+            add_bin(z0.x - z0.y, 0.0f);                                   // Nyquist
+            const float2 zm = buf[tspos<float, NC>(NC / 2)];
+            add_bin(zm.x, zm.y);                                          // |X[NC/2]| = |conj Z[NC/2]|
+        } else {
+            const float2 za = buf[tspos<float, NC>(k)], zb = cconj(buf[tspos<float, NC>(NC - k)]);
+            const float2 e = cadd(za, zb);
+            const float2 t = cmul(csub(za, zb), __ldg(a.wsplit + k));
+            const float2 xa = pfma(e, splat(0.5f), t), xb = pfma(e, splat(0.5f), make_float2(-t.x, -t.y));
+            add_bin(xa.x, xa.y);
+            add_bin(xb.x, xb.y);
         }
     }
     const double lg = warp_sum((double)lgf) * 0.693147180559945309417, ar = warp_sum((double)arf);

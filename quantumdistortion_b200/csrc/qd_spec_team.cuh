@@ -110,6 +110,28 @@ QD_DEV void t_fwd_first(V2<T> *buf, const float2 *frame, const V2<T> *wtab, cons
     }
 }
 
+// first forward pass of a sequence that already sits in the buffer (swizzled positions), no window
+template <class T, int NC, int R, int CW>
+QD_DEV void t_fwd_first_buf(V2<T> *buf, const V2<T> *tw, int lane, int wsub) {
+    constexpr int S = NC / R;
+    constexpr int NB = NC / R / 32;
+    constexpr int LG = qd_log2(R);
+#pragma unroll 1
+    for (int i = wsub; i < NB; i += CW) {
+        const int p0 = tpos<T, NC>(lane + 32 * i);
+        V2<T> v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = buf[p0 ^ tpos<T, NC>(q * S)];
+        dft_reg<R, -1, T>(v);
+        buf[p0] = v[0];
+        twiddle_walk<T, R>(tw + (i * R) * 32 + lane,
+                           [&](auto kc, V2<T> w) {
+                               constexpr int k = decltype(kc)::value;
+                               buf[p0 ^ tpos<T, NC>(k * S)] = cmul(v[qd_bitrev(k, LG)], w);
+                           });
+    }
+}
+
 template <class T, int NC, int M, int R, bool TW, int CW>
 QD_DEV void t_fwd_pass(V2<T> *buf, const V2<T> *tw, int lane, int wsub) {
     constexpr int S = M / R;
