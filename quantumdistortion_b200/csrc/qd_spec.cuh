@@ -403,7 +403,15 @@ QD_DEV float rsqrt_fast(float x) {
     return r;
 #endif
 }
-QD_DEV double rsqrt_fast(double x) { return 1.0 / sqrt(x); }
+// float64: CUDA's rsqrt() (one MUFU seed + Newton steps, 1 ulp) instead of a square root followed by an IEEE division,
+// which together were 10 % of the float64 kernels' instructions (ncu, n_fft 8192)
+QD_DEV double rsqrt_fast(double x) {
+#ifdef QD_EMU
+    return 1.0 / std::sqrt(x);
+#else
+    return rsqrt(x);
+#endif
+}
 // log2 / exp2 as single MUFU operations for the log-domain bitcrush: absolute error of lg2.approx ~1e-6 near the values
 // that matter (decisions closer than 2e-4 to a rounding boundary are re-made in double), relative error of ex2.approx 2e-7
 QD_DEV float log2_fast(float x) {
