@@ -196,6 +196,33 @@ def test_edge_cases(qd):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n_fft", [512, 1024, 4096, 8192])
+def test_edge_cases_other_frame_sizes(qd, n_fft):
+    """Ragged and tiny clips through the team kernel (n_fft != 2048): shorter than a hop, shorter than a frame, odd lengths
+    (scalar load / store paths, no bulk-copy staging), a length that is a multiple of 4 but not of the hop, multiband, and a
+    batch of unequal content -- each against the oracle."""
+    sr = 48000
+    # a single sample is a centred impulse: every bin has the same magnitude and alternating sign, the quantizer's phasor
+    # sums cancel exactly and the reference's output phase is decided by rounding noise -- compared without the quantizer
+    x1 = np.array([0.37], dtype=np.float32)
+    y, _ = qd.process_audio(x1, sr, n_fft=n_fft, passthrough_test=True, **SB)
+    _check(y, orc.process_audio(x1, sr, n_fft=n_fft, passthrough_test=True)[0], f"n_fft {n_fft} n 1 passthrough")
+    for n in (2, 7, n_fft // 4 - 1, n_fft - 1, n_fft + 3, 3 * n_fft + 5, 20000, 20001):
+        x = synth.noise_clip(300 + n % 97, n)
+        y, taps = qd.process_audio(x, sr, n_fft=n_fft, **SB)
+        ref, rt = orc.process_audio(x, sr, n_fft=n_fft)
+        _check(y, ref, f"n_fft {n_fft} n {n}")
+        _check(taps["pre_quant"], rt["pre_quant"], f"n_fft {n_fft} n {n} pre_quant")
+    n = 6 * n_fft + 2
+    xb = np.stack([synth.bass_clip(1, n, sr), np.zeros(n, dtype=np.float32), synth.noise_clip(3, n)])
+    kw = dict(use_multiband=True, crossover_hz=250.0, distortion_mode="tube", dry_wet=0.8)
+    yb, _ = qd.process_batch(xb, sr, n_fft=n_fft, **SB, **kw)
+    for i in range(3):
+        ref, _ = orc.process_audio(xb[i], sr, n_fft=n_fft, **kw)
+        _check(yb[i], ref, f"n_fft {n_fft} multiband clip {i}")
+
+
+@pytest.mark.gpu
 def test_spectral_fx_batch_shared_and_per_clip_seeds(qd):
     """BASELINE config #4 shape: Growl preset + multiband + each FX; shared-seed batch and per-clip seeds."""
     n, sr = 20000, 48000
