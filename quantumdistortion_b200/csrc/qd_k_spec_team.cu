@@ -38,6 +38,7 @@ int launch_spec_team<float>(int nc, const qd::SpecArgsT<float> &a, const qd::Tea
 
 template <>
 int launch_spec_team<double>(int nc, const qd::SpecArgsT<double> &a, const qd::TeamGather &tg, int tiles, int64_t batch, cudaStream_t st) {
+    if (nc == 1024) return launch_spec_team_t<double, 1024, 8, 2>(a, tg, tiles, batch, st);
     if (nc == 2048) return launch_spec_team_t<double, 2048, 4, 4>(a, tg, tiles, batch, st);
     if (nc == 4096) return launch_spec_team_t<double, 4096, 2, 8>(a, tg, tiles, batch, st);
     return qd_err::fail(QD_ERR_UNSUPPORTED, "no float64 team kernel for this n_fft");

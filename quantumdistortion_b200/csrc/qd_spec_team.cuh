@@ -68,6 +68,7 @@ template <> struct TeamSwz<float, 512> {   // a4 -> 0001, a5 -> 0010, a6 -> 1100
 template <> struct TeamSwz<float, 256> {   // a4 -> 0010, a5 -> 0101, a6 -> 1000, a7 -> 0010
     static __host__ __device__ constexpr int low(int a) { return (((a >> 4) & 1) << 1) ^ (((a >> 5) & 1) * 5) ^ (((a >> 6) & 1) << 3) ^ (((a >> 7) & 1) << 1); }
 };
+template <> struct TeamSwz<double, 1024> { static __host__ __device__ constexpr int low(int a) { return ((a >> 3) & 7) ^ ((a >> 6) & 7); } };   // 16 x 8 x 8
 template <> struct TeamSwz<double, 512> { static __host__ __device__ constexpr int low(int a) { return ((a >> 3) & 7) ^ ((a >> 6) & 7); } };
 template <> struct TeamSwz<double, 256> { static __host__ __device__ constexpr int low(int a) { return ((a >> 3) & 7) ^ ((a >> 6) & 3); } };
 template <class T, int NC>

@@ -228,7 +228,7 @@ def test_emu_formant_shift_pass(emu_spec, n_fft, nw, n, semitones):
 
 
 @pytest.mark.parametrize("n_fft,shape,n,tile,prec", [(512, 801, 1500, 7, "f32"), (512, 801, 24002, 64, "f32"), (1024, 801, 2100, 6, "f32"),
-                                                     (1024, 801, 24000, 64, "f32"),
+                                                     (1024, 801, 24000, 64, "f32"), (2048, 802, 6000, 64, "f64"), (2048, 802, 24000, 9, "f64"),
                                                      (4096, 704, 9000, 64, "f32"), (4096, 704, 9000, 3, "f32"),
                                                      (4096, 704, 60000, 17, "f32"),   # interior batches: bulk-copy staging
                                                      (4096, 404, 5003, 64, "f64"), (8192, 208, 17000, 64, "f64"),
@@ -245,7 +245,7 @@ def test_emu_team_kernel(emu_spec, n_fft, shape, n, tile, prec):
     assert np.max(np.abs(y - oracle_pass(x, 48000, n_fft, True, True, 1.0, 0.1))) < (1e-5 if prec == "f32" else 5e-7)
 
 
-@pytest.mark.parametrize("n_fft,shape,prec", [(512, 801, "f32"), (1024, 801, "f32"), (4096, 704, "f32"), (4096, 404, "f64"), (8192, 208, "f64")])
+@pytest.mark.parametrize("n_fft,shape,prec", [(2048, 802, "f64"), (512, 801, "f32"), (1024, 801, "f32"), (4096, 704, "f32"), (4096, 404, "f64"), (8192, 208, "f64")])
 def test_emu_team_kernel_wide_mask_and_epilogue(emu_spec, n_fft, shape, prec):
     """Targets that gather more than 32 sources (a slot's sources span several groups of its warp's list), no smoothing,
     and the wavefold epilogue."""
