@@ -112,7 +112,8 @@ namespace {
 //      FX variants read tables through L1.  Must stay in sync with the switch in dispatch_spec().
 template <class T> int pick_nw(int nc, bool fx, bool formant = false) {
     if (sizeof(T) == 4 && formant) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 1;   // scratch buffer per warp
-    if (sizeof(T) == 8 && fx) return nc <= 512 ? 8 : nc == 1024 ? 4 : nc == 2048 ? 2 : 1;  // n_fft 8192: one warp (182 KB)
+    // n_fft 8192: one warp (182 KB); n_fft 2048: six warps beside their magnitude planes, four with the formant scratch
+    if (sizeof(T) == 8 && fx) return nc <= 512 ? 8 : nc == 1024 ? (formant ? 4 : 6) : nc == 2048 ? 2 : 1;
     if (sizeof(T) == 8) return nc <= 1024 ? 8 : nc == 2048 ? 4 : 2;
     if (fx) return nc == 1024 ? 12 : nc < 1024 ? 8 : nc == 2048 ? 4 : 2;   // what fits beside the FX magnitude planes
     return nc == 1024 ? QD_NW_1024 : nc < 1024 ? 8 : 4;  // 16 = two independent groups of 8 warps per CTA
@@ -133,6 +134,7 @@ size_t spec_smem_bytes(int nc, int nw, bool ts, int n_slots, int n_src, int form
             if (nw == 16) return qd::SpecSmem<T, 1024, 8, 2>::bytes(n_slots, ts, n_src, 0, fx);
             return nw == 8 ? smem_of<T, 1024, 8>(n_slots, false, 0, fm, fx)
                  : nw == 12 ? smem_of<T, 1024, 12>(n_slots, false, 0, fm, fx)
+                 : nw == 6 ? smem_of<T, 1024, 6>(n_slots, false, 0, fm, fx)
                  : nw == 4 ? smem_of<T, 1024, 4>(n_slots, false, 0, fm, fx) : 0;
         case 2048: return nw == 4 ? smem_of<T, 2048, 4>(n_slots, false, 0, fm, fx)
                         : nw == 2 ? smem_of<T, 2048, 2>(n_slots, false, 0, fm, fx) : 0;
@@ -160,7 +162,8 @@ int dispatch_spec(int nc, int nw, bool ts, const qd::SpecArgsT<T> &a, int tiles,
                     return launch_spec_t<T, 1024, 8, true, false, 2>(a, tiles, batch, st);
                 }
             }
-            if constexpr (sizeof(T) == 8 && FX) return launch_spec_t<T, 1024, 4, false, true>(a, tiles, batch, st);
+            if constexpr (sizeof(T) == 8 && FX) return nw == 6 ? launch_spec_t<T, 1024, 6, false, true>(a, tiles, batch, st)
+                                                               : launch_spec_t<T, 1024, 4, false, true>(a, tiles, batch, st);
             else if constexpr (FX) return nw == 8 ? launch_spec_t<T, 1024, 8, false, true>(a, tiles, batch, st)
                                              : ts ? launch_spec_t<T, 1024, 12, true, true>(a, tiles, batch, st)
                                                   : launch_spec_t<T, 1024, 12, false, true>(a, tiles, batch, st);
@@ -530,7 +533,8 @@ int qd_plan_create(const qd_params *params, const qd_tables *tables, qd_plan **o
         a.q = qdev;
         a.fx = fxd;
         a.formant_idx = d_fi; a.formant_frac = d_ff; a.formant_order = p.formant_order;
-        pl->nw = pick_nw<double>(pl->nc, fx);
+        pl->nw = pick_nw<double>(pl->nc, fx, formant);
+        if (pl->nw == 6 && spec_smem_bytes<double>(pl->nc, 6, false, n_slots, qdev.n_src, 0, fx) > 227 * 1024) pl->nw = 4;  // many target slots
         pl->ts = false;
         pl->spec_smem = spec_smem_bytes<double>(pl->nc, pl->nw, false, n_slots, qdev.n_src, formant ? 1 : 0, fx);
     } else {
