@@ -227,6 +227,15 @@ def test_emu_formant_shift_pass(emu_spec, n_fft, nw, n, semitones):
     assert err < 2e-5, err
 
 
+def test_team_gather_tables_invariants(tmp_path):
+    """Host side of the team kernel: qd_host::build_team_gather on random target tables for team widths 1 / 2 / 4 / 8 --
+    32-aligned lists, every source exactly once and in order, each slot in one warp's list, off / tail per group of 32
+    (tests/emu/team_gather_check.cpp, plain g++, no CUDA)."""
+    exe = str(tmp_path / "team_gather_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(EMU_DIR, "team_gather_check.cpp")])
+    assert subprocess.check_output([exe]).decode().strip() == "ok"
+
+
 @pytest.mark.parametrize("n_fft,shape,n,tile,prec", [(512, 801, 1500, 7, "f32"), (512, 801, 24002, 64, "f32"), (1024, 801, 2100, 6, "f32"),
                                                      (1024, 801, 24000, 64, "f32"), (2048, 802, 6000, 64, "f64"), (2048, 802, 24000, 9, "f64"),
                                                      (4096, 704, 9000, 64, "f32"), (4096, 704, 9000, 3, "f32"),
