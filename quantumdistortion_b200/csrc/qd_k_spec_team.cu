@@ -1,4 +1,5 @@
-// spectral pass for long frames: teams of warps per frame (qd_spec_team.cuh), float32 n_fft 4096 and float64 n_fft 4096 / 8192
+// spectral pass for the three-pass FFT plans: teams of warps per frame on swizzled buffers (qd_spec_team.cuh) -- float32
+// n_fft 512 / 1024 / 4096, float64 n_fft 2048 / 4096 / 8192
 #include <algorithm>
 #include <atomic>
 

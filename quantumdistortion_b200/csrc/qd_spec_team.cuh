@@ -1,4 +1,5 @@
-// qd_spec_team.cuh -- the spectral pass for long frames (n_fft >= 4096): a TEAM of CW warps owns one frame.
+// qd_spec_team.cuh -- the spectral pass for the three-pass FFT plans (every n_fft but 2048 in float32, every n_fft in
+// float64): a TEAM of CW warps owns one frame, and the frame buffers are XOR-swizzled instead of padded.
 //
 // qd_spec.cuh gives every frame to one warp, whose private buffer holds the frame's spectrum.  At n_fft 4096 / 8192 that
 // buffer is 17 / 34 KB (float32) or 68 KB (float64, n_fft 8192), so only 8 / 4 / 2 warps fit one SM and the pass is bound
@@ -12,6 +13,8 @@
 //     range are computed first, by the neighbour's rule, before any warp overwrites the buffer (barrier), so the
 //     3-tap smoothing sees the same window as the one-warp walk;
 //   * staging, overlap-add, epilogue and the HBM side are those of spec_pass_kernel (one clip per CTA).
+// The short three-pass plans (n_fft 512 / 1024) run it with CW = 1: the one-warp schedule, for the swizzled layout alone
+// (the 33/32 padding of qd_spec.cuh is conflict-free only for the 32 x 32 plan of n_fft 2048; see tpos below).
 // Same arithmetic per bin as qd_spec.cuh (the helpers are shared); only the association of the Q1 partial sums differs
 // (chunks of 32 sources are counted from the start of each warp's list).  Plain variant only (no spectral FX).
 #pragma once

@@ -1,5 +1,5 @@
-// qd_spec_team_launch.hpp -- launcher of the team kernel (qd_spec_team.cuh: CW warps per frame, n_fft >= 4096, plain
-// variant).  qd_api.cu sees only this declaration; qd_k_spec_team.cu holds the definition and the instantiations.
+// qd_spec_team_launch.hpp -- launcher of the team kernel (qd_spec_team.cuh: CW warps per frame on swizzled buffers, the
+// three-pass FFT plans, plain variant).  qd_api.cu sees only this declaration; qd_k_spec_team.cu holds the definition and the instantiations.
 #pragma once
 #include <cuda_runtime.h>
 
