@@ -32,6 +32,7 @@ static int launch_spec_team_t(const qd::SpecArgsT<T> &a, const qd::TeamGather &t
 template <>
 int launch_spec_team<float>(int nc, const qd::SpecArgsT<float> &a, const qd::TeamGather &tg, int tiles, int64_t batch, cudaStream_t st) {
     if (nc == 2048) return launch_spec_team_t<float, 2048, 7, 4>(a, tg, tiles, batch, st);
+    if (nc == 4096) return launch_spec_team_t<float, 4096, 4, 4>(a, tg, tiles, batch, st);   // n_fft 8192 under precision="float32"
     if (nc == 512) return launch_spec_team_t<float, 512, 8, 1>(a, tg, tiles, batch, st);
     if (nc == 256) return launch_spec_team_t<float, 256, 8, 1>(a, tg, tiles, batch, st);
     return qd_err::fail(QD_ERR_UNSUPPORTED, "no float32 team kernel for this n_fft");

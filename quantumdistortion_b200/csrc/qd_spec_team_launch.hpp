@@ -17,7 +17,7 @@ struct TeamShape { int nf, cw; };
 // swizzled buffer layout: the padded layout of spec_pass_kernel spends 45 % / 33 % of its shared-memory wavefronts on
 // bank-conflict replays there and is bound by them (LSU data pipe 84 %).
 template <class T> inline TeamShape team_shape(int nc) {
-    if (sizeof(T) == 4) return nc == 2048 ? TeamShape{7, 4} : (nc == 256 || nc == 512) ? TeamShape{8, 1} : TeamShape{0, 0};
+    if (sizeof(T) == 4) return nc == 2048 ? TeamShape{7, 4} : nc == 4096 ? TeamShape{4, 4} : (nc == 256 || nc == 512) ? TeamShape{8, 1} : TeamShape{0, 0};
     // float64 at the default n_fft 2048 (16 x 8 x 8; what precision="auto" picks for a wide-open band mask): 8 frames x 2 warps
     return nc == 1024 ? TeamShape{8, 2} : nc == 2048 ? TeamShape{4, 4} : nc == 4096 ? TeamShape{2, 8} : TeamShape{0, 0};
 }
@@ -25,7 +25,8 @@ template <class T> inline TeamShape team_shape(int nc) {
 // dynamic shared memory of that kernel (0: none)
 template <class T> inline size_t team_smem_bytes(int nc, int n_slots) {
     if (sizeof(T) == 4)
-        return nc == 2048 ? qd::SpecSmem<float, 2048, 7>::bytes(n_slots) : nc == 512 ? qd::SpecSmem<float, 512, 8>::bytes(n_slots)
+        return nc == 2048 ? qd::SpecSmem<float, 2048, 7>::bytes(n_slots) : nc == 4096 ? qd::SpecSmem<float, 4096, 4>::bytes(n_slots)
+             : nc == 512 ? qd::SpecSmem<float, 512, 8>::bytes(n_slots)
              : nc == 256 ? qd::SpecSmem<float, 256, 8>::bytes(n_slots) : 0;
     return nc == 1024 ? qd::SpecSmem<double, 1024, 8>::bytes(n_slots) : nc == 2048 ? qd::SpecSmem<double, 2048, 4>::bytes(n_slots)
          : nc == 4096 ? qd::SpecSmem<double, 4096, 2>::bytes(n_slots) : 0;

@@ -142,7 +142,7 @@ static int go(Cli &c) {
             return 0;                                                                                                \
         }
         if constexpr (is_double) { QD_TEAMCASE(1024, 8, 2) }   // 16 x 8 x 8; the float32 plan of this size is 32 x 32 (two passes)
-        QD_TEAMCASE(256, 8, 1) QD_TEAMCASE(512, 8, 1) QD_TEAMCASE(2048, 7, 4) QD_TEAMCASE(2048, 4, 4) QD_TEAMCASE(2048, 2, 2) QD_TEAMCASE(4096, 2, 8) QD_TEAMCASE(4096, 2, 4)
+        QD_TEAMCASE(256, 8, 1) QD_TEAMCASE(512, 8, 1) QD_TEAMCASE(2048, 7, 4) QD_TEAMCASE(2048, 4, 4) QD_TEAMCASE(2048, 2, 2) QD_TEAMCASE(4096, 2, 8) QD_TEAMCASE(4096, 2, 4) QD_TEAMCASE(4096, 4, 4)
         std::cerr << "no team instantiation for nc=" << nc << " nf=" << nf << " cw=" << cw << "\n";
         return 2;
     }

@@ -240,7 +240,7 @@ def test_team_gather_tables_invariants(tmp_path):
                                                      (1024, 801, 24000, 64, "f32"), (2048, 802, 6000, 64, "f64"), (2048, 802, 24000, 9, "f64"),
                                                      (4096, 704, 9000, 64, "f32"), (4096, 704, 9000, 3, "f32"),
                                                      (4096, 704, 60000, 17, "f32"),   # interior batches: bulk-copy staging
-                                                     (4096, 404, 5003, 64, "f64"), (8192, 208, 17000, 64, "f64"),
+                                                     (4096, 404, 5003, 64, "f64"), (8192, 208, 17000, 64, "f64"), (8192, 404, 40000, 6, "f32"),
                                                      (8192, 208, 17001, 5, "f64")])
 def test_emu_team_kernel(emu_spec, n_fft, shape, n, tile, prec):
     """qd_spec_team.cuh (a team of warps per frame, n_fft >= 4096; `shape` = 100 x frames per batch + warps per frame):

@@ -105,7 +105,7 @@ def test_tiling_and_batch_size_do_not_change_bits(qd):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_fft,prec,copies", [(512, "float32", 1200), (1024, "float32", 1200), (4096, "float32", 400),
-                                               (4096, "float64", 400), (8192, "auto", 350)])
+                                               (4096, "float64", 400), (8192, "auto", 350), (8192, "float32", 350)])
 def test_team_kernel_is_deterministic_across_tilings_and_runs(qd, n_fft, prec, copies):
     """The team kernel (qd_spec_team.cuh: several warps per frame, named barriers, per-warp gather lists): the same clip
     alone (cut into time tiles), inside a batch that fills the GPU with whole-clip CTAs, and rendered three times over --
@@ -123,7 +123,11 @@ def test_team_kernel_is_deterministic_across_tilings_and_runs(qd, n_fft, prec, c
         assert torch.equal(y, runs[0])
     ref, _ = orc.process_audio(clip, sr, n_fft=n_fft)
     got = y1[0].cpu().numpy()
-    assert float(np.max(np.abs(got.astype(np.float64) - ref))) <= 1e-4 and orc.null_test_db(got, ref) <= -80.0
+    # float32 at n_fft 8192 is the one configuration known to leave the 1e-4 bound (up to 3e-4 on noise), which
+    # is why precision="auto" never picks it; forced float32 is held to 5e-4 / -60 dBFS here
+    forced_f32 = n_fft == 8192 and prec == "float32"
+    assert float(np.max(np.abs(got.astype(np.float64) - ref))) <= (5e-4 if forced_f32 else 1e-4)
+    assert orc.null_test_db(got, ref) <= (-60.0 if forced_f32 else -80.0)
 
 
 @pytest.mark.gpu
